@@ -1,0 +1,187 @@
+/*
+ * xpcs_b200.h -- C-ABI of the B200-native XPCS correlation hot path.
+ *
+ * The reference (AdvancedPhotonSource/xpcs-eigen) has no FFI; its seams for this path
+ * are two abstract C++ classes and one static class, all reading a Configuration
+ * singleton.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference root).  The host program
+ * xpcs-eigen_b200/host (our `corr`) and the ctypes layer xpcs-eigen_b200/cabi.py bind
+ * exactly these symbols; INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions: plain C, opaque handle, int status (0 = ok, negative = XPCS_E_*),
+ * xpcs_last_error() for the message, no exceptions cross the boundary, one handle per
+ * GPU, thread-compatible (not thread-safe).  Host buffers are caller-owned; device
+ * memory is owned by the handle unless an entry point says "device pointer".
+ * Layouts are the reference's: tau-major [tau][pixel] for G2/IP/IF (main.cpp:193-201,
+ * corr.cpp:395), (T, Q) for norm-0-g2 / norm-0-stderr (h5_result.cpp:80-81),
+ * [2][F] for frameSum with row 0 = 1..F (sparse_filter.cpp:189-190).
+ * There is NO CPU fallback: every compute entry point fails with XPCS_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef XPCS_B200_H
+#define XPCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XPCS_OK 0
+#define XPCS_E_ARG (-1)     /* bad argument / inconsistent configuration          */
+#define XPCS_E_CUDA (-2)    /* CUDA runtime or launch failure, or no usable device */
+#define XPCS_E_STATE (-3)   /* call sequence violated (e.g. multitau before ingest) */
+#define XPCS_E_NOMEM (-4)
+
+/* compat_flags */
+#define XPCS_COMPAT_STALE_TAIL 1u /* reproduce the reference's dropped G2 pairs: the binary
+                                     search of corr.cpp:406 runs over the un-shrunk index
+                                     vector.  Off = exact sums.            */
+
+typedef struct xpcs_handle_s *xpcs_handle;
+
+/* What Configuration::init hands to the filters and to Corr (configuration.cpp:80-242);
+ * here an explicit POD instead of a process-wide singleton. */
+typedef struct XpcsParams {
+    int32_t struct_size;           /* = sizeof(XpcsParams), ABI guard                         */
+    int32_t width, height;         /* detector x_dimension / y_dimension (:94-95); P = w*h     */
+    int32_t frames;                /* getFrameTodoCount() (:594-601): output frames F          */
+    int32_t delays_per_level;      /* <entry>/delays_per_level (:146)                          */
+    int32_t stride_frames;         /* <entry>/stride_frames (:154)                             */
+    int32_t avg_frames;            /* <entry>/avg_frames (:155)                                */
+    int32_t static_window;         /* <entry>/static_mean_window_size (:201)                   */
+    int32_t normalize_by_framesum; /* <entry>/normalize_by_framesum (:158-162)                 */
+    uint32_t compat_flags;         /* XPCS_COMPAT_*                                            */
+    float lld, sigma;              /* <entry>/lld, sigma (:176-177); used with dark frames     */
+    const int32_t *dqmap;          /* [P] row-major dynamic partition ids, 0 = masked (:97)    */
+    const int32_t *sqmap;          /* [P] static partition ids (:98)                           */
+    const double *flatfield;       /* [P] or NULL = all ones (:203-214)                        */
+    int32_t shard_index;           /* this handle's pixel shard, 0 <= shard_index < shard_count */
+    int32_t shard_count;           /* 1 = whole detector.  Shards are contiguous ranges of the  */
+                                   /* (dq, sq, pixel)-sorted pixel list cut at static-bin       */
+                                   /* boundaries and balanced by pixel count.    */
+    int64_t reserve_events;        /* optional capacity hint for the device event store         */
+} XpcsParams;
+
+typedef struct XpcsInfo {
+    int32_t n_delays;        /* T                                                            */
+    int32_t max_level;
+    int32_t n_static;        /* S = getTotalStaticPartitions()                               */
+    int32_t n_dynamic;       /* Q = getTotalDynamicPartitions()                              */
+    int32_t n_segments;      /* surviving (dq, sq) map entries, all shards                   */
+    int32_t n_rows;          /* unmasked pixels owned by this shard                          */
+    int32_t n_rows_total;    /* unmasked pixels of the whole detector                        */
+    int32_t raw_frames_seen; /* raw frames pushed so far                                     */
+    int64_t events_pushed;   /* raw events received                                          */
+    int64_t events_stored;   /* events in the pixel-major store after finish_ingest          */
+    int64_t store_words;     /* padded words of the pixel-major store                        */
+    int32_t value_kind;      /* 0 = packed integer counts (exact), 1 = float values          */
+    int32_t max_row_events;  /* longest pixel row                                            */
+} XpcsInfo;
+
+/* ---- schedule: Corr::calculateLevelMax / Corr::delaysPerLevel (corr.cpp:1133-1160) ---- */
+int xpcs_level_max(int frames, int delays_per_level);
+/* writes up to cap (level, tau) pairs, returns T */
+int xpcs_delay_schedule(int frames, int delays_per_level, int32_t *level, int32_t *tau, int cap);
+
+/* ---- lifetime ---- */
+/* replaces: Configuration::BuildQMap (configuration.cpp:244-381) + the constructors of
+ * SparseFilter / DenseFilter (sparse_filter.cpp:63-109, dense_filter.cpp:64-115).       */
+int xpcs_create(const XpcsParams *params, int device, xpcs_handle *out);
+void xpcs_destroy(xpcs_handle h);
+const char *xpcs_last_error(xpcs_handle h); /* h may be NULL: error of the last failed create */
+int xpcs_get_info(xpcs_handle h, XpcsInfo *info);
+/* detector pixel index of every row this shard owns, in store order: (dq, sq, pixel) sorted
+ * (the iteration order of Configuration::getBinMaps(), configuration.cpp:262-296); out[n_rows] */
+int xpcs_get_row_pixels(xpcs_handle h, int32_t *out);
+/* run every kernel of this handle on the caller's CUDA stream (cudaStream_t); NULL = own stream */
+int xpcs_set_stream(xpcs_handle h, void *cuda_stream);
+/* forget all ingested frames and results, keep maps, dark image and allocations */
+int xpcs_reset(xpcs_handle h);
+
+/* ---- Filter stage ---- */
+/* replaces: DarkImage::DarkImage/Compute (data_structure/dark_image.cpp:59-106) fed by
+ * reader->NextFrames(darks) (main.cpp:227-239).  frames = [n][P] raw int16, host memory. */
+int xpcs_set_dark(xpcs_handle h, const int16_t *frames, int n);
+/* DarkImage::dark_avg()/dark_std() for --darkout (main.cpp:459-477); [P] each, nullable    */
+int xpcs_get_dark(xpcs_handle h, double *avg, double *std);
+
+/* replaces: Imm::NextFrames for compressed files (io/imm.cpp:70-118) + SparseFilter::Apply
+ * (filter/sparse_filter.cpp:115-193) for `nframes` consecutive RAW frames.
+ * idx/val = the concatenated payloads (int32 pixel index, int16 value) of those frames,
+ * frame_offsets[nframes+1] = event offsets of each frame relative to idx/val,
+ * clock/ticks = Header::elapsed / Header::corecotick per raw frame (nullable).
+ * Host pointers (pinned memory makes the copies asynchronous). */
+int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val,
+                     const int64_t *frame_offsets, const double *clock, const double *ticks,
+                     int nframes);
+/* same, but idx/val/frame_offsets are DEVICE pointers that stay valid (and unmodified)
+ * until xpcs_finish_ingest returns; no copy is made.  One call per ingest. */
+int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
+                            const int64_t *d_frame_offsets, int64_t n_events, int nframes);
+/* replaces: Imm::NextFrames for uncompressed files + DenseFilter::Apply
+ * (filter/dense_filter.cpp:121-210).  frames = [nframes][P] raw int16 (host). */
+int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const double *clock,
+                    const double *ticks, int nframes);
+int xpcs_push_dense_device(xpcs_handle h, const int16_t *d_frames, int nframes);
+
+/* Ends the ingest loop of main.cpp:258-268: builds the pixel-major store (the role of
+ * data_structure::SparseData, sparse_data.cpp:59-103) and returns the Filter getters
+ * (filter/filter.h:62-96) after the post-scaling of main.cpp:313-343 and :360-378:
+ *   pixel_sum[P]        PixelsSum()/F
+ *   frame_sum[2F]       FramesSum()
+ *   part_total[S]       PartitionsMean()/(pixels_per_sbin*F)
+ *   part_partial[floor(F/window)*S]  PartialPartitionsMean()/(pixels_per_sbin*window)
+ * all nullable.  With shard_count > 1 the sums cover this shard's pixels only. */
+int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total,
+                       float *part_partial);
+/* TimestampClock()/TimestampTicks(): [2][raw frames] each (sparse_filter.cpp:134-140) */
+int xpcs_get_timestamps(xpcs_handle h, double *clock, double *ticks);
+
+/* ---- Correlation ---- */
+/* replaces: Corr::multiTau2(SparseData*, float* G2, float* IP, float* IF) (corr.cpp:315-431).
+ * G2/IP/IF: host [T][P] tau-major, fully written (zeros for masked / event-less pixels);
+ * all three NULL = keep the results on the device only (the normal path without --g2out). */
+int xpcs_multitau(xpcs_handle h, float *G2, float *IP, float *IF);
+/* replaces: Corr::normalizeG2s (corr.cpp:927-1091): g2 and std-error, host (T, Q) each.
+ * Equivalent to xpcs_normalize_partials + xpcs_normalize_finish. */
+int xpcs_normalize(xpcs_handle h, float *g2, float *stderr_out);
+
+/* Multi-GPU split of xpcs_normalize.  xpcs_normalize_partials leaves, in
+ * one device buffer of *count doubles, (a) the normalised g2 row of every static segment
+ * this shard owns (zeros elsewhere) and (b) per dynamic bin the sample count, sum and sum
+ * of squares of the per-pixel G2/(IP*IF).  Summing the buffers of all shards element-wise
+ * (ncclAllReduce / torch.distributed.all_reduce, SUM, float64, in place on *d_partials)
+ * yields the single-GPU buffer bit for bit, because every segment is owned by exactly one
+ * shard.  xpcs_normalize_finish then produces g2 / stderr from the (reduced) buffer. */
+int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t *count);
+int xpcs_normalize_finish(xpcs_handle h, float *g2, float *stderr_out);
+
+/* replaces: Corr::twotime -> twotimeQBinThreading (corr.cpp:562-572, :781-924) including
+ * Smoothing (:433-560, :1166-1305), for ONE dynamic bin `qbin`:
+ *   C[F*F] row-major upper triangle (lower = 0), g2full[F], g2partials[wsize*partials]
+ *   ([d][w]), sg[F] (or [1] when average) -- all host, nullable.
+ * smoothing_method: 0 = none, 1 = symmetric; smoothing_average: "Average" filter. */
+int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int smoothing_method, int smoothing_average,
+                 float *C, float *g2full, float *g2partials, float *sg);
+
+/* ---- measurement hooks (bench.py, profiles/) ---- */
+/* record a CUDA event pair around every kernel launch of this handle */
+int xpcs_kernel_timing(xpcs_handle h, int enable);
+/* kernels launched by this handle since the last xpcs_kernel_report_reset */
+int64_t xpcs_launch_count(xpcs_handle h);
+/* per-kernel totals since the last reset: writes up to cap entries, returns the number of
+ * distinct kernels.  names[i] points into handle-owned storage. */
+int xpcs_kernel_report(xpcs_handle h, const char **names, double *total_ms, int64_t *launches,
+                       int cap);
+int xpcs_kernel_report_reset(xpcs_handle h);
+
+/* library/ABI version, and the compute capability it was compiled for (100 = sm_100a) */
+int xpcs_abi_version(void);
+int xpcs_compiled_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPCS_B200_H */

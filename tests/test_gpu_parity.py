@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded
+inputs.  Bars (BASELINE.json north_star): integer photon-count accumulations bit-exact --
+here that covers G2, IP, IF at every level, frameSum, pixelSum, partition means and
+norm-0-g2; floating-point paths (flat-field, averaging, frame-sum normalisation, stderr)
+within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star tolerance for floating-point results
+
+
+def run_gpu(pkg, dq, sq, F, off, idx, val, want_g2=True, **kw):
+    c = pkg.Correlator(dq, sq, F, **kw)
+    c.push_sparse(idx, val, off)
+    sums = c.finish_ingest()
+    G = c.multitau(want=want_g2)
+    g2, se = c.normalize()
+    info = c.info()
+    c.close()
+    return sums, G, g2, se, info
+
+
+def run_oracle(O, dq, sq, F, off, idx, val, dpl=8, compat=True, flat=None, stride=1, avg=1, swindow=None,
+               normalize_by_framesum=False):
+    qm = O.QMap(dq, sq)
+    swindow = swindow or max(1, F // 10)
+    fo = O.sparse_filter(qm, F, off, idx, val, flat=flat, stride=stride, avg=avg, swindow=swindow)
+    sums_raw = dict(frame_sum=fo.frame_sum.copy())
+    O.post_scale(qm, F, swindow, fo, normalize_by_framesum=normalize_by_framesum)
+    G2, IP, IF = O.multitau(qm.P, F, dpl, fo.rows, compat=compat)
+    g2, se = O.normalize(qm, G2, IP, IF)
+    W = F // swindow
+    sums = dict(pixel_sum=fo.pixel_sum, frame_sum=sums_raw["frame_sum"], part_total=fo.part_total[: qm.S],
+                part_partial=fo.part_partial[: W * qm.S].reshape(W, qm.S))
+    return sums, (G2, IP, IF), g2, se
+
+
+def assert_exact(a, b, what):
+    a = np.asarray(a).ravel()
+    b = np.asarray(b).ravel()
+    bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    assert not bad.any(), "%s: %d of %d entries differ, first at %d: %r vs %r" % (
+        what, bad.sum(), a.size, np.argmax(bad), a[np.argmax(bad)], b[np.argmax(bad)])
+
+
+def assert_close(a, b, what, rtol=RTOL, atol=0.0):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    both_nan = np.isnan(a) & np.isnan(b)
+    err = np.abs(a - b)
+    bad = ~(both_nan | (err <= atol + rtol * np.abs(b)))
+    assert not bad.any(), "%s: %d of %d beyond rtol %g, worst rel %.3g" % (
+        what, bad.sum(), a.size, rtol, np.nanmax(err / np.maximum(np.abs(b), 1e-300)))
+
+
+CASES = [  # h, w, F, occupancy, seed, dpl
+    (32, 32, 100, 0.05, 1, 8),
+    (48, 40, 601, 0.02, 2, 8),     # odd frame count: last frame dropped at level 1
+    (64, 64, 1000, 0.01, 3, 8),
+    (64, 64, 1023, 0.03, 4, 4),
+    (40, 56, 2049, 0.004, 5, 8),
+    (96, 96, 4000, 0.002, 6, 8),   # sparse rows: the stale-tail regime of SURVEY.md A.4
+    (24, 24, 33, 0.3, 7, 8),       # dense rows, F barely above 2*dpl
+    (16, 16, 15, 0.5, 8, 8),       # F < 2*dpl: level 0 only, truncated
+]
+
+
+@pytest.mark.parametrize("h,w,F,occ,seed,dpl", CASES)
+def test_sparse_integer_path_bit_exact(pkg, oracle, h, w, F, occ, seed, dpl):
+    dq, sq, off, idx, val = make_case(pkg, h, w, F, occ, seed)
+    sums, G, g2, se, info = run_gpu(pkg, dq, sq, F, off, idx, val, dpl=dpl, compat=True)
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, F, off, idx, val, dpl=dpl, compat=True)
+    assert info.value_kind == 0
+    for k, name in enumerate(("G2", "IP", "IF")):
+        assert_exact(G[k], rG[k], name)
+    assert_exact(sums["frame_sum"], rs["frame_sum"], "frameSum")
+    assert_exact(sums["pixel_sum"], rs["pixel_sum"], "pixelSum")
+    assert_exact(sums["part_total"], rs["part_total"], "partition-mean-total")
+    assert_exact(sums["part_partial"], rs["part_partial"], "partition-mean-partial")
+    assert_exact(g2, rg2, "norm-0-g2")
+    assert_close(se, rse, "norm-0-stderr")
+
+
+@pytest.mark.parametrize("h,w,F,occ,seed,dpl", CASES[:6])
+def test_sparse_exact_sums_without_compat(pkg, oracle, h, w, F, occ, seed, dpl):
+    """compat off = the mathematically exact pair sums (oracle restricted to the live prefix)."""
+    dq, sq, off, idx, val = make_case(pkg, h, w, F, occ, seed)
+    _, G, _, _, _ = run_gpu(pkg, dq, sq, F, off, idx, val, dpl=dpl, compat=False)
+    _, rG, _, _ = run_oracle(oracle, dq, sq, F, off, idx, val, dpl=dpl, compat=False)
+    for k, name in enumerate(("G2", "IP", "IF")):
+        assert_exact(G[k], rG[k], name)
+
+
+def test_stale_tail_fixture(pkg, oracle):
+    """The hand example of SURVEY.md A.4, verified against the reference binary: one pixel with
+    unit counts at frames 0..31, 400, 440, F=512: the reference drops the (100,110) pair at
+    level 2, so G2[tau=40] = 0 while the exact value is (1/4*1/4)/118."""
+    F = 512
+    dq = np.ones((1, 2), np.int32)
+    sq = np.ones((1, 2), np.int32)
+    frames = list(range(32)) + [400, 440]
+    off = np.zeros(F + 1, np.int64)
+    for f in frames:
+        off[f + 1:] += 1
+    idx = np.zeros(len(frames), np.int32)
+    val = np.ones(len(frames), np.int16)
+    _, tv = oracle.delay_schedule(F, 8)
+    k = list(tv).index(40)
+    _, G, _, _, _ = run_gpu(pkg, dq, sq, F, off, idx, val, compat=True)
+    assert G[0][k, 0] == 0.0
+    assert G[1][k, 0] == np.float32(8.5) / np.float32(118)
+    _, Ge, _, _, _ = run_gpu(pkg, dq, sq, F, off, idx, val, compat=False)
+    assert Ge[0][k, 0] == np.float32(0.0625) / np.float32(118)
+    _, rG, _, _ = run_oracle(oracle, dq, sq, F, off, idx, val, compat=True)
+    assert_exact(G[0], rG[0], "G2")
+
+
+def test_adversarial_rows(pkg, oracle):
+    """Single-event rows, a duplicated pixel inside one frame, events in the dropped last frame,
+    an all-masked column, unsorted pixel order within a frame, an empty frame range."""
+    h, w, F = 8, 8, 257
+    dq, sq = pkg.synth.annular_qmaps(h, w, n_dynamic=2, static_per_dynamic=2, r_min=0.0, r_max=6.0)
+    dq[:, 0] = 0
+    rng = np.random.default_rng(5)
+    per_frame = []
+    for f in range(F):
+        if 100 <= f < 120:
+            per_frame.append((np.zeros(0, np.int32), np.zeros(0, np.int16)))
+            continue
+        n = rng.integers(0, 6)
+        p = rng.integers(0, h * w, n).astype(np.int32)
+        if f % 17 == 0 and n > 0:
+            p = np.concatenate([p, p[:1]])  # same pixel twice in one frame
+        v = rng.integers(1, 4, p.size).astype(np.int16)
+        per_frame.append((p, v))
+    per_frame[F - 1] = (np.arange(h * w, dtype=np.int32)[::-1].copy(), np.ones(h * w, np.int16))
+    per_frame[3] = (np.array([9], np.int32), np.array([2], np.int16))
+    off = np.concatenate([[0], np.cumsum([p.size for p, _ in per_frame])]).astype(np.int64)
+    idx = np.concatenate([p for p, _ in per_frame])
+    val = np.concatenate([v for _, v in per_frame])
+    sums, G, g2, se, _ = run_gpu(pkg, dq, sq, F, off, idx, val)
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, F, off, idx, val)
+    for k, name in enumerate(("G2", "IP", "IF")):
+        assert_exact(G[k], rG[k], name)
+    assert_exact(sums["frame_sum"], rs["frame_sum"], "frameSum")
+    assert_exact(sums["pixel_sum"], rs["pixel_sum"], "pixelSum")
+    assert_exact(g2, rg2, "norm-0-g2")
+    assert_close(se, rse, "norm-0-stderr")
+
+
+def test_empty_input(pkg, oracle):
+    h, w, F = 8, 8, 64
+    dq, sq = pkg.synth.annular_qmaps(h, w, n_dynamic=2, static_per_dynamic=2, r_min=0.0, r_max=6.0)
+    off = np.zeros(F + 1, np.int64)
+    idx = np.zeros(0, np.int32)
+    val = np.zeros(0, np.int16)
+    sums, G, g2, se, _ = run_gpu(pkg, dq, sq, F, off, idx, val)
+    assert not G[0].any() and not G[1].any() and not G[2].any()
+    assert not sums["pixel_sum"].any()
+    assert np.isnan(g2).all()  # 0/0 in every static bin, as the reference produces
+
+
+def test_large_counts_fall_back_to_float_path(pkg, oracle):
+    """Counts beyond the 12-bit packed field switch the store to float words; still exact here
+    because every sum stays below 2^24."""
+    dq, sq, off, idx, val = make_case(pkg, 32, 32, 300, 0.03, 21)
+    val = (val.astype(np.int32) * 3000).clip(0, 32767).astype(np.int16)
+    sums, G, g2, se, info = run_gpu(pkg, dq, sq, 300, off, idx, val)
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, 300, off, idx, val)
+    assert info.value_kind == 1
+    assert_close(G[0], rG[0], "G2")
+    assert_close(G[1], rG[1], "IP")
+    assert_close(G[2], rG[2], "IF")
+    assert_close(g2, rg2, "norm-0-g2")
+
+
+@pytest.mark.parametrize("stride,avg", [(1, 1), (2, 1), (1, 2), (2, 2), (1, 3)])
+def test_flatfield_stride_average(pkg, oracle, stride, avg):
+    h, w, F_raw = 40, 40, 1200
+    block = stride * avg if (stride > 1 and avg > 1) else max(stride, avg)
+    F = F_raw // block
+    dq, sq, off, idx, val = make_case(pkg, h, w, F_raw, 0.02, 31)
+    flat = pkg.synth.flatfield(h * w)
+    sw = max(1, F // 10)
+    sums, G, g2, se, info = run_gpu(pkg, dq, sq, F, off, idx, val, flatfield=flat, stride=stride, avg=avg,
+                                    static_window=sw)
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, F, off, idx, val, flat=flat, stride=stride, avg=avg, swindow=sw)
+    assert info.value_kind == 1
+    for k, name in enumerate(("G2", "IP", "IF")):
+        assert_close(G[k], rG[k], name)
+    assert_close(sums["frame_sum"], rs["frame_sum"], "frameSum")
+    assert_close(sums["pixel_sum"], rs["pixel_sum"], "pixelSum")
+    assert_close(sums["part_total"], rs["part_total"], "partition-mean-total")
+    assert_close(sums["part_partial"], rs["part_partial"], "partition-mean-partial")
+    assert_close(g2, rg2, "norm-0-g2")
+    assert_close(se, rse, "norm-0-stderr")
+
+
+def test_normalize_by_framesum(pkg, oracle):
+    h, w, F = 40, 40, 800
+    dq, sq, off, idx, val = make_case(pkg, h, w, F, 0.03, 41)
+    sums, G, g2, se, info = run_gpu(pkg, dq, sq, F, off, idx, val, normalize_by_framesum=True)
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, F, off, idx, val, normalize_by_framesum=True)
+    for k, name in enumerate(("G2", "IP", "IF")):
+        assert_close(G[k], rG[k], name)
+    assert_close(g2, rg2, "norm-0-g2")
+    assert_close(se, rse, "norm-0-stderr")
+
+
+def test_pushes_in_chunks_equal_one_push(pkg):
+    dq, sq, off, idx, val = make_case(pkg, 48, 48, 900, 0.02, 51)
+    F = 900
+    _, G1, g1, s1, _ = run_gpu(pkg, dq, sq, F, off, idx, val)
+    c = pkg.Correlator(dq, sq, F)
+    for a in range(0, F, 250):
+        b = min(F, a + 250)
+        c.push_sparse(idx[off[a]: off[b]], val[off[a]: off[b]], off[a: b + 1] - off[a])
+    c.finish_ingest(want=False)
+    G2 = c.multitau()
+    g2, s2 = c.normalize()
+    # a second ingest on the same handle
+    c.reset()
+    c.push_sparse(idx, val, off)
+    c.finish_ingest(want=False)
+    G3 = c.multitau()
+    c.close()
+    for k in range(3):
+        assert_exact(G1[k], G2[k], "chunked push")
+        assert_exact(G1[k], G3[k], "second ingest")
+    assert_exact(g1, g2, "g2 chunked")
+
+
+def test_shards_sum_to_single_gpu_partials(pkg):
+    """Static-bin-aligned sharding: the element-wise sum of the shards' partial
+    buffers is the single-shard buffer bit for bit, so g2/stderr do not depend on the GPU
+    count.  Both shards run on cuda:0 here; the cross-rank SUM is covered by the gloo test."""
+    import torch
+    dq, sq, off, idx, val = make_case(pkg, 64, 64, 700, 0.02, 61, n_dynamic=5, static_per_dynamic=4)
+    F = 700
+
+    def partials(k, K):
+        c = pkg.Correlator(dq, sq, F, shard_index=k, shard_count=K)
+        c.push_sparse(idx, val, off)
+        c.finish_ingest(want=False)
+        c.multitau(want=False)
+        ptr, n = c.normalize_partials()
+        torch.cuda.synchronize()
+        host = pkg.torchio.device_view(ptr, n, "float64", "cuda:0").cpu().numpy().copy()
+        g2, se = c.normalize_finish()
+        rows = c.info().n_rows
+        c.close()
+        return host, g2, se, rows
+
+    full, g2, se, rows = partials(0, 1)
+    parts = [partials(k, 3) for k in range(3)]
+    assert sum(p[3] for p in parts) == rows
+    total = parts[0][0] + parts[1][0] + parts[2][0]
+    assert_exact(total, full, "sum of shard partials")

@@ -1,0 +1,231 @@
+"""xpcs-eigen_b200: B200-native XPCS correlation hot path (IMM ingest -> Filter -> multi-tau
+G2/IP/IF -> q-bin normalisation -> two-time) behind the C-ABI of include/xpcs_b200.h.
+
+This Python layer is a thin ctypes mirror used by tests/ and bench.py; the reference-facing
+host program is the C++ `corr` under host/.  Importing the package does not need a GPU;
+creating a Correlator does, and raises XpcsError when there is none (no CPU fallback).
+
+The directory name carries a hyphen; load it with `__graft_entry__.load_package()` (module
+name `xpcs_eigen_b200`).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import cabi, synth, torchio  # noqa: F401
+from .cabi import XPCS_COMPAT_STALE_TAIL, XpcsError, XpcsInfo, XpcsParams  # noqa: F401
+
+
+def level_max(frames, dpl):
+    """Corr::calculateLevelMax (reference corr.cpp:1156-1160)."""
+    return cabi.load().xpcs_level_max(frames, dpl)
+
+
+def delay_schedule(frames, dpl):
+    """Corr::delaysPerLevel (reference corr.cpp:1133-1154) -> (level[T], tau[T])."""
+    lib = cabi.load()
+    n = lib.xpcs_delay_schedule(frames, dpl, None, None, 0)
+    lv = np.zeros(max(n, 1), np.int32)
+    tv = np.zeros(max(n, 1), np.int32)
+    lib.xpcs_delay_schedule(frames, dpl, lv.ctypes.data, tv.ctypes.data, n)
+    return lv[:n], tv[:n]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Correlator:
+    """One handle = one GPU = one pixel shard.  Method names follow the C-ABI, which in turn
+    names the reference routine each call replaces (see include/xpcs_b200.h)."""
+
+    def __init__(self, dqmap, sqmap, frames, dpl=8, flatfield=None, stride=1, avg=1, static_window=None,
+                 normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, device=0, shard_index=0,
+                 shard_count=1, reserve_events=0):
+        self._lib = cabi.load()
+        dq = np.ascontiguousarray(dqmap, np.int32)
+        sq = np.ascontiguousarray(sqmap, np.int32)
+        assert dq.ndim == 2 and dq.shape == sq.shape
+        self.height, self.width = dq.shape
+        self.P = dq.size
+        self.F = int(frames)
+        ff = None if flatfield is None else np.ascontiguousarray(flatfield, np.float64).ravel()
+        p = XpcsParams()
+        p.struct_size = C.sizeof(XpcsParams)
+        p.width, p.height = self.width, self.height
+        p.frames = self.F
+        p.delays_per_level = dpl
+        p.stride_frames, p.avg_frames = stride, avg
+        p.static_window = int(static_window) if static_window else max(1, self.F // 10)
+        p.normalize_by_framesum = int(bool(normalize_by_framesum))
+        p.compat_flags = XPCS_COMPAT_STALE_TAIL if compat else 0
+        p.lld, p.sigma = float(lld), float(sigma)
+        p.dqmap, p.sqmap = dq.ctypes.data, sq.ctypes.data
+        p.flatfield = None if ff is None else ff.ctypes.data
+        p.shard_index, p.shard_count = shard_index, shard_count
+        p.reserve_events = int(reserve_events)
+        self.params = p
+        self.static_window = p.static_window
+        h = C.c_void_p()
+        rc = self._lib.xpcs_create(C.byref(p), device, C.byref(h))
+        if rc != 0:
+            raise XpcsError(rc, (self._lib.xpcs_last_error(None) or b"").decode())
+        self._h = h
+        self._keep = []  # host buffers that must outlive asynchronous copies
+        i = self.info()
+        self.T, self.S, self.Q = i.n_delays, i.n_static, i.n_dynamic
+
+    # -- plumbing --
+    def _check(self, rc):
+        if rc != 0:
+            raise XpcsError(rc, (self._lib.xpcs_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.xpcs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        i = XpcsInfo()
+        self._check(self._lib.xpcs_get_info(self._h, C.byref(i)))
+        return i
+
+    def row_pixels(self):
+        out = np.zeros(max(self.info().n_rows, 1), np.int32)
+        self._check(self._lib.xpcs_get_row_pixels(self._h, out.ctypes.data))
+        return out[: self.info().n_rows]
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.xpcs_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def reset(self):
+        self._keep = []
+        self._check(self._lib.xpcs_reset(self._h))
+
+    # -- Filter stage --
+    def set_dark(self, frames):
+        f = np.ascontiguousarray(frames, np.int16).reshape(-1, self.P)
+        self._check(self._lib.xpcs_set_dark(self._h, f.ctypes.data, f.shape[0]))
+
+    def get_dark(self):
+        avg = np.zeros(self.P, np.float64)
+        std = np.zeros(self.P, np.float64)
+        self._check(self._lib.xpcs_get_dark(self._h, avg.ctypes.data, std.ctypes.data))
+        return avg, std
+
+    def push_sparse(self, idx, val, frame_off, clock=None, ticks=None):
+        idx = np.ascontiguousarray(idx, np.int32)
+        val = np.ascontiguousarray(val, np.int16)
+        off = np.ascontiguousarray(frame_off, np.int64)
+        ck = None if clock is None else np.ascontiguousarray(clock, np.float64)
+        tk = None if ticks is None else np.ascontiguousarray(ticks, np.float64)
+        self._keep += [idx, val]
+        self._check(self._lib.xpcs_push_sparse(self._h, idx.ctypes.data, val.ctypes.data, off.ctypes.data,
+                                               _ptr(ck), _ptr(tk), off.size - 1))
+
+    def push_sparse_raw(self, idx_ptr, val_ptr, off_ptr, nframes):
+        """Host pointers as integers (e.g. pinned torch tensors); caller keeps them alive."""
+        self._check(self._lib.xpcs_push_sparse(self._h, idx_ptr, val_ptr, off_ptr, None, None, nframes))
+
+    def push_sparse_device(self, d_idx, d_val, d_off, n_events, nframes):
+        """Device pointers (integers); buffers stay valid until finish_ingest returns."""
+        self._check(self._lib.xpcs_push_sparse_device(self._h, d_idx, d_val, d_off, n_events, nframes))
+
+    def push_dense(self, frames, clock=None, ticks=None):
+        f = np.ascontiguousarray(frames, np.int16).reshape(-1, self.P)
+        ck = None if clock is None else np.ascontiguousarray(clock, np.float64)
+        tk = None if ticks is None else np.ascontiguousarray(ticks, np.float64)
+        self._check(self._lib.xpcs_push_dense(self._h, f.ctypes.data, _ptr(ck), _ptr(tk), f.shape[0]))
+
+    def push_dense_device(self, d_frames, nframes):
+        self._check(self._lib.xpcs_push_dense_device(self._h, d_frames, nframes))
+
+    def finish_ingest(self, want=True):
+        """-> dict(pixel_sum (h,w), frame_sum (2,F), part_total (S,), part_partial (F//window, S))."""
+        if not want:
+            self._check(self._lib.xpcs_finish_ingest(self._h, None, None, None, None))
+            self._keep = []
+            return None
+        F, S = self.F, self.S
+        ps = np.zeros(self.P, np.float32)
+        fs = np.zeros(2 * F, np.float32)
+        pt = np.zeros(max(S, 1), np.float32)
+        pp = np.zeros(max((F // self.static_window) * S, 1), np.float32)
+        self._check(self._lib.xpcs_finish_ingest(self._h, ps.ctypes.data, fs.ctypes.data, pt.ctypes.data,
+                                                 pp.ctypes.data))
+        self._keep = []
+        return dict(pixel_sum=ps.reshape(self.height, self.width), frame_sum=fs.reshape(2, F),
+                    part_total=pt[:S], part_partial=pp[: (F // self.static_window) * S].reshape(-1, S))
+
+    def timestamps(self):
+        n = self.info().raw_frames_seen
+        ck = np.zeros(2 * n, np.float64)
+        tk = np.zeros(2 * n, np.float64)
+        self._check(self._lib.xpcs_get_timestamps(self._h, ck.ctypes.data, tk.ctypes.data))
+        return ck.reshape(2, n), tk.reshape(2, n)
+
+    # -- Correlation --
+    def multitau(self, want=True):
+        """Corr::multiTau2 -> (G2, IP, IF) each (T, P), or None when want is False."""
+        if not want:
+            self._check(self._lib.xpcs_multitau(self._h, None, None, None))
+            return None
+        out = [np.zeros((self.T, self.P), np.float32) for _ in range(3)]
+        self._check(self._lib.xpcs_multitau(self._h, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        return tuple(out)
+
+    def normalize(self):
+        """Corr::normalizeG2s -> (g2, stderr) each (T, Q)."""
+        g2 = np.zeros((self.T, max(self.Q, 1)), np.float32)
+        se = np.zeros((self.T, max(self.Q, 1)), np.float32)
+        self._check(self._lib.xpcs_normalize(self._h, g2.ctypes.data, se.ctypes.data))
+        return g2[:, : self.Q], se[:, : self.Q]
+
+    def normalize_partials(self):
+        """-> (device pointer, count of float64) for the cross-shard SUM all-reduce."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._check(self._lib.xpcs_normalize_partials(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def normalize_finish(self):
+        g2 = np.zeros((self.T, max(self.Q, 1)), np.float32)
+        se = np.zeros((self.T, max(self.Q, 1)), np.float32)
+        self._check(self._lib.xpcs_normalize_finish(self._h, g2.ctypes.data, se.ctypes.data))
+        return g2[:, : self.Q], se[:, : self.Q]
+
+    def twotime(self, qbin, wsize, method="symmetric", average=False):
+        F = self.F
+        partials = max((F - wsize) // wsize, 0)
+        Cm = np.zeros((F, F), np.float32)
+        gf = np.zeros(F, np.float32)
+        gp = np.zeros(max(wsize * partials, 1), np.float32)
+        sg = np.zeros(1 if average else F, np.float32)
+        m = {"none": 0, "symmetric": 1}[method.lower()]
+        self._check(self._lib.xpcs_twotime(self._h, qbin, wsize, m, int(bool(average)), Cm.ctypes.data,
+                                           gf.ctypes.data, gp.ctypes.data, sg.ctypes.data))
+        return dict(C=Cm, g2full=gf, g2partials=gp[: wsize * partials].reshape(wsize, partials), sg=sg)
+
+    # -- measurement --
+    def kernel_timing(self, on=True):
+        self._check(self._lib.xpcs_kernel_timing(self._h, int(on)))
+
+    def launch_count(self):
+        return int(self._lib.xpcs_launch_count(self._h))
+
+    def kernel_report(self, reset=False):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        ln = (C.c_int64 * cap)()
+        n = self._lib.xpcs_kernel_report(self._h, names, ms, ln, cap)
+        out = {names[i].decode(): (ms[i], ln[i]) for i in range(min(n, cap))}
+        if reset:
+            self._check(self._lib.xpcs_kernel_report_reset(self._h))
+        return out

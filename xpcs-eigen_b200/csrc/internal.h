@@ -1,0 +1,193 @@
+// internal.h -- handle layout and kernel launchers shared by the .cu files of libxpcs_b200.
+// Not part of the C-ABI (include/xpcs_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/xpcs_b200.h"
+
+namespace xpcs {
+
+constexpr int kSlice = 32;          // pixel rows per slice = lanes per warp
+constexpr int kCountBits = 12;      // packed word at level l: key << (12+l) | count
+constexpr int kMaxLevels = 24;
+constexpr int kEvPerBlock = 4096;   // events per CTA in the frame-major passes
+constexpr int kIngestThreads = 256;
+
+enum ValueKind { kPacked = 0, kFloat = 1 };
+
+// Device-side description of the correlation job of one handle.
+struct Sched {
+    int n_levels;               // max_level + 1
+    int frames;                 // F
+    int dpl;
+    int first[kMaxLevels];      // index of the level's first delay in the schedule
+    int count[kMaxLevels];      // delays emitted at that level
+    int lo[kMaxLevels];         // level-local delay tau' of the level's first delay
+};
+
+struct KernelStat {
+    double ms = 0.0;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;  // capacity in elements
+};
+
+}  // namespace xpcs
+
+struct xpcs_handle_s {
+    XpcsParams prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // ---- schedule (host) ----
+    std::vector<int> sched_level, sched_tau;
+    int T = 0, max_level = 0;
+    xpcs::Sched sched{};
+
+    // ---- partition maps (host) ----
+    int P = 0, S = 0, Q = 0;
+    int nseg_total = 0;                 // surviving (dq, sq) entries of the whole detector
+    std::vector<int> seg_dq, seg_sq;    // [nseg_total]
+    std::vector<int> seg_pixels_n;      // [nseg_total] pixels per segment
+    int seg_first = 0, seg_last = 0;    // this shard owns global segments [seg_first, seg_last)
+    int R = 0, R_pad = 0;               // rows of this shard, padded to kSlice
+    int R_total = 0;
+    int n_slices = 0;
+    std::vector<int> pixel_of_row;      // [R]
+    std::vector<int> lseg_row_start;    // [nseg_local + 1] row offsets of the owned segments
+    std::vector<int> pixels_per_sbin;   // [S]
+    std::vector<double> flat_host;      // [P] (all ones when disabled)
+    bool flat_is_one = true;
+
+    // ---- maps (device) ----
+    xpcs::DevBuf<int> d_row_of_pixel;     // [P]   -1 = masked or foreign shard
+    xpcs::DevBuf<int> d_pixel_of_row;     // [R_pad]
+    xpcs::DevBuf<int> d_sbin_of_row;      // [R_pad] sq-1
+    xpcs::DevBuf<double> d_flat;          // [P]
+    xpcs::DevBuf<int> d_lseg_row_start;   // [nseg_local+1]
+    xpcs::DevBuf<int> d_seg_dq_all;       // [nseg_total] dynamic bin of every segment (all shards)
+    xpcs::DevBuf<int> d_seg_npix_all;     // [nseg_total] pixels per segment (all shards)
+
+    // ---- dark image ----
+    bool have_dark = false;
+    xpcs::DevBuf<double> d_dark_avg, d_dark_std;
+
+    // ---- frame-major event buffers ----
+    bool dense_source = false;
+    bool external_events = false;         // push_sparse_device: buffers are the caller's
+    xpcs::DevBuf<int32_t> d_idx;
+    xpcs::DevBuf<int16_t> d_val;
+    xpcs::DevBuf<int32_t> d_evt;          // dense source: explicit output-frame id per event
+    xpcs::DevBuf<float> d_valf;           // dense source: final float value per event
+    const int32_t *ev_idx = nullptr;      // views actually used by the kernels
+    const int16_t *ev_val = nullptr;
+    const int64_t *ev_off = nullptr;      // device frame offsets [raw_frames + 1]
+    xpcs::DevBuf<int64_t> d_frame_off;
+    std::vector<int64_t> frame_off_host;  // [raw_frames + 1]
+    int64_t E = 0;                        // events pushed
+    int raw_frames = 0;
+    std::vector<double> ts_clock, ts_ticks;
+    xpcs::DevBuf<unsigned long long> d_dense_counter;
+    // pinned staging for small pushes
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // ---- pixel-major store (slices of 32 rows, column-interleaved words) ----
+    int kind = xpcs::kPacked;
+    bool ingest_done = false;
+    xpcs::DevBuf<int> d_row_count;        // [R_pad] histogram, consumed by the scatter
+    xpcs::DevBuf<int> d_row_len;          // [R_pad] events per row
+    xpcs::DevBuf<int> d_slice_len;        // [n_slices]
+    xpcs::DevBuf<int64_t> d_slice_base;   // [n_slices + 1] in words
+    xpcs::DevBuf<int> d_block_first;      // first raw frame of every event block
+    xpcs::DevBuf<uint32_t> d_store;       // words (uint32 packed, or pairs for float values)
+    int64_t store_words = 0;
+    int64_t events_stored = 0;
+    int max_row = 0;
+    xpcs::DevBuf<long long> d_summary;    // small device scratch for host-visible scalars
+    xpcs::DevBuf<double> d_frame_acc;     // [F] per-output-frame sums (exact for counts)
+    xpcs::DevBuf<double> d_row_sum;       // [R_pad]
+    xpcs::DevBuf<double> d_part_total;    // [S]
+    xpcs::DevBuf<double> d_part_partial;  // [windows * S]
+    xpcs::DevBuf<float> d_frame_scale;    // [F] normalize_by_framesum divisors
+    std::vector<float> frame_sum_host;    // [2F]
+
+    // ---- results ----
+    bool multitau_done = false;
+    bool rows_consumed = false;
+    xpcs::DevBuf<float> d_G2, d_IP, d_IF;   // [T][R_pad] row-permuted, tau-major
+    xpcs::DevBuf<double> d_partials;        // see xpcs_normalize_partials
+    int64_t partials_count = 0;
+    bool partials_done = false;
+    xpcs::DevBuf<float> d_scratch;          // staging for host-layout outputs
+
+    // ---- measurement ----
+    bool timing = false;
+    int64_t launches = 0;
+    std::map<std::string, xpcs::KernelStat> stats;
+};
+
+namespace xpcs {
+
+// RAII bracket around one kernel launch: counts it and, when timing is on, records a CUDA
+// event pair on the handle's stream.
+struct LaunchScope {
+    xpcs_handle_s *h;
+    const char *name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LaunchScope(xpcs_handle_s *h_, const char *name_);
+    ~LaunchScope();
+};
+
+int fail(xpcs_handle_s *h, int code, const char *fmt, ...);
+int check_cuda(xpcs_handle_s *h, cudaError_t e, const char *what);
+
+template <typename T>
+int ensure(xpcs_handle_s *h, DevBuf<T> &b, size_t n, const char *what)
+{
+    if (b.n >= n && b.p) return XPCS_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.n = 0;
+    size_t want = n ? n : 1;
+    cudaError_t e = cudaMalloc((void **)&b.p, want * sizeof(T));
+    if (e != cudaSuccess) return check_cuda(h, e, what);
+    b.n = want;
+    return XPCS_OK;
+}
+
+template <typename T>
+void release(DevBuf<T> &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.n = 0;
+}
+
+// ---- launchers (ingest.cu) ----
+int launch_ingest(xpcs_handle_s *h);             // histogram -> slices -> scatter -> finalize
+int launch_dark(xpcs_handle_s *h, const int16_t *d_frames, int n);
+int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw, int nframes);
+// ---- launchers (multitau.cu) ----
+int launch_multitau(xpcs_handle_s *h);
+int launch_unpermute(xpcs_handle_s *h, const float *d_src, float *d_dst);  // [T][R_pad] -> [T][P]
+// ---- launchers (normalize.cu) ----
+int launch_normalize_partials(xpcs_handle_s *h);
+int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);
+// ---- launchers (twotime.cu) ----
+int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int average, float *C,
+                   float *g2full, float *g2partials, float *sg);
+
+}  // namespace xpcs

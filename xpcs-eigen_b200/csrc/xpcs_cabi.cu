@@ -1,0 +1,806 @@
+// xpcs_cabi.cu -- the C-ABI of include/xpcs_b200.h: handle lifetime, partition maps,
+// delay schedule, host<->device plumbing around the kernels of ingest.cu, multitau.cu,
+// normalize.cu and twotime.cu.  No CPU compute path exists here: every stage runs as a CUDA
+// kernel and every entry point fails when no device is usable.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "internal.h"
+
+using namespace xpcs;
+
+static thread_local std::string g_create_error;
+
+namespace xpcs {
+
+int fail(xpcs_handle_s *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+int check_cuda(xpcs_handle_s *h, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return XPCS_OK;
+    return fail(h, XPCS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+LaunchScope::LaunchScope(xpcs_handle_s *h_, const char *name_) : h(h_), name(name_)
+{
+    h->launches++;
+    if (h->timing) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+    }
+}
+
+LaunchScope::~LaunchScope()
+{
+    KernelStat &st = h->stats[name];
+    st.launches++;
+    if (h->timing && e0) {
+        cudaEventRecord(e1, h->stream);
+        st.pending.emplace_back(e0, e1);
+    }
+}
+
+}  // namespace xpcs
+
+// ---------------------------------------------------------------------------------------
+// schedule: Corr::calculateLevelMax / Corr::delaysPerLevel (reference corr.cpp:1133-1160)
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_level_max(int frames, int dpl)
+{
+    if (dpl <= 0 || frames < dpl * 2) return 0;
+    return (int)(floor(log2((double)frames) - log2(1.0 + 1.0 / (double)dpl)) - log2((double)dpl));
+}
+
+extern "C" int xpcs_delay_schedule(int frames, int dpl, int32_t *level, int32_t *tau, int cap)
+{
+    if (dpl <= 0 || frames <= 0) return 0;
+    const int top = xpcs_level_max(frames, dpl);
+    int n = 0;
+    long long reached = 0;
+    for (int lv = 0; lv <= top; lv++) {
+        const long long step = 1LL << lv;
+        const int quota = lv == 0 ? 2 * dpl : dpl;
+        for (int j = 0; j < quota; j++) {
+            if (reached + 2 * step > frames) break;
+            reached += step;
+            if (n < cap) {
+                if (level) level[n] = lv;
+                if (tau) tau[n] = (int32_t)reached;
+            }
+            n++;
+        }
+    }
+    return n;
+}
+
+static int build_schedule(xpcs_handle_s *h)
+{
+    const int F = h->prm.frames, dpl = h->prm.delays_per_level;
+    h->max_level = xpcs_level_max(F, dpl);
+    if (h->max_level + 1 > kMaxLevels) return fail(h, XPCS_E_ARG, "too many levels (%d)", h->max_level + 1);
+    const int T = xpcs_delay_schedule(F, dpl, nullptr, nullptr, 0);
+    h->T = T;
+    h->sched_level.assign(T, 0);
+    h->sched_tau.assign(T, 0);
+    xpcs_delay_schedule(F, dpl, h->sched_level.data(), h->sched_tau.data(), T);
+    Sched &s = h->sched;
+    memset(&s, 0, sizeof(s));
+    s.n_levels = h->max_level + 1;
+    s.frames = F;
+    s.dpl = dpl;
+    for (int l = 0; l < s.n_levels; l++) { s.first[l] = 0; s.count[l] = 0; s.lo[l] = 1; }
+    for (int i = 0; i < T; i++) {
+        const int l = h->sched_level[i];
+        const int local = h->sched_tau[i] >> l;  // tau / 2^level, exact (corr.cpp:392-393)
+        if ((local << l) != h->sched_tau[i]) return fail(h, XPCS_E_ARG, "schedule: tau not a multiple of 2^level");
+        if (s.count[l] == 0) { s.first[l] = i; s.lo[l] = local; }
+        else if (local != s.lo[l] + s.count[l]) return fail(h, XPCS_E_ARG, "schedule: delays of a level not consecutive");
+        s.count[l]++;
+        if (local > 2 * dpl) return fail(h, XPCS_E_ARG, "schedule: level-local delay beyond 2*dpl");
+    }
+    return XPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// partition maps: Configuration::BuildQMap (reference configuration.cpp:244-381)
+// ---------------------------------------------------------------------------------------
+struct Cell {
+    int dq, sq;
+    int64_t start;  // into the sorted valid-pixel list
+    int n;
+    bool kept;
+};
+
+static int build_maps(xpcs_handle_s *h)
+{
+    const XpcsParams &p = h->prm;
+    const int P = h->P;
+    std::vector<int> valid;
+    valid.reserve(P);
+    int S = 0, Q = 0;
+    for (int i = 0; i < P; i++) {
+        if (p.dqmap[i] < 1 || p.sqmap[i] < 1) continue;  // configuration.cpp:256
+        valid.push_back(i);
+        Q = std::max(Q, p.dqmap[i]);
+        S = std::max(S, p.sqmap[i]);
+    }
+    h->S = S;
+    h->Q = Q;
+    h->R_total = (int)valid.size();
+    h->pixels_per_sbin.assign(S, 0);
+    for (int i : valid) h->pixels_per_sbin[p.sqmap[i] - 1]++;  // configuration.cpp:347-356
+
+    // (dq, sq, pixel) order == iteration order of the reference's nested std::map
+    std::stable_sort(valid.begin(), valid.end(), [&](int a, int b) {
+        if (p.dqmap[a] != p.dqmap[b]) return p.dqmap[a] < p.dqmap[b];
+        if (p.sqmap[a] != p.sqmap[b]) return p.sqmap[a] < p.sqmap[b];
+        return a < b;
+    });
+    std::vector<Cell> cells;
+    for (size_t i = 0; i < valid.size();) {
+        size_t j = i;
+        while (j < valid.size() && p.dqmap[valid[j]] == p.dqmap[valid[i]] && p.sqmap[valid[j]] == p.sqmap[valid[i]]) j++;
+        cells.push_back(Cell{p.dqmap[valid[i]], p.sqmap[valid[i]], (int64_t)i, (int)(j - i), true});
+        i = j;
+    }
+    // A static bin listed under several dynamic bins survives only under the one with most
+    // pixels (first such in ascending dq); the others' pixels are lost (configuration.cpp:311-345,
+    // SURVEY.md A.8-1).
+    {
+        std::map<int, int> best;  // sq -> cell index
+        std::map<int, int> owners;
+        for (size_t c = 0; c < cells.size(); c++) {
+            owners[cells[c].sq]++;
+            auto it = best.find(cells[c].sq);
+            if (it == best.end() || cells[c].n > cells[it->second].n) best[cells[c].sq] = (int)c;
+        }
+        for (size_t c = 0; c < cells.size(); c++)
+            if (owners[cells[c].sq] > 1 && best[cells[c].sq] != (int)c) cells[c].kept = false;
+    }
+    h->seg_dq.clear();
+    h->seg_sq.clear();
+    h->seg_pixels_n.clear();
+    std::vector<const Cell *> kept;
+    int64_t kept_pixels = 0;
+    for (const Cell &c : cells)
+        if (c.kept) {
+            kept.push_back(&c);
+            h->seg_dq.push_back(c.dq);
+            h->seg_sq.push_back(c.sq);
+            h->seg_pixels_n.push_back(c.n);
+            kept_pixels += c.n;
+        }
+    h->nseg_total = (int)kept.size();
+
+    // shard = contiguous segment range balanced by pixel count
+    const int K = p.shard_count, k = p.shard_index;
+    std::vector<int> cut(K + 1, h->nseg_total);
+    cut[0] = 0;
+    {
+        int64_t run = 0;
+        int next = 1;
+        for (int s = 0; s < h->nseg_total && next < K; s++) {
+            run += kept[s]->n;
+            while (next < K && run * K >= kept_pixels * next) cut[next++] = s + 1;
+        }
+        for (int i = 1; i <= K; i++) cut[i] = std::max(cut[i], cut[i - 1]);
+        cut[K] = h->nseg_total;
+    }
+    h->seg_first = cut[k];
+    h->seg_last = cut[k + 1];
+
+    h->pixel_of_row.clear();
+    h->lseg_row_start.assign(1, 0);
+    for (int s = h->seg_first; s < h->seg_last; s++) {
+        for (int i = 0; i < kept[s]->n; i++) h->pixel_of_row.push_back(valid[kept[s]->start + i]);
+        h->lseg_row_start.push_back((int)h->pixel_of_row.size());
+    }
+    if (k == K - 1) {  // pixels lost by the duplicate removal still get correlated (they are
+                       // in the mask), they just belong to no partition: last shard, trailing rows
+        std::vector<int> orphans;
+        for (const Cell &c : cells)
+            if (!c.kept)
+                for (int i = 0; i < c.n; i++) orphans.push_back(valid[c.start + i]);
+        std::sort(orphans.begin(), orphans.end());
+        for (int px : orphans) h->pixel_of_row.push_back(px);
+    }
+    h->R = (int)h->pixel_of_row.size();
+    h->R_pad = (h->R + kSlice - 1) / kSlice * kSlice;
+    if (h->R_pad == 0) h->R_pad = kSlice;
+    h->n_slices = h->R_pad / kSlice;
+
+    // device copies
+    std::vector<int> row_of_pixel(P, -1), sbin_of_row(h->R_pad, -1), pix_of_row(h->R_pad, 0);
+    for (int r = 0; r < h->R; r++) {
+        row_of_pixel[h->pixel_of_row[r]] = r;
+        sbin_of_row[r] = p.sqmap[h->pixel_of_row[r]] - 1;
+        pix_of_row[r] = h->pixel_of_row[r];
+    }
+    int rc;
+    if ((rc = ensure(h, h->d_row_of_pixel, (size_t)P, "row_of_pixel"))) return rc;
+    if ((rc = ensure(h, h->d_pixel_of_row, (size_t)h->R_pad, "pixel_of_row"))) return rc;
+    if ((rc = ensure(h, h->d_sbin_of_row, (size_t)h->R_pad, "sbin_of_row"))) return rc;
+    if ((rc = ensure(h, h->d_flat, (size_t)P, "flatfield"))) return rc;
+    if ((rc = ensure(h, h->d_lseg_row_start, h->lseg_row_start.size(), "segment rows"))) return rc;
+    if ((rc = ensure(h, h->d_seg_dq_all, (size_t)std::max(1, h->nseg_total), "segment dq"))) return rc;
+    if ((rc = ensure(h, h->d_seg_npix_all, (size_t)std::max(1, h->nseg_total), "segment sizes"))) return rc;
+    if ((rc = ensure(h, h->d_row_count, (size_t)h->R_pad, "row histogram"))) return rc;
+    if ((rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths"))) return rc;
+    if ((rc = ensure(h, h->d_slice_len, (size_t)h->n_slices, "slice lengths"))) return rc;
+    if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
+    cudaMemcpy(h->d_row_of_pixel.p, row_of_pixel.data(), sizeof(int) * P, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_pixel_of_row.p, pix_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_sbin_of_row.p, sbin_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_flat.p, h->flat_host.data(), sizeof(double) * P, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_lseg_row_start.p, h->lseg_row_start.data(), sizeof(int) * h->lseg_row_start.size(),
+               cudaMemcpyHostToDevice);
+    if (h->nseg_total > 0) {
+        cudaMemcpy(h->d_seg_dq_all.p, h->seg_dq.data(), sizeof(int) * h->nseg_total, cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_seg_npix_all.p, h->seg_pixels_n.data(), sizeof(int) * h->nseg_total, cudaMemcpyHostToDevice);
+    }
+    cudaMemset(h->d_row_count.p, 0, sizeof(int) * h->R_pad);
+    cudaMemset(h->d_row_len.p, 0, sizeof(int) * h->R_pad);
+    return check_cuda(h, cudaGetLastError(), "map upload");
+}
+
+// ---------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_abi_version(void) { return 1; }
+
+extern "C" int xpcs_compiled_arch(void)
+{
+#ifdef XPCS_ARCH
+    return XPCS_ARCH;
+#else
+    return 100;
+#endif
+}
+
+extern "C" const char *xpcs_last_error(xpcs_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static void reset_ingest(xpcs_handle_s *h)
+{
+    h->E = 0;
+    h->raw_frames = 0;
+    h->frame_off_host.assign(1, 0);
+    h->ts_clock.clear();
+    h->ts_ticks.clear();
+    h->ingest_done = false;
+    h->multitau_done = false;
+    h->partials_done = false;
+    h->rows_consumed = false;
+    h->dense_source = false;
+    h->external_events = false;
+    h->ev_idx = nullptr;
+    h->ev_val = nullptr;
+    h->ev_off = nullptr;
+    h->events_stored = 0;
+    h->store_words = 0;
+    h->max_row = 0;
+}
+
+extern "C" int xpcs_create(const XpcsParams *prm, int device, xpcs_handle *out)
+{
+    if (!out) return fail(nullptr, XPCS_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (!prm || prm->struct_size != (int32_t)sizeof(XpcsParams))
+        return fail(nullptr, XPCS_E_ARG, "XpcsParams.struct_size mismatch (caller %d, library %d)",
+                    prm ? prm->struct_size : -1, (int)sizeof(XpcsParams));
+    if (prm->width <= 0 || prm->height <= 0 || prm->frames <= 0 || prm->delays_per_level <= 0 ||
+        prm->stride_frames <= 0 || prm->avg_frames <= 0 || prm->static_window <= 0 || !prm->dqmap ||
+        !prm->sqmap || prm->shard_count <= 0 || prm->shard_index < 0 || prm->shard_index >= prm->shard_count)
+        return fail(nullptr, XPCS_E_ARG, "invalid XpcsParams (dimensions, frames, dpl, stride/avg, window, maps or shard)");
+    if ((int64_t)prm->width * prm->height > 0x7fffffffLL) return fail(nullptr, XPCS_E_ARG, "detector too large");
+    if (prm->normalize_by_framesum && prm->shard_count > 1)
+        return fail(nullptr, XPCS_E_ARG, "normalize_by_framesum needs the frame sums of all shards; not supported with shard_count > 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, XPCS_E_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, XPCS_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, XPCS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return fail(nullptr, XPCS_E_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                    prop.major, prop.minor);
+
+    xpcs_handle_s *h = new xpcs_handle_s();
+    h->prm = *prm;
+    h->device = device;
+    h->P = prm->width * prm->height;
+    h->flat_host.assign(h->P, 1.0);
+    h->flat_is_one = true;
+    if (prm->flatfield) {
+        for (int i = 0; i < h->P; i++) {
+            h->flat_host[i] = prm->flatfield[i];
+            if (prm->flatfield[i] != 1.0) h->flat_is_one = false;
+        }
+    }
+    int rc = build_schedule(h);
+    if (!rc) rc = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "stream");
+    h->own_stream = true;
+    if (!rc) rc = build_maps(h);
+    if (rc) {
+        g_create_error = h->err;
+        xpcs_destroy(h);
+        return rc;
+    }
+    // the handle keeps no pointer into caller memory
+    h->prm.dqmap = nullptr;
+    h->prm.sqmap = nullptr;
+    h->prm.flatfield = nullptr;
+    reset_ingest(h);
+    *out = h;
+    return XPCS_OK;
+}
+
+extern "C" void xpcs_destroy(xpcs_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &kv : h->stats)
+        for (auto &pr : kv.second.pending) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+    release(h->d_row_of_pixel); release(h->d_pixel_of_row); release(h->d_sbin_of_row); release(h->d_flat);
+    release(h->d_lseg_row_start); release(h->d_seg_dq_all); release(h->d_seg_npix_all);
+    release(h->d_dark_avg); release(h->d_dark_std);
+    release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
+    release(h->d_dense_counter);
+    release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
+    release(h->d_block_first); release(h->d_store); release(h->d_summary); release(h->d_frame_acc);
+    release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
+    release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch);
+    if (h->stage) cudaFreeHost(h->stage);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int xpcs_set_stream(xpcs_handle h, void *s)
+{
+    if (!h) return XPCS_E_ARG;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (s) {
+        h->stream = (cudaStream_t)s;
+        h->own_stream = false;
+    } else {
+        h->own_stream = true;
+        return check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "stream");
+    }
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_reset(xpcs_handle h)
+{
+    if (!h) return XPCS_E_ARG;
+    cudaSetDevice(h->device);
+    reset_ingest(h);
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_get_info(xpcs_handle h, XpcsInfo *info)
+{
+    if (!h || !info) return XPCS_E_ARG;
+    info->n_delays = h->T;
+    info->max_level = h->max_level;
+    info->n_static = h->S;
+    info->n_dynamic = h->Q;
+    info->n_segments = h->nseg_total;
+    info->n_rows = h->R;
+    info->n_rows_total = h->R_total;
+    info->raw_frames_seen = h->raw_frames;
+    info->events_pushed = h->E;
+    info->events_stored = h->events_stored;
+    info->store_words = h->store_words;
+    info->value_kind = h->kind;
+    info->max_row_events = h->max_row;
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_get_row_pixels(xpcs_handle h, int32_t *out)
+{
+    if (!h || !out) return XPCS_E_ARG;
+    for (int r = 0; r < h->R; r++) out[r] = h->pixel_of_row[r];
+    return XPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Filter stage
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_set_dark(xpcs_handle h, const int16_t *frames, int n)
+{
+    if (!h || !frames || n <= 0) return h ? fail(h, XPCS_E_ARG, "set_dark: bad arguments") : XPCS_E_ARG;
+    cudaSetDevice(h->device);
+    DevBuf<int16_t> tmp;
+    int rc = ensure(h, tmp, (size_t)n * h->P, "dark frames");
+    if (rc) return rc;
+    rc = check_cuda(h, cudaMemcpyAsync(tmp.p, frames, sizeof(int16_t) * (size_t)n * h->P, cudaMemcpyHostToDevice,
+                                       h->stream), "dark H2D");
+    if (!rc) rc = launch_dark(h, tmp.p, n);
+    if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "k_dark");
+    release(tmp);
+    if (!rc) h->have_dark = true;
+    return rc;
+}
+
+extern "C" int xpcs_get_dark(xpcs_handle h, double *avg, double *sd)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->have_dark) return fail(h, XPCS_E_STATE, "no dark image set");
+    cudaSetDevice(h->device);
+    if (avg) cudaMemcpyAsync(avg, h->d_dark_avg.p, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream);
+    if (sd) cudaMemcpyAsync(sd, h->d_dark_std.p, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream);
+    return check_cuda(h, cudaStreamSynchronize(h->stream), "dark D2H");
+}
+
+template <typename T>
+static int grow(xpcs_handle_s *h, DevBuf<T> &b, size_t used, size_t need, const char *what)
+{
+    if (b.n >= need && b.p) return XPCS_OK;
+    size_t cap = std::max(need, b.n + b.n / 2);
+    T *np = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np, std::max<size_t>(cap, 1) * sizeof(T));
+    if (e != cudaSuccess) return check_cuda(h, e, what);
+    if (b.p && used) cudaMemcpyAsync(np, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, h->stream);
+    if (b.p) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(b.p);
+    }
+    b.p = np;
+    b.n = cap;
+    return XPCS_OK;
+}
+
+static void push_timestamps(xpcs_handle_s *h, const double *clock, const double *ticks, int nframes)
+{
+    for (int i = 0; i < nframes; i++) {
+        h->ts_clock.push_back(clock ? clock[i] : 0.0);
+        h->ts_ticks.push_back(ticks ? ticks[i] : 0.0);
+    }
+}
+
+extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val,
+                                const int64_t *frame_offsets, const double *clock, const double *ticks,
+                                int nframes)
+{
+    if (!h || !frame_offsets || nframes < 0) return h ? fail(h, XPCS_E_ARG, "push_sparse: bad arguments") : XPCS_E_ARG;
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->external_events || (h->dense_source && h->raw_frames > 0))
+        return fail(h, XPCS_E_STATE, "cannot mix sparse, dense and device pushes in one ingest");
+    cudaSetDevice(h->device);
+    const int64_t n = frame_offsets[nframes] - frame_offsets[0];
+    if (n < 0 || (n > 0 && (!idx || !val))) return fail(h, XPCS_E_ARG, "push_sparse: bad offsets or NULL payload");
+    for (int i = 0; i < nframes; i++)
+        if (frame_offsets[i + 1] < frame_offsets[i]) return fail(h, XPCS_E_ARG, "push_sparse: frame offsets not monotone");
+    size_t need = (size_t)(h->E + n);
+    if (h->E == 0 && h->prm.reserve_events > (int64_t)need) need = (size_t)h->prm.reserve_events;
+    int rc;
+    if ((rc = grow(h, h->d_idx, (size_t)h->E, need + 8, "event indices"))) return rc;
+    if ((rc = grow(h, h->d_val, (size_t)h->E, need + 8, "event values"))) return rc;
+    if (n > 0) {
+        rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p + h->E, idx + frame_offsets[0], sizeof(int32_t) * n,
+                                           cudaMemcpyHostToDevice, h->stream), "idx H2D");
+        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p + h->E, val + frame_offsets[0], sizeof(int16_t) * n,
+                                                    cudaMemcpyHostToDevice, h->stream), "val H2D");
+        if (rc) return rc;
+    }
+    for (int i = 0; i < nframes; i++)
+        h->frame_off_host.push_back(h->E + (frame_offsets[i + 1] - frame_offsets[0]));
+    push_timestamps(h, clock, ticks, nframes);
+    h->E += n;
+    h->raw_frames += nframes;
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
+                                       const int64_t *d_frame_offsets, int64_t n_events, int nframes)
+{
+    if (!h || !d_frame_offsets || nframes < 0 || n_events < 0) return h ? fail(h, XPCS_E_ARG, "push_sparse_device: bad arguments") : XPCS_E_ARG;
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->raw_frames > 0) return fail(h, XPCS_E_STATE, "push_sparse_device must be the only push of an ingest");
+    h->external_events = true;
+    h->ev_idx = d_idx;
+    h->ev_val = d_val;
+    h->ev_off = d_frame_offsets;
+    h->E = n_events;
+    h->raw_frames = nframes;
+    h->ts_clock.assign(nframes, 0.0);
+    h->ts_ticks.assign(nframes, 0.0);
+    return XPCS_OK;
+}
+
+static int dense_prepare(xpcs_handle_s *h)
+{
+    if (h->dense_source) return XPCS_OK;
+    int rc;
+    const int F = h->prm.frames;
+    int64_t cap = h->prm.reserve_events > 0 ? h->prm.reserve_events : std::min<int64_t>((int64_t)h->R * F, 1LL << 28);
+    cap = (cap + 7) & ~7LL;
+    if ((rc = ensure(h, h->d_idx, (size_t)cap, "dense event pixels"))) return rc;
+    if ((rc = ensure(h, h->d_evt, (size_t)cap, "dense event frames"))) return rc;
+    if ((rc = ensure(h, h->d_valf, (size_t)cap, "dense event values"))) return rc;
+    if ((rc = ensure(h, h->d_dense_counter, 1, "dense counter"))) return rc;
+    if ((rc = ensure(h, h->d_summary, 8, "summary"))) return rc;
+    if ((rc = ensure(h, h->d_frame_acc, (size_t)F, "frame sums"))) return rc;
+    cudaMemsetAsync(h->d_dense_counter.p, 0, sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_summary.p, 0, sizeof(long long) * 8, h->stream);
+    cudaMemsetAsync(h->d_frame_acc.p, 0, sizeof(double) * (size_t)F, h->stream);
+    h->dense_source = true;
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_push_dense_device(xpcs_handle h, const int16_t *d_frames, int nframes)
+{
+    if (!h || !d_frames || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "push_dense_device: bad arguments") : XPCS_E_ARG;
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->external_events || (!h->dense_source && h->raw_frames > 0))
+        return fail(h, XPCS_E_STATE, "cannot mix sparse, dense and device pushes in one ingest");
+    cudaSetDevice(h->device);
+    int rc = dense_prepare(h);
+    if (rc) return rc;
+    for (int f0 = 0; f0 < nframes; f0 += 32768) {  // grid.y limit
+        const int nb = std::min(32768, nframes - f0);
+        rc = launch_dense_filter(h, d_frames + (size_t)f0 * h->P, h->raw_frames + f0, nb);
+        if (rc) return rc;
+    }
+    h->raw_frames += nframes;
+    h->ts_clock.resize(h->raw_frames, 0.0);
+    h->ts_ticks.resize(h->raw_frames, 0.0);
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const double *clock, const double *ticks,
+                               int nframes)
+{
+    if (!h || !frames || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "push_dense: bad arguments") : XPCS_E_ARG;
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    cudaSetDevice(h->device);
+    // stage through a device buffer of at most 256 MiB, frame batches in stream order
+    const size_t frame_bytes = sizeof(int16_t) * (size_t)h->P;
+    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, (256u << 20) / frame_bytes));
+    DevBuf<int16_t> tmp;
+    int rc = ensure(h, tmp, (size_t)batch * h->P, "dense staging");
+    if (rc) return rc;
+    const int before = h->raw_frames;
+    for (int f0 = 0; f0 < nframes && !rc; f0 += batch) {
+        const int nb = std::min(batch, nframes - f0);
+        rc = check_cuda(h, cudaMemcpyAsync(tmp.p, frames + (size_t)f0 * h->P, frame_bytes * nb, cudaMemcpyHostToDevice,
+                                           h->stream), "dense H2D");
+        if (!rc) rc = xpcs_push_dense_device(h, tmp.p, nb);
+    }
+    cudaStreamSynchronize(h->stream);
+    release(tmp);
+    if (rc) return rc;
+    for (int i = 0; i < nframes; i++) {
+        h->ts_clock[before + i] = clock ? clock[i] : 0.0;
+        h->ts_ticks[before + i] = ticks ? ticks[i] : 0.0;
+    }
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total,
+                                  float *part_partial)
+{
+    if (!h) return XPCS_E_ARG;
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "finish_ingest called twice (call xpcs_reset first)");
+    cudaSetDevice(h->device);
+    const int F = h->prm.frames;
+    int rc;
+    if (!h->dense_source && !h->external_events) {
+        if ((rc = ensure(h, h->d_frame_off, h->frame_off_host.size(), "frame offsets"))) return rc;
+        rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p, h->frame_off_host.data(),
+                                           sizeof(int64_t) * h->frame_off_host.size(), cudaMemcpyHostToDevice, h->stream),
+                        "frame offsets H2D");
+        if (rc) return rc;
+        h->ev_idx = h->d_idx.p;
+        h->ev_val = h->d_val.p;
+        h->ev_off = h->d_frame_off.p;
+    }
+    if (h->dense_source) {
+        if ((rc = ensure(h, h->d_summary, 8, "summary"))) return rc;
+    }
+    if ((rc = launch_ingest(h))) return rc;
+    h->ingest_done = true;
+
+    // ---- Filter getters, post-scaled as in main.cpp:339-343 and :360-378 ----
+    const int S = h->S;
+    const int windows_all = (F + h->prm.static_window - 1) / h->prm.static_window;
+    const int windows = F / h->prm.static_window;
+    std::vector<double> facc(F), racc, ptot(S), ppart((size_t)windows_all * S);
+    cudaMemcpyAsync(facc.data(), h->d_frame_acc.p, sizeof(double) * F, cudaMemcpyDeviceToHost, h->stream);
+    if (pixel_sum) {
+        racc.resize(h->R_pad);
+        cudaMemcpyAsync(racc.data(), h->d_row_sum.p, sizeof(double) * h->R_pad, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (S > 0) {
+        cudaMemcpyAsync(ptot.data(), h->d_part_total.p, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(ppart.data(), h->d_part_partial.p, sizeof(double) * (size_t)windows_all * S, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "filter sums D2H"))) return rc;
+    h->frame_sum_host.assign(2 * (size_t)F, 0.0f);
+    const float avg = (float)h->prm.avg_frames;
+    for (int f = 0; f < F; f++) {
+        h->frame_sum_host[f] = (float)(f + 1.0);
+        float fs = (float)facc[f];
+        if (h->prm.avg_frames > 1) fs = fs / avg;
+        h->frame_sum_host[F + f] = fs / (float)h->P;  // sparse_filter.cpp:190
+    }
+    if (frame_sum) memcpy(frame_sum, h->frame_sum_host.data(), sizeof(float) * 2 * (size_t)F);
+    if (pixel_sum) {
+        for (int i = 0; i < h->P; i++) pixel_sum[i] = 0.0f;
+        for (int r = 0; r < h->R; r++) pixel_sum[h->pixel_of_row[r]] = (float)racc[r] / F;  // main.cpp:339-343
+    }
+    if (part_total)
+        for (int i = 0; i < S; i++) {
+            const float denom = (float)h->pixels_per_sbin[i] * F;  // main.cpp:375-378
+            part_total[i] = (float)ptot[i] / denom;
+        }
+    if (part_partial)
+        for (int j = 0; j < windows; j++)
+            for (int i = 0; i < S; i++) {
+                const float denom = (float)h->pixels_per_sbin[i] * h->prm.static_window;  // main.cpp:363-373
+                part_partial[(size_t)j * S + i] = (float)ppart[(size_t)j * S + i] / denom;
+            }
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_get_timestamps(xpcs_handle h, double *clock, double *ticks)
+{
+    if (!h) return XPCS_E_ARG;
+    const int n = h->raw_frames;
+    for (int i = 0; i < n; i++) {
+        if (clock) { clock[i] = i + 1; clock[n + i] = h->ts_clock[i]; }
+        if (ticks) { ticks[i] = i + 1; ticks[n + i] = h->ts_ticks[i]; }
+    }
+    return XPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Correlation
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_multitau(xpcs_handle h, float *G2, float *IP, float *IF)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->ingest_done) return fail(h, XPCS_E_STATE, "multitau before finish_ingest");
+    if (h->rows_consumed) return fail(h, XPCS_E_STATE, "the event rows were consumed by a previous multitau; re-ingest");
+    cudaSetDevice(h->device);
+    int rc = launch_multitau(h);
+    if (rc) return rc;
+    h->multitau_done = true;
+    h->partials_done = false;
+    float *dst[3] = {G2, IP, IF};
+    const float *src[3] = {h->d_G2.p, h->d_IP.p, h->d_IF.p};
+    for (int k = 0; k < 3; k++) {
+        if (!dst[k]) continue;
+        const size_t n = (size_t)h->T * h->P;
+        if ((rc = ensure(h, h->d_scratch, n, "host-layout staging"))) return rc;
+        if ((rc = launch_unpermute(h, src[k], h->d_scratch.p))) return rc;
+        rc = check_cuda(h, cudaMemcpyAsync(dst[k], h->d_scratch.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream), "G2/IP/IF D2H");
+        if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "G2/IP/IF D2H");
+        if (rc) return rc;
+    }
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t *count)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->multitau_done) return fail(h, XPCS_E_STATE, "normalize before multitau");
+    cudaSetDevice(h->device);
+    int rc = launch_normalize_partials(h);
+    if (rc) return rc;
+    h->partials_done = true;
+    if (d_partials) *d_partials = h->d_partials.p;
+    if (count) *count = h->partials_count;
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_normalize_finish(xpcs_handle h, float *g2, float *se)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->partials_done) return fail(h, XPCS_E_STATE, "normalize_finish before normalize_partials");
+    cudaSetDevice(h->device);
+    const size_t n = (size_t)h->T * std::max(h->Q, 1);
+    int rc = ensure(h, h->d_scratch, 2 * n, "g2 staging");
+    if (rc) return rc;
+    if ((rc = launch_normalize_finish(h, h->d_scratch.p, h->d_scratch.p + n))) return rc;
+    const size_t bytes = sizeof(float) * (size_t)h->T * h->Q;
+    if (g2) cudaMemcpyAsync(g2, h->d_scratch.p, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (se) cudaMemcpyAsync(se, h->d_scratch.p + n, bytes, cudaMemcpyDeviceToHost, h->stream);
+    return check_cuda(h, cudaStreamSynchronize(h->stream), "g2 D2H");
+}
+
+extern "C" int xpcs_normalize(xpcs_handle h, float *g2, float *se)
+{
+    int rc = xpcs_normalize_partials(h, nullptr, nullptr);
+    if (rc) return rc;
+    return xpcs_normalize_finish(h, g2, se);
+}
+
+extern "C" int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int method, int average, float *C,
+                            float *g2full, float *g2partials, float *sg)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->ingest_done) return fail(h, XPCS_E_STATE, "twotime before finish_ingest");
+    if (h->rows_consumed) return fail(h, XPCS_E_STATE, "the event rows were consumed by multitau; re-ingest");
+    cudaSetDevice(h->device);
+    return launch_twotime(h, qbin, wsize, method, average, C, g2full, g2partials, sg);
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement hooks
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_kernel_timing(xpcs_handle h, int enable)
+{
+    if (!h) return XPCS_E_ARG;
+    h->timing = enable != 0;
+    return XPCS_OK;
+}
+
+extern "C" int64_t xpcs_launch_count(xpcs_handle h) { return h ? h->launches : -1; }
+
+static void drain_events(xpcs_handle_s *h)
+{
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &kv : h->stats) {
+        for (auto &pr : kv.second.pending) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) kv.second.ms += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        kv.second.pending.clear();
+    }
+}
+
+extern "C" int xpcs_kernel_report(xpcs_handle h, const char **names, double *total_ms, int64_t *launches, int cap)
+{
+    if (!h) return XPCS_E_ARG;
+    drain_events(h);
+    int i = 0;
+    for (auto &kv : h->stats) {
+        if (i < cap) {
+            if (names) names[i] = kv.first.c_str();
+            if (total_ms) total_ms[i] = kv.second.ms;
+            if (launches) launches[i] = kv.second.launches;
+        }
+        i++;
+    }
+    return i;
+}
+
+extern "C" int xpcs_kernel_report_reset(xpcs_handle h)
+{
+    if (!h) return XPCS_E_ARG;
+    drain_events(h);
+    for (auto &kv : h->stats) {
+        kv.second.ms = 0.0;
+        kv.second.launches = 0;
+    }
+    h->launches = 0;
+    return XPCS_OK;
+}
