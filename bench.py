@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py -- multi-tau G2 throughput of the B200-native XPCS hot path (BASELINE.json metric).
+
+One "step" = one whole correlation job over one batch of synthetic input:
+    frame-major sparse IMM events -> Filter/ingest (pixel-major store) -> multi-tau G2/IP/IF
+    -> q-bin normalisation (norm-0-g2, norm-0-stderr)
+Workload (default `c3`): BASELINE.json configs[2], the configuration north_star's target is
+quoted on -- sparse 1 Mpixel detector (1024x1024), 100 000 frames, 0.1 % occupancy, dpl 8,
+36 dynamic / 360 static annular q-bins.  With N GPUs the detector has N such 1-Mpixel modules
+sharing the q-bins, pixel-sharded at static-bin boundaries: every rank owns ~1 Mpixel worth of
+rows and receives only its own (demultiplexed) events, so per-GPU work is fixed ("weak").
+`value` counts 1-Mpixel-detector frames per second: N * F / t (at N=1 plain frames/s).
+`--workload c2` runs BASELINE.json configs[1] (dense 1024x1024 int16, dark/flat/threshold).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+
+Contract keys: metric/value/unit/n_gpus/steps/warmup/ms_per_step/higher_is_better/scaling/
+vs_baseline/dtype/data/config + clocks, e2e, gpu_launches, roofline, cpu_baseline.
+The oracle (oracle/) is executed here only for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "multi-tau G2 frames/sec"
+UNIT = "frames/s"
+
+WORKLOADS = {
+    # name: (module h, module w, frames, occupancy, description)
+    "c3": dict(h=1024, w=1024, F=100000, occ=0.001, kind="sparse",
+               name="sparse IMM 1 Mpixel (1024x1024), 100k frames, 0.1% occupancy, dpl 8, 36 dynamic/360 static q-bins (BASELINE configs[2])"),
+    "c1": dict(h=512, w=512, F=10000, occ=0.01, kind="sparse",
+               name="sparse IMM 512x512, 10k frames, 1% occupancy, dpl 8, 36 dynamic q-bins (BASELINE configs[0])"),
+    "c2": dict(h=1024, w=1024, F=20000, occ=None, kind="dense",
+               name="non-sparse IMM 1024x1024 int16, 20k frames, dark/flat correction + threshold (BASELINE configs[1])"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic input
+# ----------------------------------------------------------------------------------------
+def module_maps(pkg, wl, n_modules):
+    dq, sq = pkg.synth.annular_qmaps(wl["h"], wl["w"], n_dynamic=36, static_per_dynamic=10, r_min=8.0)
+    if n_modules > 1:
+        dq = np.tile(dq, (n_modules, 1))
+        sq = np.tile(sq, (n_modules, 1))
+    return np.ascontiguousarray(dq), np.ascontiguousarray(sq)
+
+
+def gen_sparse_device(torch, pixels_dev, n_pix, F, occ, seed, device):
+    """Every (frame, pixel) cell of this rank's pixel universe fires with probability occ
+    (geometric gaps), count = 1 + Poisson(0.1).  pixels_dev = sorted int32 pixel ids (or None
+    for 0..n_pix-1).  Returns device tensors idx int32[E], val int16[E], off int64[F+1]."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cells = int(n_pix) * int(F)
+    expect = cells * occ
+    n = int(expect + 6.0 * np.sqrt(expect + 1.0) + 1024)
+    gaps = torch.empty(n, dtype=torch.float64, device=device).geometric_(occ, generator=g)
+    pos = torch.cumsum(gaps.to(torch.int64), 0) - 1
+    del gaps
+    pos = pos[pos < cells]
+    fr = torch.div(pos, n_pix, rounding_mode="floor")
+    j = (pos - fr * n_pix)
+    off = torch.searchsorted(pos, torch.arange(F + 1, device=device, dtype=torch.int64) * n_pix)
+    del pos, fr
+    idx = j.to(torch.int32) if pixels_dev is None else pixels_dev[j]
+    del j
+    lam = torch.full((idx.numel(),), 0.1, dtype=torch.float32, device=device)
+    val = (1 + torch.poisson(lam, generator=g)).clamp_(1, 4000).to(torch.int16)
+    return idx.contiguous(), val.contiguous(), off.contiguous()
+
+
+def gen_sparse_host(pkg, P, F, occ, seed):
+    return pkg.synth.sparse_frames(P, F, occ, seed=seed)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------
+def cpu_sample_job(pkg, O, wl, F_s, seed=1234):
+    """One bounded CPU sample of the same workload: same detector, occupancy, q-maps and dpl,
+    F_s frames.  Uses oracle/_ref (the compiled reference) when present, else the C port."""
+    h, w, occ = wl["h"], wl["w"], wl["occ"]
+    P = h * w
+    dq, sq = module_maps(pkg, wl, 1)
+    off, idx, val = gen_sparse_host(pkg, P, F_s, occ, seed)
+    ref = None
+    try:
+        from oracle import refdrv
+        if refdrv.available():
+            ref = refdrv
+    except Exception:
+        ref = None
+    threads = O.max_threads()
+    if ref is not None:
+        def run():
+            t0 = time.perf_counter()
+            st = ref.run_sparse(dq, sq, F_s, off, idx, val, dpl=8, swindow=max(1, F_s // 10), threads=threads)
+            return time.perf_counter() - t0, st
+        kind = "reference"
+    else:
+        qm = O.QMap(dq, sq)
+
+        def run():
+            t0 = time.perf_counter()
+            fo = O.sparse_filter(qm, F_s, off, idx, val, swindow=max(1, F_s // 10))
+            t1 = time.perf_counter()
+            G2, IP, IF = O.multitau(P, F_s, 8, fo.rows, compat=True, nthreads=threads)
+            t2 = time.perf_counter()
+            O.normalize(qm, G2, IP, IF)
+            t3 = time.perf_counter()
+            return t3 - t0, {"filter_s": t1 - t0, "multitau_s": t2 - t1, "normalize_s": t3 - t2}
+        kind = "port"
+    return run, kind, threads, int(idx.size)
+
+
+def run_reference_arm(args, wl, wl_key):
+    """--impl reference: the reference's CPU implementation of the path on this box's host
+    cores (oracle/_ref when it was compiled, else the oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg = entry.load_package()
+    O = entry.load_oracle()
+    if wl["kind"] != "sparse":
+        wl = WORKLOADS["c3"]
+        wl_key = "c3"
+    F_s = args.cpu_frames or 6000
+    run, kind, threads, E = cpu_sample_job(pkg, O, wl, F_s)
+    for _ in range(args.warmup):
+        run()
+    ts, stages = [], None
+    for _ in range(args.steps):
+        t, stages = run()
+        ts.append(t)
+    t = float(np.mean(ts))
+    value = F_s / t
+    sample = "%d of %d frames of the %s detector at %.3g occupancy (%d events), all stages; frames/s of the sample" % (
+        F_s, wl["F"], "%dx%d" % (wl["h"], wl["w"]), wl["occ"], E)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "workload_key": wl_key, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "stages_s": stages},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+KERNEL_GROUP = {  # kernel name -> stage of SURVEY.md 8(d)
+    "k_block_frames": "K1", "k_hist": "K1", "k_slice_len": "K1", "k_slice_scan": "K1", "k_scatter": "K1",
+    "k_finalize": "K1", "k_frame_scale": "K1", "k_hist_dense": "K1", "k_scatter_dense": "K1",
+    "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_unpermute": "K4",
+    "k_segment_reduce": "K6", "k_normalize_finish": "K6",
+}
+
+
+def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
+    """Algorithmic bytes per launch of each kernel (DESIGN.md 'Kernels' table; SURVEY.md 8d:
+    one event = 6 B, one correlator value = 4 B)."""
+    tbl = {
+        "k_hist": 6 * E,                       # one read of the frame-major events
+        "k_scatter": 12 * E,                   # read frame-major, write pixel-major
+        "k_finalize": 12 * E,                  # read + write the pixel-major rows once
+        "k_multitau": 6 * E + 12 * T * R,      # read each event once, write G2/IP/IF once
+        "k_segment_reduce": 12 * T * R,        # read G2/IP/IF once
+        "k_normalize_finish": 8 * T * Q,
+        "k_dense_filter": 2 * P * F_dense + 16 * P,
+        "k_unpermute": 8 * T * R,
+    }
+    return tbl.get(name, 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-compat", action="store_true", help="exact sums instead of the reference's stale-tail behaviour")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames:
+        wl["F"] = args.frames
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args, wl, args.workload)
+
+    if wl["kind"] == "dense":
+        raise SystemExit("bench.py: the dense workload (c2) bench leg is not wired yet")
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = entry.load_package()
+    F, occ = wl["F"], wl["occ"]
+    dq, sq = module_maps(pkg, wl, world)
+    P = dq.size
+    E_est = int(wl["h"] * wl["w"] * F * occ * 1.02) + 4096
+    c = pkg.Correlator(dq, sq, F, dpl=8, compat=not args.no_compat, device=local, shard_index=rank,
+                       shard_count=world, reserve_events=E_est)
+    info = c.info()
+    T, Q, R = c.T, c.Q, info.n_rows
+    stream = torch.cuda.Stream(device=dev)
+    c.set_stream(stream.cuda_stream)
+
+    # this rank's demultiplexed pixel universe: its own rows + its share of the masked pixels
+    if world == 1:
+        pixels_dev, n_pix = None, P
+    else:
+        own = c.row_pixels()
+        masked = np.nonzero((dq.ravel() < 1) | (sq.ravel() < 1))[0].astype(np.int32)[rank::world]
+        uni = np.sort(np.concatenate([own, masked])).astype(np.int32)
+        pixels_dev, n_pix = torch.from_numpy(uni).to(dev), int(uni.size)
+    d_idx, d_val, d_off = gen_sparse_device(torch, pixels_dev, n_pix, F, occ, 1234 + rank, dev)
+    E = int(d_idx.numel())
+    h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
+    h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
+    h_off = torch.empty(F + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
+    torch.cuda.synchronize()
+
+    def allreduce_partials(ptr, n):
+        if world == 1:
+            return
+        t = pkg.torchio.device_view(ptr, n, "float64", "cuda:%d" % local)
+        with torch.cuda.stream(stream):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def step_device():
+        c.reset()
+        c.push_sparse_device(d_idx.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), E, F)
+        c.finish_ingest(want=False)
+        c.multitau(want=False)
+        allreduce_partials(*c.normalize_partials())
+        return c.normalize_finish()
+
+    def step_e2e():
+        c.reset()
+        c.push_sparse_raw(h_idx.data_ptr(), h_val.data_ptr(), h_off.data_ptr(), F)
+        sums = c.finish_ingest(want=True)
+        c.multitau(want=False)
+        allreduce_partials(*c.normalize_partials())
+        g2, se = c.normalize_finish()
+        return sums, g2, se
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing (value) ----
+    for _ in range(args.warmup):
+        g2, se = step_device()
+    c.kernel_report(reset=True)
+    c.kernel_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        g2, se = step_device()
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = int(sum_over_ranks(c.launch_count()))
+    report = c.kernel_report(reset=True)
+    c.kernel_timing(False)
+    finite_g2 = bool(np.isfinite(g2).all())
+
+    # ---- end-to-end timing through the public API with host buffers ----
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        sums, g2e, see = step_e2e()
+    e1.record(stream)
+    barrier()
+    wall = (time.perf_counter() - t0) / args.steps
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, 1e3 * wall))
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = 4 * E + 2 * E + 8 * (F + 1)
+    S = c.S
+    d2h = 4 * (P + 2 * F + S + (F // c.static_window) * S) + 2 * 4 * T * Q
+    E_total = sum_over_ranks(E)
+    R_total = sum_over_ranks(R)
+
+    value = world * F / (ms_dev * 1e-3)
+    e2e_value = world * F / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's launches) ----
+    peak, peak_src = peaks()
+    Es = int(c.info().events_stored)
+    kern = {}
+    for name, (ms, n) in report.items():
+        if n <= 0:
+            continue
+        per = ms / n
+        b = algorithmic_bytes(name, Es if name in ("k_finalize", "k_multitau") else E, T, R, Q, P)
+        kern[name] = {"ms_per_launch": per, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,
+                      "algo_bytes": b, "gbs": (b / (per * 1e-3) / 1e9) if per > 0 and b else None,
+                      "stage": KERNEL_GROUP.get(name, "?")}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roof = None
+    if dom:
+        k = kern[dom]
+        roof = {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (k["gbs"] / peak) if k["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                "algo_bytes_per_launch": k["algo_bytes"], "ms_per_launch": k["ms_per_launch"],
+                "kernel_share_of_step": k["ms_per_step"] / ms_dev}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the ncu --set full capture
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(args.workload, {}).get(dom)
+            except Exception:
+                pass
+    pipeline_bytes = 18 * E + 12 * T * R
+    kernels_ms = sum(k["ms_per_step"] for k in kern.values())
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64 numerators / f32 quotients", "data": "synthetic",
+        "config": {"workload": wl["name"], "workload_key": args.workload, "detector_pixels": int(P),
+                   "pixels_per_gpu_rows": int(R), "frames": F, "events_per_gpu": E, "delays": T, "q_bins": Q,
+                   "static_bins": S, "parallelism": "pixel-shard x%d (static-bin aligned, demultiplexed events)" % world,
+                   "value_definition": "1-Mpixel-detector frames/s = n_gpus*F/t (all stages: ingest, multi-tau, normalise)",
+                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (6 * E / 1e6),
+                   "compat_stale_tail": not args.no_compat},
+        "pixel_frames_per_s": float(R_total) * F / (ms_dev * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "api": "Correlator.push_sparse/finish_ingest/multitau/normalize (C-ABI xpcs_*)"},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "pipeline": {"algo_bytes_per_step": pipeline_bytes, "formula": "18*E + 12*T*P_valid (SURVEY 8d PRIMARY)",
+                     "kernel_ms_per_step": kernels_ms, "gbs_over_step": pipeline_bytes / (ms_dev * 1e-3) / 1e9,
+                     "frac_of_peak_over_step": pipeline_bytes / (ms_dev * 1e-3) / 1e9 / peak,
+                     "gbs_over_kernel_time": pipeline_bytes / (kernels_ms * 1e-3) / 1e9 if kernels_ms else None},
+        "kernels": kern,
+        "results_finite": finite_g2,
+    }
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
+    if rank == 0 and world == 1 and not args.no_cpu:
+        O = entry.load_oracle()
+        F_s = args.cpu_frames or 6000
+        run, kind, threads, E_s = cpu_sample_job(pkg, O, wl, F_s)
+        t, stages = run()
+        line["cpu_baseline"] = {
+            "value": F_s / t, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "%d of %d frames, same detector/occupancy/q-maps (%d events), all stages, one pass" % (F_s, F, E_s),
+            "seconds": t, "stages_s": stages}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

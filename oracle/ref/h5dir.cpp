@@ -1,0 +1,468 @@
+// h5dir.cpp -- directory-backed implementation of the HDF5 C-API subset declared in
+// oracle/ref/include/hdf5.h (TEST INFRASTRUCTURE: lets the unmodified reference link and run
+// in an image without libhdf5; see that header).  A "file" is a directory, a group a
+// sub-directory, a dataset one regular file:
+//     64-byte header { "H5DIRDS1", u32 type code, u32 element size, u32 rank, u32 0,
+//                      u64 dims[4], u64 data bytes } followed by the raw little-endian elements.
+// Type codes: 1 i32, 2 i64, 3 f32, 4 f64, 5 u32, 6 u16, 7 i16, 8 u64, 9 fixed-length string.
+// oracle/refdrv.py reads and writes the same layout from Python.
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "hdf5.h"
+
+namespace {
+
+enum Kind { K_FREE = 0, K_FILE, K_GROUP, K_DSET, K_SPACE, K_TYPE, K_PLIST };
+enum TCode { T_NONE = 0, T_I32 = 1, T_I64, T_F32, T_F64, T_U32, T_U16, T_I16, T_U64, T_STR };
+
+struct Obj {
+    Kind kind = K_FREE;
+    std::string path;   // file / group / dataset: filesystem path
+    int tcode = T_NONE; // dataset / type
+    size_t esize = 0;
+    int rank = 0;
+    hsize_t dims[4] = {0, 0, 0, 0};
+    bool selected = false;
+};
+
+std::mutex g_mu;
+std::vector<Obj> g_objs;
+const hid_t kBase = 0x1000;
+
+hid_t put(const Obj &o)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_objs.size(); i++)
+        if (g_objs[i].kind == K_FREE) {
+            g_objs[i] = o;
+            return kBase + (hid_t)i;
+        }
+    g_objs.push_back(o);
+    return kBase + (hid_t)g_objs.size() - 1;
+}
+
+bool get(hid_t id, Obj &o)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (id < kBase || (size_t)(id - kBase) >= g_objs.size()) return false;
+    o = g_objs[id - kBase];
+    return o.kind != K_FREE;
+}
+
+void drop(hid_t id)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (id >= kBase && (size_t)(id - kBase) < g_objs.size()) g_objs[id - kBase] = Obj();
+}
+
+size_t tsize(int tc)
+{
+    switch (tc) {
+    case T_I32: case T_F32: case T_U32: return 4;
+    case T_I64: case T_F64: case T_U64: return 8;
+    case T_U16: case T_I16: return 2;
+    default: return 1;
+    }
+}
+
+// native constant or type handle -> (code, element size)
+bool resolve_type(hid_t t, int &tc, size_t &es)
+{
+    switch (t) {
+    case H5T_NATIVE_INT: tc = T_I32; break;
+    case H5T_NATIVE_LONG: tc = T_I64; break;
+    case H5T_NATIVE_FLOAT: tc = T_F32; break;
+    case H5T_NATIVE_DOUBLE: tc = T_F64; break;
+    case H5T_NATIVE_UINT32: tc = T_U32; break;
+    case H5T_NATIVE_UINT16: tc = T_U16; break;
+    case H5T_NATIVE_SHORT: tc = T_I16; break;
+    case H5T_NATIVE_ULONG: tc = T_U64; break;
+    case H5T_C_S1: tc = T_STR; es = 1; return true;
+    default: {
+        Obj o;
+        if (!get(t, o) || o.kind != K_TYPE) return false;
+        tc = o.tcode;
+        es = o.esize;
+        return true;
+    }
+    }
+    es = tsize(tc);
+    return true;
+}
+
+bool is_dir(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
+bool is_file(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
+std::string join(const Obj &loc, const char *name)
+{
+    // absolute names ("/exchange") are relative to the file root: walk up to the K_FILE path
+    std::string n(name);
+    if (!n.empty() && n[0] == '/') {
+        std::string root = loc.path;
+        // groups remember their full path; the file root is the prefix ending in the container dir
+        size_t pos = root.find(".h5dir");
+        if (pos != std::string::npos) {
+            size_t end = root.find('/', pos);
+            if (end != std::string::npos) root = root.substr(0, end);
+        }
+        while (n.size() > 1 && n[0] == '/' && n[1] == '/') n.erase(0, 1);
+        return root + n;
+    }
+    return loc.path + "/" + n;
+}
+
+struct Header {
+    char magic[8];
+    uint32_t tcode, esize, rank, pad;
+    uint64_t dims[4];
+    uint64_t nbytes;
+};
+static_assert(sizeof(Header) == 64, "dataset header must be 64 bytes");
+
+bool read_header(const std::string &p, Header &h)
+{
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) return false;
+    bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "H5DIRDS1", 8) == 0;
+    fclose(f);
+    return ok;
+}
+
+double load_num(const void *p, int tc, size_t i)
+{
+    switch (tc) {
+    case T_I32: return (double)((const int32_t *)p)[i];
+    case T_I64: return (double)((const int64_t *)p)[i];
+    case T_F32: return (double)((const float *)p)[i];
+    case T_F64: return ((const double *)p)[i];
+    case T_U32: return (double)((const uint32_t *)p)[i];
+    case T_U16: return (double)((const uint16_t *)p)[i];
+    case T_I16: return (double)((const int16_t *)p)[i];
+    case T_U64: return (double)((const uint64_t *)p)[i];
+    default: return 0.0;
+    }
+}
+
+long long load_int(const void *p, int tc, size_t i)
+{
+    switch (tc) {
+    case T_I32: return ((const int32_t *)p)[i];
+    case T_I64: return ((const int64_t *)p)[i];
+    case T_U32: return ((const uint32_t *)p)[i];
+    case T_U16: return ((const uint16_t *)p)[i];
+    case T_I16: return ((const int16_t *)p)[i];
+    case T_U64: return (long long)((const uint64_t *)p)[i];
+    case T_F32: return (long long)((const float *)p)[i];
+    case T_F64: return (long long)((const double *)p)[i];
+    default: return 0;
+    }
+}
+
+bool is_float(int tc) { return tc == T_F32 || tc == T_F64; }
+
+void convert(const void *src, int stc, void *dst, int dtc, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        if (is_float(stc) || is_float(dtc)) {
+            double v = load_num(src, stc, i);
+            switch (dtc) {
+            case T_I32: ((int32_t *)dst)[i] = (int32_t)v; break;
+            case T_I64: ((int64_t *)dst)[i] = (int64_t)v; break;
+            case T_F32: ((float *)dst)[i] = (float)v; break;
+            case T_F64: ((double *)dst)[i] = v; break;
+            case T_U32: ((uint32_t *)dst)[i] = (uint32_t)v; break;
+            case T_U16: ((uint16_t *)dst)[i] = (uint16_t)v; break;
+            case T_I16: ((int16_t *)dst)[i] = (int16_t)v; break;
+            case T_U64: ((uint64_t *)dst)[i] = (uint64_t)v; break;
+            }
+        } else {
+            long long v = load_int(src, stc, i);
+            switch (dtc) {
+            case T_I32: ((int32_t *)dst)[i] = (int32_t)v; break;
+            case T_I64: ((int64_t *)dst)[i] = (int64_t)v; break;
+            case T_U32: ((uint32_t *)dst)[i] = (uint32_t)v; break;
+            case T_U16: ((uint16_t *)dst)[i] = (uint16_t)v; break;
+            case T_I16: ((int16_t *)dst)[i] = (int16_t)v; break;
+            case T_U64: ((uint64_t *)dst)[i] = (uint64_t)v; break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+hid_t H5Fopen(const char *name, unsigned, hid_t)
+{
+    if (!name || !is_dir(name)) return -1;
+    Obj o;
+    o.kind = K_FILE;
+    o.path = name;
+    while (o.path.size() > 1 && o.path.back() == '/') o.path.pop_back();
+    return put(o);
+}
+
+herr_t H5Fclose(hid_t f) { drop(f); return 0; }
+
+hid_t H5Gopen2(hid_t loc, const char *name, hid_t)
+{
+    Obj l;
+    if (!get(loc, l) || !name) return -1;
+    std::string p = join(l, name);
+    if (!is_dir(p)) return -1;
+    Obj o;
+    o.kind = K_GROUP;
+    o.path = p;
+    return put(o);
+}
+
+hid_t H5Gcreate2(hid_t loc, const char *name, hid_t, hid_t, hid_t)
+{
+    Obj l;
+    if (!get(loc, l) || !name) return -1;
+    std::string p = join(l, name);
+    if (mkdir(p.c_str(), 0777) != 0 && errno != EEXIST) return -1;  // single level, like H5Gcreate
+    Obj o;
+    o.kind = K_GROUP;
+    o.path = p;
+    return put(o);
+}
+
+herr_t H5Gclose(hid_t g) { drop(g); return 0; }
+
+hid_t H5Dopen2(hid_t loc, const char *name, hid_t)
+{
+    Obj l;
+    if (!get(loc, l) || !name) return -1;
+    std::string p = join(l, name);
+    if (!is_file(p)) return -1;
+    Header h;
+    if (!read_header(p, h)) return -1;
+    Obj o;
+    o.kind = K_DSET;
+    o.path = p;
+    o.tcode = (int)h.tcode;
+    o.esize = h.esize;
+    o.rank = (int)h.rank;
+    for (int i = 0; i < 4; i++) o.dims[i] = h.dims[i];
+    return put(o);
+}
+
+hid_t H5Dcreate2(hid_t loc, const char *name, hid_t type, hid_t space, hid_t, hid_t, hid_t)
+{
+    Obj l, s;
+    if (!get(loc, l) || !name || !get(space, s) || s.kind != K_SPACE) return -1;
+    int tc;
+    size_t es;
+    if (!resolve_type(type, tc, es)) return -1;
+    Obj o;
+    o.kind = K_DSET;
+    o.path = join(l, name);
+    o.tcode = tc;
+    o.esize = es;
+    o.rank = s.rank;
+    size_t n = 1;
+    for (int i = 0; i < 4; i++) o.dims[i] = s.dims[i];
+    for (int i = 0; i < s.rank; i++) n *= (size_t)s.dims[i];
+    Header h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "H5DIRDS1", 8);
+    h.tcode = (uint32_t)tc;
+    h.esize = (uint32_t)es;
+    h.rank = (uint32_t)s.rank;
+    for (int i = 0; i < 4; i++) h.dims[i] = s.dims[i];
+    h.nbytes = (uint64_t)n * es;
+    FILE *f = fopen(o.path.c_str(), "wb");
+    if (!f) return -1;
+    fwrite(&h, sizeof(h), 1, f);
+    fclose(f);
+    return put(o);
+}
+
+herr_t H5Dclose(hid_t d) { drop(d); return 0; }
+
+hid_t H5Dget_space(hid_t d)
+{
+    Obj o;
+    if (!get(d, o) || o.kind != K_DSET) return -1;
+    Obj s;
+    s.kind = K_SPACE;
+    s.rank = o.rank;
+    for (int i = 0; i < 4; i++) s.dims[i] = o.dims[i];
+    return put(s);
+}
+
+hid_t H5Dget_type(hid_t d)
+{
+    Obj o;
+    if (!get(d, o) || o.kind != K_DSET) return -1;
+    Obj t;
+    t.kind = K_TYPE;
+    t.tcode = o.tcode;
+    t.esize = o.esize;
+    return put(t);
+}
+
+hsize_t H5Dget_storage_size(hid_t d)
+{
+    Obj o;
+    if (!get(d, o) || o.kind != K_DSET) return 0;
+    size_t n = 1;
+    for (int i = 0; i < o.rank; i++) n *= (size_t)o.dims[i];
+    return (hsize_t)(n * o.esize);
+}
+
+herr_t H5Dread(hid_t d, hid_t mem_type, hid_t, hid_t file_space, hid_t, void *buf)
+{
+    Obj o;
+    if (!get(d, o) || o.kind != K_DSET || !buf) return -1;
+    if (file_space != H5S_ALL) {
+        Obj fs;
+        if (get(file_space, fs) && fs.selected) return -1;  // hyperslab reads: not needed on this path
+    }
+    int mtc;
+    size_t mes;
+    if (!resolve_type(mem_type, mtc, mes)) return -1;
+    size_t n = 1;
+    for (int i = 0; i < o.rank; i++) n *= (size_t)o.dims[i];
+    const size_t bytes = n * o.esize;
+    std::vector<unsigned char> raw(bytes ? bytes : 1);
+    FILE *f = fopen(o.path.c_str(), "rb");
+    if (!f) return -1;
+    fseek(f, sizeof(Header), SEEK_SET);
+    size_t got = fread(raw.data(), 1, bytes, f);
+    fclose(f);
+    if (got != bytes) return -1;
+    if (mtc == o.tcode || o.tcode == T_STR || mtc == T_STR) memcpy(buf, raw.data(), bytes);  // no conversion
+    else convert(raw.data(), o.tcode, buf, mtc, n);
+    return 0;
+}
+
+herr_t H5Dwrite(hid_t d, hid_t mem_type, hid_t, hid_t, hid_t, const void *buf)
+{
+    Obj o;
+    if (!get(d, o) || o.kind != K_DSET || !buf) return -1;
+    int mtc;
+    size_t mes;
+    if (!resolve_type(mem_type, mtc, mes)) return -1;
+    size_t n = 1;
+    for (int i = 0; i < o.rank; i++) n *= (size_t)o.dims[i];
+    const size_t bytes = n * o.esize;
+    std::vector<unsigned char> raw(bytes ? bytes : 1);
+    if (mtc == o.tcode || o.tcode == T_STR) memcpy(raw.data(), buf, bytes);
+    else convert(buf, mtc, raw.data(), o.tcode, n);
+    FILE *f = fopen(o.path.c_str(), "r+b");
+    if (!f) return -1;
+    fseek(f, sizeof(Header), SEEK_SET);
+    fwrite(raw.data(), 1, bytes, f);
+    fclose(f);
+    return 0;
+}
+
+hid_t H5Screate_simple(int rank, const hsize_t *dims, const hsize_t *)
+{
+    if (rank < 0 || rank > 4) return -1;
+    Obj s;
+    s.kind = K_SPACE;
+    s.rank = rank;
+    for (int i = 0; i < rank; i++) s.dims[i] = dims[i];
+    return put(s);
+}
+
+herr_t H5Sclose(hid_t s) { drop(s); return 0; }
+
+int H5Sget_simple_extent_dims(hid_t s, hsize_t *dims, hsize_t *maxdims)
+{
+    Obj o;
+    if (!get(s, o) || o.kind != K_SPACE) return -1;
+    for (int i = 0; i < o.rank; i++) {
+        if (dims) dims[i] = o.dims[i];
+        if (maxdims) maxdims[i] = o.dims[i];
+    }
+    return o.rank;
+}
+
+int H5Sget_simple_extent_ndims(hid_t s)
+{
+    Obj o;
+    if (!get(s, o) || o.kind != K_SPACE) return -1;
+    return o.rank;
+}
+
+herr_t H5Sselect_hyperslab(hid_t s, H5S_seloper_t, const hsize_t *start, const hsize_t *, const hsize_t *count,
+                           const hsize_t *)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (s < kBase || (size_t)(s - kBase) >= g_objs.size()) return -1;
+    Obj &o = g_objs[s - kBase];
+    if (o.kind != K_SPACE) return -1;
+    bool whole = true;
+    for (int i = 0; i < o.rank; i++)
+        if (start[i] != 0 || count[i] != o.dims[i]) whole = false;
+    o.selected = !whole;
+    return 0;
+}
+
+htri_t H5Tis_variable_str(hid_t) { return 0; }  // strings are stored fixed-length here
+
+hid_t H5Tget_native_type(hid_t t, H5T_direction_t)
+{
+    int tc;
+    size_t es;
+    if (!resolve_type(t, tc, es)) return -1;
+    Obj o;
+    o.kind = K_TYPE;
+    o.tcode = tc;
+    o.esize = es;
+    return put(o);
+}
+
+size_t H5Tget_size(hid_t t)
+{
+    int tc;
+    size_t es;
+    return resolve_type(t, tc, es) ? es : 0;
+}
+
+htri_t H5Tequal(hid_t a, hid_t b)
+{
+    int ta, tb;
+    size_t ea, eb;
+    if (!resolve_type(a, ta, ea) || !resolve_type(b, tb, eb)) return -1;
+    return ta == tb && ea == eb;
+}
+
+herr_t H5Tclose(hid_t t) { if (t >= kBase) drop(t); return 0; }
+
+hid_t H5Pcreate(hid_t)
+{
+    Obj o;
+    o.kind = K_PLIST;
+    return put(o);
+}
+
+herr_t H5Pclose(hid_t p) { drop(p); return 0; }
+herr_t H5Pset_chunk(hid_t, int, const hsize_t *) { return 0; }
+herr_t H5Pset_deflate(hid_t, unsigned) { return 0; }
+herr_t H5Eset_auto2(hid_t, H5E_auto2_t, void *) { return 0; }
+
+}  // extern "C"
