@@ -41,38 +41,87 @@ __device__ __forceinline__ float scaled_div(float num, int neff)
     return neff > 0 ? __fdiv_rn(num, (float)neff) : num;
 }
 
-// ---- integer path ------------------------------------------------------------------
-// Replays the probe sequence of libstdc++'s std::lower_bound over the n0 slots of the row:
-// slots below n hold level-l keys, slots at or above n hold what earlier levels left there.
-__device__ __forceinline__ int packed_slot_key(const uint32_t *col, int p, int n, int cb, int level,
-                                               const int *nhist)
-{
-    if (p < n) return (int)(col[p * kSlice] >> cb);
-    int lv = level - 1;
-    while (lv > 0 && nhist[lv] <= p) lv--;
-    return (int)(col[p * kSlice] >> (kCountBits + lv));
-}
-
-__device__ bool packed_ref_search_hits(const uint32_t *col, int n0, int n, int cb, int level,
-                                       const int *nhist, int target)
+// ---- compat: the reference's binary search over the un-shrunk vector ------------------
+// std::lower_bound (corr.cpp:406) runs over all n0 slots of the row: slots [0, n) hold the
+// live level-l keys, slots [n, n0) whatever earlier levels left there.  For a target that
+// sits at live position q the search is correct at every live probe; at a stale probe p >= n
+// it must go left, which needs V[p] >= target.  So the pair is found iff every stale slot on
+// the search path to q holds a value >= target, and the stale slots on that path depend on q
+// only: walking the implicit search tree along the live/stale boundary gives a step function
+// M(q) (minimum stale value probed before position q branches off), non-increasing in q.
+// Keys increase with q, hence "lost" (M(q) < key[q]) is monotone: there is one threshold key
+// K* such that exactly the targets with key >= K* are never found.
+// KEYAT(p) decodes the value the reference sees in slot p.
+template <typename KeyAt>
+__device__ __forceinline__ int stale_tail_threshold(int n0, int n, KeyAt key_at)
 {
     int first = 0, len = n0;
+    int curmin = 0x7fffffff;
     while (len > 0) {
-        int half = len >> 1;
-        int mid = first + half;
-        if (packed_slot_key(col, mid, n, cb, level, nhist) < target) {
+        const int half = len >> 1;
+        const int mid = first + half;
+        if (mid >= n) {  // stale probe: every live position of this range goes left of it
+            curmin = min(curmin, key_at(mid));
+            len = half;
+        } else {         // live probe: positions [first, mid] leave the boundary path here
+            if (curmin != 0x7fffffff && key_at(mid) > curmin) {
+                int q = first;
+                while (key_at(q) <= curmin) q++;
+                return key_at(q);
+            }
             first = mid + 1;
             len = len - half - 1;
-        } else len = half;
+        }
     }
-    return first < n && (int)(col[first * kSlice] >> cb) == target;
+    return 0x7fffffff;
 }
 
-template <bool COMPAT>
-__device__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, int r, const MtArgs &a)
+// ---- integer path ------------------------------------------------------------------
+// Dense-level pair sums.  When a level holds more than about one bin in six, walking the
+// sparse list pair by pair costs far more than sliding a register window over ALL bins of
+// the level: win[] holds the counts of bins t .. t+2*DPL (zero where the row has no event,
+// zero from K* on in compat mode -- lost targets form a suffix, so sources from K* on have
+// no surviving target either), and every bin t adds win[t] * win[t+DPL+1 .. t+2*DPL] to the
+// DPL accumulators.  The window rotates by renaming (the loop is unrolled by its length).
+template <int DPL>
+__device__ __forceinline__ void dense_level_pairs(const uint32_t *col, int n, int cb, uint32_t cmask, int L,
+                                                  int kstar, unsigned long long (&acc)[DPL])
+{
+    constexpr int W = 2 * DPL + 1;
+    uint32_t win[W];
+    int p = 0;
+    uint32_t wp = n > 0 ? col[0] : 0u;
+    int kp = n > 0 ? (int)(wp >> cb) : 0x7fffffff;
+    auto fetch = [&](int key) -> uint32_t {  // keys are requested in ascending order, none skipped
+        uint32_t v = 0;
+        if (kp == key) {
+            v = key < kstar ? (wp & cmask) : 0u;
+            p++;
+            if (p < n) {
+                wp = col[p * kSlice];
+                kp = (int)(wp >> cb);
+            } else kp = 0x7fffffff;
+        }
+        return v;
+    };
+#pragma unroll
+    for (int k = 0; k < W; k++) win[k] = fetch(k);
+    for (int t0 = 0; t0 < L - DPL - 1; t0 += W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const uint32_t src = win[u];
+#pragma unroll
+            for (int d = 0; d < DPL; d++)
+                acc[d] += (unsigned long long)src * (unsigned long long)win[(u + DPL + 1 + d) % W];
+            win[u] = fetch(t0 + u + W);
+        }
+    }
+}
+
+template <bool COMPAT, int DPL>
+__device__ __forceinline__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, int r, const MtArgs &a)
 {
     const int F = a.sched.frames;
-    const int hi = a.hi;
     int n = n0;
     int L = F;
     int cb = kCountBits;
@@ -80,23 +129,27 @@ __device__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, int r
     int stale_min = 0x7fffffff;
     for (int l = 0; l < a.sched.n_levels; l++) {
         if (l > 0) {
+            // in-place compaction of corr.cpp:349-390: keys halve, equal keys merge, keys >= L drop
             L >>= 1;
             cb++;
             const uint32_t clr = ~(1u << (cb - 1));
             const uint32_t cmask = (1u << cb) - 1u;
             int m = 0;
             uint32_t prev = 0xffffffffu;
+            uint32_t cur = 0;
             for (int j = 0; j < n; j++) {
-                uint32_t w = col[j * kSlice] & clr;
-                uint32_t key = w >> cb;
+                const uint32_t w = col[j * kSlice] & clr;
+                const uint32_t key = w >> cb;
                 if ((int)key >= L) break;
-                if (key == prev) col[(m - 1) * kSlice] += (w & cmask);
+                if (key == prev) cur += (w & cmask);
                 else {
-                    col[m * kSlice] = w;
+                    if (m > 0) col[(m - 1) * kSlice] = cur;
+                    cur = w;
                     m++;
                     prev = key;
                 }
             }
+            if (m > 0) col[(m - 1) * kSlice] = cur;
             if (COMPAT && m < n) stale_min = min(stale_min, (int)(col[m * kSlice] >> (cb - 1)));
             n = m;
         }
@@ -105,58 +158,86 @@ __device__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, int r
         if (cnt == 0) continue;
         const uint32_t cmask = (1u << cb) - 1u;
         const int lo = a.sched.lo[l];
+        const int top = lo + cnt - 1;  // largest level-local delay needed
         const int first = a.sched.first[l];
-        const bool verify = COMPAT && l > 0 && stale_min < L;
-        // ---- G2: pairs of bins at key distance <= hi
-        for (int d = 0; d <= hi; d++) acc[d * kSlice] = 0;
-        long long total = 0;
-        for (int i = 0; i < n; i++) {
-            const uint32_t wi = col[i * kSlice];
-            const int ki = (int)(wi >> cb);
-            const int ci = (int)(wi & cmask);
-            total += ci;
-            for (int j = i + 1; j < n; j++) {
-                const uint32_t wj = col[j * kSlice];
-                const int d = (int)(wj >> cb) - ki;
-                if (d > hi) break;
-                if (COMPAT && verify && d >= lo &&
-                    !packed_ref_search_hits(col, n0, n, cb, l, nhist, ki + d))
-                    continue;
-                acc[d * kSlice] += (long long)ci * (long long)(wj & cmask);
-            }
+        int kstar = 0x7fffffff;
+        if (COMPAT && l > 0 && stale_min < L && n < n0) {
+            const int level = l;
+            kstar = stale_tail_threshold(n0, n, [&](int p) -> int {
+                if (p < n) return (int)(col[p * kSlice] >> cb);
+                int lv = level - 1;
+                while (lv > 0 && nhist[lv] <= p) lv--;
+                return (int)(col[p * kSlice] >> (kCountBits + lv));
+            });
         }
         const float s2 = pow2_neg(2 * l), s1 = pow2_neg(l);
-        for (int k = 0; k < cnt; k++) {
-            const int tp = lo + k;
-            a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)acc[tp * kSlice] * s2, L - tp);
+        // ---- G2: pairs of bins at key distance lo..top (the later bin is the search target)
+        bool dense = false;
+        if (DPL > 0 && l > 0 && lo == DPL + 1)
+            dense = (long long)__reduce_add_sync(0xffffffffu, n) * 6 > (long long)L * 32;
+        long long total = 0;
+        if (DPL > 0 && dense) {
+            unsigned long long pairs[DPL > 0 ? DPL : 1];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) pairs[d] = 0ull;
+            dense_level_pairs<(DPL > 0 ? DPL : 1)>(col, n, cb, cmask, L, kstar, pairs);
+            for (int i = 0; i < n; i++) total += (long long)(col[i * kSlice] & cmask);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < DPL; k++)
+                if (k < cnt)
+                    a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)(long long)pairs[k] * s2, L - (lo + k));
+        } else {
+            for (int d = lo; d <= top; d++) acc[d * kSlice] = 0;
+            uint32_t wnext = n > 0 ? col[0] : 0u;
+            for (int i = 0; i < n; i++) {
+                const uint32_t wi = wnext;
+                const int ki = (int)(wi >> cb);
+                const int ci = (int)(wi & cmask);
+                total += ci;
+                if (i + 1 < n) wnext = col[(i + 1) * kSlice];
+                uint32_t wj = wnext;
+                for (int j = i + 1; j < n;) {
+                    const int kj = (int)(wj >> cb);
+                    const int d = kj - ki;
+                    if (d > top) break;
+                    if (d >= lo && kj < kstar) acc[d * kSlice] += (long long)ci * (long long)(wj & cmask);
+                    if (++j < n) wj = col[j * kSlice];
+                }
+            }
+            __syncwarp();
+            for (int k = 0; k < cnt; k++) {
+                const int tp = lo + k;
+                a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)acc[tp * kSlice] * s2, L - tp);
+            }
         }
         // ---- IF: total minus the bins with key < tau'
-        for (int d = 0; d <= hi; d++) acc[d * kSlice] = 0;
+        for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
         for (int i = 0; i < n; i++) {
             const uint32_t wi = col[i * kSlice];
             const int ki = (int)(wi >> cb);
-            if (ki >= hi) break;
-            acc[ki * kSlice] += (int)(wi & cmask);
+            if (ki >= top) break;
+            acc[ki * kSlice] = (long long)(wi & cmask);
         }
         {
             long long run = 0;
-            for (int tp = 1; tp < lo + cnt; tp++) {
+            for (int tp = 1; tp <= top; tp++) {
                 run += acc[(tp - 1) * kSlice];
                 if (tp >= lo)
                     a.IF[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
             }
         }
         // ---- IP: total minus the bins with key >= L - tau'
-        for (int d = 0; d <= hi; d++) acc[d * kSlice] = 0;
+        for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
         for (int i = n - 1; i >= 0; i--) {
             const uint32_t wi = col[i * kSlice];
             const int x = L - 1 - (int)(wi >> cb);
-            if (x >= hi) break;
-            acc[x * kSlice] += (int)(wi & cmask);
+            if (x >= top) break;
+            acc[x * kSlice] = (long long)(wi & cmask);
         }
         {
             long long run = 0;
-            for (int tp = 1; tp < lo + cnt; tp++) {
+            for (int tp = 1; tp <= top; tp++) {
                 run += acc[(tp - 1) * kSlice];
                 if (tp >= lo)
                     a.IP[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
@@ -173,20 +254,6 @@ __device__ __forceinline__ float f_val(u64 w) { return __uint_as_float((uint32_t
 __device__ __forceinline__ u64 f_make(int key, float v)
 {
     return ((u64)(uint32_t)key << 32) | (u64)__float_as_uint(v);
-}
-
-__device__ bool float_ref_search_hits(const u64 *col, int n0, int n, int target)
-{
-    int first = 0, len = n0;
-    while (len > 0) {
-        int half = len >> 1;
-        int mid = first + half;
-        if (f_key(col[mid * kSlice]) < target) {
-            first = mid + 1;
-            len = len - half - 1;
-        } else len = half;
-    }
-    return first < n && f_key(col[first * kSlice]) == target;
 }
 
 template <bool COMPAT>
@@ -225,10 +292,13 @@ __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const Mt
         const int cnt = a.sched.count[l];
         if (cnt == 0) continue;
         const int lo = a.sched.lo[l];
+        const int top = lo + cnt - 1;
         const int first = a.sched.first[l];
-        const bool verify = COMPAT && l > 0 && stale_min < L;
+        int kstar = 0x7fffffff;
+        if (COMPAT && l > 0 && stale_min < L && n < n0)
+            kstar = stale_tail_threshold(n0, n, [&](int p) -> int { return f_key(col[p * kSlice]); });
         // ---- G2 in the reference's order: for each source ascending, product then add
-        for (int d = 0; d <= hi; d++) acc[d * kSlice] = 0.0f;
+        for (int d = lo; d <= top; d++) acc[d * kSlice] = 0.0f;
         double total = 0.0;
         for (int i = 0; i < n; i++) {
             const u64 wi = col[i * kSlice];
@@ -237,12 +307,13 @@ __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const Mt
             total += (double)vi;
             for (int j = i + 1; j < n; j++) {
                 const u64 wj = col[j * kSlice];
-                const int d = f_key(wj) - ki;
-                if (d > hi) break;
-                if (COMPAT && verify && d >= lo && !float_ref_search_hits(col, n0, n, ki + d)) continue;
-                acc[d * kSlice] = __fadd_rn(acc[d * kSlice], __fmul_rn(vi, f_val(wj)));
+                const int kj = f_key(wj);
+                const int d = kj - ki;
+                if (d > top) break;
+                if (d >= lo && kj < kstar) acc[d * kSlice] = __fadd_rn(acc[d * kSlice], __fmul_rn(vi, f_val(wj)));
             }
         }
+        __syncwarp();
         for (int k = 0; k < cnt; k++) {
             const int tp = lo + k;
             a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div(acc[tp * kSlice], L - tp);
@@ -288,7 +359,7 @@ __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const Mt
     }
 }
 
-template <int KIND, bool COMPAT>
+template <int KIND, bool COMPAT, int DPL>
 __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,14 +371,13 @@ __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
     const bool in_smem = len <= a.smem_len;
     if (KIND == kPacked) {
         uint32_t *g = reinterpret_cast<uint32_t *>(a.store) + a.slice_base[s] + lane;
-        uint32_t *col = g;
         long long *acc = reinterpret_cast<long long *>(smem_raw) + lane;
-        if (in_smem) {
-            col = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(a.hi + 1) * kSlice * 8) + lane;
+        if (in_smem) {  // two call sites so that the common one compiles to LDS/STS
+            uint32_t *col = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(a.hi + 1) * kSlice * 8) + lane;
             for (int j = 0; j < len; j++)
                 if (j < n0) col[j * kSlice] = g[(int64_t)j * kSlice];
-        }
-        row_multitau_packed<COMPAT>(col, acc, n0, r, a);
+            row_multitau_packed<COMPAT, DPL>(col, acc, n0, r, a);
+        } else row_multitau_packed<COMPAT, 0>(g, acc, n0, r, a);
     } else {
         u64 *g = reinterpret_cast<u64 *>(a.store) + a.slice_base[s] + lane;
         u64 *col = g;
@@ -331,7 +401,7 @@ __global__ void k_unpermute(const float *__restrict__ src, float *__restrict__ d
     dst[(int64_t)t * P + pixel_of_row[r]] = src[(int64_t)t * R_pad + r];
 }
 
-template <int KIND, bool COMPAT>
+template <int KIND, bool COMPAT, int DPL>
 static int run_multitau(xpcs_handle_s *h, MtArgs &a)
 {
     int smem_cap = 0;
@@ -345,13 +415,13 @@ static int run_multitau(xpcs_handle_s *h, MtArgs &a)
     a.smem_len = smem_len;
     if (h->max_row > smem_len) h->rows_consumed = true;  // long rows are compacted in place
     const size_t bytes = acc_bytes + (size_t)smem_len * kSlice * wbytes;
-    int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau<KIND, COMPAT>,
+    int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau<KIND, COMPAT, DPL>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                         "multitau smem attr");
     if (rc) return rc;
     if (h->n_slices > 0) {
         LaunchScope ls(h, "k_multitau");
-        k_multitau<KIND, COMPAT><<<h->n_slices, 32, bytes, h->stream>>>(a);
+        k_multitau<KIND, COMPAT, DPL><<<h->n_slices, 32, bytes, h->stream>>>(a);
     }
     return check_cuda(h, cudaGetLastError(), "k_multitau");
 }
@@ -376,9 +446,14 @@ int launch_multitau(xpcs_handle_s *h)
     a.hi = 2 * h->prm.delays_per_level;
     a.compat = (h->prm.compat_flags & XPCS_COMPAT_STALE_TAIL) ? 1 : 0;
     a.sched = h->sched;
-    if (h->kind == kPacked)
-        return a.compat ? run_multitau<kPacked, true>(h, a) : run_multitau<kPacked, false>(h, a);
-    return a.compat ? run_multitau<kFloat, true>(h, a) : run_multitau<kFloat, false>(h, a);
+    if (h->kind == kPacked) {
+        // the register-window path for dense levels is instantiated for the usual delays-per-level
+        const int dpl = h->prm.delays_per_level;
+        if (dpl == 8) return a.compat ? run_multitau<kPacked, true, 8>(h, a) : run_multitau<kPacked, false, 8>(h, a);
+        if (dpl == 4) return a.compat ? run_multitau<kPacked, true, 4>(h, a) : run_multitau<kPacked, false, 4>(h, a);
+        return a.compat ? run_multitau<kPacked, true, 0>(h, a) : run_multitau<kPacked, false, 0>(h, a);
+    }
+    return a.compat ? run_multitau<kFloat, true, 0>(h, a) : run_multitau<kFloat, false, 0>(h, a);
 }
 
 int launch_unpermute(xpcs_handle_s *h, const float *d_src, float *d_dst)
