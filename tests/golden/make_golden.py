@@ -1,0 +1,104 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/corr_ref, built
+by oracle/ref/Makefile from /root/reference) on small seeded inputs.  Each fixture holds the
+inputs (so nothing has to be regenerated bit-for-bit at test time) and every result dataset
+the reference wrote.  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the CPU oracle (tests/test_oracle_golden.py, CPU) and the CUDA path
+(tests/test_gpu_golden.py, -m gpu) to the reference's own outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+from oracle import refdrv  # noqa: E402
+
+pkg = entry.load_package()
+S = pkg.synth
+
+
+def save(name, inputs, res, info):
+    out = {("in_" + k): v for k, v in inputs.items() if v is not None}
+    for k, v in res.items():
+        out["ref_" + k.replace("/", "__")] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, name + ".npz"))
+    print("%-22s %6.0f kB  datasets: %s" % (name, sz / 1e3, " ".join(sorted(res))))
+
+
+def sparse_case(name, h, w, F_raw, occ, seed, dpl=8, nd=4, spd=3, r_min=2.0, flat=False, stride=1, avg=1,
+                norm=False, events=None):
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=nd, static_per_dynamic=spd, r_min=r_min)
+    if events is None:
+        off, idx, val = S.sparse_frames(h * w, F_raw, occ, seed=seed)
+    else:
+        dq, sq, off, idx, val = events
+    ff = S.flatfield(h * w, seed=seed + 100) if flat else None
+    block = stride * avg if (stride > 1 and avg > 1) else max(stride, avg)
+    F = F_raw // block
+    sw = max(1, F // 10)
+    res, info = refdrv.run_case(S, dq, sq, F_raw, sparse=(off, idx, val), g2out=True, dpl=dpl, stride=stride, avg=avg,
+                                static_window=sw, flatfield=ff, normalize_by_framesum=norm)
+    save(name, dict(kind=np.array("sparse"), dq=dq, sq=sq, off=off, idx=idx, val=val, flat=ff,
+                    params=np.array([F_raw, dpl, stride, avg, sw, int(norm)], np.int64)), res, info)
+
+
+def main():
+    if not refdrv.available():
+        raise SystemExit("oracle/_ref/corr_ref missing: run `make -C oracle ref` (needs /root/reference)")
+    sparse_case("sparse_int_24x24", 24, 24, 600, 0.03, 1)
+    sparse_case("sparse_odd_dpl4", 20, 28, 1001, 0.012, 2, dpl=4)
+    sparse_case("sparse_staletail_32x32", 32, 32, 4000, 0.004, 3)   # rows hit the lower_bound quirk
+    # the hand example of SURVEY.md A.4: one pixel, unit counts at frames 0..31, 400, 440, F = 512
+    F = 512
+    frames = list(range(32)) + [400, 440]
+    off = np.zeros(F + 1, np.int64)
+    for f in frames:
+        off[f + 1:] += 1
+    ev = (np.ones((1, 2), np.int32), np.ones((1, 2), np.int32), off, np.zeros(len(frames), np.int32),
+          np.ones(len(frames), np.int16))
+    sparse_case("staletail_hand_example", 1, 2, F, 0, 0, events=ev)
+    sparse_case("sparse_flat_stride2_avg2", 24, 24, 1200, 0.03, 5, flat=True, stride=2, avg=2)
+    sparse_case("sparse_flat_avg3", 24, 24, 900, 0.03, 6, flat=True, avg=3)
+    sparse_case("sparse_framesum_norm", 24, 24, 500, 0.04, 7, norm=True)
+
+    # dense int16 source with dark frames, flat-field and threshold (DenseFilter + DarkImage)
+    h = w = 16
+    darks, F = 12, 300
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=3, static_per_dynamic=2, r_min=1.0)
+    fr = S.dense_frames(h * w, F, darks=darks, mu=0.05, seed=8)
+    ff = S.flatfield(h * w, seed=108)
+    lld, sigma = 5.0, 3.0
+    res, info = refdrv.run_case(S, dq, sq, F, dense=fr, g2out=True, darkout=True, dpl=8, darks=darks, lld=lld,
+                                sigma=sigma, flatfield=ff, static_window=30)
+    save("dense_dark_flat_16x16", dict(kind=np.array("dense"), dq=dq, sq=sq, frames=fr, flat=ff,
+                                       params=np.array([F, 8, 1, 1, 30, 0, darks], np.int64),
+                                       thresh=np.array([lld, sigma], np.float32)), res, info)
+    # dense without darks (threshold 0)
+    fr2 = (S.dense_frames(h * w, 200, darks=0, mu=0.05, offset=0.0, read_noise=0.4, seed=9)).astype(np.int16)
+    res, info = refdrv.run_case(S, dq, sq, 200, dense=fr2, g2out=True, dpl=8, static_window=20)
+    save("dense_nodark_16x16", dict(kind=np.array("dense"), dq=dq, sq=sq, frames=fr2,
+                                    params=np.array([200, 8, 1, 1, 20, 0, 0], np.int64)), res, info)
+
+    # two-time, symmetric smoothing, with and without the "Average" filter
+    h = w = 16
+    F = 200
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=3, static_per_dynamic=2, r_min=1.0)
+    off, idx, val = S.sparse_frames(h * w, F, 0.06, seed=10)
+    for tag, filt in (("none", "None"), ("average", "Average")):
+        res, info = refdrv.run_case(S, dq, sq, F, sparse=(off, idx, val), g2out=False, dpl=8, static_window=20,
+                                    twotime=dict(qbins=[1, 3], wsize=10, method="symmetric", filter=filt))
+        save("twotime_symmetric_" + tag, dict(kind=np.array("twotime"), dq=dq, sq=sq, off=off, idx=idx, val=val,
+                                              params=np.array([F, 8, 1, 1, 20, 0], np.int64),
+                                              qbins=np.array([1, 3], np.int32), wsize=np.array(10),
+                                              filt=np.array(filt)), res, info)
+
+
+if __name__ == "__main__":
+    main()
