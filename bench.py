@@ -171,10 +171,11 @@ def cpu_sample_job(pkg, O, wl, F_s, seed=1234):
         ref = None
     threads = O.max_threads()
     if ref is not None:
+        job = ref.SparseJob(dq, sq, F_s, off, idx, val, dpl=8, swindow=max(1, F_s // 10))
+
         def run():
-            t0 = time.perf_counter()
-            st = ref.run_sparse(dq, sq, F_s, off, idx, val, dpl=8, swindow=max(1, F_s // 10), threads=threads)
-            return time.perf_counter() - t0, st
+            st = job.run(threads=threads)
+            return float(st["total_s"]), st  # the reference's own "Total" scope (main.cpp:108)
         kind = "reference"
     else:
         qm = O.QMap(dq, sq)
@@ -203,7 +204,7 @@ def run_reference_arm(args, wl, wl_key):
     if wl["kind"] != "sparse":
         wl = WORKLOADS["c3"]
         wl_key = "c3"
-    F_s = args.cpu_frames or 6000
+    F_s = args.cpu_frames or 5000
     run, kind, threads, E = cpu_sample_job(pkg, O, wl, F_s)
     for _ in range(args.warmup):
         run()
@@ -465,7 +466,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
     if rank == 0 and world == 1 and not args.no_cpu:
         O = entry.load_oracle()
-        F_s = args.cpu_frames or 6000
+        F_s = args.cpu_frames or 5000
         run, kind, threads, E_s = cpu_sample_job(pkg, O, wl, F_s)
         t, stages = run()
         line["cpu_baseline"] = {

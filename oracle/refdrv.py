@@ -192,12 +192,28 @@ def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout
             shutil.rmtree(d, ignore_errors=True)
 
 
-def run_sparse(dq, sq, frames, off, idx, val, dpl=8, swindow=None, threads=None):
-    """bench.py helper: time one sparse multi-tau job; returns the reference's own stage scopes."""
-    from __graft_entry__ import load_package
-    synth = load_package().synth
-    _, info = run_case(synth, dq, sq, frames, sparse=(off, idx, val), g2out=False, threads=threads, dpl=dpl,
-                       static_window=swindow)
-    s = info["scopes"]
-    return {"total_s": s.get("Total"), "load_s": s.get("Loading data"), "multitau_s": s.get("Computing G2 MultiTau"),
-            "normalize_s": s.get("Normalizing Data"), "wall_s": info["seconds"]}
+class SparseJob:
+    """bench.py helper: the files of one sparse multi-tau job are written once; run() executes the
+    reference binary on them and returns its own stage scopes (seconds)."""
+
+    def __init__(self, dq, sq, frames, off, idx, val, dpl=8, swindow=None):
+        from __graft_entry__ import load_package
+        synth = load_package().synth
+        self.dir = scratch_dir()
+        self.imm = os.path.join(self.dir, "data.imm")
+        h, w = np.asarray(dq).shape
+        synth.write_imm_sparse(self.imm, h, w, off, idx, val)
+        self.root = os.path.join(self.dir, "case.h5dir")
+        write_config(self.root, dq, sq, frames, self.imm, dpl=dpl, static_window=swindow)
+        import atexit
+        atexit.register(self.close)
+
+    def run(self, threads=None):
+        info = run(self.root, self.imm, g2out=False, threads=threads, cwd=self.dir)
+        s = info["scopes"]
+        return {"total_s": s.get("Total"), "load_s": s.get("Loading data"),
+                "multitau_s": s.get("Computing G2 MultiTau"), "normalize_s": s.get("Normalizing Data"),
+                "wall_s": info["seconds"]}
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
