@@ -85,6 +85,20 @@ int xpcs_level_max(int frames, int delays_per_level);
 /* writes up to cap (level, tau) pairs, returns T */
 int xpcs_delay_schedule(int frames, int delays_per_level, int32_t *level, int32_t *tau, int cap);
 
+/* ---- pixel sharding (host only: callable on a box without a GPU) ---- */
+typedef struct XpcsShardPlan {
+    int32_t n_static, n_dynamic; /* S, Q                                                          */
+    int32_t n_segments;          /* surviving (dq, sq) map entries of the whole detector          */
+    int32_t seg_first, seg_last; /* this shard owns global segments [seg_first, seg_last)          */
+    int32_t n_rows;              /* unmasked pixels owned by this shard                            */
+    int32_t n_rows_total;
+    int32_t n_delays;            /* T                                                              */
+} XpcsShardPlan;
+/* The partition maps of Configuration::BuildQMap (configuration.cpp:244-381) and the shard
+ * (params->shard_index of shard_count) xpcs_create would build, without touching a device.
+ * row_pixels (nullable, capacity cap): detector pixel of every owned row in store order. */
+int xpcs_plan_shard(const XpcsParams *params, XpcsShardPlan *plan, int32_t *row_pixels, int64_t cap);
+
 /* ---- lifetime ---- */
 /* replaces: Configuration::BuildQMap (configuration.cpp:244-381) + the constructors of
  * SparseFilter / DenseFilter (sparse_filter.cpp:63-109, dense_filter.cpp:64-115).       */

@@ -23,7 +23,7 @@ def test_header_symbols_exported(pkg):
 
 
 def test_struct_sizes_match(pkg):
-    assert C.sizeof(pkg.XpcsParams) == 88 and C.sizeof(pkg.XpcsInfo) == 64  # sizeof() in C
+    assert C.sizeof(pkg.XpcsParams) == 88 and C.sizeof(pkg.XpcsInfo) == 64 and C.sizeof(pkg.XpcsShardPlan) == 32  # sizeof() in C
     assert pkg.cabi.load().xpcs_compiled_arch() == 100
     assert pkg.cabi.load().xpcs_abi_version() == 1
 

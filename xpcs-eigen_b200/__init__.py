@@ -13,7 +13,47 @@ import ctypes as C
 import numpy as np
 
 from . import cabi, synth, torchio  # noqa: F401
-from .cabi import XPCS_COMPAT_STALE_TAIL, XpcsError, XpcsInfo, XpcsParams  # noqa: F401
+from .cabi import XPCS_COMPAT_STALE_TAIL, XpcsError, XpcsInfo, XpcsParams, XpcsShardPlan  # noqa: F401
+
+
+def make_params(dqmap, sqmap, frames, dpl=8, flatfield=None, stride=1, avg=1, static_window=None,
+                normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, shard_index=0, shard_count=1,
+                reserve_events=0):
+    """XpcsParams from numpy maps; returns (params, keepalive list)."""
+    dq = np.ascontiguousarray(dqmap, np.int32)
+    sq = np.ascontiguousarray(sqmap, np.int32)
+    assert dq.ndim == 2 and dq.shape == sq.shape
+    ff = None if flatfield is None else np.ascontiguousarray(flatfield, np.float64).ravel()
+    p = XpcsParams()
+    p.struct_size = C.sizeof(XpcsParams)
+    p.width, p.height = dq.shape[1], dq.shape[0]
+    p.frames = int(frames)
+    p.delays_per_level = dpl
+    p.stride_frames, p.avg_frames = stride, avg
+    p.static_window = int(static_window) if static_window else max(1, int(frames) // 10)
+    p.normalize_by_framesum = int(bool(normalize_by_framesum))
+    p.compat_flags = XPCS_COMPAT_STALE_TAIL if compat else 0
+    p.lld, p.sigma = float(lld), float(sigma)
+    p.dqmap, p.sqmap = dq.ctypes.data, sq.ctypes.data
+    p.flatfield = None if ff is None else ff.ctypes.data
+    p.shard_index, p.shard_count = shard_index, shard_count
+    p.reserve_events = int(reserve_events)
+    return p, [dq, sq, ff]
+
+
+def plan_shard(dqmap, sqmap, frames, shard_index=0, shard_count=1, dpl=8):
+    """Host-only: (XpcsShardPlan, row_pixels) of one pixel shard -- what xpcs_create would build."""
+    lib = cabi.load()
+    p, keep = make_params(dqmap, sqmap, frames, dpl=dpl, shard_index=shard_index, shard_count=shard_count)
+    plan = XpcsShardPlan()
+    rc = lib.xpcs_plan_shard(C.byref(p), C.byref(plan), None, 0)
+    if rc != 0:
+        raise XpcsError(rc, (lib.xpcs_last_error(None) or b"").decode())
+    rows = np.zeros(max(plan.n_rows, 1), np.int32)
+    rc = lib.xpcs_plan_shard(C.byref(p), C.byref(plan), rows.ctypes.data, rows.size)
+    if rc != 0:
+        raise XpcsError(rc, (lib.xpcs_last_error(None) or b"").decode())
+    return plan, rows[: plan.n_rows]
 
 
 def level_max(frames, dpl):
@@ -43,27 +83,13 @@ class Correlator:
                  normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, device=0, shard_index=0,
                  shard_count=1, reserve_events=0):
         self._lib = cabi.load()
-        dq = np.ascontiguousarray(dqmap, np.int32)
-        sq = np.ascontiguousarray(sqmap, np.int32)
-        assert dq.ndim == 2 and dq.shape == sq.shape
-        self.height, self.width = dq.shape
-        self.P = dq.size
+        p, self._maps = make_params(dqmap, sqmap, frames, dpl=dpl, flatfield=flatfield, stride=stride, avg=avg,
+                                    static_window=static_window, normalize_by_framesum=normalize_by_framesum,
+                                    compat=compat, lld=lld, sigma=sigma, shard_index=shard_index,
+                                    shard_count=shard_count, reserve_events=reserve_events)
+        self.height, self.width = p.height, p.width
+        self.P = p.width * p.height
         self.F = int(frames)
-        ff = None if flatfield is None else np.ascontiguousarray(flatfield, np.float64).ravel()
-        p = XpcsParams()
-        p.struct_size = C.sizeof(XpcsParams)
-        p.width, p.height = self.width, self.height
-        p.frames = self.F
-        p.delays_per_level = dpl
-        p.stride_frames, p.avg_frames = stride, avg
-        p.static_window = int(static_window) if static_window else max(1, self.F // 10)
-        p.normalize_by_framesum = int(bool(normalize_by_framesum))
-        p.compat_flags = XPCS_COMPAT_STALE_TAIL if compat else 0
-        p.lld, p.sigma = float(lld), float(sigma)
-        p.dqmap, p.sqmap = dq.ctypes.data, sq.ctypes.data
-        p.flatfield = None if ff is None else ff.ctypes.data
-        p.shard_index, p.shard_count = shard_index, shard_count
-        p.reserve_events = int(reserve_events)
         self.params = p
         self.static_window = p.static_window
         h = C.c_void_p()

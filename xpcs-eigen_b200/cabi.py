@@ -47,11 +47,18 @@ class XpcsInfo(C.Structure):
     ]
 
 
+class XpcsShardPlan(C.Structure):
+    _fields_ = [("n_static", C.c_int32), ("n_dynamic", C.c_int32), ("n_segments", C.c_int32),
+                ("seg_first", C.c_int32), ("seg_last", C.c_int32), ("n_rows", C.c_int32),
+                ("n_rows_total", C.c_int32), ("n_delays", C.c_int32)]
+
+
 # every symbol include/xpcs_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
     "xpcs_level_max": (_i, [_i, _i]),
     "xpcs_delay_schedule": (_i, [_i, _i, _vp, _vp, _i]),
+    "xpcs_plan_shard": (_i, [C.POINTER(XpcsParams), C.POINTER(XpcsShardPlan), _vp, _i64]),
     "xpcs_create": (_i, [C.POINTER(XpcsParams), _i, C.POINTER(_vp)]),
     "xpcs_destroy": (None, [_vp]),
     "xpcs_last_error": (C.c_char_p, [_vp]),

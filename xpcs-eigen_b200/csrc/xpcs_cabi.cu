@@ -127,7 +127,8 @@ struct Cell {
     bool kept;
 };
 
-static int build_maps(xpcs_handle_s *h)
+// host-only part: partition maps, segments, shard cut, row order (no CUDA call)
+static int plan_maps(xpcs_handle_s *h)
 {
     const XpcsParams &p = h->prm;
     const int P = h->P;
@@ -224,7 +225,15 @@ static int build_maps(xpcs_handle_s *h)
     h->R_pad = (h->R + kSlice - 1) / kSlice * kSlice;
     if (h->R_pad == 0) h->R_pad = kSlice;
     h->n_slices = h->R_pad / kSlice;
+    return XPCS_OK;
+}
 
+static int build_maps(xpcs_handle_s *h)
+{
+    int rc0 = plan_maps(h);
+    if (rc0) return rc0;
+    const XpcsParams &p = h->prm;
+    const int P = h->P;
     // device copies
     std::vector<int> row_of_pixel(P, -1), sbin_of_row(h->R_pad, -1), pix_of_row(h->R_pad, 0);
     for (int r = 0; r < h->R; r++) {
@@ -296,10 +305,8 @@ static void reset_ingest(xpcs_handle_s *h)
     h->max_row = 0;
 }
 
-extern "C" int xpcs_create(const XpcsParams *prm, int device, xpcs_handle *out)
+static int check_params(const XpcsParams *prm)
 {
-    if (!out) return fail(nullptr, XPCS_E_ARG, "out is NULL");
-    *out = nullptr;
     if (!prm || prm->struct_size != (int32_t)sizeof(XpcsParams))
         return fail(nullptr, XPCS_E_ARG, "XpcsParams.struct_size mismatch (caller %d, library %d)",
                     prm ? prm->struct_size : -1, (int)sizeof(XpcsParams));
@@ -310,6 +317,42 @@ extern "C" int xpcs_create(const XpcsParams *prm, int device, xpcs_handle *out)
     if ((int64_t)prm->width * prm->height > 0x7fffffffLL) return fail(nullptr, XPCS_E_ARG, "detector too large");
     if (prm->normalize_by_framesum && prm->shard_count > 1)
         return fail(nullptr, XPCS_E_ARG, "normalize_by_framesum needs the frame sums of all shards; not supported with shard_count > 1");
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_plan_shard(const XpcsParams *prm, XpcsShardPlan *plan, int32_t *row_pixels, int64_t cap)
+{
+    int rc = check_params(prm);
+    if (rc) return rc;
+    if (!plan) return fail(nullptr, XPCS_E_ARG, "plan is NULL");
+    xpcs_handle_s tmp;
+    tmp.prm = *prm;
+    tmp.P = prm->width * prm->height;
+    if ((rc = build_schedule(&tmp)) || (rc = plan_maps(&tmp))) {
+        g_create_error = tmp.err;
+        return rc;
+    }
+    plan->n_static = tmp.S;
+    plan->n_dynamic = tmp.Q;
+    plan->n_segments = tmp.nseg_total;
+    plan->seg_first = tmp.seg_first;
+    plan->seg_last = tmp.seg_last;
+    plan->n_rows = tmp.R;
+    plan->n_rows_total = tmp.R_total;
+    plan->n_delays = tmp.T;
+    if (row_pixels)
+        for (int r = 0; r < tmp.R && r < cap; r++) row_pixels[r] = tmp.pixel_of_row[r];
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_create(const XpcsParams *prm, int device, xpcs_handle *out)
+{
+    if (!out) return fail(nullptr, XPCS_E_ARG, "out is NULL");
+    *out = nullptr;
+    {
+        int rc = check_params(prm);
+        if (rc) return rc;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0)
