@@ -77,65 +77,15 @@ __device__ __forceinline__ int stale_tail_threshold(int n0, int n, KeyAt key_at)
 }
 
 // ---- integer path ------------------------------------------------------------------
-// In-place level compaction of corr.cpp:349-390, one element at a time: keys halve, equal keys
-// merge (counts add), keys >= L_next drop.  Fused into the pass that evaluates the pair sums of
-// the current level: element i is compacted at the moment it becomes the pair source, the
-// finished next-level bin is written at slot m-1 <= i-1, behind every slot the current level
-// still has to read.  Slots >= m are never written, so the stale tail the reference's binary
-// search runs into stays exactly where the reference leaves it.
-struct NextLevel {
-    uint32_t *col;
-    uint32_t clr, cmask, prev, cur;
-    int cb2, L2, m;
-    long long total;
-    bool active;
-    __device__ __forceinline__ void init(uint32_t *c, int cb, int L, bool on)
-    {
-        col = c;
-        cb2 = cb + 1;
-        clr = ~(1u << cb);
-        cmask = (1u << cb) - 1u;
-        L2 = L >> 1;
-        prev = 0xffffffffu;
-        cur = 0u;
-        m = 0;
-        total = 0;
-        active = on;
-    }
-    __device__ __forceinline__ void push(uint32_t w)
-    {
-        if (!active) return;
-        const uint32_t w2 = w & clr;
-        const uint32_t key = w2 >> cb2;
-        if ((int)key >= L2) {
-            active = false;
-            return;
-        }
-        total += (long long)(w & cmask);
-        if (key == prev) cur += (w & cmask);
-        else {
-            if (m > 0) col[(m - 1) * kSlice] = cur;
-            cur = w2;
-            m++;
-            prev = key;
-        }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (m > 0) col[(m - 1) * kSlice] = cur;
-    }
-};
-
 // Dense-level pair sums.  When a level holds more than about one bin in six, walking the
 // sparse list pair by pair costs far more than sliding a register window over ALL bins of
 // the level: win[] holds the counts of bins t .. t+2*DPL (zero where the row has no event,
 // zero from K* on in compat mode -- lost targets form a suffix, so sources from K* on have
 // no surviving target either), and every bin t adds win[t] * win[t+DPL+1 .. t+2*DPL] to the
 // DPL accumulators.  The window rotates by renaming (the loop is unrolled by its length).
-// Every element fetched into the window is handed to the next level's compaction.
 template <int DPL>
 __device__ __forceinline__ void dense_level_pairs(const uint32_t *col, int n, int cb, uint32_t cmask, int L,
-                                                  int kstar, unsigned long long (&acc)[DPL], NextLevel &nx)
+                                                  int kstar, unsigned long long (&acc)[DPL])
 {
     constexpr int W = 2 * DPL + 1;
     uint32_t win[W];
@@ -146,19 +96,17 @@ __device__ __forceinline__ void dense_level_pairs(const uint32_t *col, int n, in
         uint32_t v = 0;
         if (kp == key) {
             v = key < kstar ? (wp & cmask) : 0u;
-            const uint32_t w = wp;
             p++;
             if (p < n) {
                 wp = col[p * kSlice];
                 kp = (int)(wp >> cb);
             } else kp = 0x7fffffff;
-            nx.push(w);  // after the read of slot p: the write goes to a slot below p
         }
         return v;
     };
 #pragma unroll
     for (int k = 0; k < W; k++) win[k] = fetch(k);
-    for (int t0 = 0; t0 < L - DPL - 1 || kp != 0x7fffffff; t0 += W) {
+    for (int t0 = 0; t0 < L - DPL - 1; t0 += W) {
 #pragma unroll
         for (int u = 0; u < W; u++) {
             const uint32_t src = win[u];
@@ -171,140 +119,129 @@ __device__ __forceinline__ void dense_level_pairs(const uint32_t *col, int n, in
 }
 
 template <bool COMPAT, int DPL>
-__device__ __forceinline__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, long long total,
-                                                    int r, const MtArgs &a)
+__device__ __forceinline__ void row_multitau_packed(uint32_t *col, long long *acc, int n0, int r, const MtArgs &a)
 {
+    const int F = a.sched.frames;
     int n = n0;
-    int L = a.sched.frames;
+    int L = F;
     int cb = kCountBits;
     int nhist[kMaxLevels];
     int stale_min = 0x7fffffff;
-    const int nl = a.sched.n_levels;
-    for (int l = 0; l < nl; l++) {
+    for (int l = 0; l < a.sched.n_levels; l++) {
+        if (l > 0) {
+            // in-place compaction of corr.cpp:349-390: keys halve, equal keys merge, keys >= L drop
+            L >>= 1;
+            cb++;
+            const uint32_t clr = ~(1u << (cb - 1));
+            const uint32_t cmask = (1u << cb) - 1u;
+            int m = 0;
+            uint32_t prev = 0xffffffffu;
+            uint32_t cur = 0;
+            for (int j = 0; j < n; j++) {
+                const uint32_t w = col[j * kSlice] & clr;
+                const uint32_t key = w >> cb;
+                if ((int)key >= L) break;
+                if (key == prev) cur += (w & cmask);
+                else {
+                    if (m > 0) col[(m - 1) * kSlice] = cur;
+                    cur = w;
+                    m++;
+                    prev = key;
+                }
+            }
+            if (m > 0) col[(m - 1) * kSlice] = cur;
+            if (COMPAT && m < n) stale_min = min(stale_min, (int)(col[m * kSlice] >> (cb - 1)));
+            n = m;
+        }
         if (COMPAT) nhist[l] = n;
         const int cnt = a.sched.count[l];
+        if (cnt == 0) continue;
         const uint32_t cmask = (1u << cb) - 1u;
         const int lo = a.sched.lo[l];
         const int top = lo + cnt - 1;  // largest level-local delay needed
         const int first = a.sched.first[l];
+        int kstar = 0x7fffffff;
+        if (COMPAT && l > 0 && stale_min < L && n < n0) {
+            const int level = l;
+            kstar = stale_tail_threshold(n0, n, [&](int p) -> int {
+                if (p < n) return (int)(col[p * kSlice] >> cb);
+                int lv = level - 1;
+                while (lv > 0 && nhist[lv] <= p) lv--;
+                return (int)(col[p * kSlice] >> (kCountBits + lv));
+            });
+        }
         const float s2 = pow2_neg(2 * l), s1 = pow2_neg(l);
-        NextLevel nx;
-        nx.init(col, cb, L, l + 1 < nl);
-        if (cnt == 0) {  // no delay at this level: only feed the next one
-            for (int i = 0; i < n; i++) nx.push(col[i * kSlice]);
+        // ---- G2: pairs of bins at key distance lo..top (the later bin is the search target)
+        bool dense = false;
+        if (DPL > 0 && l > 0 && lo == DPL + 1)
+            dense = (long long)__reduce_add_sync(0xffffffffu, n) * 6 > (long long)L * 32;
+        long long total = 0;
+        if (DPL > 0 && dense) {
+            unsigned long long pairs[DPL > 0 ? DPL : 1];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) pairs[d] = 0ull;
+            dense_level_pairs<(DPL > 0 ? DPL : 1)>(col, n, cb, cmask, L, kstar, pairs);
+            for (int i = 0; i < n; i++) total += (long long)(col[i * kSlice] & cmask);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < DPL; k++)
+                if (k < cnt)
+                    a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)(long long)pairs[k] * s2, L - (lo + k));
         } else {
-            int kstar = 0x7fffffff;
-            if (COMPAT && l > 0 && stale_min < L && n < n0) {
-                const int level = l;
-                kstar = stale_tail_threshold(n0, n, [&](int p) -> int {
-                    if (p < n) return (int)(col[p * kSlice] >> cb);
-                    int lv = level - 1;
-                    while (lv > 0 && nhist[lv] <= p) lv--;
-                    return (int)(col[p * kSlice] >> (kCountBits + lv));
-                });
-            }
-            // ---- IF: total minus the bins with key < tau'   (before the level is overwritten)
-            for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
+            for (int d = lo; d <= top; d++) acc[d * kSlice] = 0;
+            uint32_t wnext = n > 0 ? col[0] : 0u;
             for (int i = 0; i < n; i++) {
-                const uint32_t wi = col[i * kSlice];
+                const uint32_t wi = wnext;
                 const int ki = (int)(wi >> cb);
-                if (ki >= top) break;
-                acc[ki * kSlice] = (long long)(wi & cmask);
-            }
-            __syncwarp();
-            {
-                long long run = 0;
-                for (int tp = 1; tp <= top; tp++) {
-                    run += acc[(tp - 1) * kSlice];
-                    if (tp >= lo)
-                        a.IF[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
-                }
-            }
-            // ---- IP: total minus the bins with key >= L - tau'
-            for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
-            for (int i = n - 1; i >= 0; i--) {
-                const uint32_t wi = col[i * kSlice];
-                const int x = L - 1 - (int)(wi >> cb);
-                if (x >= top) break;
-                acc[x * kSlice] = (long long)(wi & cmask);
-            }
-            __syncwarp();
-            {
-                long long run = 0;
-                for (int tp = 1; tp <= top; tp++) {
-                    run += acc[(tp - 1) * kSlice];
-                    if (tp >= lo)
-                        a.IP[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
-                }
-            }
-            // ---- G2: pairs of bins at key distance lo..top (the later bin is the search target),
-            //      fused with the compaction into level l+1
-            bool dense = false;
-            if (DPL > 0 && l > 0 && lo == DPL + 1)
-                dense = (long long)__reduce_add_sync(0xffffffffu, n) * 6 > (long long)L * 32;
-            if (DPL > 0 && dense) {
-                unsigned long long pairs[DPL > 0 ? DPL : 1];
-#pragma unroll
-                for (int d = 0; d < DPL; d++) pairs[d] = 0ull;
-                dense_level_pairs<(DPL > 0 ? DPL : 1)>(col, n, cb, cmask, L, kstar, pairs, nx);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < DPL; k++)
-                    if (k < cnt)
-                        a.G2[(int64_t)(first + k) * a.R_pad + r] =
-                            scaled_div((float)(long long)pairs[k] * s2, L - (lo + k));
-            } else {
-                for (int d = lo; d <= top; d++) acc[d * kSlice] = 0;
-                // flattened two-pointer walk: every iteration either takes the next source or
-                // visits one candidate target, so lanes with different rows never wait in a
-                // nested loop for each other
-                int i = -1, j = 0, ki = 0, ci = 0;
-                uint32_t wj = 0;
-                bool have_wj = false, adv = true;
-                for (;;) {
-                    if (adv) {
-                        uint32_t wi;
-                        i++;
-                        if (i >= n) break;
-                        if (have_wj && j == i) wi = wj;
-                        else wi = col[i * kSlice];
-                        ki = (int)(wi >> cb);
-                        ci = (int)(wi & cmask);
-                        nx.push(wi);
-                        j = i + 1;
-                        have_wj = false;
-                        adv = false;
-                    }
-                    if (j >= n) {
-                        adv = true;
-                        continue;
-                    }
-                    wj = col[j * kSlice];
-                    have_wj = true;
+                const int ci = (int)(wi & cmask);
+                total += ci;
+                if (i + 1 < n) wnext = col[(i + 1) * kSlice];
+                uint32_t wj = wnext;
+                for (int j = i + 1; j < n;) {
                     const int kj = (int)(wj >> cb);
                     const int d = kj - ki;
-                    if (d > top) {
-                        adv = true;
-                        continue;
-                    }
+                    if (d > top) break;
                     if (d >= lo && kj < kstar) acc[d * kSlice] += (long long)ci * (long long)(wj & cmask);
-                    j++;
-                    have_wj = false;
-                }
-                __syncwarp();
-                for (int k = 0; k < cnt; k++) {
-                    const int tp = lo + k;
-                    a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)acc[tp * kSlice] * s2, L - tp);
+                    if (++j < n) wj = col[j * kSlice];
                 }
             }
+            __syncwarp();
+            for (int k = 0; k < cnt; k++) {
+                const int tp = lo + k;
+                a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div((float)acc[tp * kSlice] * s2, L - tp);
+            }
         }
-        nx.finish();
-        if (l + 1 < nl) {
-            if (COMPAT && nx.m < n) stale_min = min(stale_min, (int)(col[nx.m * kSlice] >> cb));
-            n = nx.m;
-            L >>= 1;
-            cb++;
-            total = nx.total;
+        // ---- IF: total minus the bins with key < tau'
+        for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
+        for (int i = 0; i < n; i++) {
+            const uint32_t wi = col[i * kSlice];
+            const int ki = (int)(wi >> cb);
+            if (ki >= top) break;
+            acc[ki * kSlice] = (long long)(wi & cmask);
+        }
+        {
+            long long run = 0;
+            for (int tp = 1; tp <= top; tp++) {
+                run += acc[(tp - 1) * kSlice];
+                if (tp >= lo)
+                    a.IF[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
+            }
+        }
+        // ---- IP: total minus the bins with key >= L - tau'
+        for (int d = 0; d < top; d++) acc[d * kSlice] = 0;
+        for (int i = n - 1; i >= 0; i--) {
+            const uint32_t wi = col[i * kSlice];
+            const int x = L - 1 - (int)(wi >> cb);
+            if (x >= top) break;
+            acc[x * kSlice] = (long long)(wi & cmask);
+        }
+        {
+            long long run = 0;
+            for (int tp = 1; tp <= top; tp++) {
+                run += acc[(tp - 1) * kSlice];
+                if (tp >= lo)
+                    a.IP[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run) * s1, L - tp);
+            }
         }
     }
 }
@@ -437,19 +374,10 @@ __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
         long long *acc = reinterpret_cast<long long *>(smem_raw) + lane;
         if (in_smem) {  // two call sites so that the common one compiles to LDS/STS
             uint32_t *col = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(a.hi + 1) * kSlice * 8) + lane;
-            long long total = 0;
             for (int j = 0; j < len; j++)
-                if (j < n0) {
-                    const uint32_t w = g[(int64_t)j * kSlice];
-                    col[j * kSlice] = w;
-                    total += (long long)(w & ((1u << kCountBits) - 1u));
-                }
-            row_multitau_packed<COMPAT, DPL>(col, acc, n0, total, r, a);
-        } else {
-            long long total = 0;
-            for (int j = 0; j < n0; j++) total += (long long)(g[(int64_t)j * kSlice] & ((1u << kCountBits) - 1u));
-            row_multitau_packed<COMPAT, 0>(g, acc, n0, total, r, a);
-        }
+                if (j < n0) col[j * kSlice] = g[(int64_t)j * kSlice];
+            row_multitau_packed<COMPAT, DPL>(col, acc, n0, r, a);
+        } else row_multitau_packed<COMPAT, 0>(g, acc, n0, r, a);
     } else {
         u64 *g = reinterpret_cast<u64 *>(a.store) + a.slice_base[s] + lane;
         u64 *col = g;
