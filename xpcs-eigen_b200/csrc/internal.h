@@ -133,6 +133,13 @@ struct xpcs_handle_s {
     bool partials_done = false;
     xpcs::DevBuf<float> d_scratch;          // staging for host-layout outputs
 
+    // ---- two-time (one dynamic partition at a time) ----
+    xpcs::DevBuf<unsigned short> d_tt_hi, d_tt_lo;  // fp16 operands Xt[F][npad] (value = hi + lo)
+    xpcs::DevBuf<float> d_tt_C;                     // [F][F]
+    xpcs::DevBuf<float> d_tt_sg, d_tt_out;
+    xpcs::DevBuf<unsigned int> d_tt_sgint;
+    xpcs::DevBuf<double> d_tt_diag;
+
     // ---- measurement ----
     bool timing = false;
     int64_t launches = 0;

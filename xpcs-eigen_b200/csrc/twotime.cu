@@ -1,13 +1,462 @@
-// twotime.cu -- two-time correlation for one dynamic bin (reference corr.cpp:781-924).
+// twotime.cu -- two-time correlation of one dynamic partition (reference corr.cpp:781-924,
+// smoothing corr.cpp:433-560 / :1166-1305), the one dense contraction of the path and the one
+// stage on the tensor cores.
+//
+// For the N pixels of the partition and F frames, with X[t][p] the filtered intensity:
+//     sg[t]   = (1/N) sum_p X[t][p]                    (ComputeSGSymmetric, corr.cpp:1166-1226;
+//                                                        "Average": its mean over t)
+//     C[t1,t2] = (1/N) sum_p X[t1][p] X[t2][p] / (sg[t1] sg[t2])   for t2 >= t1, 0 below
+//     g2full[d] = mean of the d-th diagonal, g2partials[d][w] windowed diagonal sums / wsize
+// i.e. C = triu(X X^T) scaled in the epilogue: the reference divides every event by sg first
+// (corr.cpp:516-536), which for symmetric smoothing factors out of the contraction, so the
+// tensor cores see the raw photon counts -- exact in fp16, exact fp32 accumulation -- and the
+// only rounding happens in the epilogue.
+//
+// k_twotime_gemm: one CTA per 128x128 tile of the upper triangle.  Operands are 128x64 fp16
+// tiles of the frame-major matrix Xt[F][Npad] (K-major for both A and B), fetched by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a 4-stage mbarrier ring; one thread issues
+// tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with the fp32 accumulator in TMEM
+// (128 columns); tcgen05.commit releases smem stages and finally signals the epilogue, whose
+// four warps read TMEM with tcgen05.ld.32x32b, scale and store.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+// Float-valued rows (flat-field, averaging) are split x = hi + lo in fp16 and contracted in
+// three passes (hi*hi + hi*lo + lo*hi) into the same accumulator (~2e-7 relative).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "internal.h"
 
 namespace xpcs {
 
-int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int average, float *C,
-                   float *g2full, float *g2partials, float *sg)
+constexpr int kTtBM = 128, kTtBN = 128, kTtBK = 64, kTtStages = 4;
+constexpr int kTtTileBytes = kTtBM * kTtBK * 2;  // 16 KiB per operand tile
+constexpr int kTtThreads = 192;
+constexpr int kTtTmemCols = 128;
+constexpr size_t kTtSmemBytes = (size_t)kTtStages * 2 * kTtTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    (void)qbin; (void)wsize; (void)method; (void)average; (void)C; (void)g2full; (void)g2partials; (void)sg;
-    return fail(h, XPCS_E_STATE, "two-time correlation is not built yet");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row atoms of 1024 B (SBO = 1024),
+// LBO = 16 B (unused for swizzled K-major), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16: A = B = fp16 (0), D = fp32 (1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kTtIdesc = (1u << 4) | ((uint32_t)(kTtBN >> 3) << 17) | ((uint32_t)(kTtBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kTtIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TtGemmArgs {
+    float *C;           // [F][F] row-major, pre-zeroed
+    const float *sg;    // [F] (or [1] when sg_scalar)
+    int F, kblocks, npass, sg_scalar, use_sg;
+    float npix;
+};
+
+__global__ void __launch_bounds__(kTtThreads, 1)
+k_twotime_gemm(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TtGemmArgs a)
+{
+    const int mt = blockIdx.y, nt = blockIdx.x;
+    if (nt < mt) return;  // lower triangle stays zero (corr.cpp:826: k starts at j)
+    extern __shared__ unsigned char tt_smem_raw[];
+    const uint32_t base = (smem_u32(tt_smem_raw) + 1023u) & ~1023u;
+    const uint32_t tiles = base;                                    // [stage][A|B] 16 KiB each
+    const uint32_t bars = base + kTtStages * 2 * kTtTileBytes;      // full[4], empty[4], tmem_full, tmem_slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kTtStages + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * kTtStages);
+    const uint32_t tmem_slot = bars + 8u * (2 * kTtStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_kb = a.kblocks * a.npass;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kTtStages; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTtTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < total_kb; kb++) {
+                const int s = kb % kTtStages;
+                const uint32_t ph = (uint32_t)(kb / kTtStages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int pass = kb / a.kblocks, kk = kb - pass * a.kblocks;
+                const CUtensorMap *ma = pass == 2 ? &map_lo : &map_hi;
+                const CUtensorMap *mb = pass == 1 ? &map_lo : &map_hi;
+                mbar_expect_tx(full_bar(s), 2 * kTtTileBytes);
+                tma_load_2d(tiles + (uint32_t)(s * 2) * kTtTileBytes, ma, kk * kTtBK, mt * kTtBM, full_bar(s));
+                tma_load_2d(tiles + (uint32_t)(s * 2 + 1) * kTtTileBytes, mb, kk * kTtBK, nt * kTtBN, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            for (int kb = 0; kb < total_kb; kb++) {
+                const int s = kb % kTtStages;
+                const uint32_t ph = (uint32_t)(kb / kTtStages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = tiles + (uint32_t)(s * 2) * kTtTileBytes;
+                const uint32_t sb = sa + kTtTileBytes;
+#pragma unroll
+                for (int k = 0; k < kTtBK / 16; k++) {
+                    // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom
+                    umma_f16(tmem_base, umma_desc_sw128(sa + 32u * k), umma_desc_sw128(sb + 32u * k),
+                             (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {  // ===== epilogue: warps 2..5 own TMEM lane quadrants 2,3,0,1 =====
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = mt * kTtBM + q * 32 + lane;
+        float s_row = 1.0f;
+        if (a.use_sg && row < a.F) s_row = a.sg_scalar ? a.sg[0] : a.sg[row];
+        for (int c = 0; c < kTtBN / 32; c++) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int col0 = nt * kTtBN + c * 32;
+            if (row < a.F) {
+                float *dst = a.C + (size_t)row * a.F + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int col = col0 + j;
+                    if (col < a.F && col >= row) {
+                        float x = __uint_as_float(v[j]);
+                        if (x != 0.0f) {
+                            if (a.use_sg) {
+                                const float s_col = a.sg_scalar ? s_row : a.sg[col];
+                                x = __fdiv_rn(x, __fmul_rn(s_row, s_col));
+                            }
+                            x = __fdiv_rn(x, a.npix);
+                        }
+                        dst[j] = x;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTtTmemCols));
+    }
+}
+
+// ---- operand construction from the pixel-major store -----------------------------------
+struct TtBuildArgs {
+    const void *store;
+    const int64_t *slice_base;
+    const int *row_len;
+    __half *xt_hi, *xt_lo;        // [F][npad]
+    unsigned int *sg_int;         // [F] integer column sums (packed rows)
+    float *sg_f;                  // [F] float column sums
+    int row0, row1, npad, F, n_slices;
+};
+
+template <int KIND>
+__global__ void k_twotime_build(TtBuildArgs a)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (s >= a.n_slices) return;
+    const int r = s * kSlice + lane;
+    if (r < a.row0 || r >= a.row1) return;
+    const int n = a.row_len[r];
+    const int p = r - a.row0;
+    if (KIND == kPacked) {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane;
+        for (int j = 0; j < n; j++) {
+            const uint32_t w = g[(int64_t)j * kSlice];
+            const int t = (int)(w >> kCountBits);
+            const unsigned c = w & ((1u << kCountBits) - 1u);
+            if (t < a.F) {
+                a.xt_hi[(size_t)t * a.npad + p] = __float2half_rn((float)c);
+                atomicAdd(a.sg_int + t, c);
+            }
+        }
+    } else {
+        const unsigned long long *g = reinterpret_cast<const unsigned long long *>(a.store) + a.slice_base[s] + lane;
+        for (int j = 0; j < n; j++) {
+            const unsigned long long w = g[(int64_t)j * kSlice];
+            const int t = (int)(w >> 32);
+            const float x = __uint_as_float((uint32_t)w);
+            if (t < a.F) {
+                const __half hi = __float2half_rn(x);
+                a.xt_hi[(size_t)t * a.npad + p] = hi;
+                a.xt_lo[(size_t)t * a.npad + p] = __float2half_rn(__fsub_rn(x, __half2float(hi)));
+                atomicAdd(a.sg_f + t, x);
+            }
+        }
+    }
+}
+
+// sg[t] = column sum / N (corr.cpp:1207-1215); "Average": one value, the fp32 mean over t in
+// frame order (corr.cpp:1217-1224)
+__global__ void k_twotime_sg(const unsigned int *sg_int, const float *sg_f, float *sg, float *sg_avg, int F,
+                             float npix, int packed)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < F) sg[t] = __fdiv_rn(packed ? (float)sg_int[t] : sg_f[t], npix);
+}
+__global__ void k_twotime_sg_average(const float *sg, float *sg_avg, int F)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float acc = 0.0f;
+        for (int t = 0; t < F; t++) acc = __fadd_rn(acc, sg[t]);
+        sg_avg[0] = __fdiv_rn(acc, (float)F);
+    }
+}
+
+// Diagonal statistics of C (corr.cpp:842-866): thread = diagonal d, rows in chunks; adjacent
+// threads read adjacent addresses.  Sums in fp64, combined with atomics.
+__global__ void k_twotime_diag(const float *__restrict__ C, double *__restrict__ full, double *__restrict__ part,
+                               int F, int wsize, int partials, int rows_per_block)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= F) return;
+    const int x0 = blockIdx.y * rows_per_block;
+    const int x1 = min(F - d, x0 + rows_per_block);
+    double acc = 0.0, wacc = 0.0;
+    int win = -1;
+    for (int x = x0; x < x1; x++) {
+        const float v = C[(size_t)x * F + x + d];
+        acc += (double)v;
+        if (d < wsize) {
+            const int w = x / wsize;
+            if (w != win) {
+                if (win >= 0 && win < partials) atomicAdd(part + (size_t)d * partials + win, wacc);
+                win = w;
+                wacc = 0.0;
+            }
+            wacc += (double)v;
+        }
+    }
+    if (d < wsize && win >= 0 && win < partials) atomicAdd(part + (size_t)d * partials + win, wacc);
+    if (x1 > x0) atomicAdd(full + d, acc);
+}
+__global__ void k_twotime_diag_finish(const double *full, const double *part, float *g2full, float *g2part, int F,
+                                      int wsize, int partials)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) g2full[i] = __fdiv_rn((float)full[i], (float)(F - i));
+    if (i < wsize * partials) g2part[i] = __fdiv_rn((float)part[i], (float)wsize);
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_operand_map(xpcs_handle_s *h, CUtensorMap *map, const __half *ptr, int F, int npad)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !p) return fail(h, XPCS_E_CUDA, "cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)npad, (cuuint64_t)F};
+    const cuuint64_t strides[1] = {(cuuint64_t)npad * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTtBK, (cuuint32_t)kTtBM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, XPCS_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return XPCS_OK;
+}
+
+int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int average, float *C, float *g2full,
+                   float *g2partials, float *sg)
+{
+    const int F = h->prm.frames;
+    if (method != 0 && method != 1) return fail(h, XPCS_E_ARG, "two-time: smoothing method %d not built (0 = none, 1 = symmetric)", method);
+    if (wsize <= 0) return fail(h, XPCS_E_ARG, "two-time: twotime2onetime_window_size must be > 0 (corr.cpp:796 divides by it)");
+    if (h->prm.shard_count != 1) return fail(h, XPCS_E_ARG, "two-time runs one dynamic partition per GPU: create the handle with shard_count = 1");
+    // rows of the dynamic partition: contiguous, because rows are sorted by (dq, sq, pixel)
+    int row0 = -1, row1 = -1;
+    for (int s = h->seg_first; s < h->seg_last; s++)
+        if (h->seg_dq[s] == qbin) {
+            if (row0 < 0) row0 = h->lseg_row_start[s - h->seg_first];
+            row1 = h->lseg_row_start[s - h->seg_first + 1];
+        }
+    if (row0 < 0) return fail(h, XPCS_E_ARG, "two-time: dynamic partition %d has no pixels", qbin);
+    const int N = row1 - row0;
+    const int npad = (N + kTtBK - 1) / kTtBK * kTtBK;
+    const int partials = (F - wsize) / wsize > 0 ? (F - wsize) / wsize : 0;
+    const bool packed = h->kind == kPacked;
+    int rc;
+    const size_t xt_elems = (size_t)F * npad;
+    if ((rc = ensure(h, h->d_tt_hi, xt_elems, "two-time operand"))) return rc;
+    if (!packed && (rc = ensure(h, h->d_tt_lo, xt_elems, "two-time operand (low part)"))) return rc;
+    if ((rc = ensure(h, h->d_tt_C, (size_t)F * F, "two-time matrix"))) return rc;
+    if ((rc = ensure(h, h->d_tt_sg, (size_t)2 * F + 8, "two-time sg"))) return rc;
+    if ((rc = ensure(h, h->d_tt_sgint, (size_t)F, "two-time sg sums"))) return rc;
+    if ((rc = ensure(h, h->d_tt_diag, (size_t)F + (size_t)wsize * (partials > 0 ? partials : 1), "two-time diagonals"))) return rc;
+    if ((rc = ensure(h, h->d_tt_out, (size_t)F + (size_t)wsize * (partials > 0 ? partials : 1), "two-time diagonal means"))) return rc;
+    cudaStream_t st = h->stream;
+    cudaMemsetAsync(h->d_tt_hi.p, 0, xt_elems * sizeof(__half), st);
+    if (!packed) cudaMemsetAsync(h->d_tt_lo.p, 0, xt_elems * sizeof(__half), st);
+    cudaMemsetAsync(h->d_tt_C.p, 0, (size_t)F * F * sizeof(float), st);
+    cudaMemsetAsync(h->d_tt_sg.p, 0, ((size_t)2 * F + 8) * sizeof(float), st);
+    cudaMemsetAsync(h->d_tt_sgint.p, 0, (size_t)F * sizeof(unsigned int), st);
+    cudaMemsetAsync(h->d_tt_diag.p, 0, ((size_t)F + (size_t)wsize * (partials > 0 ? partials : 1)) * sizeof(double), st);
+
+    float *d_sg = h->d_tt_sg.p;           // [F] per-frame sg
+    float *d_sg_f = h->d_tt_sg.p + F;     // [F] float column sums
+    float *d_sg_avg = h->d_tt_sg.p + 2 * F;
+    {
+        TtBuildArgs b{};
+        b.store = h->d_store.p;
+        b.slice_base = h->d_slice_base.p;
+        b.row_len = h->d_row_len.p;
+        b.xt_hi = (__half *)h->d_tt_hi.p;
+        b.xt_lo = packed ? nullptr : (__half *)h->d_tt_lo.p;
+        b.sg_int = h->d_tt_sgint.p;
+        b.sg_f = d_sg_f;
+        b.row0 = row0;
+        b.row1 = row1;
+        b.npad = npad;
+        b.F = F;
+        b.n_slices = h->n_slices;
+        LaunchScope ls(h, "k_twotime_build");
+        const int wpb = 8;
+        if (packed) k_twotime_build<kPacked><<<(h->n_slices + wpb - 1) / wpb, wpb * 32, 0, st>>>(b);
+        else k_twotime_build<kFloat><<<(h->n_slices + wpb - 1) / wpb, wpb * 32, 0, st>>>(b);
+    }
+    {
+        LaunchScope ls(h, "k_twotime_sg");
+        k_twotime_sg<<<(F + 255) / 256, 256, 0, st>>>(h->d_tt_sgint.p, d_sg_f, d_sg, d_sg_avg, F, (float)N, packed ? 1 : 0);
+    }
+    if (average) {
+        LaunchScope ls(h, "k_twotime_sg_average");
+        k_twotime_sg_average<<<1, 32, 0, st>>>(d_sg, d_sg_avg, F);
+    }
+    CUtensorMap map_hi, map_lo;
+    if ((rc = make_operand_map(h, &map_hi, (const __half *)h->d_tt_hi.p, F, npad))) return rc;
+    if ((rc = make_operand_map(h, &map_lo, (const __half *)(packed ? h->d_tt_hi.p : h->d_tt_lo.p), F, npad))) return rc;
+    {
+        TtGemmArgs g{};
+        g.C = h->d_tt_C.p;
+        g.sg = average ? d_sg_avg : d_sg;
+        g.F = F;
+        g.kblocks = npad / kTtBK;
+        g.npass = packed ? 1 : 3;
+        g.sg_scalar = average ? 1 : 0;
+        g.use_sg = method == 1 ? 1 : 0;
+        g.npix = (float)N;
+        rc = check_cuda(h, cudaFuncSetAttribute(k_twotime_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTtSmemBytes),
+                        "two-time smem attr");
+        if (rc) return rc;
+        const int tn = (F + kTtBM - 1) / kTtBM;
+        LaunchScope ls(h, "k_twotime_gemm");
+        k_twotime_gemm<<<dim3(tn, tn), kTtThreads, kTtSmemBytes, st>>>(map_hi, map_lo, g);
+    }
+    if ((rc = check_cuda(h, cudaGetLastError(), "k_twotime_gemm"))) return rc;
+    double *d_full = h->d_tt_diag.p;
+    double *d_part = h->d_tt_diag.p + F;
+    float *d_g2full = h->d_tt_out.p;
+    float *d_g2part = h->d_tt_out.p + F;
+    {
+        const int rows_per_block = 256;
+        LaunchScope ls(h, "k_twotime_diag");
+        k_twotime_diag<<<dim3((F + 127) / 128, (F + rows_per_block - 1) / rows_per_block), 128, 0, st>>>(
+            h->d_tt_C.p, d_full, d_part, F, wsize, partials, rows_per_block);
+    }
+    {
+        const int n = F > wsize * partials ? F : wsize * partials;
+        LaunchScope ls(h, "k_twotime_diag_finish");
+        k_twotime_diag_finish<<<(n + 255) / 256, 256, 0, st>>>(d_full, d_part, d_g2full, d_g2part, F, wsize, partials);
+    }
+    if (C) cudaMemcpyAsync(C, h->d_tt_C.p, (size_t)F * F * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (g2full) cudaMemcpyAsync(g2full, d_g2full, (size_t)F * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (g2partials && partials > 0)
+        cudaMemcpyAsync(g2partials, d_g2part, (size_t)wsize * partials * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (sg) {
+        if (method == 1) cudaMemcpyAsync(sg, average ? d_sg_avg : d_sg, (average ? 1 : (size_t)F) * sizeof(float), cudaMemcpyDeviceToHost, st);
+        else for (int i = 0; i < (average ? 1 : F); i++) sg[i] = 1.0f;
+    }
+    return check_cuda(h, cudaStreamSynchronize(st), "two-time");
 }
 
 }  // namespace xpcs

@@ -415,6 +415,8 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_block_first); release(h->d_store); release(h->d_summary); release(h->d_frame_acc);
     release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
     release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch);
+    release(h->d_tt_hi); release(h->d_tt_lo); release(h->d_tt_C); release(h->d_tt_sg); release(h->d_tt_out);
+    release(h->d_tt_sgint); release(h->d_tt_diag);
     if (h->stage) cudaFreeHost(h->stage);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
