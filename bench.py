@@ -42,6 +42,8 @@ WORKLOADS = {
                name="sparse IMM 1 Mpixel (1024x1024), 100k frames, 0.1% occupancy, dpl 8, 36 dynamic/360 static q-bins (BASELINE configs[2])"),
     "c1": dict(h=512, w=512, F=10000, occ=0.01, kind="sparse",
                name="sparse IMM 512x512, 10k frames, 1% occupancy, dpl 8, 36 dynamic q-bins (BASELINE configs[0])"),
+    "c4": dict(h=256, w=256, F=10000, occ=0.02, kind="twotime",
+               name="two-time correlation, 64k-pixel q ROI (256x256), 10k frames, 2% occupancy, symmetric smoothing (BASELINE configs[3])"),
     "c2": dict(h=1024, w=1024, F=20000, occ=None, kind="dense",
                name="non-sparse IMM 1024x1024 int16, 20k frames, dark/flat correction + threshold (BASELINE configs[1])"),
 }
@@ -257,6 +259,68 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
     return tbl.get(name, 0)
 
 
+def bench_twotime(args, wl):
+    """BASELINE configs[3]: two-time correlation of one 64k-pixel dynamic partition over 10k
+    frames -- the tensor-core stage.  One step = sg + operand build + C = triu(X X^T) scaled +
+    diagonal statistics, device-resident (events already ingested); C stays on the device."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    pkg = entry.load_package()
+    h, w, F, occ = wl["h"], wl["w"], wl["F"], wl["occ"]
+    P = h * w
+    dq = np.ones((h, w), np.int32)
+    sq = (1 + (np.arange(P) // 4096)).astype(np.int32).reshape(h, w)   # 16 static bins inside the ROI
+    dev = torch.device("cuda", 0)
+    d_idx, d_val, d_off = gen_sparse_device(torch, None, P, F, occ, 4321, dev)
+    E = int(d_idx.numel())
+    c = pkg.Correlator(dq, sq, F, dpl=8, device=0, reserve_events=E)
+    c.push_sparse_device(d_idx.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), E, F)
+    c.finish_ingest(want=False)
+    wsize = 100
+    for _ in range(max(args.warmup, 1)):
+        c.twotime(1, wsize, want_c=False)
+    c.kernel_report(reset=True)
+    c.kernel_timing(True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = c.twotime(1, wsize, want_c=False)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    rep = c.kernel_report(reset=True)
+    gemm_ms = rep["k_twotime_gemm"][0] / max(rep["k_twotime_gemm"][1], 1)
+    flops = float(P) * F * (F + 1)            # upper triangle incl. diagonal, 2 flop per MAC
+    tn = (F + 127) // 128
+    flops_issued = 2.0 * (tn * (tn + 1) / 2) * 128 * 128 * (-(-P // 64) * 64)
+    peak_tf = 1402.4
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    line = {
+        "metric": "two-time correlation frames/sec", "value": F / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp16 operands (exact counts) / fp32 TMEM accumulate", "data": "synthetic",
+        "config": {"workload": wl["name"], "workload_key": "c4", "roi_pixels": P, "frames": F, "events": E,
+                   "l2": "operand matrix %.0f MB + C %.0f MB exceed L2" % (2.0 * P * F / 1e6, 4.0 * F * F / 1e6)},
+        "clocks": clocks, "gpu_launches": int(c.launch_count()),
+        "roofline": {"kernel": "k_twotime_gemm", "bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak_tf,
+                     "traffic": None, "flops_algorithmic": flops, "flops_issued": flops_issued,
+                     "achieved_issued": flops_issued / (gemm_ms * 1e-3) / 1e12, "ms_per_launch": gemm_ms,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same rate)"},
+        "kernels": {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in rep.items() if v[1]},
+        "g2full_head": [float(x) for x in r["g2full"][:4]],
+    }
+    print(json.dumps(line))
+    c.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -280,6 +344,8 @@ def main():
 
     if wl["kind"] == "dense":
         raise SystemExit("bench.py: the dense workload (c2) bench leg is not wired yet")
+    if wl["kind"] == "twotime":
+        return bench_twotime(args, wl)
 
     import torch
     import torch.distributed as dist

@@ -226,15 +226,15 @@ class Correlator:
         self._check(self._lib.xpcs_normalize_finish(self._h, g2.ctypes.data, se.ctypes.data))
         return g2[:, : self.Q], se[:, : self.Q]
 
-    def twotime(self, qbin, wsize, method="symmetric", average=False):
+    def twotime(self, qbin, wsize, method="symmetric", average=False, want_c=True):
         F = self.F
         partials = max((F - wsize) // wsize, 0)
-        Cm = np.zeros((F, F), np.float32)
+        Cm = np.zeros((F, F), np.float32) if want_c else None
         gf = np.zeros(F, np.float32)
         gp = np.zeros(max(wsize * partials, 1), np.float32)
         sg = np.zeros(1 if average else F, np.float32)
         m = {"none": 0, "symmetric": 1}[method.lower()]
-        self._check(self._lib.xpcs_twotime(self._h, qbin, wsize, m, int(bool(average)), Cm.ctypes.data,
+        self._check(self._lib.xpcs_twotime(self._h, qbin, wsize, m, int(bool(average)), _ptr(Cm),
                                            gf.ctypes.data, gp.ctypes.data, sg.ctypes.data))
         return dict(C=Cm, g2full=gf, g2partials=gp[: wsize * partials].reshape(wsize, partials), sg=sg)
 
