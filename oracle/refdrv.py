@@ -74,14 +74,13 @@ def listing(root, group):
     return out
 
 
-def write_config(root, dq, sq, frames, imm_path, dpl=8, begin=1, darks=0, lld=0.0, sigma=0.0, stride=1, avg=1,
+def config_items(dq, sq, frames, imm_path, dpl=8, begin=1, darks=0, lld=0.0, sigma=0.0, stride=1, avg=1,
                  static_window=None, flatfield=None, normalize_by_framesum=False, twotime=None, entry="/xpcs",
                  output="/exchange"):
-    """frames = number of RAW data frames to do (data_begin_todo = begin, 1-based, after the darks).
+    """[(dataset path, value)] of one configuration: every key Configuration::init reads
+    (configuration.cpp:80-242) with the on-disk types of SURVEY.md B.1.
+    frames = number of RAW data frames to do (data_begin_todo = begin, 1-based, after the darks).
     twotime = dict(qbins=[...], wsize=int, method="symmetric", filter="None") or None."""
-    if os.path.exists(root):
-        shutil.rmtree(root)
-    os.makedirs(root)
     dq = np.ascontiguousarray(dq, "<i4")
     sq = np.ascontiguousarray(sq, "<i4")
     h, w = dq.shape
@@ -89,49 +88,61 @@ def write_config(root, dq, sq, frames, imm_path, dpl=8, begin=1, darks=0, lld=0.
     i32 = lambda v: np.array([[v]], "<i4")  # noqa: E731
     f32 = lambda v: np.array([[v]], "<f4")  # noqa: E731
     i64 = lambda v: np.array([[v]], "<i8")  # noqa: E731
-    put(root, e + "/compression", "ENABLED")
-    put(root, e + "/output_data", output)
-    put(root, "/measurement/instrument/detector/x_dimension", i32(w))
-    put(root, "/measurement/instrument/detector/y_dimension", i32(h))
-    put(root, e + "/dqmap", dq)
-    put(root, e + "/sqmap", sq)
     first = begin + darks
-    put(root, e + "/data_begin", i32(first))
-    put(root, e + "/data_end", i32(first + frames - 1))
-    put(root, e + "/data_begin_todo", i32(first))
-    put(root, e + "/data_end_todo", i32(first + frames - 1))
-    put(root, e + "/delays_per_level", i32(dpl))
-    put(root, e + "/dark_begin_todo", i32(1 if darks else 0))
-    put(root, e + "/dark_end_todo", i32(darks if darks else 0))
-    put(root, e + "/lld", f32(lld))
-    put(root, e + "/sigma", f32(sigma))
-    put(root, e + "/stride_frames", i64(stride))
-    put(root, e + "/avg_frames", i64(avg))
-    put(root, e + "/normalize_by_framesum", i32(1 if normalize_by_framesum else 0))
-    for k, v in (("x_pixel_size", 7.5e-5), ("y_pixel_size", 7.5e-5), ("adu_per_photon", 1.0), ("exposure_time", 1e-3),
-                 ("efficiency", 1.0), ("distance", 4.0)):
-        put(root, "/measurement/instrument/detector/" + k, f32(v))
-    put(root, "/measurement/instrument/source_begin/beam_intensity_transmitted", f32(1e10))
-    put(root, "/measurement/sample/thickness", f32(1.0))
     block = stride * avg if (stride > 1 and avg > 1) else max(stride, avg)
     F = frames // block
-    put(root, e + "/static_mean_window_size", i32(static_window or max(1, F // 10)))
+    it = [
+        (e + "/compression", "ENABLED"),
+        (e + "/output_data", output),
+        ("/measurement/instrument/detector/x_dimension", i32(w)),
+        ("/measurement/instrument/detector/y_dimension", i32(h)),
+        (e + "/dqmap", dq),
+        (e + "/sqmap", sq),
+        (e + "/data_begin", i32(first)),
+        (e + "/data_end", i32(first + frames - 1)),
+        (e + "/data_begin_todo", i32(first)),
+        (e + "/data_end_todo", i32(first + frames - 1)),
+        (e + "/delays_per_level", i32(dpl)),
+        (e + "/dark_begin_todo", i32(1 if darks else 0)),
+        (e + "/dark_end_todo", i32(darks if darks else 0)),
+        (e + "/lld", f32(lld)),
+        (e + "/sigma", f32(sigma)),
+        (e + "/stride_frames", i64(stride)),
+        (e + "/avg_frames", i64(avg)),
+        (e + "/normalize_by_framesum", i32(1 if normalize_by_framesum else 0)),
+    ]
+    for k, v in (("x_pixel_size", 7.5e-5), ("y_pixel_size", 7.5e-5), ("adu_per_photon", 1.0), ("exposure_time", 1e-3),
+                 ("efficiency", 1.0), ("distance", 4.0)):
+        it.append(("/measurement/instrument/detector/" + k, f32(v)))
+    it.append(("/measurement/instrument/source_begin/beam_intensity_transmitted", f32(1e10)))
+    it.append(("/measurement/sample/thickness", f32(1.0)))
+    it.append((e + "/static_mean_window_size", i32(static_window or max(1, F // 10))))
     if flatfield is not None:
-        put(root, e + "/flatfield_enabled", "ENABLED")
-        put(root, "/measurement/instrument/detector/flatfield", np.ascontiguousarray(flatfield, "<f8").reshape(h, w))
+        it.append((e + "/flatfield_enabled", "ENABLED"))
+        it.append(("/measurement/instrument/detector/flatfield", np.ascontiguousarray(flatfield, "<f8").reshape(h, w)))
     else:
-        put(root, e + "/flatfield_enabled", "DISABLED")
+        it.append((e + "/flatfield_enabled", "DISABLED"))
     if twotime:
-        put(root, e + "/analysis_type", "Twotime")
-        put(root, e + "/smoothing_method", twotime.get("method", "symmetric"))
-        put(root, e + "/smoothing_filter", twotime.get("filter", "None"))
-        put(root, e + "/qphi_bin_to_process", np.asarray(twotime["qbins"], "<i8").reshape(-1, 1))
-        put(root, e + "/twotime2onetime_window_size", i32(twotime["wsize"]))
+        it.append((e + "/analysis_type", "Twotime"))
+        it.append((e + "/smoothing_method", twotime.get("method", "symmetric")))
+        it.append((e + "/smoothing_filter", twotime.get("filter", "None")))
+        it.append((e + "/qphi_bin_to_process", np.asarray(twotime["qbins"], "<i8").reshape(-1, 1)))
+        it.append((e + "/twotime2onetime_window_size", i32(twotime["wsize"])))
     else:
-        put(root, e + "/analysis_type", "Multitau")
-        put(root, e + "/twotime2onetime_window_size", i32(1))
-    put(root, e + "/input_file_local", imm_path)
-    os.makedirs(os.path.join(root, output.strip("/")), exist_ok=True) if False else None
+        it.append((e + "/analysis_type", "Multitau"))
+        it.append((e + "/twotime2onetime_window_size", i32(1)))
+    it.append((e + "/input_file_local", imm_path))
+    return it, F
+
+
+def write_config(root, dq, sq, frames, imm_path, **kw):
+    """The configuration as a directory-backed container (oracle/ref/h5dir.cpp) for corr_ref."""
+    if os.path.exists(root):
+        shutil.rmtree(root)
+    os.makedirs(root)
+    items, F = config_items(dq, sq, frames, imm_path, **kw)
+    for path, value in items:
+        put(root, path, value)
     return F
 
 

@@ -1,0 +1,82 @@
+"""End to end through the host program: `corr config.hdf5 --imm data.imm [--g2out] [--darkout]`
+(the reference's entry point) on the inputs of every golden fixture, results read back from the
+configuration HDF5 file and compared dataset by dataset -- name, shape, dtype, values -- with
+what the unmodified reference binary wrote (tests/golden/make_golden.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as G
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import refdrv  # noqa: E402  (config key list shared with the reference runs)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _run_corr(pkg, c, tmp_path, extra=()):
+    corr = os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
+    imm = str(tmp_path / "data.imm")
+    h, w = c.dq.shape
+    kw = dict(dpl=c.dpl, stride=c.stride, avg=c.avg, static_window=c.swindow, flatfield=c.flat,
+              normalize_by_framesum=bool(c.norm))
+    if c.kind == "dense":
+        pkg.synth.write_imm_dense(imm, h, w, c.inp["frames"])
+        kw.update(darks=c.darks)
+        if "thresh" in c.inp:
+            kw.update(lld=float(c.inp["thresh"][0]), sigma=float(c.inp["thresh"][1]))
+    else:
+        pkg.synth.write_imm_sparse(imm, h, w, c.inp["off"], c.inp["idx"], c.inp["val"])
+    if c.kind == "twotime":
+        kw.update(twotime=dict(qbins=[int(q) for q in c.inp["qbins"]], wsize=int(c.inp["wsize"]), method="symmetric",
+                               filter=str(c.inp["filt"])))
+    cfg = str(tmp_path / "config.hdf5")
+    f = pkg.h5lite.File()
+    for path, value in refdrv.config_items(c.dq, c.sq, c.F_raw, imm, **kw)[0]:
+        f.put(path, value)
+    f.save(cfg)
+    f.close()
+    p = subprocess.run([corr, cfg, "--g2out", "--darkout"] + list(extra), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    g = pkg.h5lite.File(cfg)
+    res = g.walk("/exchange")
+    assert g.get("/xpcs/delays_per_level")[0, 0] == c.dpl   # the configuration survives the rewrite
+    g.close()
+    return res, p.stdout
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_corr_matches_reference_result_file(pkg, tmp_path, name):
+    c = G.Case(name)
+    res, log = _run_corr(pkg, c, tmp_path)
+    assert sorted(res) == sorted(c.ref), "result dataset names differ from the reference's"
+    for k, ref in c.ref.items():
+        got = res[k]
+        assert got.shape == ref.shape, "%s: shape %s vs reference %s" % (k, got.shape, ref.shape)
+        assert got.dtype == ref.dtype, "%s: dtype %s vs reference %s" % (k, got.dtype, ref.dtype)
+        err, nanmis = G.rel_err(got, ref)
+        assert nanmis == 0 and err <= RTOL, "%s: worst relative error %.3g" % (k, err)
+    for stage in ("Loading data", "Total"):
+        assert stage + " took" in log
+
+
+def test_corr_integer_fixture_is_bit_exact(pkg, tmp_path):
+    c = G.Case("sparse_staletail_32x32")
+    res, _ = _run_corr(pkg, c, tmp_path)
+    for k in ("G2", "IP", "IF", "norm-0-g2", "pixelSum", "frameSum", "partition-mean-total",
+              "partition-mean-partial", "tau", "partition_norm_factor", "timestamp_clock", "timestamp_tick"):
+        assert G.n_diff(res[k], c.ref[k]) == 0, k
+
+
+def test_corr_positional_imm_and_no_compat(pkg, tmp_path):
+    """`corr config.hdf5 data.imm` (README form) and --no_compat (exact pair sums)."""
+    c = G.Case("staletail_hand_example")
+    res, _ = _run_corr(pkg, c, tmp_path, extra=[str(tmp_path / "data.imm"), "--no_compat"])
+    k = list(c.ref["tau"].ravel()).index(40.0)
+    assert c.ref["G2"][k, 0] == 0.0                                  # the reference drops the pair
+    assert res["G2"][k, 0] == np.float32(0.0625) / np.float32(118)   # the exact value

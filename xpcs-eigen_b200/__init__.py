@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import cabi, synth, torchio  # noqa: F401
+from . import cabi, h5lite, synth, torchio  # noqa: F401
 from .cabi import XPCS_COMPAT_STALE_TAIL, XpcsError, XpcsInfo, XpcsParams, XpcsShardPlan  # noqa: F401
 
 
