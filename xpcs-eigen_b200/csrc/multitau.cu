@@ -17,8 +17,6 @@
 // XPCS_COMPAT_STALE_TAIL: the compaction leaves the words beyond the live prefix exactly
 // where the reference leaves its stale vector tail, and each candidate pair is confirmed by
 // replaying std::lower_bound over that array.
-#include <algorithm>
-
 #include "internal.h"
 
 namespace xpcs {
@@ -29,7 +27,7 @@ struct MtArgs {
     const int *slice_len;
     const int *row_len;
     float *G2, *IP, *IF;
-    int R_pad, n_slices, smem_len, hi, compat, acc_bytes;
+    int R_pad, n_slices, smem_len, hi, compat;
     Sched sched;
 };
 
@@ -248,210 +246,6 @@ __device__ __forceinline__ void row_multitau_packed(uint32_t *col, long long *ac
     }
 }
 
-// ---- integer path, sparse levels by event-pair enumeration ------------------------------
-// At ~100 events per row most levels are sparse, and walking every level's list for pairs costs
-// far more than the pairs there are.  The pair sums are bilinear in the events:
-//     S_l(d) = sum over EVENT pairs i < j of c_i c_j [ (t_j >> l) - (t_i >> l) == d ],
-// (bins merge events, products of bin counts expand into products of event counts), and an
-// event pair with gap g = t_j - t_i can only reach the needed lags dpl+1..2*dpl of a level
-// l >= 1 when g >> l lies in dpl..2*dpl, i.e. at l = la or la - 1 with la = floor(log2 g) - log2 dpl.
-// So ONE walk over the level-0 events with a look-ahead window of (2*dpl+1) << ls frames yields
-// the pair sums of all levels 0..ls at once (32-bit accumulators in shared memory: every sum is
-// bounded by the square of the row's photon total, and the path is taken only when that is
-// below 2^32).  ls is chosen per warp so that the look-ahead visits about 2.7 events per
-// source; the levels above it are dense and use the register window.  Level lists are still
-// compacted in place level by level (cheap, and the stale-tail emulation needs them); in compat
-// mode the products whose target lies at or beyond K* are subtracted again.
-constexpr int kEnumMaxLevel = 8;
-
-template <int DPL>
-__device__ __forceinline__ int enum_slot(int l, int d)  // accumulator slot of (level, lag)
-{
-    return l == 0 ? d - 1 : 2 * DPL + (l - 1) * DPL + (d - DPL - 1);
-}
-
-template <bool COMPAT, int DPL>
-__device__ __forceinline__ void row_multitau_packed_enum(uint32_t *col, uint32_t *accs, int n0, long long total,
-                                                         int r, const MtArgs &a)
-{
-    constexpr int kLog2Dpl = DPL == 8 ? 3 : 2;
-    static_assert(DPL == 8 || DPL == 4, "enumeration is instantiated for dpl 4 and 8");
-    const int F = a.sched.frames;
-    const int nl = a.sched.n_levels;
-    // ---- choose the last enumerated level (warp uniform)
-    const long long sum_n = (long long)__reduce_add_sync(0xffffffffu, n0);
-    int ls = 0;
-    for (int l = 1; l <= kEnumMaxLevel && l < nl; l++)
-        if ((long long)((2 * DPL + 1) << l) * sum_n * 10 <= 27ll * 32 * F) ls = l;
-    const int nslots = 2 * DPL + ls * DPL;
-    for (int k = 0; k < nslots; k++) accs[k * kSlice] = 0u;
-    // ---- phase A: event pairs within the look-ahead window
-    {
-        const int wmax = (2 * DPL + 1) << ls;
-        const uint32_t cmask0 = (1u << kCountBits) - 1u;
-        const int top0 = a.sched.lo[0] + a.sched.count[0] - 1;
-        uint32_t wnext = n0 > 0 ? col[0] : 0u;
-        for (int i = 0; i < n0; i++) {
-            const uint32_t wi = wnext;
-            const int ti = (int)(wi >> kCountBits);
-            const uint32_t ci = wi & cmask0;
-            if (i + 1 < n0) wnext = col[(i + 1) * kSlice];
-            uint32_t wj = wnext;
-            for (int j = i + 1; j < n0;) {
-                const int tj = (int)(wj >> kCountBits);
-                const int g = tj - ti;
-                if (g >= wmax) break;
-                const uint32_t prod = ci * (wj & cmask0);
-                if (g <= top0) accs[(g - 1) * kSlice] += prod;
-                const int la = 31 - __clz(g) - kLog2Dpl;
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const int l = la - k;
-                    if (l >= 1 && l <= ls) {
-                        const int kj = tj >> l;
-                        const int d = kj - (ti >> l);
-                        if (d > DPL && d <= 2 * DPL && kj < (F >> l)) accs[enum_slot<DPL>(l, d) * kSlice] += prod;
-                    }
-                }
-                if (++j < n0) wj = col[j * kSlice];
-            }
-        }
-    }
-    // ---- phase B: level by level
-    int n = n0;
-    int L = F;
-    int cb = kCountBits;
-    int nhist[kMaxLevels];
-    int stale_min = 0x7fffffff;
-    for (int l = 0; l < nl; l++) {
-        if (l > 0) {  // in-place compaction of corr.cpp:349-390
-            L >>= 1;
-            cb++;
-            const uint32_t clr = ~(1u << (cb - 1));
-            const uint32_t cm = (1u << cb) - 1u;
-            int m = 0;
-            uint32_t prev = 0xffffffffu, cur = 0;
-            long long kept = 0;
-            for (int j = 0; j < n; j++) {
-                const uint32_t w = col[j * kSlice] & clr;
-                const uint32_t key = w >> cb;
-                if ((int)key >= L) break;
-                kept += (long long)(w & cm);
-                if (key == prev) cur += (w & cm);
-                else {
-                    if (m > 0) col[(m - 1) * kSlice] = cur;
-                    cur = w;
-                    m++;
-                    prev = key;
-                }
-            }
-            if (m > 0) col[(m - 1) * kSlice] = cur;
-            if (COMPAT && m < n) stale_min = min(stale_min, (int)(col[m * kSlice] >> (cb - 1)));
-            n = m;
-            total = kept;
-        }
-        if (COMPAT) nhist[l] = n;
-        const int cnt = a.sched.count[l];
-        if (cnt == 0) continue;
-        const uint32_t cmask = (1u << cb) - 1u;
-        const int lo = a.sched.lo[l];
-        const int top = lo + cnt - 1;
-        const int first = a.sched.first[l];
-        const float s2 = pow2_neg(2 * l), s1 = pow2_neg(l);
-        int kstar = 0x7fffffff;
-        if (COMPAT && l > 0 && stale_min < L && n < n0) {
-            const int level = l;
-            kstar = stale_tail_threshold(n0, n, [&](int p) -> int {
-                if (p < n) return (int)(col[p * kSlice] >> cb);
-                int lv = level - 1;
-                while (lv > 0 && nhist[lv] <= p) lv--;
-                return (int)(col[p * kSlice] >> (kCountBits + lv));
-            });
-        }
-        // ---- IF / IP: total minus the head / tail bins; keys are distinct, so stepping tau' by
-        //      one moves each cursor by at most one bin
-        {
-            long long head = 0, tail = 0;
-            int p = 0, q = n - 1;
-            __syncwarp();
-            for (int tp = 1; tp <= top; tp++) {
-                if (p < n) {
-                    const uint32_t w = col[p * kSlice];
-                    if ((int)(w >> cb) == tp - 1) {
-                        head += (long long)(w & cmask);
-                        p++;
-                    }
-                }
-                if (q >= 0) {
-                    const uint32_t w = col[q * kSlice];
-                    if ((int)(w >> cb) == L - tp) {
-                        tail += (long long)(w & cmask);
-                        q--;
-                    }
-                }
-                if (tp >= lo) {
-                    const int64_t o = (int64_t)(first + tp - lo) * a.R_pad + r;
-                    a.IF[o] = scaled_div((float)(total - head) * s1, L - tp);
-                    a.IP[o] = scaled_div((float)(total - tail) * s1, L - tp);
-                }
-            }
-        }
-        // ---- G2
-        if (l <= ls) {
-            if (COMPAT && n > 0 && kstar <= (int)(col[(n - 1) * kSlice] >> cb)) {
-                // take back the products whose target bin the reference's search never finds
-                for (int q = n - 1; q >= 0; q--) {
-                    const uint32_t wq = col[q * kSlice];
-                    const int kq = (int)(wq >> cb);
-                    if (kq < kstar) break;
-                    for (int sidx = q - 1; sidx >= 0; sidx--) {
-                        const uint32_t ws = col[sidx * kSlice];
-                        const int d = kq - (int)(ws >> cb);
-                        if (d > top) break;
-                        if (d >= lo) accs[enum_slot<DPL>(l, d) * kSlice] -= (ws & cmask) * (wq & cmask);
-                    }
-                }
-            }
-            __syncwarp();
-            for (int k = 0; k < cnt; k++)
-                a.G2[(int64_t)(first + k) * a.R_pad + r] =
-                    scaled_div((float)accs[enum_slot<DPL>(l, lo + k) * kSlice] * s2, L - (lo + k));
-        } else {
-            const bool dense = lo == DPL + 1 && (long long)__reduce_add_sync(0xffffffffu, n) * 6 > (long long)L * 32;
-            if (dense) {
-                unsigned long long pairs[DPL];
-#pragma unroll
-                for (int d = 0; d < DPL; d++) pairs[d] = 0ull;
-                dense_level_pairs<DPL>(col, n, cb, cmask, L, kstar, pairs);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < DPL; k++)
-                    if (k < cnt)
-                        a.G2[(int64_t)(first + k) * a.R_pad + r] =
-                            scaled_div((float)(long long)pairs[k] * s2, L - (lo + k));
-            } else {
-                // sparse look-ahead on this level's list; the level-0 slots are free by now
-                for (int d = lo; d <= top; d++) accs[(d - 1) * kSlice] = 0u;
-                for (int i = 0; i < n; i++) {
-                    const uint32_t wi = col[i * kSlice];
-                    const int ki = (int)(wi >> cb);
-                    for (int j = i + 1; j < n; j++) {
-                        const uint32_t wj = col[j * kSlice];
-                        const int kj = (int)(wj >> cb);
-                        const int d = kj - ki;
-                        if (d > top) break;
-                        if (d >= lo && kj < kstar) accs[(d - 1) * kSlice] += (wi & cmask) * (wj & cmask);
-                    }
-                }
-                __syncwarp();
-                for (int k = 0; k < cnt; k++)
-                    a.G2[(int64_t)(first + k) * a.R_pad + r] =
-                        scaled_div((float)accs[(lo + k - 1) * kSlice] * s2, L - (lo + k));
-            }
-        }
-    }
-}
-
 // ---- float path --------------------------------------------------------------------
 typedef unsigned long long u64;
 
@@ -579,26 +373,17 @@ __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
         uint32_t *g = reinterpret_cast<uint32_t *>(a.store) + a.slice_base[s] + lane;
         long long *acc = reinterpret_cast<long long *>(smem_raw) + lane;
         if (in_smem) {  // two call sites so that the common one compiles to LDS/STS
-            uint32_t *col = reinterpret_cast<uint32_t *>(smem_raw + (size_t)a.acc_bytes) + lane;
-            long long total = 0;
+            uint32_t *col = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(a.hi + 1) * kSlice * 8) + lane;
             for (int j = 0; j < len; j++)
-                if (j < n0) {
-                    const uint32_t w = g[(int64_t)j * kSlice];
-                    col[j * kSlice] = w;
-                    total += (long long)(w & ((1u << kCountBits) - 1u));
-                }
-            // the 32-bit enumeration path needs every pair sum (<= total^2) to fit 32 bits
-            if (DPL > 0 && !__any_sync(0xffffffffu, total >= 65536))
-                row_multitau_packed_enum<COMPAT, (DPL > 0 ? DPL : 8)>(col, reinterpret_cast<uint32_t *>(smem_raw) + lane, n0,
-                                                                    total, r, a);
-            else row_multitau_packed<COMPAT, DPL>(col, acc, n0, r, a);
+                if (j < n0) col[j * kSlice] = g[(int64_t)j * kSlice];
+            row_multitau_packed<COMPAT, DPL>(col, acc, n0, r, a);
         } else row_multitau_packed<COMPAT, 0>(g, acc, n0, r, a);
     } else {
         u64 *g = reinterpret_cast<u64 *>(a.store) + a.slice_base[s] + lane;
         u64 *col = g;
         float *acc = reinterpret_cast<float *>(smem_raw) + lane;
         if (in_smem) {
-            col = reinterpret_cast<u64 *>(smem_raw + (size_t)a.acc_bytes) + lane;
+            col = reinterpret_cast<u64 *>(smem_raw + (size_t)(a.hi + 1) * kSlice * 8) + lane;
             for (int j = 0; j < len; j++)
                 if (j < n0) col[j * kSlice] = g[(int64_t)j * kSlice];
         }
@@ -623,10 +408,7 @@ static int run_multitau(xpcs_handle_s *h, MtArgs &a)
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     smem_cap -= 1024;
     const size_t wbytes = KIND == kPacked ? 4 : 8;
-    size_t acc_bytes = (size_t)(a.hi + 1) * kSlice * 8;
-    if (KIND == kPacked && DPL > 0)  // 32-bit slots of the enumeration path: level 0 + kEnumMaxLevel levels
-        acc_bytes = std::max(acc_bytes, (size_t)(2 * DPL + kEnumMaxLevel * DPL) * kSlice * 4);
-    a.acc_bytes = (int)acc_bytes;
+    const size_t acc_bytes = (size_t)(a.hi + 1) * kSlice * 8;
     int smem_len = h->max_row;
     if (acc_bytes + (size_t)smem_len * kSlice * wbytes > (size_t)smem_cap)
         smem_len = (int)((smem_cap - acc_bytes) / (kSlice * wbytes));
