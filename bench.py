@@ -259,6 +259,148 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
     return tbl.get(name, 0)
 
 
+def gen_dense_device(torch, P, F, darks, mu, dev, seed=99, chunk=200):
+    """int16 [darks + F][P] on the device: offset 100 ADU + N(0, 2) read noise; data frames add
+    20 ADU per photon, photons ~ Poisson(mu)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((darks + F, P), dtype=torch.int16, device=dev)
+    for f0 in range(0, darks + F, chunk):
+        n = min(chunk, darks + F - f0)
+        fr = 100.0 + 2.0 * torch.randn((n, P), device=dev, generator=g)
+        lam = torch.full((n, P), mu, device=dev)
+        ph = torch.poisson(lam, generator=g)
+        if f0 < darks:
+            ph[: max(0, min(n, darks - f0))] = 0.0
+        out[f0: f0 + n] = torch.round(fr + 20.0 * ph).clamp_(-32768, 32767).to(torch.int16)
+    return out
+
+
+def bench_dense(args, wl):
+    """BASELINE configs[1]: non-sparse IMM 1024x1024 int16, 20k frames, 100 dark frames, flat-field,
+    threshold lld + sigma*dark_std, then multi-tau + normalisation -- one B200."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    pkg = entry.load_package()
+    h, w, F = wl["h"], wl["w"], wl["F"]
+    P = h * w
+    darks, mu, lld, sigma = 100, 0.02, 5.0, 3.0
+    dev = torch.device("cuda", 0)
+    dq, sq = module_maps(pkg, wl, 1)
+    # flat-field spread 1 %: the reference subtracts dark_avg = mean(raw*flat) from the un-flat-fielded raw
+    # value (SURVEY A.6), so a wide flat-field turns the 100 ADU offset into spurious survivors
+    flat = pkg.synth.flatfield(P, sigma=0.01)
+    frames = gen_dense_device(torch, P, F, darks, mu, dev)
+    E_est = int(P * F * mu * 1.3) + (1 << 20)
+    c = pkg.Correlator(dq, sq, F, dpl=8, flatfield=flat, lld=lld, sigma=sigma, device=0, reserve_events=E_est,
+                       compat=not args.no_compat)
+    c.set_dark(frames[:darks].cpu().numpy())
+    data = frames[darks:]
+    T, Q, S = c.T, c.Q, c.S
+    stream = torch.cuda.Stream(device=dev)
+    c.set_stream(stream.cuda_stream)
+
+    def step_device():
+        c.reset()
+        c.push_dense_device(data.data_ptr(), F)
+        c.finish_ingest(want=False)
+        c.multitau(want=False)
+        return c.normalize()
+
+    for _ in range(max(args.warmup, 1)):
+        g2, se = step_device()
+    info = c.info()
+    E, R = int(info.events_stored), int(info.n_rows)
+    c.kernel_report(reset=True)
+    c.kernel_timing(True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        g2, se = step_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = int(c.launch_count())
+    report = c.kernel_report(reset=True)
+    c.kernel_timing(False)
+    # end to end: 42 GB of pinned host frames through the public API
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((F, P), dtype=torch.int16, pin_memory=True)
+        host.copy_(data)
+        torch.cuda.synchronize()
+        nst = max(1, min(args.steps, 3))
+
+        def step_e2e():
+            c.reset()
+            c.push_dense_raw(host.data_ptr(), F)
+            sums = c.finish_ingest(want=True)
+            c.multitau(want=False)
+            return sums, c.normalize()
+
+        step_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            step_e2e()
+        torch.cuda.synchronize()
+        ms_e2e = 1e3 * (time.perf_counter() - t0) / nst
+        e2e = {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * P * F,
+               "d2h_bytes_per_step": 4 * (P + 2 * F + S + (F // c.static_window) * S) + 8 * T * Q, "ms_per_step": ms_e2e,
+               "steps": nst, "api": "Correlator.push_dense/finish_ingest/multitau/normalize (C-ABI xpcs_*)"}
+    clocks = sampler.stop()
+    peak, peak_src = peaks()
+    kern = {}
+    for name, (ms, n) in report.items():
+        if n <= 0:
+            continue
+        b = algorithmic_bytes(name, E, T, R, Q, P, F_dense=F)
+        if name == "k_dense_filter":
+            b = 2 * P * F + 16 * P          # whole job; launched in frame batches
+            per = ms / args.steps
+        else:
+            per = ms / n
+        kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,
+                      "algo_bytes": b, "gbs": (b / (per * 1e-3) / 1e9) if b else None, "stage": KERNEL_GROUP.get(name, "?")}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    k = kern[dom]
+    line = {
+        "metric": METRIC, "value": F / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (dark/flat/threshold in f64 where the reference does)", "data": "synthetic",
+        "config": {"workload": wl["name"], "workload_key": "c2", "detector_pixels": P, "frames": F, "dark_frames": darks,
+                   "photons_per_pixel_frame": mu, "lld": lld, "sigma": sigma, "events_after_threshold": E, "delays": T,
+                   "l2": "inputs (%.1f GB/step) exceed the 126 MB L2" % (2.0 * P * F / 1e9)},
+        "pixel_frames_per_s": float(P) * F / (ms_dev * 1e-3), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": (k["gbs"] / peak) if k["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                     "algo_bytes_per_step": k["algo_bytes"], "kernel_share_of_step": k["ms_per_step"] / ms_dev},
+        "kernels": kern, "results_finite": bool(np.isfinite(g2).all()),
+    }
+    if not args.no_cpu:
+        try:
+            from oracle import refdrv
+            if refdrv.available():
+                F_s, d_s = args.cpu_frames or 300, 20
+                fr = gen_dense_device(torch, P, F_s, d_s, mu, dev, seed=7).cpu().numpy()
+                job = refdrv.SparseJob(dq, sq, F_s, dense=fr, dpl=8, swindow=max(1, F_s // 10), darks=d_s, lld=lld,
+                                       sigma=sigma, flatfield=flat)
+                st = job.run(threads=os.cpu_count())
+                line["cpu_baseline"] = {"value": F_s / st["total_s"], "unit": UNIT, "cores": os.cpu_count(),
+                                        "kind": "reference", "seconds": st["total_s"], "stages_s": st,
+                                        "sample": "%d of %d frames (+%d darks), same detector, flat-field and threshold" % (F_s, F, d_s)}
+        except Exception as ex:  # the bench line must still be printed
+            line["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(line))
+    c.close()
+    return 0
+
+
 def bench_twotime(args, wl):
     """BASELINE configs[3]: two-time correlation of one 64k-pixel dynamic partition over 10k
     frames -- the tensor-core stage.  One step = sg + operand build + C = triu(X X^T) scaled +
@@ -331,6 +473,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (c2: 42 GB pinned)")
     ap.add_argument("--no-compat", action="store_true", help="exact sums instead of the reference's stale-tail behaviour")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -343,7 +486,7 @@ def main():
         return run_reference_arm(args, wl, args.workload)
 
     if wl["kind"] == "dense":
-        raise SystemExit("bench.py: the dense workload (c2) bench leg is not wired yet")
+        return bench_dense(args, wl)
     if wl["kind"] == "twotime":
         return bench_twotime(args, wl)
 

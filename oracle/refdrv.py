@@ -204,18 +204,22 @@ def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout
 
 
 class SparseJob:
-    """bench.py helper: the files of one sparse multi-tau job are written once; run() executes the
-    reference binary on them and returns its own stage scopes (seconds)."""
+    """bench.py helper: the files of one multi-tau job are written once; run() executes the
+    reference binary on them and returns its own stage scopes (seconds).  Sparse by default;
+    dense=(int16 frames [darks + frames][P]) with darks / lld / sigma / flatfield for the dense path."""
 
-    def __init__(self, dq, sq, frames, off, idx, val, dpl=8, swindow=None):
+    def __init__(self, dq, sq, frames, off=None, idx=None, val=None, dpl=8, swindow=None, dense=None, **cfg):
         from __graft_entry__ import load_package
         synth = load_package().synth
         self.dir = scratch_dir()
         self.imm = os.path.join(self.dir, "data.imm")
         h, w = np.asarray(dq).shape
-        synth.write_imm_sparse(self.imm, h, w, off, idx, val)
+        if dense is not None:
+            synth.write_imm_dense(self.imm, h, w, dense)
+        else:
+            synth.write_imm_sparse(self.imm, h, w, off, idx, val)
         self.root = os.path.join(self.dir, "case.h5dir")
-        write_config(self.root, dq, sq, frames, self.imm, dpl=dpl, static_window=swindow)
+        write_config(self.root, dq, sq, frames, self.imm, dpl=dpl, static_window=swindow, **cfg)
         import atexit
         atexit.register(self.close)
 

@@ -169,6 +169,10 @@ class Correlator:
         tk = None if ticks is None else np.ascontiguousarray(ticks, np.float64)
         self._check(self._lib.xpcs_push_dense(self._h, f.ctypes.data, _ptr(ck), _ptr(tk), f.shape[0]))
 
+    def push_dense_raw(self, frames_ptr, nframes):
+        """Host pointer as an integer (e.g. a pinned torch tensor); caller keeps it alive."""
+        self._check(self._lib.xpcs_push_dense(self._h, frames_ptr, None, None, nframes))
+
     def push_dense_device(self, d_frames, nframes):
         self._check(self._lib.xpcs_push_dense_device(self._h, d_frames, nframes))
 

@@ -489,52 +489,116 @@ struct DenseArgs {
     long long *summary;
 };
 
-// dense_filter.cpp:150-174 for a batch of raw frames; survivors are appended to the
-// frame-major event list (pixel, output frame, value) with one atomic per warp.
-__global__ void __launch_bounds__(256) k_dense_filter(DenseArgs a)
+// dense_filter.cpp:150-174 for a batch of raw frames.  One CTA owns 512 pixels (two per thread)
+// and walks kDfFrames consecutive frames: the per-pixel constants (mask, dark average,
+// threshold, flat-field) are loaded once into registers instead of once per frame, the frames
+// are read as coalesced 4-byte pairs, survivors are staged in shared memory and appended to the
+// frame-major event list (pixel, output frame, value) with ONE global atomic per flush and
+// coalesced stores, and the per-frame sums leave the CTA as one atomic per frame.
+constexpr int kDfThreads = 256;
+constexpr int kDfPixels = 2 * kDfThreads;
+constexpr int kDfFrames = 64;
+constexpr int kDfCap = 3072;        // staged events per CTA
+constexpr int kDfFlushEvery = 4;    // frames between fill checks
+
+__global__ void __launch_bounds__(kDfThreads) k_dense_filter(DenseArgs a)
 {
-    const int fr = blockIdx.y;
-    const int raw = a.first_raw + fr;
-    const int t = out_frame(raw, a.rawblock, a.stride, a.F);
-    if (t < 0) return;
-    const int16_t *src = a.frames + (int64_t)fr * a.P;
-    double fsum = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ((a.P + 31) & ~31);
-         j += gridDim.x * blockDim.x) {
-        bool keep = false;
-        float v = 0.0f;
-        if (j < a.P && a.row_of_pixel[j] >= 0) {
-            v = (float)src[j];
-            float thresh = 0.0f;
+    __shared__ int s_pix[kDfCap];
+    __shared__ int s_t[kDfCap];
+    __shared__ float s_v[kDfCap];
+    __shared__ double s_fsum[kDfFrames];
+    __shared__ int s_count;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    const int j0 = (blockIdx.x * kDfThreads + tid) * 2;
+    const int f_begin = blockIdx.y * kDfFrames;
+    const int f_end = min(a.nframes, f_begin + kDfFrames);
+    if (tid == 0) s_count = 0;
+    for (int i = tid; i < kDfFrames; i += kDfThreads) s_fsum[i] = 0.0;
+    // per-pixel constants
+    bool valid[2];
+    double davg[2] = {0.0, 0.0}, flat[2] = {1.0, 1.0};
+    float thresh[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int j = j0 + k;
+        valid[k] = j < a.P && a.row_of_pixel[j] >= 0;
+        if (valid[k]) {
+            flat[k] = a.flat[j];
             if (a.dark_avg) {
-                v = (float)__dsub_rn((double)v, a.dark_avg[j]);
-                v = fmaxf(v, 0.0f);
-                thresh = (float)__dadd_rn((double)a.lld, __dmul_rn((double)a.sigma, a.dark_std[j]));
-            }
-            if (!(v <= thresh)) {
-                v = (float)__dmul_rn((double)v, a.flat[j]);
-                keep = true;
-            }
-        }
-        unsigned ball = __ballot_sync(0xffffffffu, keep);
-        if (ball) {
-            unsigned long long basepos = 0;
-            const int lane = threadIdx.x & 31;
-            if (lane == 0) basepos = atomicAdd(a.counter, (unsigned long long)__popc(ball));
-            basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (keep) {
-                unsigned long long pos = basepos + __popc(ball & ((1u << lane) - 1));
-                if (pos < a.capacity) {
-                    a.out_idx[pos] = j;
-                    a.out_t[pos] = t;
-                    a.out_v[pos] = v;
-                } else a.summary[kSumOverflow] = 2;
-                fsum += (double)v;
+                davg[k] = a.dark_avg[j];
+                thresh[k] = (float)__dadd_rn((double)a.lld, __dmul_rn((double)a.sigma, a.dark_std[j]));
             }
         }
     }
-    fsum = warp_sum(fsum);
-    if ((threadIdx.x & 31) == 0 && fsum != 0.0) atomicAdd(a.frame_acc + t, fsum);
+    const bool pair_ok = (a.P & 1) == 0 && j0 + 1 < a.P;  // aligned 4-byte loads
+    __syncthreads();
+
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const int n = min(s_count, kDfCap);
+        if (tid == 0) s_base = atomicAdd(a.counter, (unsigned long long)n);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (int i = tid; i < n; i += kDfThreads) {
+            const unsigned long long pos = base + i;
+            if (pos < a.capacity) {
+                a.out_idx[pos] = s_pix[i];
+                a.out_t[pos] = s_t[i];
+                a.out_v[pos] = s_v[i];
+            } else a.summary[kSumOverflow] = 2;
+        }
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+    };
+
+    for (int fr = f_begin; fr < f_end; fr++) {
+        const int t = out_frame(a.first_raw + fr, a.rawblock, a.stride, a.F);
+        if (t >= 0) {
+            const int16_t *src = a.frames + (int64_t)fr * a.P;
+            short raw[2] = {0, 0};
+            if (pair_ok) {
+                const short2 r2 = *reinterpret_cast<const short2 *>(src + j0);
+                raw[0] = r2.x;
+                raw[1] = r2.y;
+            } else {
+                if (j0 < a.P) raw[0] = src[j0];
+                if (j0 + 1 < a.P) raw[1] = src[j0 + 1];
+            }
+            double fsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (!valid[k]) continue;
+                float v = (float)raw[k];
+                if (a.dark_avg) {
+                    v = (float)__dsub_rn((double)v, davg[k]);
+                    v = fmaxf(v, 0.0f);
+                }
+                if (!(v <= thresh[k])) {
+                    v = (float)__dmul_rn((double)v, flat[k]);
+                    const int pos = atomicAdd(&s_count, 1);
+                    if (pos < kDfCap) {
+                        s_pix[pos] = j0 + k;
+                        s_t[pos] = t;
+                        s_v[pos] = v;
+                    } else a.summary[kSumOverflow] = 2;
+                    fsum += (double)v;
+                }
+            }
+            fsum = warp_sum(fsum);
+            if ((tid & 31) == 0 && fsum != 0.0) atomicAdd(&s_fsum[fr - f_begin], fsum);
+        }
+        if (((fr - f_begin) % kDfFlushEvery) == kDfFlushEvery - 1) {
+            __syncthreads();
+            if (s_count > kDfCap - kDfFlushEvery * kDfPixels) flush();
+        }
+    }
+    flush();
+    for (int i = tid; i < f_end - f_begin; i += kDfThreads) {
+        const int t = out_frame(a.first_raw + f_begin + i, a.rawblock, a.stride, a.F);
+        if (t >= 0 && s_fsum[i] != 0.0) atomicAdd(a.frame_acc + t, s_fsum[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -754,12 +818,10 @@ int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw
     a.capacity = h->d_idx.n;
     a.frame_acc = h->d_frame_acc.p;
     a.summary = h->d_summary.p;
-    int gx = (h->P + 256 * 8 - 1) / (256 * 8);
-    if (gx < 1) gx = 1;
-    dim3 grid(gx, nframes);
+    dim3 grid((h->P + kDfPixels - 1) / kDfPixels, (nframes + kDfFrames - 1) / kDfFrames);
     {
         LaunchScope ls(h, "k_dense_filter");
-        k_dense_filter<<<grid, 256, 0, h->stream>>>(a);
+        k_dense_filter<<<grid, kDfThreads, 0, h->stream>>>(a);
     }
     return check_cuda(h, cudaGetLastError(), "k_dense_filter");
 }

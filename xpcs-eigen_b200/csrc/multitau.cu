@@ -256,7 +256,44 @@ __device__ __forceinline__ u64 f_make(int key, float v)
     return ((u64)(uint32_t)key << 32) | (u64)__float_as_uint(v);
 }
 
-template <bool COMPAT>
+// Register-window pair sums of a dense level, float rows.  Per lag the products are added in
+// bin order, which is the reference's order (sources ascending, corr.cpp:397-411); the zero
+// products of empty bins leave an fp32 sum unchanged, so the result is bit-identical to the
+// sparse walk.
+template <int DPL>
+__device__ __forceinline__ void dense_level_pairs_float(const u64 *col, int n, int L, int kstar, float (&acc)[DPL])
+{
+    constexpr int W = 2 * DPL + 1;
+    float win[W];
+    int p = 0;
+    u64 wp = n > 0 ? col[0] : 0ull;
+    int kp = n > 0 ? f_key(wp) : 0x7fffffff;
+    auto fetch = [&](int key) -> float {
+        float v = 0.0f;
+        if (kp == key) {
+            v = key < kstar ? f_val(wp) : 0.0f;
+            p++;
+            if (p < n) {
+                wp = col[p * kSlice];
+                kp = f_key(wp);
+            } else kp = 0x7fffffff;
+        }
+        return v;
+    };
+#pragma unroll
+    for (int k = 0; k < W; k++) win[k] = fetch(k);
+    for (int t0 = 0; t0 < L - DPL - 1; t0 += W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const float src = win[u];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] = __fadd_rn(acc[d], __fmul_rn(src, win[(u + DPL + 1 + d) % W]));
+            win[u] = fetch(t0 + u + W);
+        }
+    }
+}
+
+template <bool COMPAT, int DPL>
 __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const MtArgs &a)
 {
     const int F = a.sched.frames;
@@ -298,25 +335,40 @@ __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const Mt
         if (COMPAT && l > 0 && stale_min < L && n < n0)
             kstar = stale_tail_threshold(n0, n, [&](int p) -> int { return f_key(col[p * kSlice]); });
         // ---- G2 in the reference's order: for each source ascending, product then add
-        for (int d = lo; d <= top; d++) acc[d * kSlice] = 0.0f;
         double total = 0.0;
-        for (int i = 0; i < n; i++) {
-            const u64 wi = col[i * kSlice];
-            const int ki = f_key(wi);
-            const float vi = f_val(wi);
-            total += (double)vi;
-            for (int j = i + 1; j < n; j++) {
-                const u64 wj = col[j * kSlice];
-                const int kj = f_key(wj);
-                const int d = kj - ki;
-                if (d > top) break;
-                if (d >= lo && kj < kstar) acc[d * kSlice] = __fadd_rn(acc[d * kSlice], __fmul_rn(vi, f_val(wj)));
+        bool dense = false;
+        if (DPL > 0 && l > 0 && lo == DPL + 1)
+            dense = (long long)__reduce_add_sync(0xffffffffu, n) * 6 > (long long)L * 32;
+        if (DPL > 0 && dense) {
+            float pairs[DPL > 0 ? DPL : 1];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) pairs[d] = 0.0f;
+            dense_level_pairs_float<(DPL > 0 ? DPL : 1)>(col, n, L, kstar, pairs);
+            for (int i = 0; i < n; i++) total += (double)f_val(col[i * kSlice]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < DPL; k++)
+                if (k < cnt) a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div(pairs[k], L - (lo + k));
+        } else {
+            for (int d = lo; d <= top; d++) acc[d * kSlice] = 0.0f;
+            for (int i = 0; i < n; i++) {
+                const u64 wi = col[i * kSlice];
+                const int ki = f_key(wi);
+                const float vi = f_val(wi);
+                total += (double)vi;
+                for (int j = i + 1; j < n; j++) {
+                    const u64 wj = col[j * kSlice];
+                    const int kj = f_key(wj);
+                    const int d = kj - ki;
+                    if (d > top) break;
+                    if (d >= lo && kj < kstar) acc[d * kSlice] = __fadd_rn(acc[d * kSlice], __fmul_rn(vi, f_val(wj)));
+                }
             }
-        }
-        __syncwarp();
-        for (int k = 0; k < cnt; k++) {
-            const int tp = lo + k;
-            a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div(acc[tp * kSlice], L - tp);
+            __syncwarp();
+            for (int k = 0; k < cnt; k++) {
+                const int tp = lo + k;
+                a.G2[(int64_t)(first + k) * a.R_pad + r] = scaled_div(acc[tp * kSlice], L - tp);
+            }
         }
         // ---- IP: the running fp32 prefix sum at the moment the key reaches L - tau'
         {
@@ -387,7 +439,7 @@ __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
             for (int j = 0; j < len; j++)
                 if (j < n0) col[j * kSlice] = g[(int64_t)j * kSlice];
         }
-        row_multitau_float<COMPAT>(col, acc, n0, r, a);
+        row_multitau_float<COMPAT, DPL>(col, acc, n0, r, a);
     }
 }
 
@@ -452,6 +504,11 @@ int launch_multitau(xpcs_handle_s *h)
         if (dpl == 8) return a.compat ? run_multitau<kPacked, true, 8>(h, a) : run_multitau<kPacked, false, 8>(h, a);
         if (dpl == 4) return a.compat ? run_multitau<kPacked, true, 4>(h, a) : run_multitau<kPacked, false, 4>(h, a);
         return a.compat ? run_multitau<kPacked, true, 0>(h, a) : run_multitau<kPacked, false, 0>(h, a);
+    }
+    {
+        const int dpl = h->prm.delays_per_level;
+        if (dpl == 8) return a.compat ? run_multitau<kFloat, true, 8>(h, a) : run_multitau<kFloat, false, 8>(h, a);
+        if (dpl == 4) return a.compat ? run_multitau<kFloat, true, 4>(h, a) : run_multitau<kFloat, false, 4>(h, a);
     }
     return a.compat ? run_multitau<kFloat, true, 0>(h, a) : run_multitau<kFloat, false, 0>(h, a);
 }

@@ -606,8 +606,8 @@ extern "C" int xpcs_push_dense_device(xpcs_handle h, const int16_t *d_frames, in
     cudaSetDevice(h->device);
     int rc = dense_prepare(h);
     if (rc) return rc;
-    for (int f0 = 0; f0 < nframes; f0 += 32768) {  // grid.y limit
-        const int nb = std::min(32768, nframes - f0);
+    for (int f0 = 0; f0 < nframes; f0 += 65535 * 64) {  // grid.y limit (64 frames per CTA row)
+        const int nb = std::min(65535 * 64, nframes - f0);
         rc = launch_dense_filter(h, d_frames + (size_t)f0 * h->P, h->raw_frames + f0, nb);
         if (rc) return rc;
     }

@@ -110,7 +110,7 @@ def write_imm_sparse(path, h, w, frame_off, idx, val, dt=1e-3):
 
 
 def write_imm_dense(path, h, w, frames, dt=1e-3):
-    frames = np.asarray(frames, np.int16).reshape(-1, h * w)
+    frames = np.asarray(frames).reshape(-1, h * w)
     elapsed, tick = frame_clock(frames.shape[0], dt)
     with open(path, "wb") as fh:
         for f in range(frames.shape[0]):
