@@ -38,6 +38,10 @@ extern "C" {
 #define XPCS_COMPAT_STALE_TAIL 1u /* reproduce the reference's dropped G2 pairs: the binary
                                      search of corr.cpp:406 runs over the un-shrunk index
                                      vector.  Off = exact sums.            */
+#define XPCS_FLAG_LANE_MULTITAU 0x100u /* diagnostics: run the lane-per-row multi-tau kernel on
+                                          every slice instead of the warp-per-row one (both are
+                                          exact on integer counts; used by the parity tests to
+                                          cross-check the two).                              */
 
 typedef struct xpcs_handle_s *xpcs_handle;
 
@@ -190,6 +194,11 @@ int64_t xpcs_launch_count(xpcs_handle h);
 int xpcs_kernel_report(xpcs_handle h, const char **names, double *total_ms, int64_t *launches,
                        int cap);
 int xpcs_kernel_report_reset(xpcs_handle h);
+
+/* slices (32 pixel rows) the warp-per-row multi-tau kernel left to the lane-per-row kernel in
+ * the last xpcs_multitau (rows beyond its shared-memory budget or with counts summing to 2^16
+ * or more); -1 when the warp kernel did not run (float values, unusual delays-per-level). */
+int64_t xpcs_multitau_fallback_slices(xpcs_handle h);
 
 /* library/ABI version, and the compute capability it was compiled for (100 = sm_100a) */
 int xpcs_abi_version(void);

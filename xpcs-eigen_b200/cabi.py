@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxpcs_b200.so")
 
 XPCS_COMPAT_STALE_TAIL = 1
+XPCS_FLAG_LANE_MULTITAU = 0x100
 
 
 class XpcsError(RuntimeError):
@@ -81,6 +82,7 @@ SYMBOLS = {
     "xpcs_twotime": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "xpcs_kernel_timing": (_i, [_vp, _i]),
     "xpcs_launch_count": (_i64, [_vp]),
+    "xpcs_multitau_fallback_slices": (_i64, [_vp]),
     "xpcs_kernel_report": (_i, [_vp, _vp, _vp, _vp, _i]),
     "xpcs_kernel_report_reset": (_i, [_vp]),
     "xpcs_abi_version": (_i, []),

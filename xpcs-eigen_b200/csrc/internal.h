@@ -36,6 +36,19 @@ struct KernelStat {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+// Arguments of the multi-tau kernels (multitau.cu: one lane per row; multitau_warp.cu: one
+// warp per row).
+struct MtArgs {
+    void *store;
+    const int64_t *slice_base;
+    const int *slice_len;
+    const int *row_len;
+    float *G2, *IP, *IF;
+    int R_pad, n_slices, smem_len, hi, compat;
+    const unsigned char *only_flagged;  // lane-per-row kernel: process only slices flagged here (nullptr = all)
+    Sched sched;
+};
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -126,8 +139,10 @@ struct xpcs_handle_s {
 
     // ---- results ----
     bool multitau_done = false;
+    bool mt_warp_ran = false;             // last multi-tau used the warp-per-row kernel
     bool rows_consumed = false;
     xpcs::DevBuf<float> d_G2, d_IP, d_IF;   // [T][R_pad] row-permuted, tau-major
+    xpcs::DevBuf<unsigned char> d_mt_fallback;  // [n_slices] slices the warp-per-row kernel leaves to the lane-per-row one
     xpcs::DevBuf<double> d_partials;        // see xpcs_normalize_partials
     int64_t partials_count = 0;
     bool partials_done = false;
@@ -190,6 +205,9 @@ int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw
 // ---- launchers (multitau.cu) ----
 int launch_multitau(xpcs_handle_s *h);
 int launch_unpermute(xpcs_handle_s *h, const float *d_src, float *d_dst);  // [T][R_pad] -> [T][P]
+// ---- launchers (multitau_warp.cu) ----
+bool multitau_warp_eligible(const xpcs_handle_s *h);
+int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a);   // fills h->d_mt_fallback
 // ---- launchers (normalize.cu) ----
 int launch_normalize_partials(xpcs_handle_s *h);
 int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);

@@ -21,16 +21,6 @@
 
 namespace xpcs {
 
-struct MtArgs {
-    void *store;
-    const int64_t *slice_base;
-    const int *slice_len;
-    const int *row_len;
-    float *G2, *IP, *IF;
-    int R_pad, n_slices, smem_len, hi, compat;
-    Sched sched;
-};
-
 __device__ __forceinline__ float pow2_neg(int e)  // 2^-e, exact
 {
     return __int_as_float((127 - e) << 23);
@@ -416,6 +406,7 @@ __global__ void __launch_bounds__(32) k_multitau(MtArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int s = blockIdx.x;
+    if (a.only_flagged && !a.only_flagged[s]) return;  // slice already done by k_multitau_warp
     const int lane = threadIdx.x;
     const int r = s * kSlice + lane;
     const int len = a.slice_len[s];
@@ -498,6 +489,15 @@ int launch_multitau(xpcs_handle_s *h)
     a.hi = 2 * h->prm.delays_per_level;
     a.compat = (h->prm.compat_flags & XPCS_COMPAT_STALE_TAIL) ? 1 : 0;
     a.sched = h->sched;
+    a.only_flagged = nullptr;
+    h->mt_warp_ran = false;
+    if (multitau_warp_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+        // warp-per-row kernel first; it flags the slices it leaves (rows too long for its shared
+        // memory, or counts too large for 32-bit numerators) and the lane-per-row kernel redoes those
+        if ((rc = launch_multitau_warp(h, a))) return rc;
+        a.only_flagged = h->d_mt_fallback.p;
+        h->mt_warp_ran = true;
+    }
     if (h->kind == kPacked) {
         // the register-window path for dense levels is instantiated for the usual delays-per-level
         const int dpl = h->prm.delays_per_level;

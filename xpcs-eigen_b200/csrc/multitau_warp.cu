@@ -1,0 +1,480 @@
+// multitau_warp.cu -- multi-tau correlator, one WARP per pixel row (integer photon counts).
+//
+// Replaces Corr::multiTau2 (reference corr.cpp:315-431) for the packed store
+// (word = frame << 12 | count).  One CTA owns one slice of 32 rows: the slice tile is read
+// once with coalesced 128-byte lines and transposed into shared memory (row-major, odd pitch),
+// then each warp works through its rows with lanes over events / bins / delays, and the
+// 32 x T x 3 results leave through a shared-memory stage as full 128-byte lines.
+//
+// Nothing is compacted level by level.  Every quantity is a function of the level-0 events
+// (f_i, c_i) of the row (tests/multitau_model.py restates this on the CPU and is checked bit
+// for bit against the oracle):
+//   L_l = F >> l, lim_l = L_l << l;  an event is live at level l iff f < lim_l  (corr.cpp:349-390)
+//   IP(l,t') = PS((L_l - t') << l),  IF(l,t') = PS(lim_l) - PS(t' << l)           (corr.cpp:403,414-416)
+//       with PS(x) = sum of the counts of the events with f < x (prefix sums + binary search)
+//   G2, sparse levels (l < ld): ONE pass over event pairs i < j with d = f_j - f_i < (2dpl+1) << (ld-1);
+//       a pair lands at level 0 when d <= 2dpl, and for d >= 2dpl only at the levels
+//       l0 = bitlength(d) - log2(dpl) - 1 (bin distance b = (f_j >> l0) - (f_i >> l0) in dpl..2dpl)
+//       and l0 - 1 (only b == 2dpl);                                               (corr.cpp:397-411)
+//   G2, dense levels (l >= ld, the first level with L_l <= 4 n): 16-bit bin arrays B_l[t]
+//       (B_{l+1}[t] = B_l[2t] + B_l[2t+1]) and windowed products, lanes over t.
+//   All numerators are exact integers (< 2^32 because the row's counts sum to < 2^16; rows
+//   beyond that go to the lane-per-row kernel), one IEEE division per output.
+// XPCS_COMPAT_STALE_TAIL: the reference's binary search runs over the stale
+// tail of its un-shrunk vector.  V_l[p] = A_m[p], m = max{ j <= l : n_j > p }, is a pure
+// function of the level-0 events: the live counts n_l come from the merge levels
+// bitlength(f_i ^ f_{i-1}); the first stale slot of each level (its key is what can steer a
+// search wrong) is bounded from below on the sparse levels and tracked exactly on the dense
+// ones; only when it drops below L_l is the boundary walk of multitau.cu replayed, with
+// rank/select over the events instead of a materialised array.
+#include "internal.h"
+
+namespace xpcs {
+
+constexpr int kMwWarps = 16;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kInf = 0x7fffffff;
+constexpr int kMwTables = 6 * 32;  // per-warp tables: tot, flim, cnts, cntml, nlive, smin
+
+struct MwArgs {
+    unsigned char *fallback;   // [n_slices]
+    int len_cap;               // longest slice handled here
+    int pitch_e;               // odd
+    int pitch_t;               // odd, >= T
+    int warp_words;            // per-warp shared words
+    int T;
+};
+
+__device__ __forceinline__ float mw_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
+__device__ __forceinline__ float mw_scaled_div(float num, int neff)
+{
+    return neff > 0 ? __fdiv_rn(num, (float)neff) : num;
+}
+
+// first index in [0, n) whose word is >= key (words ascend with the frame)
+__device__ __forceinline__ int mw_lower_bound(const uint32_t *ev, int n, uint32_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ev[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// event index of the p-th (0-based) event that starts a bin at `level`; warp-uniform
+__device__ __forceinline__ int mw_select_head(const uint32_t *ev, int n, int level, int p, int lane)
+{
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int i = c0 + lane;
+        bool head = false;
+        if (i < n) head = (i == 0) || ((((ev[i] ^ ev[i - 1]) >> kCountBits) >> level) != 0u);
+        const unsigned mk = __ballot_sync(kFull, head);
+        const int c = __popc(mk);
+        if (p < base + c) return c0 + (int)__fns(mk, 0, p - base + 1);
+        base += c;
+    }
+    return n - 1;
+}
+
+// value the reference sees in slot p of its vector at `level`; warp-uniform
+__device__ __forceinline__ int mw_key_at(const uint32_t *ev, int n, const uint32_t *nlive, int level, int p, int lane)
+{
+    int lv = level;
+    if (p >= (int)nlive[level]) {
+        lv = level - 1;
+        while (lv > 0 && (int)nlive[lv] <= p) lv--;
+    }
+    const int i = mw_select_head(ev, n, lv, p, lane);
+    return (int)((ev[i] >> kCountBits) >> lv);
+}
+
+// threshold key K*: targets with key >= K* are never found by the reference's search
+__device__ __forceinline__ int mw_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level, int lane)
+{
+    const int nl = (int)nlive[level];
+    int first = 0, len = n;
+    int curmin = kInf;
+    while (len > 0) {
+        const int half = len >> 1;
+        const int mid = first + half;
+        if (mid >= nl) {
+            curmin = min(curmin, mw_key_at(ev, n, nlive, level, mid, lane));
+            len = half;
+        } else {
+            if (curmin != kInf && mw_key_at(ev, n, nlive, level, mid, lane) > curmin) {
+                const int k1 = mw_key_at(ev, n, nlive, level, first, lane);
+                const int j = mw_lower_bound(ev, n, ((uint32_t)(curmin + 1) << level) << kCountBits);
+                const int k2 = j < n ? (int)((ev[j] >> kCountBits) >> level) : kInf;
+                return max(k1, k2);
+            }
+            first = mid + 1;
+            len = len - half - 1;
+        }
+    }
+    return kInf;
+}
+
+template <int DPL, bool COMPAT>
+__global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArgs m)
+{
+    constexpr int LG = DPL == 8 ? 3 : 2;
+    constexpr int LO = DPL + 1;
+    extern __shared__ __align__(16) uint32_t mw_smem[];
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len = a.slice_len[s];
+    if (len > m.len_cap) {  // CTA-uniform
+        if (tid == 0) m.fallback[s] = 1;
+        return;
+    }
+    uint32_t *evT = mw_smem;                              // [32][pitch_e]
+    uint32_t *outS = evT + 32 * m.pitch_e;                // [3][32][pitch_t]
+    uint32_t *wsm = outS + 3 * 32 * m.pitch_t + warp * m.warp_words;
+    uint32_t *ps = wsm;                                   // [len_cap + 1]
+    uint32_t *bw = ps + (m.len_cap + 1);                  // [2 * len_cap + 64] words = 16-bit bins
+    unsigned short *bh = reinterpret_cast<unsigned short *>(bw);
+    uint32_t *tb = bw + 2 * m.len_cap + 64;
+    uint32_t *tot = tb, *flim = tb + 32, *cnts = tb + 64, *cntml = tb + 96, *nlive = tb + 128, *sminS = tb + 160;
+
+    const int F = a.sched.frames;
+    const int nl = a.sched.n_levels;
+    const int T = m.T;
+    const int cnt0 = a.sched.count[0];
+    const int lo0 = a.sched.lo[0];
+
+    // ---- phase 0: slice tile -> row-major shared memory (lane = row on the way in)
+    const int my_len = a.row_len[s * kSlice + lane];
+    {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane;
+        uint32_t *dst = evT + lane * m.pitch_e;
+#pragma unroll 4
+        for (int j = warp; j < len; j += kMwWarps)
+            if (j < my_len) dst[j] = g[(int64_t)j * kSlice];
+    }
+    __syncthreads();
+
+    for (int rr = warp; rr < kSlice; rr += kMwWarps) {
+        const int n = __shfl_sync(kFull, my_len, rr);
+        const uint32_t *ev = evT + rr * m.pitch_e;
+        uint32_t *H = outS + rr * m.pitch_t;              // G2 numerators, later the G2 floats
+        uint32_t *oIP = H + 32 * m.pitch_t;
+        uint32_t *oIF = oIP + 32 * m.pitch_t;
+
+        // ---- phase 1: prefix sums of the counts, merge-level histogram
+        for (int t = lane; t < T; t += 32) H[t] = 0u;
+        if (COMPAT) cntml[lane] = 0u;
+        if (lane == 0) ps[0] = 0u;
+        __syncwarp();
+        uint32_t carry = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int i = c0 + lane;
+            const uint32_t w = i < n ? ev[i] : 0u;
+            uint32_t x = w & ((1u << kCountBits) - 1u);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, x, o);
+                if (lane >= o) x += y;
+            }
+            if (i < n) ps[i + 1] = carry + x;
+            carry += __shfl_sync(kFull, x, 31);
+            if (COMPAT && i >= 1 && i < n) {
+                const int ml = 32 - __clz((int)((w ^ ev[i - 1]) >> kCountBits));
+                atomicAdd(&cntml[ml], 1u);
+            }
+        }
+        if (carry >= 65536u) {  // 32-bit numerators could overflow: the lane-per-row kernel redoes the slice
+            if (lane == 0) m.fallback[s] = 1;
+            continue;
+        }
+        __syncwarp();
+
+        // first dense level: L_l <= 4 n
+        int ld;
+        {
+            const unsigned mk = __ballot_sync(kFull, lane >= 1 && lane < nl && (F >> lane) <= 4 * max(n, 1));
+            ld = mk ? (__ffs(mk) - 1) : nl;
+        }
+
+        // ---- phase 2: per-level tables (lane = level)
+        {
+            const int l = lane;
+            const bool lv_ok = l < nl;
+            const int Ll = lv_ok ? (F >> l) : 0;
+            const int liml = lv_ok ? (Ll << l) : 0;
+            const int cnt_l = lv_ok ? a.sched.count[l] : 0;
+            tot[l] = ps[mw_lower_bound(ev, n, (uint32_t)liml << kCountBits)];
+            cnts[l] = (l < ld) ? (uint32_t)cnt_l : 0u;
+            uint32_t fl = (l < ld) ? (uint32_t)liml : 0u;
+            if (COMPAT) {
+                uint32_t ab = cntml[l];  // events that are not the first of their bin from level ml on
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, ab, o);
+                    if (lane >= o) ab += y;
+                }
+                const int dropped = (n > 0 && lv_ok && (int)((ev[n - 1] >> kCountBits) >> l) >= Ll) ? 1 : 0;
+                const int nv = n - (int)ab - dropped;
+                int prev = __shfl_up_sync(kFull, nv, 1);
+                if (lane == 0) prev = n;
+                int sb = kInf;
+                if (l >= 1 && lv_ok && nv < prev) sb = (int)((ev[nv] >> kCountBits) >> (l - 1));
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(kFull, sb, o);
+                    if (lane >= o) sb = min(sb, y);
+                }
+                nlive[l] = (uint32_t)nv;
+                sminS[l] = (uint32_t)sb;
+                __syncwarp();
+                const bool fire = l >= 1 && l < ld && cnt_l > 0 && nv < n && sb < Ll;
+                unsigned mk = __ballot_sync(kFull, fire);
+                while (mk) {
+                    const int lv = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int ks = mw_stale_threshold(ev, n, nlive, lv, lane);
+                    if (lane == lv && ks != kInf) fl = min(fl, (uint32_t)ks << lv);
+                }
+            }
+            flim[l] = fl;
+        }
+        __syncwarp();
+
+        // ---- phase 3: sparse levels, one pass over event pairs
+        {
+            const uint32_t dmax = (uint32_t)(2 * DPL + 1) << (ld - 1);
+            const uint32_t top0 = (uint32_t)(lo0 + cnt0 - 1);
+            const uint32_t flim0 = flim[0];
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int i = c0 + lane;
+                const uint32_t wi = i < n ? ev[i] : 0u;
+                const uint32_t fi = wi >> kCountBits, ci = wi & ((1u << kCountBits) - 1u);
+                for (int k = 1;; k++) {
+                    const int j = i + k;
+                    const uint32_t wj = j < n ? ev[j] : 0xffffffffu;
+                    const uint32_t fj = wj >> kCountBits;
+                    const uint32_t d = fj - fi;
+                    const bool act = j < n && d < dmax;
+                    if (!__any_sync(kFull, act)) break;
+                    if (act) {
+                        const uint32_t cc = ci * (wj & ((1u << kCountBits) - 1u));
+                        if (d <= top0 && d >= (uint32_t)lo0 && fj < flim0) atomicAdd(&H[d - lo0], cc);
+                        if (d >= 2u * DPL) {
+                            const int l0 = (32 - __clz((int)d)) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
+                            const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
+                            if (b0 < cnts[l0] && fj < flim[l0]) atomicAdd(&H[cnt0 + (l0 - 1) * DPL + b0], cc);
+                            const int l1 = l0 - 1;
+                            if (l1 >= 1) {
+                                const uint32_t b1 = (fj >> l1) - (fi >> l1);
+                                if (b1 == 2u * DPL && (uint32_t)(DPL - 1) < cnts[l1] && fj < flim[l1])
+                                    atomicAdd(&H[cnt0 + (l1 - 1) * DPL + (DPL - 1)], cc);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- phase 4: dense levels, 16-bit bin arrays
+        if (ld < nl) {
+            int smin_run = COMPAT ? (int)sminS[ld] : kInf;
+            for (int l = ld; l < nl; l++) {
+                const int cnt_l = a.sched.count[l];
+                if (cnt_l == 0) break;
+                const int Ll = F >> l;
+                if (l == ld) {
+                    const int words = (Ll + 64) >> 1;
+                    for (int t = lane; t < words; t += 32) bw[t] = 0u;
+                    __syncwarp();
+                    const uint32_t liml = (uint32_t)Ll << l;
+                    for (int c0 = 0; c0 < n; c0 += 32) {
+                        const int i = c0 + lane;
+                        if (i < n) {
+                            const uint32_t w = ev[i];
+                            const uint32_t f = w >> kCountBits;
+                            if (f < liml) {
+                                const uint32_t key = f >> l;
+                                atomicAdd(&bw[key >> 1], (w & ((1u << kCountBits) - 1u)) << ((key & 1u) * 16u));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    // B_l[t] = B_{l-1}[2t] + B_{l-1}[2t+1]; the key of the occupied level-(l-1) bin of rank
+                    // n_l is the first stale slot this level leaves behind (compat)
+                    const int want = COMPAT ? (int)nlive[l] : 0;
+                    const bool track = COMPAT && nlive[l] < nlive[l - 1];
+                    int base = 0, cand = kInf;
+                    for (int t0 = 0; t0 < Ll + 48; t0 += 32) {
+                        const int t = t0 + lane;
+                        const uint32_t word = t < Ll ? bw[t] : 0u;
+                        const uint32_t vlo = word & 0xffffu, vhi = word >> 16;
+                        if (track) {
+                            const unsigned mlo = __ballot_sync(kFull, vlo != 0u), mhi = __ballot_sync(kFull, vhi != 0u);
+                            const int c = __popc(mlo) + __popc(mhi);
+                            if (want >= base && want < base + c) {
+                                const unsigned lt = (1u << lane) - 1u;
+                                const int rk = base + __popc(mlo & lt) + __popc(mhi & lt);
+                                int mine = kInf;
+                                if (vlo != 0u && rk == want) mine = 2 * t;
+                                if (vhi != 0u && rk + (vlo != 0u ? 1 : 0) == want) mine = 2 * t + 1;
+                                cand = min(cand, __reduce_min_sync(kFull, mine));
+                            }
+                            base += c;
+                        }
+                        __syncwarp();
+                        bh[t] = (unsigned short)(vlo + vhi);
+                        __syncwarp();
+                    }
+                    if (track) smin_run = min(smin_run, cand);
+                }
+                int klim = Ll;
+                if (COMPAT && (int)nlive[l] < n && smin_run < Ll) klim = min(Ll, mw_stale_threshold(ev, n, nlive, l, lane));
+                uint32_t acc[DPL];
+#pragma unroll
+                for (int k = 0; k < DPL; k++) acc[k] = 0u;
+                if (klim == Ll) {
+                    for (int t0 = 0; t0 < Ll - LO; t0 += 32) {
+                        const int t = t0 + lane;
+                        const uint32_t x = bh[t];
+#pragma unroll
+                        for (int k = 0; k < DPL; k++) acc[k] += x * (uint32_t)bh[t + LO + k];
+                    }
+                } else {
+                    for (int t0 = 0; t0 < klim - LO; t0 += 32) {
+                        const int t = t0 + lane;
+                        const uint32_t x = bh[t];
+#pragma unroll
+                        for (int k = 0; k < DPL; k++)
+                            if (t + LO + k < klim) acc[k] += x * (uint32_t)bh[t + LO + k];
+                    }
+                }
+                uint32_t mine = 0u;
+#pragma unroll
+                for (int k = 0; k < DPL; k++) {
+                    const uint32_t sum = __reduce_add_sync(kFull, acc[k]);
+                    if (lane == k) mine = sum;
+                }
+                if (lane < cnt_l) H[cnt0 + (l - 1) * DPL + lane] = mine;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 5: one IEEE division per output (lane = delay)
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int ti = t0 + lane;
+            if (ti < T) {
+                int l, tp;
+                if (ti < cnt0) {
+                    l = 0;
+                    tp = lo0 + ti;
+                } else {
+                    const int q = ti - cnt0;
+                    l = 1 + q / DPL;
+                    tp = LO + q % DPL;
+                }
+                const int Ll = F >> l;
+                const int neff = Ll - tp;
+                const float s2 = mw_pow2_neg(2 * l), s1 = mw_pow2_neg(l);
+                const uint32_t num = H[ti];
+                const uint32_t ipn = ps[mw_lower_bound(ev, n, ((uint32_t)max(neff, 0) << l) << kCountBits)];
+                const uint32_t ifn = tot[l] - ps[mw_lower_bound(ev, n, ((uint32_t)tp << l) << kCountBits)];
+                H[ti] = __float_as_uint(mw_scaled_div((float)num * s2, neff));
+                oIP[ti] = __float_as_uint(mw_scaled_div((float)ipn * s1, neff));
+                oIF[ti] = __float_as_uint(mw_scaled_div((float)ifn * s1, neff));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- results: [3][32 rows][T] stage -> [T][R_pad], one 128-byte line per (array, delay)
+    {
+        float *dst[3] = {a.G2, a.IP, a.IF};
+        const int64_t r0 = (int64_t)s * kSlice + lane;
+#pragma unroll
+        for (int arr = 0; arr < 3; arr++) {
+            const uint32_t *src = outS + arr * 32 * m.pitch_t + lane * m.pitch_t;
+            float *d = dst[arr] + r0;
+            for (int t = warp; t < T; t += kMwWarps) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
+        }
+    }
+}
+
+// The warp kernel covers: integer counts, dpl 4 or 8, frames below 2^20, and the regular
+// schedule (level 0: delays 1.., level l >= 1: dpl+1..2dpl, no gaps).
+bool multitau_warp_eligible(const xpcs_handle_s *h)
+{
+    if (h->kind != kPacked) return false;
+    const int dpl = h->prm.delays_per_level;
+    if (dpl != 4 && dpl != 8) return false;
+    const Sched &sc = h->sched;
+    if (sc.frames >= (1 << (32 - kCountBits)) || sc.n_levels > 24 || sc.n_levels < 1) return false;
+    if (sc.count[0] < 1 || sc.lo[0] != 1 || sc.first[0] != 0) return false;
+    bool ended = false;
+    for (int l = 1; l < sc.n_levels; l++) {
+        if (sc.count[l] == 0) {
+            ended = true;
+            continue;
+        }
+        if (ended) return false;
+        if (sc.lo[l] != dpl + 1 || sc.first[l] != sc.count[0] + (l - 1) * dpl || sc.count[l] > dpl) return false;
+        if (l + 1 < sc.n_levels && sc.count[l + 1] > 0 && sc.count[l] != dpl) return false;
+    }
+    return true;
+}
+
+template <int DPL, bool COMPAT>
+static int run_warp(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes)
+{
+    int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau_warp<DPL, COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)bytes), "multitau_warp smem attr");
+    if (rc) return rc;
+    LaunchScope ls(h, "k_multitau_warp");
+    k_multitau_warp<DPL, COMPAT><<<h->n_slices, kMwWarps * 32, bytes, h->stream>>>(a, m);
+    return XPCS_OK;
+}
+
+int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
+{
+    int rc = ensure(h, h->d_mt_fallback, (size_t)(h->n_slices > 0 ? h->n_slices : 1), "multitau fallback flags");
+    if (rc) return rc;
+    cudaMemsetAsync(h->d_mt_fallback.p, 0, (size_t)(h->n_slices > 0 ? h->n_slices : 1), h->stream);
+    if (h->n_slices == 0) return XPCS_OK;
+    int smem_cap = 0;
+    cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    MwArgs m{};
+    m.fallback = h->d_mt_fallback.p;
+    m.T = h->T;
+    m.pitch_t = h->T | 1;
+    const size_t out_bytes = (size_t)3 * 32 * m.pitch_t * 4;
+    // bytes(len) = out + 4 * (32 * (len | 1) + warps * (3 len + 65 + tables)); two CTAs per SM when the
+    // longest row allows it, one otherwise; longer slices go to the lane-per-row kernel
+    auto bytes_for = [&](int len) {
+        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)kMwWarps * (3 * (size_t)len + 65 + kMwTables));
+    };
+    const size_t budget2 = (size_t)(smem_cap + 1024) / 2 - 1024 - 512;  // two resident CTAs (1 KB reserved each)
+    int len_cap = h->max_row > 0 ? h->max_row : 1;
+    if (bytes_for(len_cap) > budget2) {
+        const size_t budget1 = (size_t)smem_cap - 512;
+        while (len_cap > 1 && bytes_for(len_cap) > budget1) len_cap = len_cap * 3 / 4;
+    }
+    if (bytes_for(len_cap) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
+        cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
+        return XPCS_OK;
+    }
+    m.len_cap = len_cap;
+    m.pitch_e = len_cap | 1;
+    m.warp_words = 3 * len_cap + 65 + kMwTables;
+    const size_t bytes = bytes_for(len_cap);
+    const bool compat = a.compat != 0;
+    const int dpl = h->prm.delays_per_level;
+    if (dpl == 8) rc = compat ? run_warp<8, true>(h, a, m, bytes) : run_warp<8, false>(h, a, m, bytes);
+    else rc = compat ? run_warp<4, true>(h, a, m, bytes) : run_warp<4, false>(h, a, m, bytes);
+    if (rc) return rc;
+    return check_cuda(h, cudaGetLastError(), "k_multitau_warp");
+}
+
+}  // namespace xpcs

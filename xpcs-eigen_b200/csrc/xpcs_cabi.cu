@@ -414,7 +414,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
     release(h->d_block_first); release(h->d_store); release(h->d_summary); release(h->d_frame_acc);
     release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
-    release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch);
+    release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch); release(h->d_mt_fallback);
     release(h->d_tt_hi); release(h->d_tt_lo); release(h->d_tt_C); release(h->d_tt_sg); release(h->d_tt_out);
     release(h->d_tt_sgint); release(h->d_tt_diag);
     if (h->stage) cudaFreeHost(h->stage);
@@ -806,6 +806,19 @@ extern "C" int xpcs_kernel_timing(xpcs_handle h, int enable)
 }
 
 extern "C" int64_t xpcs_launch_count(xpcs_handle h) { return h ? h->launches : -1; }
+
+extern "C" int64_t xpcs_multitau_fallback_slices(xpcs_handle h)
+{
+    if (!h || !h->multitau_done || !h->mt_warp_ran) return -1;
+    cudaSetDevice(h->device);
+    std::vector<unsigned char> f((size_t)h->n_slices);
+    if (h->n_slices == 0) return 0;
+    cudaStreamSynchronize(h->stream);
+    if (cudaMemcpy(f.data(), h->d_mt_fallback.p, f.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t n = 0;
+    for (unsigned char c : f) n += c ? 1 : 0;
+    return n;
+}
 
 static void drain_events(xpcs_handle_s *h)
 {
