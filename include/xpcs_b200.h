@@ -42,6 +42,9 @@ extern "C" {
                                           every slice instead of the warp-per-row one (both are
                                           exact on integer counts; used by the parity tests to
                                           cross-check the two).                              */
+#define XPCS_FLAG_SCALAR_DENSE 0x200u  /* diagnostics: run the scalar dense-filter kernel (the one
+                                          used for detectors whose pixel count is not a multiple
+                                          of 8) instead of the vectorised one.                */
 
 typedef struct xpcs_handle_s *xpcs_handle;
 

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libxpcs_b200.so")
 
 XPCS_COMPAT_STALE_TAIL = 1
 XPCS_FLAG_LANE_MULTITAU = 0x100
+XPCS_FLAG_SCALAR_DENSE = 0x200
 
 
 class XpcsError(RuntimeError):

@@ -16,6 +16,9 @@
 //               kFloat   uint64  (frame << 32) | float bits
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace xpcs {
@@ -293,6 +296,8 @@ struct FinalizeArgs {
     const float *frame_scale;  // nullptr unless normalize_by_framesum
     long long *summary;
     int n_slices, S, swindow, avg, smem_len;
+    unsigned char *flagged;  // warp-per-row kernel: slices it leaves; lane-per-row kernel: only those (nullptr = all)
+    int row_cap, window;     // warp-per-row kernel: longest row it takes, first ranking window
 };
 
 template <int KIND>
@@ -314,6 +319,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     const int s = blockIdx.x;
     const int lane = threadIdx.x;
     const int r = s * kSlice + lane;
+    if (a.flagged && !a.flagged[s]) return;  // done by k_finalize_warp
     const int len = a.slice_len[s];
     if (len == 0) {
         a.row_sum[r] = 0.0;
@@ -428,6 +434,147 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
         __syncwarp();
         for (int j = 0; j < len; j++)
             if (j < m) g[(int64_t)j * kSlice] = col[j * kSlice];
+    }
+}
+
+// ---- warp-per-row finalisation (long rows) ---------------------------------------------------
+// Same job as k_finalize, organised for rows of hundreds of events, where a whole slice per
+// lane-per-row warp no longer fits shared memory at a useful occupancy: a CTA owns a slice,
+// each warp takes rows in turn into a private double buffer.  The scatter leaves a row nearly
+// sorted (atomics of concurrently running CTAs only swap neighbours), so the sort is a ranking
+// pass over a +-window neighbourhood, position = index - (larger words before) + (smaller words
+// after), checked afterwards (the target buffer is pre-filled with a sentinel: a collision
+// leaves a hole, a hole or an inversion fails the check) and redone over the whole row when the
+// window was too small -- with the whole row as window the formula is the stable rank, always a
+// permutation.  Merging, /avg, frame-sum scaling and the sums run lanes-over-events with
+// ballot compaction and a segmented scan per static window.
+constexpr int kFwWarps = 16;
+
+template <int KIND>
+__global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
+{
+    typedef typename WordT<KIND>::type W;
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len = a.slice_len[s];
+    if (len > a.row_cap) {  // CTA-uniform: the lane-per-row kernel works this slice in global memory
+        if (tid == 0) a.flagged[s] = 1;
+        return;
+    }
+    if (len == 0) {
+        if (tid < kSlice) a.row_sum[s * kSlice + tid] = 0.0;
+        return;
+    }
+    const W kMaxW = ~(W)0;
+    W *bufA = reinterpret_cast<W *>(fw_smem) + (size_t)warp * 2 * a.row_cap;
+    W *bufB = bufA + a.row_cap;
+    constexpr int kShift = KIND == kPacked ? kCountBits : 32;
+
+    for (int rr = warp; rr < kSlice; rr += kFwWarps) {
+        const int r = s * kSlice + rr;
+        const int n = a.row_len[r];
+        W *g = reinterpret_cast<W *>(a.store) + a.slice_base[s] + rr;
+        W *A = bufA, *B = bufB;
+        for (int j = lane; j < n; j += 32) A[j] = g[(int64_t)j * kSlice];
+        __syncwarp();
+        // ---- sort by (frame, value bits)
+        bool sorted = true;
+        for (int i = lane; i + 1 < n; i += 32) sorted = sorted && !(A[i] > A[i + 1]);
+        if (!__all_sync(0xffffffffu, sorted)) {
+            int D = n > 4 * a.window ? a.window : n;
+            for (;;) {
+                for (int j = lane; j < n; j += 32) B[j] = kMaxW;
+                __syncwarp();
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    const int i = c0 + lane;
+                    if (i < n) {
+                        const W key = A[i];
+                        int pos = i;
+                        const int lo = max(0, i - D), hi = min(n - 1, i + D);
+                        for (int j = lo; j < i; j++) pos -= A[j] > key ? 1 : 0;
+                        for (int j = i + 1; j <= hi; j++) pos += A[j] < key ? 1 : 0;
+                        B[pos] = key;
+                    }
+                }
+                __syncwarp();
+                bool ok = true;
+                for (int i = lane; i < n; i += 32) ok = ok && B[i] != kMaxW && (i + 1 >= n || !(B[i] > B[i + 1]));
+                if (__all_sync(0xffffffffu, ok) || D >= n) break;
+                D = n;
+                __syncwarp();
+            }
+            W *t = A;
+            A = B;
+            B = t;
+        }
+        __syncwarp();
+        // ---- merge equal frames, /avg, frame-sum scaling, sums; compacted row goes to B
+        const int sb = a.sbin_of_row[r];
+        int m_base = 0;
+        double tot = 0.0;
+        long long itot = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int i = c0 + lane;
+            const bool valid = i < n;
+            const W w = valid ? A[i] : kMaxW;
+            const uint32_t key = (uint32_t)(w >> kShift);
+            const bool head = valid && (i == 0 || (uint32_t)(A[i - 1] >> kShift) != key);
+            W outw = w;
+            double v = 0.0;
+            if (head) {
+                if (KIND == kPacked) {
+                    uint32_t c = (uint32_t)w & ((1u << kCountBits) - 1u);
+                    for (int k = i + 1; k < n && (uint32_t)(A[k] >> kShift) == key; k++)
+                        c += (uint32_t)A[k] & ((1u << kCountBits) - 1u);
+                    if (c >= (1u << kCountBits)) a.summary[kSumOverflow] = 1;
+                    outw = (W)((key << kCountBits) | (c & ((1u << kCountBits) - 1u)));
+                    itot += c;
+                    v = (double)c;
+                } else {
+                    float x = __uint_as_float((uint32_t)w);
+                    for (int k = i + 1; k < n && (uint32_t)(A[k] >> kShift) == key; k++)
+                        x = __fadd_rn(x, __uint_as_float((uint32_t)A[k]));
+                    if (a.avg > 1) x = __fdiv_rn(x, (float)a.avg);
+                    tot += (double)x;
+                    v = (double)x;
+                    if (a.frame_scale) x = __fdiv_rn(x, a.frame_scale[key]);
+                    outw = (W)(((unsigned long long)key << 32) | (unsigned long long)__float_as_uint(x));
+                }
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, head);
+            if (head) B[m_base + __popc(mk & ((1u << lane) - 1u))] = outw;
+            m_base += __popc(mk);
+            // per-static-window sums: the frames ascend, so a window is a run of lanes
+            int wi = valid ? (int)(key / (uint32_t)a.swindow) : 0x7fffffff;
+            double x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, x, o);
+                const int wo = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o && wo == wi) x += y;
+            }
+            const int wn = __shfl_down_sync(0xffffffffu, wi, 1);
+            if (valid && sb >= 0 && (lane == 31 || wn != wi) && x != 0.0)
+                atomicAdd(a.part_partial + (int64_t)wi * a.S + sb, x);
+        }
+        __syncwarp();
+        for (int j = lane; j < m_base; j += 32) g[(int64_t)j * kSlice] = B[j];
+        double total;
+        if (KIND == kPacked) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) itot += __shfl_xor_sync(0xffffffffu, itot, o);
+            total = (double)itot;
+        } else {
+            total = warp_sum(tot);
+            total = (double)(float)total;
+        }
+        if (lane == 0) {
+            a.row_sum[r] = total;
+            a.row_len[r] = m_base;
+            if (sb >= 0 && m_base > 0) atomicAdd(a.part_total + sb, total);
+        }
+        __syncwarp();
     }
 }
 
@@ -601,6 +748,201 @@ __global__ void __launch_bounds__(kDfThreads) k_dense_filter(DenseArgs a)
     }
 }
 
+// ---- vectorised dense filter ------------------------------------------------------------
+// dense_filter.cpp:150-174 again, arranged so that the 2 bytes per sample are all that moves:
+// the whole test (dark subtraction in fp64, clamp, lld + sigma*std) is monotone in the raw
+// int16 value, so it collapses, per pixel, into one int16 bound: a sample survives iff
+// raw > bound.  k_dense_bounds finds that bound by bisection over the 65536 raw values with
+// the very arithmetic of the reference; the hot loop then compares eight samples per 16-byte
+// load with four SIMD halfword compares and only the survivors (a few percent) take the exact
+// path that recomputes their value.  Each thread keeps kDvGroup independent 16-byte loads in
+// flight; a CTA covers 1024 pixels x kDvFrames frames and appends its survivors through a
+// shared-memory stage (one global atomic per flush, coalesced stores).
+constexpr int kDvThreads = 128;
+constexpr int kDvPix = 8;            // pixels per thread (one 16-byte load)
+constexpr int kDvGroup = 8;          // frames in flight per thread
+constexpr int kDvFrames = 64;        // frames per CTA
+constexpr int kDvCap = 2048;         // staged survivors per CTA
+
+__device__ __forceinline__ bool dense_sample(short raw, bool have_dark, double davg, float thresh, float &v)
+{
+    v = (float)raw;
+    if (have_dark) {
+        v = (float)__dsub_rn((double)v, davg);
+        v = fmaxf(v, 0.0f);
+    }
+    return !(v <= thresh);
+}
+
+// bound[j]: survive iff raw > bound[j]; every[g] != 0 when a pixel of the 8-pixel group g lets
+// even raw = -32768 through (the bound would be -32769), which sends the group down the exact path.
+__global__ void k_dense_bounds(int P, const int *__restrict__ row_of_pixel, const double *__restrict__ dark_avg,
+                               const double *__restrict__ dark_std, float lld, float sigma,
+                               int16_t *__restrict__ bound, unsigned char *__restrict__ every)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g * kDvPix >= P) return;
+    unsigned char ev = 0;
+    for (int k = 0; k < kDvPix; k++) {
+        const int j = g * kDvPix + k;
+        if (j >= P) break;
+        int b = 32767;
+        if (row_of_pixel[j] >= 0) {
+            const bool hd = dark_avg != nullptr;
+            const double davg = hd ? dark_avg[j] : 0.0;
+            const float thresh = hd ? (float)__dadd_rn((double)lld, __dmul_rn((double)sigma, dark_std[j])) : 0.0f;
+            int lo = -32768, hi = 32768;  // smallest surviving raw value lies in [lo, hi]; hi = none
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                float v;
+                if (dense_sample((short)mid, hd, davg, thresh, v)) hi = mid;
+                else lo = mid + 1;
+            }
+            if (lo == -32768) {
+                ev = 1;
+                b = -32768;
+            } else b = lo - 1;
+        }
+        bound[j] = (int16_t)b;
+    }
+    every[g] = ev;
+}
+
+__global__ void __launch_bounds__(kDvThreads) k_dense_filter_vec(DenseArgs a, const int16_t *__restrict__ bound,
+                                                                  const unsigned char *__restrict__ every)
+{
+    // candidates: pixel, (frame slot << 16 | raw); their values are worked out at flush time,
+    // where the per-pixel constants are fetched by all threads at once instead of one
+    // dependent chain per survivor inside the streaming loop
+    __shared__ int s_pix[kDvCap];
+    __shared__ int s_sr[kDvCap];
+    __shared__ float s_v[kDvCap];
+    __shared__ double s_fsum[kDvFrames];
+    __shared__ int s_count, s_pass, s_cursor;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = blockIdx.x * kDvThreads + tid;
+    const int j0 = g * kDvPix;
+    const bool active = j0 < a.P;
+    const int f_begin = blockIdx.y * kDvFrames;
+    const int f_end = min(a.nframes, f_begin + kDvFrames);
+    if (tid == 0) s_count = 0;
+    for (int i = tid; i < kDvFrames; i += kDvThreads) s_fsum[i] = 0.0;
+    uint4 bd = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
+    bool all_pass = false;
+    if (active) {
+        bd = *reinterpret_cast<const uint4 *>(bound + j0);
+        all_pass = every[g] != 0;
+    }
+    const bool have_dark = a.dark_avg != nullptr;
+    __syncthreads();
+
+    // exact test and value of one sample (dense_filter.cpp:150-174)
+    auto exact = [&](int j, short raw, float &v) -> bool {
+        if (a.row_of_pixel[j] < 0) return false;
+        const double davg = have_dark ? a.dark_avg[j] : 0.0;
+        const float thresh =
+            have_dark ? (float)__dadd_rn((double)a.lld, __dmul_rn((double)a.sigma, a.dark_std[j])) : 0.0f;
+        if (!dense_sample(raw, have_dark, davg, thresh, v)) return false;
+        v = (float)__dmul_rn((double)v, a.flat[j]);
+        return true;
+    };
+
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const int n = min(s_count, kDvCap);
+        if (tid == 0) { s_pass = 0; s_cursor = 0; }
+        __syncthreads();
+        for (int i = tid; i < n; i += kDvThreads) {
+            const int j = s_pix[i];
+            const int sr = s_sr[i];
+            float v;
+            if (exact(j, (short)(sr & 0xffff), v)) {
+                s_v[i] = v;
+                atomicAdd(&s_fsum[sr >> 16], (double)v);
+                atomicAdd(&s_pass, 1);
+            } else s_pix[i] = -1;
+        }
+        __syncthreads();
+        if (tid == 0) s_base = atomicAdd(a.counter, (unsigned long long)s_pass);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (int i0 = 0; i0 < n; i0 += kDvThreads) {  // warp-uniform trip count
+            const int i = i0 + tid;
+            const bool ok = i < n && s_pix[i] >= 0;
+            const unsigned mk = __ballot_sync(0xffffffffu, ok);
+            int wbase = 0;
+            if (lane == 0 && mk) wbase = atomicAdd(&s_cursor, __popc(mk));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (ok) {
+                const unsigned long long pos = base + wbase + __popc(mk & ((1u << lane) - 1u));
+                if (pos < a.capacity) {
+                    a.out_idx[pos] = s_pix[i];
+                    a.out_t[pos] = out_frame(a.first_raw + f_begin + (s_sr[i] >> 16), a.rawblock, a.stride, a.F);
+                    a.out_v[pos] = s_v[i];
+                } else a.summary[kSumOverflow] = 2;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+    };
+
+    auto push = [&](int j, unsigned raw16, int slot) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kDvCap) {
+            s_pix[pos] = j;
+            s_sr[pos] = (slot << 16) | (int)raw16;
+        } else {  // stage full (nearly every sample survives): settle it here and append directly
+            float v;
+            if (exact(j, (short)raw16, v)) {
+                atomicAdd(&s_fsum[slot], (double)v);
+                const unsigned long long gp = atomicAdd(a.counter, 1ull);
+                if (gp < a.capacity) {
+                    a.out_idx[gp] = j;
+                    a.out_t[gp] = out_frame(a.first_raw + f_begin + slot, a.rawblock, a.stride, a.F);
+                    a.out_v[gp] = v;
+                } else a.summary[kSumOverflow] = 2;
+            }
+        }
+    };
+
+    for (int f0 = f_begin; f0 < f_end; f0 += kDvGroup) {
+        uint4 rw[kDvGroup];
+#pragma unroll
+        for (int u = 0; u < kDvGroup; u++) {
+            rw[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+            if (active && f0 + u < f_end)
+                rw[u] = __ldcs(reinterpret_cast<const uint4 *>(a.frames + (int64_t)(f0 + u) * a.P + j0));
+        }
+#pragma unroll
+        for (int u = 0; u < kDvGroup; u++) {
+            const int fr = f0 + u;
+            if (fr >= f_end || !active) continue;
+            unsigned h0 = __vcmpgts2(rw[u].x, bd.x), h1 = __vcmpgts2(rw[u].y, bd.y);
+            unsigned h2 = __vcmpgts2(rw[u].z, bd.z), h3 = __vcmpgts2(rw[u].w, bd.w);
+            if (all_pass) h0 = h1 = h2 = h3 = 0xffffffffu;
+            if ((h0 | h1 | h2 | h3) == 0u) continue;
+            if (out_frame(a.first_raw + fr, a.rawblock, a.stride, a.F) < 0) continue;
+            const int slot = fr - f_begin;
+            if (h0 & 0xffffu) push(j0 + 0, rw[u].x & 0xffffu, slot);
+            if (h0 >> 16) push(j0 + 1, rw[u].x >> 16, slot);
+            if (h1 & 0xffffu) push(j0 + 2, rw[u].y & 0xffffu, slot);
+            if (h1 >> 16) push(j0 + 3, rw[u].y >> 16, slot);
+            if (h2 & 0xffffu) push(j0 + 4, rw[u].z & 0xffffu, slot);
+            if (h2 >> 16) push(j0 + 5, rw[u].z >> 16, slot);
+            if (h3 & 0xffffu) push(j0 + 6, rw[u].w & 0xffffu, slot);
+            if (h3 >> 16) push(j0 + 7, rw[u].w >> 16, slot);
+        }
+        if (__syncthreads_or(s_count > kDvCap / 2)) flush();
+    }
+    flush();
+    for (int i = tid; i < f_end - f_begin; i += kDvThreads) {
+        const int t = out_frame(a.first_raw + f_begin + i, a.rawblock, a.stride, a.F);
+        if (t >= 0 && s_fsum[i] != 0.0) atomicAdd(a.frame_acc + t, s_fsum[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------
@@ -675,18 +1017,42 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         fa.frame_scale = h->d_frame_scale.p;
     }
     const int smem_cap = max_dyn_smem(h->device) - 1024;
+    // Short rows (a slice fits 24 KB): one lane per row, the whole slice in shared memory.  Longer
+    // rows: one warp per row; slices beyond its buffers are flagged and left to the lane-per-row
+    // kernel, which then works in global memory.
+    const size_t lane_bytes_all = (size_t)h->max_row * kSlice * sizeof(W);
+    const bool use_warp = lane_bytes_all > 24 * 1024 && !getenv("XPCS_FIN_LANE");
+    fa.flagged = nullptr;
+    if (use_warp && h->n_slices > 0) {
+        rc = ensure(h, h->d_mt_fallback, (size_t)h->n_slices, "finalize flags");
+        if (rc) return rc;
+        cudaMemsetAsync(h->d_mt_fallback.p, 0, (size_t)h->n_slices, h->stream);
+        int row_cap = std::min<int>(h->max_row, (int)(smem_cap / (kFwWarps * 2 * sizeof(W))));
+        size_t wbytes = (size_t)kFwWarps * 2 * row_cap * sizeof(W);
+        fa.flagged = h->d_mt_fallback.p;
+        fa.row_cap = row_cap;
+        fa.window = 16;
+        if (const char *e = getenv("XPCS_FIN_WINDOW")) fa.window = std::max(1, atoi(e));
+        rc = check_cuda(h, cudaFuncSetAttribute(k_finalize_warp<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)wbytes), "finalize_warp smem attr");
+        if (rc) return rc;
+        LaunchScope ls(h, "k_finalize_warp");
+        k_finalize_warp<KIND><<<h->n_slices, kFwWarps * 32, wbytes, h->stream>>>(fa);
+    }
     int smem_len = h->max_row;
     size_t bytes = (size_t)smem_len * kSlice * sizeof(W);
-    if ((long long)bytes > smem_cap) {
+    if (use_warp) {  // only flagged (very long) slices arrive here: global-memory path
+        smem_len = 0;
+        bytes = 0;
+    } else if ((long long)bytes > smem_cap) {
         smem_len = (int)(smem_cap / (kSlice * sizeof(W)));
-        // keep several warps per SM when only a few slices are long
         bytes = (size_t)smem_len * kSlice * sizeof(W);
     }
     fa.smem_len = smem_len;
     rc = check_cuda(h, cudaFuncSetAttribute(k_finalize<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)bytes), "finalize smem attr");
     if (rc) return rc;
-    if (h->n_slices > 0) {
+    if (h->n_slices > 0 && (!use_warp || h->max_row > fa.row_cap)) {
         LaunchScope ls(h, "k_finalize");
         k_finalize<KIND><<<h->n_slices, 32, bytes, h->stream>>>(fa);
     }
@@ -818,8 +1184,25 @@ int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw
     a.capacity = h->d_idx.n;
     a.frame_acc = h->d_frame_acc.p;
     a.summary = h->d_summary.p;
-    dim3 grid((h->P + kDfPixels - 1) / kDfPixels, (nframes + kDfFrames - 1) / kDfFrames);
-    {
+    // vector path: whole 16-byte groups of pixels, aligned frames
+    const bool vec = (h->P % kDvPix) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15u) == 0 &&
+                     !(h->prm.compat_flags & XPCS_FLAG_SCALAR_DENSE);
+    if (vec) {
+        if (!h->dense_bounds_ready) {
+            int rc;
+            if ((rc = ensure(h, h->d_dense_bound, (size_t)h->P, "dense bounds"))) return rc;
+            if ((rc = ensure(h, h->d_dense_every, (size_t)(h->P / kDvPix), "dense bounds"))) return rc;
+            LaunchScope ls(h, "k_dense_bounds");
+            const int groups = h->P / kDvPix;
+            k_dense_bounds<<<(groups + 127) / 128, 128, 0, h->stream>>>(h->P, a.row_of_pixel, a.dark_avg, a.dark_std, a.lld,
+                                                                        a.sigma, h->d_dense_bound.p, h->d_dense_every.p);
+            h->dense_bounds_ready = true;
+        }
+        dim3 grid((h->P / kDvPix + kDvThreads - 1) / kDvThreads, (nframes + kDvFrames - 1) / kDvFrames);
+        LaunchScope ls(h, "k_dense_filter");
+        k_dense_filter_vec<<<grid, kDvThreads, 0, h->stream>>>(a, h->d_dense_bound.p, h->d_dense_every.p);
+    } else {
+        dim3 grid((h->P + kDfPixels - 1) / kDfPixels, (nframes + kDfFrames - 1) / kDfFrames);
         LaunchScope ls(h, "k_dense_filter");
         k_dense_filter<<<grid, kDfThreads, 0, h->stream>>>(a);
     }

@@ -96,6 +96,13 @@ struct xpcs_handle_s {
     // ---- dark image ----
     bool have_dark = false;
     xpcs::DevBuf<double> d_dark_avg, d_dark_std;
+    xpcs::DevBuf<int16_t> d_dense_bound;        // [P] dense filter: a sample survives iff raw > bound
+    xpcs::DevBuf<unsigned char> d_dense_every;  // [P/8] group holds a pixel that lets every raw value through
+    bool dense_bounds_ready = false;
+    // push_dense: double-buffered device staging, H2D on its own stream
+    xpcs::DevBuf<int16_t> d_dense_stage[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_filtered[2] = {nullptr, nullptr};
 
     // ---- frame-major event buffers ----
     bool dense_source = false;
@@ -208,6 +215,9 @@ int launch_unpermute(xpcs_handle_s *h, const float *d_src, float *d_dst);  // [T
 // ---- launchers (multitau_warp.cu) ----
 bool multitau_warp_eligible(const xpcs_handle_s *h);
 int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a);   // fills h->d_mt_fallback
+// ---- launchers (multitau_warpf.cu) ----
+bool multitau_warpf_eligible(const xpcs_handle_s *h);
+int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
 // ---- launchers (normalize.cu) ----
 int launch_normalize_partials(xpcs_handle_s *h);
 int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);

@@ -498,6 +498,12 @@ int launch_multitau(xpcs_handle_s *h)
         a.only_flagged = h->d_mt_fallback.p;
         h->mt_warp_ran = true;
     }
+    if (multitau_warpf_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+        // float rows: same split between the warp-per-row kernel and the lane-per-row one
+        if ((rc = launch_multitau_warpf(h, a))) return rc;
+        a.only_flagged = h->d_mt_fallback.p;
+        h->mt_warp_ran = true;
+    }
     if (h->kind == kPacked) {
         // the register-window path for dense levels is instantiated for the usual delays-per-level
         const int dpl = h->prm.delays_per_level;

@@ -408,7 +408,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
         }
     release(h->d_row_of_pixel); release(h->d_pixel_of_row); release(h->d_sbin_of_row); release(h->d_flat);
     release(h->d_lseg_row_start); release(h->d_seg_dq_all); release(h->d_seg_npix_all);
-    release(h->d_dark_avg); release(h->d_dark_std);
+    release(h->d_dark_avg); release(h->d_dark_std); release(h->d_dense_bound); release(h->d_dense_every);
     release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
     release(h->d_dense_counter);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
@@ -418,6 +418,12 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_tt_hi); release(h->d_tt_lo); release(h->d_tt_C); release(h->d_tt_sg); release(h->d_tt_out);
     release(h->d_tt_sgint); release(h->d_tt_diag);
     if (h->stage) cudaFreeHost(h->stage);
+    release(h->d_dense_stage[0]); release(h->d_dense_stage[1]);
+    for (int b = 0; b < 2; b++) {
+        if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+        if (h->ev_filtered[b]) cudaEventDestroy(h->ev_filtered[b]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -488,6 +494,7 @@ extern "C" int xpcs_set_dark(xpcs_handle h, const int16_t *frames, int n)
     if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "k_dark");
     release(tmp);
     if (!rc) h->have_dark = true;
+    h->dense_bounds_ready = false;
     return rc;
 }
 
@@ -623,21 +630,38 @@ extern "C" int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const doubl
     if (!h || !frames || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "push_dense: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
     cudaSetDevice(h->device);
-    // stage through a device buffer of at most 256 MiB, frame batches in stream order
+    // Two device staging buffers of at most 128 MiB each: batch k+1 crosses PCIe on the copy
+    // stream while the filter works on batch k on the handle's stream (events order the reuse
+    // of a buffer after the filter that read it).
     const size_t frame_bytes = sizeof(int16_t) * (size_t)h->P;
-    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, (256u << 20) / frame_bytes));
-    DevBuf<int16_t> tmp;
-    int rc = ensure(h, tmp, (size_t)batch * h->P, "dense staging");
-    if (rc) return rc;
-    const int before = h->raw_frames;
-    for (int f0 = 0; f0 < nframes && !rc; f0 += batch) {
-        const int nb = std::min(batch, nframes - f0);
-        rc = check_cuda(h, cudaMemcpyAsync(tmp.p, frames + (size_t)f0 * h->P, frame_bytes * nb, cudaMemcpyHostToDevice,
-                                           h->stream), "dense H2D");
-        if (!rc) rc = xpcs_push_dense_device(h, tmp.p, nb);
+    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, (128u << 20) / frame_bytes));
+    int rc = XPCS_OK;
+    if (!h->copy_stream) rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream");
+    for (int b = 0; b < 2 && !rc; b++) {
+        if (nframes > batch || b == 0) rc = ensure(h, h->d_dense_stage[b], (size_t)batch * h->P, "dense staging");
+        if (!rc && !h->ev_copied[b]) rc = check_cuda(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming), "event");
+        if (!rc && !h->ev_filtered[b]) rc = check_cuda(h, cudaEventCreateWithFlags(&h->ev_filtered[b], cudaEventDisableTiming), "event");
     }
-    cudaStreamSynchronize(h->stream);
-    release(tmp);
+    if (rc) return rc;
+    // the copy stream starts behind whatever the handle's stream has queued so far
+    cudaEventRecord(h->ev_filtered[0], h->stream);
+    cudaEventRecord(h->ev_filtered[1], h->stream);
+    const int before = h->raw_frames;
+    int k = 0;
+    for (int f0 = 0; f0 < nframes && !rc; f0 += batch, k++) {
+        const int nb = std::min(batch, nframes - f0);
+        const int b = k & 1;
+        cudaStreamWaitEvent(h->copy_stream, h->ev_filtered[b], 0);
+        rc = check_cuda(h, cudaMemcpyAsync(h->d_dense_stage[b].p, frames + (size_t)f0 * h->P, frame_bytes * nb,
+                                           cudaMemcpyHostToDevice, h->copy_stream), "dense H2D");
+        if (rc) break;
+        cudaEventRecord(h->ev_copied[b], h->copy_stream);
+        cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0);
+        rc = xpcs_push_dense_device(h, h->d_dense_stage[b].p, nb);
+        cudaEventRecord(h->ev_filtered[b], h->stream);
+    }
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->stream);  // the caller may reuse `frames` on return
     if (rc) return rc;
     for (int i = 0; i < nframes; i++) {
         h->ts_clock[before + i] = clock ? clock[i] : 0.0;
