@@ -70,14 +70,22 @@ def compare(got, ref, what="", check_n=True):
     assert_close(got["sums"]["part_total"], ref["part_total"], what + "partition-mean-total", rtol=AUX_RTOL)
     assert_close(got["sums"]["part_partial"], ref["part_partial"], what + "partition-mean-partial", rtol=AUX_RTOL)
     assert_close(got["g2"], ref["g2"], what + "norm-0-g2")
+    # at the last delays one bin pair is left and every pixel's G2/(IP*IF) is the same number:
+    # the reference's spread is exactly 0 there, a one-ulp difference in IP or IF makes ours ~1e-8
+    # (typical values are 1e-2); hence the absolute floor
     ok = np.isfinite(ref["se"])
-    assert_close(got["se"][ok], ref["se"][ok], what + "norm-0-stderr")
+    assert_close(got["se"][ok], ref["se"][ok], what + "norm-0-stderr", atol=1e-6)
 
 
-def make_dense(pkg, h, w, F, darks, seed, mu=0.05):
+def make_dense(pkg, h, w, F, darks, seed, mu=0.05, flat_sigma=0.05):
+    """Dark offset 100 ADU, 20 ADU per photon.  The reference subtracts dark_avg = mean(raw * flat)
+    from the un-flat-fielded raw value, so with the default 5 % flat-field spread a
+    few percent of the pixels sit above their threshold in nearly every frame: rows of thousands
+    of events next to rows of tens, which exercises the long-row paths (warp-per-row finalize,
+    lane-per-row multi-tau) alongside the short-row ones."""
     dq, sq = pkg.synth.annular_qmaps(h, w, n_dynamic=4, static_per_dynamic=3, r_min=2.0)
     fr = pkg.synth.dense_frames(h * w, F, darks=darks, mu=mu, seed=seed)
-    flat = pkg.synth.flatfield(h * w, seed=seed + 1)
+    flat = pkg.synth.flatfield(h * w, sigma=flat_sigma, seed=seed + 1)
     return dq, sq, fr[:darks], fr[darks:], flat
 
 
@@ -109,7 +117,7 @@ def test_vector_and_scalar_filters_agree_exactly(pkg):
 
 
 def test_warp_and_lane_multitau_agree_on_float_rows(pkg, oracle):
-    dq, sq, dk, data, flat = make_dense(pkg, 32, 32, 2000, 10, 8)
+    dq, sq, dk, data, flat = make_dense(pkg, 32, 32, 2000, 40, 8, flat_sigma=0.005)  # no hot pixels
     a = gpu_dense(pkg, dq, sq, 2000, data, darks=dk, flatfield=flat, lld=5.0, sigma=3.0)
     b = gpu_dense(pkg, dq, sq, 2000, data, darks=dk, flatfield=flat, lld=5.0, sigma=3.0, lane_multitau=True)
     assert a["fallback"] == 0, "the float warp-per-row kernel did not take every slice"

@@ -476,7 +476,9 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
         const int n = a.row_len[r];
         W *g = reinterpret_cast<W *>(a.store) + a.slice_base[s] + rr;
         W *A = bufA, *B = bufB;
-        for (int j = lane; j < n; j += 32) A[j] = g[(int64_t)j * kSlice];
+        // the scatter filled the row from the top down: reverse while loading so that it is close
+        // to ascending already
+        for (int j = lane; j < n; j += 32) A[n - 1 - j] = g[(int64_t)j * kSlice];
         __syncwarp();
         // ---- sort by (frame, value bits)
         bool sorted = true;
@@ -737,8 +739,8 @@ __global__ void __launch_bounds__(kDfThreads) k_dense_filter(DenseArgs a)
             if ((tid & 31) == 0 && fsum != 0.0) atomicAdd(&s_fsum[fr - f_begin], fsum);
         }
         if (((fr - f_begin) % kDfFlushEvery) == kDfFlushEvery - 1) {
-            __syncthreads();
-            if (s_count > kDfCap - kDfFlushEvery * kDfPixels) flush();
+            // the last thread to arrive reads the final count, so the OR is the exact, CTA-uniform answer
+            if (__syncthreads_or(s_count > kDfCap - kDfFlushEvery * kDfPixels)) flush();
         }
     }
     flush();
@@ -749,20 +751,24 @@ __global__ void __launch_bounds__(kDfThreads) k_dense_filter(DenseArgs a)
 }
 
 // ---- vectorised dense filter ------------------------------------------------------------
-// dense_filter.cpp:150-174 again, arranged so that the 2 bytes per sample are all that moves:
-// the whole test (dark subtraction in fp64, clamp, lld + sigma*std) is monotone in the raw
+// dense_filter.cpp:150-174 again, arranged so that the 2 bytes per sample are all that moves.
+// The whole test (dark subtraction in fp64, clamp, lld + sigma*std) is monotone in the raw
 // int16 value, so it collapses, per pixel, into one int16 bound: a sample survives iff
 // raw > bound.  k_dense_bounds finds that bound by bisection over the 65536 raw values with
-// the very arithmetic of the reference; the hot loop then compares eight samples per 16-byte
-// load with four SIMD halfword compares and only the survivors (a few percent) take the exact
-// path that recomputes their value.  Each thread keeps kDvGroup independent 16-byte loads in
-// flight; a CTA covers 1024 pixels x kDvFrames frames and appends its survivors through a
-// shared-memory stage (one global atomic per flush, coalesced stores).
+// the very arithmetic of the reference.  The streaming loop keeps kDvGroup independent
+// 16-byte loads (8 pixels x 8 frames) in flight per thread, reduces them to the per-pixel
+// maximum over the group with the 16x2 SIMD max (VIMNMX3.S16x2), compares once against the
+// bounds (VIMNMX.S16x2 with its two predicates), and only for a word whose maximum passes
+// looks at the individual frames.  Candidates (pixel, frame slot, raw) go to private
+// shared-memory slots -- no atomics in the loop; each warp settles and flushes its own
+// candidates: the exact value is computed there, with the per-pixel constants fetched by all
+// lanes at once, per-frame sums go to the CTA's shared accumulators, and the events are
+// appended with one global atomic per flush and coalesced stores.
 constexpr int kDvThreads = 128;
 constexpr int kDvPix = 8;            // pixels per thread (one 16-byte load)
 constexpr int kDvGroup = 8;          // frames in flight per thread
 constexpr int kDvFrames = 64;        // frames per CTA
-constexpr int kDvCap = 2048;         // staged survivors per CTA
+constexpr int kDvSlots = 12;         // private candidate slots per thread
 
 __device__ __forceinline__ bool dense_sample(short raw, bool have_dark, double davg, float thresh, float &v)
 {
@@ -775,7 +781,8 @@ __device__ __forceinline__ bool dense_sample(short raw, bool have_dark, double d
 }
 
 // bound[j]: survive iff raw > bound[j]; every[g] != 0 when a pixel of the 8-pixel group g lets
-// even raw = -32768 through (the bound would be -32769), which sends the group down the exact path.
+// even raw = -32768 through (the bound would be -32769), which makes every sample of the group
+// a candidate for the exact test.
 __global__ void k_dense_bounds(int P, const int *__restrict__ row_of_pixel, const double *__restrict__ dark_avg,
                                const double *__restrict__ dark_std, float lld, float sigma,
                                int16_t *__restrict__ bound, unsigned char *__restrict__ every)
@@ -808,25 +815,66 @@ __global__ void k_dense_bounds(int P, const int *__restrict__ row_of_pixel, cons
     every[g] = ev;
 }
 
-__global__ void __launch_bounds__(kDvThreads) k_dense_filter_vec(DenseArgs a, const int16_t *__restrict__ bound,
+// value of a sample that is known to survive (raw > bound[j], dense_filter.cpp:150-174): the
+// bound already stands for the mask and the threshold
+__device__ __forceinline__ float dense_value(const DenseArgs &a, int j, short raw)
+{
+    float v = (float)raw;
+    if (a.dark_avg != nullptr) {
+        v = (float)__dsub_rn((double)v, a.dark_avg[j]);
+        v = fmaxf(v, 0.0f);
+    }
+    return (float)__dmul_rn((double)v, a.flat[j]);
+}
+
+// exact test and value of one sample (dense_filter.cpp:150-174)
+__device__ __forceinline__ bool dense_exact(const DenseArgs &a, int j, short raw, float &v)
+{
+    if (a.row_of_pixel[j] < 0) return false;
+    const bool have_dark = a.dark_avg != nullptr;
+    const double davg = have_dark ? a.dark_avg[j] : 0.0;
+    const float thresh = have_dark ? (float)__dadd_rn((double)a.lld, __dmul_rn((double)a.sigma, a.dark_std[j])) : 0.0f;
+    if (!dense_sample(raw, have_dark, davg, thresh, v)) return false;
+    v = (float)__dmul_rn((double)v, a.flat[j]);
+    return true;
+}
+
+// a thread whose private slots are full (nearly every sample survives) settles the sample on
+// the spot and appends it directly; kept out of line, the streaming loop has 64 call sites
+__device__ __noinline__ void dense_settle_direct(const DenseArgs *ga, double *s_fsum, int j, unsigned raw16, int slot,
+                                                 int raw_begin)
+{
+    // ga: the launch-invariant arguments in global memory (reading the kernel parameters from
+    // an out-of-line function would cost every thread a stack copy of them)
+    const DenseArgs &a = *ga;
+    float v;
+    if (!dense_exact(a, j, (short)raw16, v)) return;
+    atomicAdd(&s_fsum[slot], (double)v);
+    const unsigned long long gp = atomicAdd(a.counter, 1ull);
+    if (gp < a.capacity) {
+        a.out_idx[gp] = j;
+        a.out_t[gp] = out_frame(raw_begin + slot, a.rawblock, a.stride, a.F);
+        a.out_v[gp] = v;
+    } else a.summary[kSumOverflow] = 2;
+}
+
+__global__ void __launch_bounds__(kDvThreads) k_dense_filter_vec(DenseArgs a, const DenseArgs *__restrict__ ga,
+                                                                  const int16_t *__restrict__ bound,
                                                                   const unsigned char *__restrict__ every)
 {
-    // candidates: pixel, (frame slot << 16 | raw); their values are worked out at flush time,
-    // where the per-pixel constants are fetched by all threads at once instead of one
-    // dependent chain per survivor inside the streaming loop
-    __shared__ int s_pix[kDvCap];
-    __shared__ int s_sr[kDvCap];
-    __shared__ float s_v[kDvCap];
+    __shared__ unsigned s_cand[kDvSlots][kDvThreads];   // private: (slot << 19 | pixel-in-group << 16 | raw)
+    __shared__ int s_pix[kDvThreads * kDvSlots];        // per warp: settled events awaiting the copy-out
+    __shared__ int s_slot[kDvThreads * kDvSlots];
+    __shared__ float s_v[kDvThreads * kDvSlots];
     __shared__ double s_fsum[kDvFrames];
-    __shared__ int s_count, s_pass, s_cursor;
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ unsigned s_valid[kDvFrames / 32];
+    __shared__ uint4 s_raw[kDvGroup][kDvThreads];        // private: the current group's samples of a thread with hits
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x * kDvThreads + tid;
     const int j0 = g * kDvPix;
     const bool active = j0 < a.P;
     const int f_begin = blockIdx.y * kDvFrames;
     const int f_end = min(a.nframes, f_begin + kDvFrames);
-    if (tid == 0) s_count = 0;
     for (int i = tid; i < kDvFrames; i += kDvThreads) s_fsum[i] = 0.0;
     uint4 bd = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
     bool all_pass = false;
@@ -834,109 +882,176 @@ __global__ void __launch_bounds__(kDvThreads) k_dense_filter_vec(DenseArgs a, co
         bd = *reinterpret_cast<const uint4 *>(bound + j0);
         all_pass = every[g] != 0;
     }
-    const bool have_dark = a.dark_avg != nullptr;
+    int *w_pix = s_pix + warp * 32 * kDvSlots;
+    int *w_slot = s_slot + warp * 32 * kDvSlots;
+    float *w_v = s_v + warp * 32 * kDvSlots;
+    int cnt = 0;
+    if (tid < kDvFrames) {  // warps 0 and 1: which of the CTA's 64 frames exist and map to an output frame
+        const bool ok = f_begin + tid < f_end && out_frame(a.first_raw + f_begin + tid, a.rawblock, a.stride, a.F) >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_valid[warp] = m;
+    }
     __syncthreads();
 
-    // exact test and value of one sample (dense_filter.cpp:150-174)
-    auto exact = [&](int j, short raw, float &v) -> bool {
-        if (a.row_of_pixel[j] < 0) return false;
-        const double davg = have_dark ? a.dark_avg[j] : 0.0;
-        const float thresh =
-            have_dark ? (float)__dadd_rn((double)a.lld, __dmul_rn((double)a.sigma, a.dark_std[j])) : 0.0f;
-        if (!dense_sample(raw, have_dark, davg, thresh, v)) return false;
-        v = (float)__dmul_rn((double)v, a.flat[j]);
-        return true;
-    };
-
-    auto flush = [&]() {  // all threads
-        __syncthreads();
-        const int n = min(s_count, kDvCap);
-        if (tid == 0) { s_pass = 0; s_cursor = 0; }
-        __syncthreads();
-        for (int i = tid; i < n; i += kDvThreads) {
-            const int j = s_pix[i];
-            const int sr = s_sr[i];
-            float v;
-            if (exact(j, (short)(sr & 0xffff), v)) {
-                s_v[i] = v;
-                atomicAdd(&s_fsum[sr >> 16], (double)v);
-                atomicAdd(&s_pass, 1);
-            } else s_pix[i] = -1;
+    auto warp_flush = [&]() {  // all lanes of the warp
+        __syncwarp();
+        int x = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
         }
-        __syncthreads();
-        if (tid == 0) s_base = atomicAdd(a.counter, (unsigned long long)s_pass);
-        __syncthreads();
-        const unsigned long long base = s_base;
-        for (int i0 = 0; i0 < n; i0 += kDvThreads) {  // warp-uniform trip count
-            const int i = i0 + tid;
-            const bool ok = i < n && s_pix[i] >= 0;
-            const unsigned mk = __ballot_sync(0xffffffffu, ok);
-            int wbase = 0;
-            if (lane == 0 && mk) wbase = atomicAdd(&s_cursor, __popc(mk));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        const int base = x - cnt;
+        const int total = __shfl_sync(0xffffffffu, x, 31);
+        for (int i = 0; i < cnt; i++) {
+            const unsigned e = s_cand[i][tid];
+            const int j = j0 + (int)((e >> 16) & 7u);
+            const int slot = (int)(e >> 19);
+            float v;
+            bool ok = true;
+            if (all_pass) ok = dense_exact(a, j, (short)(e & 0xffffu), v);  // bound -32768 is not exact
+            else v = dense_value(a, j, (short)(e & 0xffffu));
             if (ok) {
-                const unsigned long long pos = base + wbase + __popc(mk & ((1u << lane) - 1u));
+                w_pix[base + i] = j;
+                w_slot[base + i] = slot;
+                w_v[base + i] = v;
+                // per-frame sum: a fire-and-forget fp64 reduction in L2 (a shared-memory fp64 add is a
+                // compare-and-swap loop, and all lanes of a flush meet on a handful of frames)
+                atomicAdd(a.frame_acc + out_frame(a.first_raw + f_begin + slot, a.rawblock, a.stride, a.F), (double)v);
+            } else w_pix[base + i] = -1;
+        }
+        cnt = 0;
+        __syncwarp();
+        int npass = 0;
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            npass += __popc(__ballot_sync(0xffffffffu, i < total && w_pix[i] >= 0));
+        }
+        unsigned long long gbase = 0;
+        if (lane == 0 && npass > 0) gbase = atomicAdd(a.counter, (unsigned long long)npass);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        int run = 0;
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i < total && w_pix[i] >= 0;
+            const unsigned mk = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned long long pos = gbase + run + __popc(mk & ((1u << lane) - 1u));
                 if (pos < a.capacity) {
-                    a.out_idx[pos] = s_pix[i];
-                    a.out_t[pos] = out_frame(a.first_raw + f_begin + (s_sr[i] >> 16), a.rawblock, a.stride, a.F);
-                    a.out_v[pos] = s_v[i];
+                    a.out_idx[pos] = w_pix[i];
+                    a.out_t[pos] = out_frame(a.first_raw + f_begin + w_slot[i], a.rawblock, a.stride, a.F);
+                    a.out_v[pos] = w_v[i];
                 } else a.summary[kSumOverflow] = 2;
             }
+            run += __popc(mk);
         }
-        __syncthreads();
-        if (tid == 0) s_count = 0;
-        __syncthreads();
+        __syncwarp();
     };
 
-    auto push = [&](int j, unsigned raw16, int slot) {
-        const int pos = atomicAdd(&s_count, 1);
-        if (pos < kDvCap) {
-            s_pix[pos] = j;
-            s_sr[pos] = (slot << 16) | (int)raw16;
-        } else {  // stage full (nearly every sample survives): settle it here and append directly
-            float v;
-            if (exact(j, (short)raw16, v)) {
-                atomicAdd(&s_fsum[slot], (double)v);
-                const unsigned long long gp = atomicAdd(a.counter, 1ull);
-                if (gp < a.capacity) {
-                    a.out_idx[gp] = j;
-                    a.out_t[gp] = out_frame(a.first_raw + f_begin + slot, a.rawblock, a.stride, a.F);
-                    a.out_v[gp] = v;
-                } else a.summary[kSumOverflow] = 2;
-            }
-        }
+    auto candidate = [&](int k, unsigned raw16, int slot) {
+        if (cnt < kDvSlots) {
+            s_cand[cnt][tid] = ((unsigned)slot << 19) | ((unsigned)k << 16) | raw16;
+            cnt++;
+        } else dense_settle_direct(ga, s_fsum, j0 + k, raw16, slot, a.first_raw + f_begin);
     };
 
     for (int f0 = f_begin; f0 < f_end; f0 += kDvGroup) {
+        // frames of this group that exist and map to an output frame (warp-uniform)
+        const unsigned fmask = (s_valid[(f0 - f_begin) >> 5] >> ((f0 - f_begin) & 31)) & 0xffu;
         uint4 rw[kDvGroup];
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.frames + (int64_t)f0 * a.P + j0);
+        const int fstride = a.P / kDvPix;  // frame pitch in 16-byte units
+        if (active && fmask == 0xffu) {
 #pragma unroll
-        for (int u = 0; u < kDvGroup; u++) {
-            rw[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
-            if (active && f0 + u < f_end)
-                rw[u] = __ldcs(reinterpret_cast<const uint4 *>(a.frames + (int64_t)(f0 + u) * a.P + j0));
-        }
+            for (int u = 0; u < kDvGroup; u++) rw[u] = __ldcs(src + (int64_t)u * fstride);
+        } else {
 #pragma unroll
-        for (int u = 0; u < kDvGroup; u++) {
-            const int fr = f0 + u;
-            if (fr >= f_end || !active) continue;
-            unsigned h0 = __vcmpgts2(rw[u].x, bd.x), h1 = __vcmpgts2(rw[u].y, bd.y);
-            unsigned h2 = __vcmpgts2(rw[u].z, bd.z), h3 = __vcmpgts2(rw[u].w, bd.w);
-            if (all_pass) h0 = h1 = h2 = h3 = 0xffffffffu;
-            if ((h0 | h1 | h2 | h3) == 0u) continue;
-            if (out_frame(a.first_raw + fr, a.rawblock, a.stride, a.F) < 0) continue;
-            const int slot = fr - f_begin;
-            if (h0 & 0xffffu) push(j0 + 0, rw[u].x & 0xffffu, slot);
-            if (h0 >> 16) push(j0 + 1, rw[u].x >> 16, slot);
-            if (h1 & 0xffffu) push(j0 + 2, rw[u].y & 0xffffu, slot);
-            if (h1 >> 16) push(j0 + 3, rw[u].y >> 16, slot);
-            if (h2 & 0xffffu) push(j0 + 4, rw[u].z & 0xffffu, slot);
-            if (h2 >> 16) push(j0 + 5, rw[u].z >> 16, slot);
-            if (h3 & 0xffffu) push(j0 + 6, rw[u].w & 0xffffu, slot);
-            if (h3 >> 16) push(j0 + 7, rw[u].w >> 16, slot);
+            for (int u = 0; u < kDvGroup; u++) {
+                rw[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+                if (active && ((fmask >> u) & 1u)) rw[u] = __ldcs(src + (int64_t)u * fstride);
+            }
         }
-        if (__syncthreads_or(s_count > kDvCap / 2)) flush();
+        // per-pixel maximum over the group, one compare against the bounds per word
+        bool hw[4];
+        {
+            unsigned mx[4];
+            mx[0] = __vimax3_s16x2(rw[0].x, rw[1].x, rw[2].x);
+            mx[1] = __vimax3_s16x2(rw[0].y, rw[1].y, rw[2].y);
+            mx[2] = __vimax3_s16x2(rw[0].z, rw[1].z, rw[2].z);
+            mx[3] = __vimax3_s16x2(rw[0].w, rw[1].w, rw[2].w);
+            mx[0] = __vimax3_s16x2(mx[0], rw[3].x, rw[4].x);
+            mx[1] = __vimax3_s16x2(mx[1], rw[3].y, rw[4].y);
+            mx[2] = __vimax3_s16x2(mx[2], rw[3].z, rw[4].z);
+            mx[3] = __vimax3_s16x2(mx[3], rw[3].w, rw[4].w);
+            mx[0] = __vimax3_s16x2(mx[0], rw[5].x, rw[6].x);
+            mx[1] = __vimax3_s16x2(mx[1], rw[5].y, rw[6].y);
+            mx[2] = __vimax3_s16x2(mx[2], rw[5].z, rw[6].z);
+            mx[3] = __vimax3_s16x2(mx[3], rw[5].w, rw[6].w);
+            mx[0] = __vimax3_s16x2(mx[0], rw[7].x, rw[7].x);
+            mx[1] = __vimax3_s16x2(mx[1], rw[7].y, rw[7].y);
+            mx[2] = __vimax3_s16x2(mx[2], rw[7].z, rw[7].z);
+            mx[3] = __vimax3_s16x2(mx[3], rw[7].w, rw[7].w);
+            const unsigned bdw[4] = {bd.x, bd.y, bd.z, bd.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                bool ph, pl;  // bound >= max: no frame of the group passes for that pixel
+                (void)__vibmax_s16x2(bdw[w], mx[w], &ph, &pl);
+                hw[w] = !(ph && pl) || all_pass;
+            }
+        }
+        if (active && (hw[0] || hw[1] || hw[2] || hw[3])) {
+            // which (frame, pixel) samples of the group pass: bit u*8 + k, frames 0-3 / 4-7 apart
+            const unsigned bdw[4] = {bd.x, bd.y, bd.z, bd.w};
+            unsigned mlo = 0u, mhi = 0u;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                if (!hw[w]) continue;
+#pragma unroll
+                for (int u = 0; u < kDvGroup; u++) {
+                    const unsigned word = w == 0 ? rw[u].x : w == 1 ? rw[u].y : w == 2 ? rw[u].z : rw[u].w;
+                    bool ph, pl;
+                    (void)__vibmax_s16x2(bdw[w], word, &ph, &pl);
+                    const unsigned blo = 1u << ((u & 3) * 8 + 2 * w), bhi = blo << 1;
+                    if (u < 4) {
+                        if (!pl) mlo |= blo;
+                        if (!ph) mlo |= bhi;
+                    } else {
+                        if (!pl) mhi |= blo;
+                        if (!ph) mhi |= bhi;
+                    }
+                }
+            }
+            if (all_pass) mlo = mhi = 0xffffffffu;
+            // frames that do not exist or map to no output frame drop out (fmask is warp-uniform)
+            mlo &= ((fmask & 1u) ? 0xffu : 0u) | ((fmask & 2u) ? 0xff00u : 0u) | ((fmask & 4u) ? 0xff0000u : 0u) |
+                   ((fmask & 8u) ? 0xff000000u : 0u);
+            mhi &= ((fmask & 16u) ? 0xffu : 0u) | ((fmask & 32u) ? 0xff00u : 0u) | ((fmask & 64u) ? 0xff0000u : 0u) |
+                   ((fmask & 128u) ? 0xff000000u : 0u);
+            // the few survivors: re-read the sample (it has just been streamed through L2)
+            if (mlo | mhi) {
+                // the few survivors: park the group's samples in shared memory to pick them by index
+#pragma unroll
+                for (int u = 0; u < kDvGroup; u++) s_raw[u][tid] = rw[u];
+                const unsigned short *mine = reinterpret_cast<const unsigned short *>(&s_raw[0][tid]);
+                while (mlo | mhi) {
+                    int b;
+                    if (mlo) {
+                        b = __ffs(mlo) - 1;
+                        mlo &= mlo - 1u;
+                    } else {
+                        b = 32 + __ffs(mhi) - 1;
+                        mhi &= mhi - 1u;
+                    }
+                    const int u = b >> 3, k = b & 7;
+                    const unsigned raw16 = mine[u * (kDvThreads * kDvPix) + k];
+                    candidate(k, raw16, f0 + u - f_begin);
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, cnt > kDvSlots - 4)) warp_flush();
     }
-    flush();
+    warp_flush();
+    __syncthreads();
     for (int i = tid; i < f_end - f_begin; i += kDvThreads) {
         const int t = out_frame(a.first_raw + f_begin + i, a.rawblock, a.stride, a.F);
         if (t >= 0 && s_fsum[i] != 0.0) atomicAdd(a.frame_acc + t, s_fsum[i]);
@@ -1198,9 +1313,19 @@ int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw
                                                                         a.sigma, h->d_dense_bound.p, h->d_dense_every.p);
             h->dense_bounds_ready = true;
         }
+        // the launch-invariant arguments once per ingest in global memory, for the out-of-line path
+        DenseArgs *ga = reinterpret_cast<DenseArgs *>(h->d_dense_args.p);
+        if (!h->dense_args_ready) {
+            int rc;
+            if ((rc = ensure(h, h->d_dense_args, sizeof(DenseArgs), "dense args"))) return rc;
+            ga = reinterpret_cast<DenseArgs *>(h->d_dense_args.p);
+            rc = check_cuda(h, cudaMemcpyAsync(ga, &a, sizeof(DenseArgs), cudaMemcpyHostToDevice, h->stream), "dense args");
+            if (rc) return rc;
+            h->dense_args_ready = true;
+        }
         dim3 grid((h->P / kDvPix + kDvThreads - 1) / kDvThreads, (nframes + kDvFrames - 1) / kDvFrames);
         LaunchScope ls(h, "k_dense_filter");
-        k_dense_filter_vec<<<grid, kDvThreads, 0, h->stream>>>(a, h->d_dense_bound.p, h->d_dense_every.p);
+        k_dense_filter_vec<<<grid, kDvThreads, 0, h->stream>>>(a, ga, h->d_dense_bound.p, h->d_dense_every.p);
     } else {
         dim3 grid((h->P + kDfPixels - 1) / kDfPixels, (nframes + kDfFrames - 1) / kDfFrames);
         LaunchScope ls(h, "k_dense_filter");

@@ -99,6 +99,8 @@ struct xpcs_handle_s {
     xpcs::DevBuf<int16_t> d_dense_bound;        // [P] dense filter: a sample survives iff raw > bound
     xpcs::DevBuf<unsigned char> d_dense_every;  // [P/8] group holds a pixel that lets every raw value through
     bool dense_bounds_ready = false;
+    xpcs::DevBuf<unsigned char> d_dense_args;   // launch-invariant dense filter arguments in global memory
+    bool dense_args_ready = false;
     // push_dense: double-buffered device staging, H2D on its own stream
     xpcs::DevBuf<int16_t> d_dense_stage[2];
     cudaStream_t copy_stream = nullptr;

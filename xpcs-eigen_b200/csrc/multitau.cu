@@ -382,22 +382,20 @@ __device__ void row_multitau_float(u64 *col, float *acc, int n0, int r, const Mt
                 a.IP[(int64_t)(first + k) * a.R_pad + r] = scaled_div(acc[t2 * kSlice], L - t2);
             }
         }
-        // ---- IF: fp64 total minus the head bins (keys are distinct, one value per key)
-        for (int d = 0; d <= hi; d++) acc[d * kSlice] = 0.0f;
+        // ---- IF in the reference's order (corr.cpp:414-416): for every delay its own sequential fp32
+        // chain over the bins with key >= tau' -- the chains differ in where they start, hence in
+        // every rounding after that, and a long row's chain carries more than 1e-5 of rounding,
+        // so only the same order reproduces the reference
+        for (int tp = lo; tp <= top; tp++) acc[tp * kSlice] = 0.0f;
         for (int i = 0; i < n; i++) {
             const u64 wi = col[i * kSlice];
             const int ki = f_key(wi);
-            if (ki >= hi) break;
-            acc[ki * kSlice] = f_val(wi);
+            const float vi = f_val(wi);
+            const int last = min(ki, top);
+            for (int tp = lo; tp <= last; tp++) acc[tp * kSlice] = __fadd_rn(acc[tp * kSlice], vi);
         }
-        {
-            double run = 0.0;
-            for (int tp = 1; tp < lo + cnt; tp++) {
-                run += (double)acc[(tp - 1) * kSlice];
-                if (tp >= lo)
-                    a.IF[(int64_t)(first + tp - lo) * a.R_pad + r] = scaled_div((float)(total - run), L - tp);
-            }
-        }
+        for (int k = 0; k < cnt; k++)
+            a.IF[(int64_t)(first + k) * a.R_pad + r] = scaled_div(acc[(lo + k) * kSlice], L - (lo + k));
     }
 }
 

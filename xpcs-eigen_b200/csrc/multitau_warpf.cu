@@ -14,8 +14,9 @@
 //       B_{l+1}[t] = B_l[2t] + B_l[2t+1] -- the reference's own cascade without its exact /2 --
 //       and windowed products, lanes over t, fixed-shape reductions.
 // One rounding to fp32 and one IEEE division per output.  The reference accumulates the same
-// sums sequentially in fp32; the two agree to ~1e-6 relative (north_star tolerance 1e-5,
-// tests/test_gpu_dense.py, tests/test_gpu_parity.py).
+// sums sequentially in fp32; for rows of up to ~1000 events the two agree to ~1e-6 relative
+// (north_star tolerance 1e-5, tests/test_gpu_dense.py, tests/test_gpu_parity.py); longer rows
+// are left to the lane-per-row kernel, which reproduces the reference's summation order.
 // XPCS_COMPAT_STALE_TAIL depends on the frames only and is handled exactly as
 // in multitau_warp.cu: live counts from the merge levels, the first stale slot of every level
 // as a filter, the boundary walk with rank/select over the events when it can matter.
@@ -23,6 +24,8 @@
 // A CTA owns one slice of 32 rows; each warp pulls its rows straight from the slice (the
 // rows in flight at any moment are neighbours, so their 32-byte sectors are shared through
 // L1), and the 32 x T x 3 results leave through a shared-memory stage as 128-byte lines.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace xpcs {
@@ -30,6 +33,7 @@ namespace xpcs {
 constexpr uint32_t kFullF = 0xffffffffu;
 constexpr int kInfF = 0x7fffffff;
 constexpr int kMfMaxWarps = 16;
+constexpr int kMfExactLen = 1024;
 
 struct MfArgs {
     unsigned char *fallback;   // [n_slices]
@@ -461,7 +465,11 @@ int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a)
     auto warp_words = [&](int len) { return (size_t)2 * m.T + 64 + 160 + (size_t)2 * len + (size_t)4 * len + 64; };
     // the longest row decides the per-warp area; as many warps as fit (at least 4, at most 16: two
     // CTAs share an SM when the rows are short); longer slices go to the lane-per-row kernel
-    int len_cap = h->max_row > 0 ? h->max_row : 1;
+    // Rows beyond kMfExactLen events stay with the lane-per-row kernel, which keeps the reference's
+    // sequential fp32 order: the reference's own rounding grows with the length of its chains
+    // (1.7e-5 on a 3000-event row), and beyond ~1000 events sums that are more exact than the
+    // reference's stop agreeing with it within the 1e-5 tolerance.
+    int len_cap = h->max_row > 0 ? std::min(h->max_row, kMfExactLen) : 1;
     const size_t budget1 = ((size_t)smem_cap - 512) / 4;
     while (len_cap > 1 && out_words + 4 * warp_words(len_cap) > budget1) len_cap = len_cap * 3 / 4;
     if (out_words + 4 * warp_words(len_cap) > budget1) {  // T too large for the stage: everything falls back

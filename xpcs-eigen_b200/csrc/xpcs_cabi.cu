@@ -296,6 +296,7 @@ static void reset_ingest(xpcs_handle_s *h)
     h->partials_done = false;
     h->rows_consumed = false;
     h->dense_source = false;
+    h->dense_args_ready = false;
     h->external_events = false;
     h->ev_idx = nullptr;
     h->ev_val = nullptr;
@@ -408,7 +409,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
         }
     release(h->d_row_of_pixel); release(h->d_pixel_of_row); release(h->d_sbin_of_row); release(h->d_flat);
     release(h->d_lseg_row_start); release(h->d_seg_dq_all); release(h->d_seg_npix_all);
-    release(h->d_dark_avg); release(h->d_dark_std); release(h->d_dense_bound); release(h->d_dense_every);
+    release(h->d_dark_avg); release(h->d_dark_std); release(h->d_dense_bound); release(h->d_dense_every); release(h->d_dense_args);
     release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
     release(h->d_dense_counter);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
@@ -495,6 +496,7 @@ extern "C" int xpcs_set_dark(xpcs_handle h, const int16_t *frames, int n)
     release(tmp);
     if (!rc) h->have_dark = true;
     h->dense_bounds_ready = false;
+    h->dense_args_ready = false;
     return rc;
 }
 
