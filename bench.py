@@ -44,6 +44,8 @@ WORKLOADS = {
                name="sparse IMM 512x512, 10k frames, 1% occupancy, dpl 8, 36 dynamic q-bins (BASELINE configs[0])"),
     "c4": dict(h=256, w=256, F=10000, occ=0.02, kind="twotime",
                name="two-time correlation, 64k-pixel q ROI (256x256), 10k frames, 2% occupancy, symmetric smoothing (BASELINE configs[3])"),
+    "c5": dict(h=2048, w=2048, F=1000000, occ=0.0001, kind="sparse",
+               name="high-rate sparse sweep 2048x2048, 1M frames, 0.01% occupancy (low end of BASELINE configs[4]; --occupancy overrides)"),
     "c2": dict(h=1024, w=1024, F=20000, occ=None, kind="dense",
                name="non-sparse IMM 1024x1024 int16, 20k frames, dark/flat correction + threshold (BASELINE configs[1])"),
 }
@@ -476,6 +478,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
+    ap.add_argument("--occupancy", type=float, default=0.0, help="override the occupancy of a sparse workload (c5 sweep)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (c2: 42 GB pinned)")
@@ -484,6 +487,9 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
         wl["F"] = args.frames
+    if args.occupancy and wl["kind"] == "sparse":
+        wl["occ"] = args.occupancy
+        wl["name"] += " [occupancy %g]" % args.occupancy
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 0)
 

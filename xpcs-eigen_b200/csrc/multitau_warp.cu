@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
     extern __shared__ __align__(16) uint32_t mw_smem[];
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
     const int len = a.slice_len[s];
     if (len > m.len_cap) {  // CTA-uniform
         if (tid == 0) m.fallback[s] = 1;
@@ -151,12 +152,12 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane;
         uint32_t *dst = evT + lane * m.pitch_e;
 #pragma unroll 4
-        for (int j = warp; j < len; j += kMwWarps)
+        for (int j = warp; j < len; j += nwarps)
             if (j < my_len) dst[j] = g[(int64_t)j * kSlice];
     }
     __syncthreads();
 
-    for (int rr = warp; rr < kSlice; rr += kMwWarps) {
+    for (int rr = warp; rr < kSlice; rr += nwarps) {
         const int n = __shfl_sync(kFull, my_len, rr);
         const uint32_t *ev = evT + rr * m.pitch_e;
         uint32_t *H = outS + rr * m.pitch_t;              // G2 numerators, later the G2 floats
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         for (int arr = 0; arr < 3; arr++) {
             const uint32_t *src = outS + arr * 32 * m.pitch_t + lane * m.pitch_t;
             float *d = dst[arr] + r0;
-            for (int t = warp; t < T; t += kMwWarps) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
+            for (int t = warp; t < T; t += nwarps) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
         }
     }
 }
@@ -427,13 +428,13 @@ bool multitau_warp_eligible(const xpcs_handle_s *h)
 }
 
 template <int DPL, bool COMPAT>
-static int run_warp(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes)
+static int run_warp(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes, int warps)
 {
     int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau_warp<DPL, COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)bytes), "multitau_warp smem attr");
     if (rc) return rc;
     LaunchScope ls(h, "k_multitau_warp");
-    k_multitau_warp<DPL, COMPAT><<<h->n_slices, kMwWarps * 32, bytes, h->stream>>>(a, m);
+    k_multitau_warp<DPL, COMPAT><<<h->n_slices, warps * 32, bytes, h->stream>>>(a, m);
     return XPCS_OK;
 }
 
@@ -450,29 +451,35 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     m.T = h->T;
     m.pitch_t = h->T | 1;
     const size_t out_bytes = (size_t)3 * 32 * m.pitch_t * 4;
-    // bytes(len) = out + 4 * (32 * (len | 1) + warps * (3 len + 65 + tables)); two CTAs per SM when the
-    // longest row allows it, one otherwise; longer slices go to the lane-per-row kernel
-    auto bytes_for = [&](int len) {
-        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)kMwWarps * (3 * (size_t)len + 65 + kMwTables));
+    // bytes(len, warps) = out + 4 * (32 * (len | 1) + warps * (3 len + 65 + tables)).  Two CTAs per SM when
+    // the longest row allows it -- with 16 warps each, else with 12 or 8 (a long delay schedule makes the
+    // result stage large) -- one CTA of 16 warps otherwise; longer slices go to the lane-per-row kernel
+    auto bytes_for = [&](int len, int warps) {
+        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)warps * (3 * (size_t)len + 65 + kMwTables));
     };
     const size_t budget2 = (size_t)(smem_cap + 1024) / 2 - 1024 - 512;  // two resident CTAs (1 KB reserved each)
     int len_cap = h->max_row > 0 ? h->max_row : 1;
-    if (bytes_for(len_cap) > budget2) {
-        const size_t budget1 = (size_t)smem_cap - 512;
-        while (len_cap > 1 && bytes_for(len_cap) > budget1) len_cap = len_cap * 3 / 4;
+    int warps = kMwWarps;
+    if (bytes_for(len_cap, 16) > budget2) {
+        if (bytes_for(len_cap, 12) <= budget2) warps = 12;
+        else if (bytes_for(len_cap, 8) <= budget2) warps = 8;
+        else {
+            const size_t budget1 = (size_t)smem_cap - 512;
+            while (len_cap > 1 && bytes_for(len_cap, 16) > budget1) len_cap = len_cap * 3 / 4;
+        }
     }
-    if (bytes_for(len_cap) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
+    if (bytes_for(len_cap, warps) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
         return XPCS_OK;
     }
     m.len_cap = len_cap;
     m.pitch_e = len_cap | 1;
     m.warp_words = 3 * len_cap + 65 + kMwTables;
-    const size_t bytes = bytes_for(len_cap);
+    const size_t bytes = bytes_for(len_cap, warps);
     const bool compat = a.compat != 0;
     const int dpl = h->prm.delays_per_level;
-    if (dpl == 8) rc = compat ? run_warp<8, true>(h, a, m, bytes) : run_warp<8, false>(h, a, m, bytes);
-    else rc = compat ? run_warp<4, true>(h, a, m, bytes) : run_warp<4, false>(h, a, m, bytes);
+    if (dpl == 8) rc = compat ? run_warp<8, true>(h, a, m, bytes, warps) : run_warp<8, false>(h, a, m, bytes, warps);
+    else rc = compat ? run_warp<4, true>(h, a, m, bytes, warps) : run_warp<4, false>(h, a, m, bytes, warps);
     if (rc) return rc;
     return check_cuda(h, cudaGetLastError(), "k_multitau_warp");
 }
