@@ -184,3 +184,36 @@ def row_multitau_model(f, c, F, dpl, sched, compat=True, stats=None):
             jf = sdiv(np.float32(total - PS(tp << l)) * s1)
             out[first[l] + k] = (g2, ip, jf)
     return out
+
+
+def ipif_first_delay(f, F, dpl, sched):
+    """Closed forms used by phase 1 of k_multitau_warp: the IF thresholds t' << l ascend with the delay
+    index ti and the IP thresholds (L_l - t') << l descend, so an event at frame f only needs
+      a = #{ti : t' << l <= f}        (it counts in PS(t' << l) for ti >= a), and
+      b = #{ti : (L_l - t') << l > f} (it counts in PS((L_l - t') << l) for ti < b);
+    both follow from the bit length of f and of F - f for the regular schedule."""
+    nl, first, count, lo = sched
+    lg = dpl.bit_length() - 1
+    cnt0 = count[0]
+    T = sum(count)
+    lastl = max([l for l in range(nl) if count[l] > 0] + [0])
+    cnt_last = count[lastl] if lastl >= 1 else 0
+
+    def cum(l):  # delays of the levels 1..l
+        if l <= 0 or lastl < 1:
+            return 0
+        return dpl * l if l < lastl else dpl * (lastl - 1) + cnt_last
+
+    if f < 2 * dpl:
+        a = min(f, cnt0)
+    else:
+        ls = f.bit_length() - lg - 1
+        a = min(cnt0 + dpl * (ls - 1) + (f >> ls) - dpl, T)
+    g = F - f
+    lc = g.bit_length() - lg - 1
+    b = min(g - 1, cnt0) + cum(lc - 2)
+    for l in (lc - 1, lc):
+        if l >= 1:
+            u = (F >> l) - 1 - (f >> l)
+            b += min(max(u - dpl, 0), cum(l) - cum(l - 1))
+    return a, min(b, T)

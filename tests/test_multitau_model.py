@@ -63,3 +63,22 @@ def test_model_matches_oracle(F, dpl, seed, compat):
             assert b == IF[ti, p], (p, ti, b, IF[ti, p])
     if compat and F == 512:
         assert stats.get("lost", 0) > 0  # the quirk is exercised
+
+
+@pytest.mark.parametrize("dpl", [4, 8])
+def test_ipif_threshold_histogram_closed_forms(dpl):
+    """The first-delay indices phase 1 of k_multitau_warp derives from bit lengths equal the counts over
+    the actual thresholds (corr.cpp:403, 414-416), for every frame of every F tried."""
+    for F in list(range(2 * dpl + 2, 300)) + [1000, 1023, 1024, 1025, 4097, 10000]:
+        lv, tv = O.delay_schedule(F, dpl)
+        sched = M.build_sched(lv, tv)
+        lvl = lv.astype(np.int64)
+        tp = tv.astype(np.int64) >> lvl
+        thr_if = tp << lvl
+        thr_ip = np.maximum((F >> lvl) - tp, 0) << lvl
+        assert np.all(np.diff(thr_if) > 0) and np.all(np.diff(thr_ip) < 0)
+        frames = range(F) if F <= 1025 else list(range(0, 300)) + list(range(F - 300, F)) + list(range(0, F, 37))
+        for f in frames:
+            a, b = M.ipif_first_delay(f, F, dpl, sched)
+            assert a == int(np.sum(thr_if <= f)), (F, f)
+            assert b == int(np.sum(thr_ip > f)), (F, f)

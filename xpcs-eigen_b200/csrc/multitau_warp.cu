@@ -43,6 +43,7 @@ struct MwArgs {
     int pitch_t;               // odd, >= T
     int warp_words;            // per-warp shared words
     int T;
+    int lastl, cnt_last;       // last level >= 1 with delays (0 = none) and its delay count
 };
 
 __device__ __forceinline__ float mw_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
     const int T = m.T;
     const int cnt0 = a.sched.count[0];
     const int lo0 = a.sched.lo[0];
+    const int cumlast = m.lastl >= 1 ? DPL * (m.lastl - 1) + m.cnt_last : 0;
 
     // ---- phase 0: slice tile -> row-major shared memory (lane = row on the way in)
     const int my_len = a.row_len[s * kSlice + lane];
@@ -164,8 +166,16 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         uint32_t *oIP = H + 32 * m.pitch_t;
         uint32_t *oIF = oIP + 32 * m.pitch_t;
 
-        // ---- phase 1: prefix sums of the counts, merge-level histogram
-        for (int t = lane; t < T; t += 32) H[t] = 0u;
+        // ---- phase 1: prefix sums of the counts, merge-level histogram, IP / IF threshold histograms.
+        // The IF thresholds t' << l ascend with the delay index and the IP thresholds (L_l - t') << l
+        // descend, so an event only has to know the first delay it counts for: oIF[a] += c with
+        // a = #{ti : t' << l <= f}, oIP[b] += c with b = #{ti : (L_l - t') << l > f} (closed forms from
+        // the bit length of f and of F - f); phase 5 turns both into running sums.
+        for (int t = lane; t < T; t += 32) {
+            H[t] = 0u;
+            oIP[t] = 0u;
+            oIF[t] = 0u;
+        }
         if (COMPAT) cntml[lane] = 0u;
         if (lane == 0) ps[0] = 0u;
         __syncwarp();
@@ -173,13 +183,38 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int i = c0 + lane;
             const uint32_t w = i < n ? ev[i] : 0u;
-            uint32_t x = w & ((1u << kCountBits) - 1u);
+            const uint32_t c = w & ((1u << kCountBits) - 1u);
+            uint32_t x = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t y = __shfl_up_sync(kFull, x, o);
                 if (lane >= o) x += y;
             }
-            if (i < n) ps[i + 1] = carry + x;
+            if (i < n) {
+                ps[i + 1] = carry + x;
+                const int f = (int)(w >> kCountBits);
+                int ai;
+                if (f < 2 * DPL) ai = min(f, cnt0);
+                else {
+                    const int ls = (32 - __clz(f)) - (LG + 1);
+                    ai = cnt0 + DPL * (ls - 1) + (f >> ls) - DPL;
+                }
+                if (ai < T) atomicAdd(&oIF[ai], c);
+                const int g = F - f;
+                const int lc = (32 - __clz(g)) - (LG + 1);
+                const int lf = lc - 2;  // levels 1..lf are full
+                int bi = min(g - 1, cnt0) + (lf <= 0 ? 0 : (lf < m.lastl ? DPL * lf : cumlast));
+#pragma unroll
+                for (int q = 1; q >= 0; q--) {
+                    const int l = lc - q;
+                    if (l >= 1) {
+                        const int cl = l < m.lastl ? DPL : (l == m.lastl ? m.cnt_last : 0);
+                        const int u = (F >> l) - 1 - (f >> l);
+                        bi += min(max(u - DPL, 0), cl);
+                    }
+                }
+                if (bi < T) atomicAdd(&oIP[bi], c);
+            }
             carry += __shfl_sync(kFull, x, 31);
             if (COMPAT && i >= 1 && i < n) {
                 const int ml = 32 - __clz((int)((w ^ ev[i - 1]) >> kCountBits));
@@ -243,39 +278,85 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         }
         __syncwarp();
 
-        // ---- phase 3: sparse levels, one pass over event pairs
+        // ---- phase 3: sparse levels, one pass over the event pairs i < j with f_j - f_i < dmax.
+        // The pairs are flattened so that every lane carries one: pair p belongs to the event ("owner") with
+        // Qc[k] <= p < Qc[k+1]; the owners that start inside a 32-pair chunk mark their first lane in a
+        // bit mask, a lane's owner is the number of marks at or below it.
         {
             const uint32_t dmax = (uint32_t)(2 * DPL + 1) << (ld - 1);
             const uint32_t top0 = (uint32_t)(lo0 + cnt0 - 1);
             const uint32_t flim0 = flim[0];
+            // events that have partners, compacted: Ic[k] = event index, Qc[k] = index of its first pair
+            uint32_t *Qc = bw;
+            uint32_t *Ic = bw + m.len_cap + 34;
+            uint32_t npairs = 0;
+            int nact = 0;
+            const int topstep = n > 0 ? (1 << (31 - __clz(n))) : 1;
             for (int c0 = 0; c0 < n; c0 += 32) {
                 const int i = c0 + lane;
-                const uint32_t wi = i < n ? ev[i] : 0u;
-                const uint32_t fi = wi >> kCountBits, ci = wi & ((1u << kCountBits) - 1u);
-                for (int k = 1;; k++) {
-                    const int j = i + k;
-                    const uint32_t wj = j < n ? ev[j] : 0xffffffffu;
-                    const uint32_t fj = wj >> kCountBits;
+                // pos = last index with f < f_i + dmax: galloping start (most events have < 8 partners)
+                const uint32_t key = i < n ? (min((ev[i] >> kCountBits) + dmax, (uint32_t)F) << kCountBits) : 0u;
+                int pos = i;
+                if (__any_sync(kFull, i + 8 < n && ev[min(i + 8, n - 1)] < key)) {
+                    for (int step = topstep; step >= 8; step >>= 1) {
+                        const int k2 = pos + step;
+                        if (k2 < n && ev[k2] < key) pos = k2;
+                    }
+                }
+#pragma unroll
+                for (int step = 4; step >= 1; step >>= 1) {
+                    const int k2 = pos + step;
+                    if (k2 < n && ev[k2] < key) pos = k2;
+                }
+                const uint32_t mi = i < n ? (uint32_t)(pos - i) : 0u;
+                uint32_t x = mi;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, x, o);
+                    if (lane >= o) x += y;
+                }
+                const unsigned act = __ballot_sync(kFull, mi > 0u);
+                if (mi > 0u) {
+                    const int k = nact + __popc(act & ((1u << lane) - 1u));
+                    Qc[k] = npairs + x - mi;
+                    Ic[k] = (uint32_t)i;
+                }
+                nact += __popc(act);
+                npairs += __shfl_sync(kFull, x, 31);
+            }
+            Qc[nact + lane] = 0xffffffffu;  // sentinels: no further owner starts
+            if (lane < 2) Qc[nact + 32 + lane] = 0xffffffffu;
+            __syncwarp();
+            int kbase = 0;  // compacted index of the owner of pair p0
+            for (uint32_t p0 = 0; p0 < npairs; p0 += 32) {
+                // owners that start inside this chunk set a bit at their first lane
+                const uint32_t sl = Qc[kbase + 1 + lane] - p0;
+                const unsigned bits = __reduce_or_sync(kFull, sl < 32u ? (1u << sl) : 0u);
+                const int k = kbase + __popc(bits & (0xffffffffu >> (31 - lane)));
+                kbase += __popc(bits);
+                const uint32_t p = p0 + lane;
+                if (p < npairs) {
+                    const int i = (int)Ic[k];
+                    const int j = i + 1 + (int)(p - Qc[k]);
+                    const uint32_t wi = ev[i], wj = ev[j];
+                    const uint32_t fi = wi >> kCountBits, fj = wj >> kCountBits;
                     const uint32_t d = fj - fi;
-                    const bool act = j < n && d < dmax;
-                    if (!__any_sync(kFull, act)) break;
-                    if (act) {
-                        const uint32_t cc = ci * (wj & ((1u << kCountBits) - 1u));
-                        if (d <= top0 && d >= (uint32_t)lo0 && fj < flim0) atomicAdd(&H[d - lo0], cc);
-                        if (d >= 2u * DPL) {
-                            const int l0 = (32 - __clz((int)d)) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
-                            const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
-                            if (b0 < cnts[l0] && fj < flim[l0]) atomicAdd(&H[cnt0 + (l0 - 1) * DPL + b0], cc);
-                            const int l1 = l0 - 1;
-                            if (l1 >= 1) {
-                                const uint32_t b1 = (fj >> l1) - (fi >> l1);
-                                if (b1 == 2u * DPL && (uint32_t)(DPL - 1) < cnts[l1] && fj < flim[l1])
-                                    atomicAdd(&H[cnt0 + (l1 - 1) * DPL + (DPL - 1)], cc);
-                            }
+                    const uint32_t cc = (wi & ((1u << kCountBits) - 1u)) * (wj & ((1u << kCountBits) - 1u));
+                    if (d <= top0 && d >= (uint32_t)lo0 && fj < flim0) atomicAdd(&H[d - lo0], cc);
+                    if (d >= 2u * DPL) {
+                        const int l0 = (32 - __clz((int)d)) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
+                        const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
+                        if (b0 < cnts[l0] && fj < flim[l0]) atomicAdd(&H[cnt0 + (l0 - 1) * DPL + b0], cc);
+                        const int l1 = l0 - 1;
+                        if (l1 >= 1) {
+                            const uint32_t b1 = (fj >> l1) - (fi >> l1);
+                            if (b1 == 2u * DPL && (uint32_t)(DPL - 1) < cnts[l1] && fj < flim[l1])
+                                atomicAdd(&H[cnt0 + (l1 - 1) * DPL + (DPL - 1)], cc);
                         }
                     }
                 }
             }
+            __syncwarp();
         }
 
         // ---- phase 4: dense levels, 16-bit bin arrays
@@ -363,28 +444,44 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         }
         __syncwarp();
 
-        // ---- phase 5: one IEEE division per output (lane = delay)
-        for (int t0 = 0; t0 < T; t0 += 32) {
-            const int ti = t0 + lane;
-            if (ti < T) {
-                int l, tp;
-                if (ti < cnt0) {
-                    l = 0;
-                    tp = lo0 + ti;
-                } else {
-                    const int q = ti - cnt0;
-                    l = 1 + q / DPL;
-                    tp = LO + q % DPL;
+        // ---- phase 5: running sums of the threshold histograms, one IEEE division per output (lane = delay)
+        {
+            uint32_t runC = 0, runD = 0;
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int ti = t0 + lane;
+                uint32_t xc = ti < T ? oIF[ti] : 0u, xd = ti < T ? oIP[ti] : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t yc = __shfl_up_sync(kFull, xc, o), yd = __shfl_up_sync(kFull, xd, o);
+                    if (lane >= o) {
+                        xc += yc;
+                        xd += yd;
+                    }
                 }
-                const int Ll = F >> l;
-                const int neff = Ll - tp;
-                const float s2 = mw_pow2_neg(2 * l), s1 = mw_pow2_neg(l);
-                const uint32_t num = H[ti];
-                const uint32_t ipn = ps[mw_lower_bound(ev, n, ((uint32_t)max(neff, 0) << l) << kCountBits)];
-                const uint32_t ifn = tot[l] - ps[mw_lower_bound(ev, n, ((uint32_t)tp << l) << kCountBits)];
-                H[ti] = __float_as_uint(mw_scaled_div((float)num * s2, neff));
-                oIP[ti] = __float_as_uint(mw_scaled_div((float)ipn * s1, neff));
-                oIF[ti] = __float_as_uint(mw_scaled_div((float)ifn * s1, neff));
+                xc += runC;
+                xd += runD;
+                runC = __shfl_sync(kFull, xc, 31);
+                runD = __shfl_sync(kFull, xd, 31);
+                if (ti < T) {
+                    int l, tp;
+                    if (ti < cnt0) {
+                        l = 0;
+                        tp = lo0 + ti;
+                    } else {
+                        const int q = ti - cnt0;
+                        l = 1 + q / DPL;
+                        tp = LO + q % DPL;
+                    }
+                    const int Ll = F >> l;
+                    const int neff = Ll - tp;
+                    const float s2 = mw_pow2_neg(2 * l), s1 = mw_pow2_neg(l);
+                    const uint32_t num = H[ti];
+                    const uint32_t ipn = carry - xd;   // PS((L_l - t') << l)
+                    const uint32_t ifn = tot[l] - xc;  // PS(lim_l) - PS(t' << l)
+                    H[ti] = __float_as_uint(mw_scaled_div((float)num * s2, neff));
+                    oIP[ti] = __float_as_uint(mw_scaled_div((float)ipn * s1, neff));
+                    oIF[ti] = __float_as_uint(mw_scaled_div((float)ifn * s1, neff));
+                }
             }
         }
         __syncwarp();
@@ -450,6 +547,11 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     m.fallback = h->d_mt_fallback.p;
     m.T = h->T;
     m.pitch_t = h->T | 1;
+    for (int l = 1; l < h->sched.n_levels; l++)
+        if (h->sched.count[l] > 0) {
+            m.lastl = l;
+            m.cnt_last = h->sched.count[l];
+        }
     const size_t out_bytes = (size_t)3 * 32 * m.pitch_t * 4;
     // bytes(len, warps) = out + 4 * (32 * (len | 1) + warps * (3 len + 65 + tables)).  Two CTAs per SM when
     // the longest row allows it -- with 16 warps each, else with 12 or 8 (a long delay schedule makes the
