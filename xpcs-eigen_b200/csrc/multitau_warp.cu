@@ -11,7 +11,10 @@
 // for bit against the oracle):
 //   L_l = F >> l, lim_l = L_l << l;  an event is live at level l iff f < lim_l  (corr.cpp:349-390)
 //   IP(l,t') = PS((L_l - t') << l),  IF(l,t') = PS(lim_l) - PS(t' << l)           (corr.cpp:403,414-416)
-//       with PS(x) = sum of the counts of the events with f < x (prefix sums + binary search)
+//       with PS(x) = sum of the counts of the events with f < x: the thresholds are monotone in the delay
+//       index, so every event adds its count to the first delay it matters for (closed form from bit
+//       lengths) and running sums over the delays give all PS at once; PS(lim_l) likewise from the level
+//       bitlength(f ^ F) at which an event dies
 //   G2, sparse levels (l < ld): ONE pass over event pairs i < j with d = f_j - f_i < (2dpl+1) << (ld-1);
 //       a pair lands at level 0 when d <= 2dpl, and for d >= 2dpl only at the levels
 //       l0 = bitlength(d) - log2(dpl) - 1 (bin distance b = (f_j >> l0) - (f_i >> l0) in dpl..2dpl)
@@ -135,8 +138,7 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
     uint32_t *evT = mw_smem;                              // [32][pitch_e]
     uint32_t *outS = evT + 32 * m.pitch_e;                // [3][32][pitch_t]
     uint32_t *wsm = outS + 3 * 32 * m.pitch_t + warp * m.warp_words;
-    uint32_t *ps = wsm;                                   // [len_cap + 1]
-    uint32_t *bw = ps + (m.len_cap + 1);                  // [2 * len_cap + 64] words = 16-bit bins
+    uint32_t *bw = wsm;                                   // [2 * len_cap + 64] words = 16-bit bins
     unsigned short *bh = reinterpret_cast<unsigned short *>(bw);
     uint32_t *tb = bw + 2 * m.len_cap + 64;
     uint32_t *tot = tb, *flim = tb + 32, *cnts = tb + 64, *cntml = tb + 96, *nlive = tb + 128, *sminS = tb + 160;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
         uint32_t *oIP = H + 32 * m.pitch_t;
         uint32_t *oIF = oIP + 32 * m.pitch_t;
 
-        // ---- phase 1: prefix sums of the counts, merge-level histogram, IP / IF threshold histograms.
+        // ---- phase 1: count total, merge-level histogram, dead-level and IP / IF threshold histograms.
         // The IF thresholds t' << l ascend with the delay index and the IP thresholds (L_l - t') << l
         // descend, so an event only has to know the first delay it counts for: oIF[a] += c with
         // a = #{ti : t' << l <= f}, oIP[b] += c with b = #{ti : (L_l - t') << l > f} (closed forms from
@@ -177,21 +179,15 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
             oIF[t] = 0u;
         }
         if (COMPAT) cntml[lane] = 0u;
-        if (lane == 0) ps[0] = 0u;
+        tot[lane] = 0u;  // until phase 2: counts of the events that die at level lane
         __syncwarp();
-        uint32_t carry = 0;
+        uint32_t csum = 0;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int i = c0 + lane;
             const uint32_t w = i < n ? ev[i] : 0u;
             const uint32_t c = w & ((1u << kCountBits) - 1u);
-            uint32_t x = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(kFull, x, o);
-                if (lane >= o) x += y;
-            }
+            csum += c;
             if (i < n) {
-                ps[i + 1] = carry + x;
                 const int f = (int)(w >> kCountBits);
                 int ai;
                 if (f < 2 * DPL) ai = min(f, cnt0);
@@ -214,13 +210,15 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
                     }
                 }
                 if (bi < T) atomicAdd(&oIP[bi], c);
+                // f >= lim_l  <=>  f >> l == F >> l  <=>  bitlength(f ^ F) <= l
+                atomicAdd(&tot[32 - __clz(f ^ F)], c);
             }
-            carry += __shfl_sync(kFull, x, 31);
             if (COMPAT && i >= 1 && i < n) {
                 const int ml = 32 - __clz((int)((w ^ ev[i - 1]) >> kCountBits));
                 atomicAdd(&cntml[ml], 1u);
             }
         }
+        const uint32_t carry = __reduce_add_sync(kFull, csum);
         if (carry >= 65536u) {  // 32-bit numerators could overflow: the lane-per-row kernel redoes the slice
             if (lane == 0) m.fallback[s] = 1;
             continue;
@@ -241,7 +239,16 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
             const int Ll = lv_ok ? (F >> l) : 0;
             const int liml = lv_ok ? (Ll << l) : 0;
             const int cnt_l = lv_ok ? a.sched.count[l] : 0;
-            tot[l] = ps[mw_lower_bound(ev, n, (uint32_t)liml << kCountBits)];
+            {  // PS(lim_l) = all counts - counts of the events dead at level l
+                uint32_t dead = tot[l];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, dead, o);
+                    if (lane >= o) dead += y;
+                }
+                __syncwarp();
+                tot[l] = carry - dead;
+            }
             cnts[l] = (l < ld) ? (uint32_t)cnt_l : 0u;
             uint32_t fl = (l < ld) ? (uint32_t)liml : 0u;
             if (COMPAT) {
@@ -446,22 +453,18 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
 
         // ---- phase 5: running sums of the threshold histograms, one IEEE division per output (lane = delay)
         {
-            uint32_t runC = 0, runD = 0;
+            uint32_t run = 0;  // both running sums in one word: each stays below 2^16
             for (int t0 = 0; t0 < T; t0 += 32) {
                 const int ti = t0 + lane;
-                uint32_t xc = ti < T ? oIF[ti] : 0u, xd = ti < T ? oIP[ti] : 0u;
+                uint32_t x = ti < T ? (oIF[ti] | (oIP[ti] << 16)) : 0u;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t yc = __shfl_up_sync(kFull, xc, o), yd = __shfl_up_sync(kFull, xd, o);
-                    if (lane >= o) {
-                        xc += yc;
-                        xd += yd;
-                    }
+                    const uint32_t y = __shfl_up_sync(kFull, x, o);
+                    if (lane >= o) x += y;
                 }
-                xc += runC;
-                xd += runD;
-                runC = __shfl_sync(kFull, xc, 31);
-                runD = __shfl_sync(kFull, xd, 31);
+                x += run;
+                run = __shfl_sync(kFull, x, 31);
+                const uint32_t xc = x & 0xffffu, xd = x >> 16;
                 if (ti < T) {
                     int l, tp;
                     if (ti < cnt0) {
@@ -553,11 +556,11 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
             m.cnt_last = h->sched.count[l];
         }
     const size_t out_bytes = (size_t)3 * 32 * m.pitch_t * 4;
-    // bytes(len, warps) = out + 4 * (32 * (len | 1) + warps * (3 len + 65 + tables)).  Two CTAs per SM when
+    // bytes(len, warps) = out + 4 * (32 * (len | 1) + warps * (2 len + 64 + tables)).  Two CTAs per SM when
     // the longest row allows it -- with 16 warps each, else with 12 or 8 (a long delay schedule makes the
     // result stage large) -- one CTA of 16 warps otherwise; longer slices go to the lane-per-row kernel
     auto bytes_for = [&](int len, int warps) {
-        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)warps * (3 * (size_t)len + 65 + kMwTables));
+        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)warps * (2 * (size_t)len + 64 + kMwTables));
     };
     const size_t budget2 = (size_t)(smem_cap + 1024) / 2 - 1024 - 512;  // two resident CTAs (1 KB reserved each)
     int len_cap = h->max_row > 0 ? h->max_row : 1;
@@ -576,7 +579,7 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     }
     m.len_cap = len_cap;
     m.pitch_e = len_cap | 1;
-    m.warp_words = 3 * len_cap + 65 + kMwTables;
+    m.warp_words = 2 * len_cap + 64 + kMwTables;
     const size_t bytes = bytes_for(len_cap, warps);
     const bool compat = a.compat != 0;
     const int dpl = h->prm.delays_per_level;
