@@ -271,29 +271,70 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
             const uint32_t dmax = (uint32_t)(2 * DPL + 1) << (ld - 1);
             const uint32_t top0 = (uint32_t)(lo0 + cnt0 - 1);
             const uint32_t flim0 = flim[0];
+            // flattened as in multitau_warp.cu: events with partners compacted (Ic = event, Qc = its first
+            // pair), owners that start inside a 32-pair chunk mark their first lane in a bit mask
+            uint32_t *Qc = U;
+            uint32_t *Ic = U + m.len_cap + 34;
+            uint32_t npairs = 0;
+            int nact = 0;
+            const int topstep = n > 0 ? (1 << (31 - __clz(n))) : 1;
             for (int c0 = 0; c0 < n; c0 += 32) {
                 const int i = c0 + lane;
-                const uint32_t fi = i < n ? fr[i] : 0u;
-                const float vi = i < n ? vl[i] : 0.0f;
-                for (int k = 1;; k++) {
-                    const int j = i + k;
-                    const uint32_t fj = j < n ? fr[j] : 0xffffffffu;
+                const uint32_t key = i < n ? min(fr[i] + dmax, (uint32_t)F) : 0u;  // partners: f_j < key
+                int pos = i;
+                if (__any_sync(kFullF, i + 8 < n && fr[min(i + 8, n - 1)] < key)) {
+                    for (int step = topstep; step >= 8; step >>= 1) {
+                        const int k2 = pos + step;
+                        if (k2 < n && fr[k2] < key) pos = k2;
+                    }
+                }
+#pragma unroll
+                for (int step = 4; step >= 1; step >>= 1) {
+                    const int k2 = pos + step;
+                    if (k2 < n && fr[k2] < key) pos = k2;
+                }
+                const uint32_t mi = i < n ? (uint32_t)(pos - i) : 0u;
+                uint32_t x = mi;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFullF, x, o);
+                    if (lane >= o) x += y;
+                }
+                const unsigned act = __ballot_sync(kFullF, mi > 0u);
+                if (mi > 0u) {
+                    const int k = nact + __popc(act & ((1u << lane) - 1u));
+                    Qc[k] = npairs + x - mi;
+                    Ic[k] = (uint32_t)i;
+                }
+                nact += __popc(act);
+                npairs += __shfl_sync(kFullF, x, 31);
+            }
+            Qc[nact + lane] = 0xffffffffu;
+            if (lane < 2) Qc[nact + 32 + lane] = 0xffffffffu;
+            __syncwarp();
+            int kbase = 0;
+            for (uint32_t p0 = 0; p0 < npairs; p0 += 32) {
+                const uint32_t sl = Qc[kbase + 1 + lane] - p0;
+                const unsigned bits = __reduce_or_sync(kFullF, sl < 32u ? (1u << sl) : 0u);
+                const int k = kbase + __popc(bits & (0xffffffffu >> (31 - lane)));
+                kbase += __popc(bits);
+                const uint32_t p = p0 + lane;
+                if (p < npairs) {
+                    const int i = (int)Ic[k];
+                    const int j = i + 1 + (int)(p - Qc[k]);
+                    const uint32_t fi = fr[i], fj = fr[j];
                     const uint32_t d = fj - fi;
-                    const bool act = j < n && d < dmax;
-                    if (!__any_sync(kFullF, act)) break;
-                    if (act) {
-                        const double cc = (double)vi * (double)vl[j];
-                        if (d <= top0 && d >= (uint32_t)lo0 && fj < flim0) atomicAdd(&Hacc[d - lo0], cc);
-                        if (d >= 2u * DPL) {
-                            const int l0 = (32 - __clz((int)d)) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
-                            const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
-                            if (b0 < cnts[l0] && fj < flim[l0]) atomicAdd(&Hacc[cnt0 + (l0 - 1) * DPL + b0], cc);
-                            const int l1 = l0 - 1;
-                            if (l1 >= 1) {
-                                const uint32_t b1 = (fj >> l1) - (fi >> l1);
-                                if (b1 == 2u * DPL && (uint32_t)(DPL - 1) < cnts[l1] && fj < flim[l1])
-                                    atomicAdd(&Hacc[cnt0 + (l1 - 1) * DPL + (DPL - 1)], cc);
-                            }
+                    const double cc = (double)vl[i] * (double)vl[j];
+                    if (d <= top0 && d >= (uint32_t)lo0 && fj < flim0) atomicAdd(&Hacc[d - lo0], cc);
+                    if (d >= 2u * DPL) {
+                        const int l0 = (32 - __clz((int)d)) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
+                        const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
+                        if (b0 < cnts[l0] && fj < flim[l0]) atomicAdd(&Hacc[cnt0 + (l0 - 1) * DPL + b0], cc);
+                        const int l1 = l0 - 1;
+                        if (l1 >= 1) {
+                            const uint32_t b1 = (fj >> l1) - (fi >> l1);
+                            if (b1 == 2u * DPL && (uint32_t)(DPL - 1) < cnts[l1] && fj < flim[l1])
+                                atomicAdd(&Hacc[cnt0 + (l1 - 1) * DPL + (DPL - 1)], cc);
                         }
                     }
                 }
