@@ -41,6 +41,7 @@ struct MfArgs {
     int pitch_t;               // odd, >= T
     int warp_words;            // per-warp shared words
     int T;
+    int bin_cap;               // bins a warp can hold (dense levels start at L_l <= min(4 n, bin_cap))
 };
 
 __device__ __forceinline__ float mf_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
     float *vl = reinterpret_cast<float *>(fr + m.len_cap);       // [len_cap]
     uint32_t *U = fr + 2 * m.len_cap;                            // 8-byte aligned: ps (double), later bins (float)
     double *ps = reinterpret_cast<double *>(U);                  // [len_cap + 1]
-    float *bh = reinterpret_cast<float *>(U);                    // [4 len_cap + 64]
+    float *bh = reinterpret_cast<float *>(U);                    // [bin_cap + 64]
 
     const int F = a.sched.frames;
     const int nl = a.sched.n_levels;
@@ -191,10 +192,11 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
         }
         __syncwarp();
 
-        // first dense level: L_l <= 4 n
+        // first dense level: L_l <= 4 n (and the bins must fit the warp's area)
         int ld;
         {
-            const unsigned mk = __ballot_sync(kFullF, lane >= 1 && lane < nl && (F >> lane) <= 4 * max(n, 1));
+            const unsigned mk =
+                __ballot_sync(kFullF, lane >= 1 && lane < nl && (F >> lane) <= min(4 * max(n, 1), m.bin_cap));
             ld = mk ? (__ffs(mk) - 1) : nl;
         }
 
@@ -501,26 +503,41 @@ int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a)
     m.T = h->T;
     m.pitch_t = h->T | 1;
     // shared words: stage [3][32][pitch_t] (even), then per warp Hacc (2T) + tot (64) + tables (160)
-    // + frames and values (2 len) + max(prefix sums 2 (len + 1), bins 4 len + 64): every area even
+    // + frames and values (2 len) + max(prefix sums 2 (len + 1), bins bin_cap + 64): every area even
     const size_t out_words = (size_t)3 * 32 * m.pitch_t;
-    auto warp_words = [&](int len) { return (size_t)2 * m.T + 64 + 160 + (size_t)2 * len + (size_t)4 * len + 64; };
-    // the longest row decides the per-warp area; as many warps as fit (at least 4, at most 16: two
-    // CTAs share an SM when the rows are short); longer slices go to the lane-per-row kernel
+    auto warp_words = [&](int len, int bins) {
+        return (size_t)2 * m.T + 64 + 160 + (size_t)2 * len + std::max((size_t)bins + 64, (size_t)2 * len + 2);
+    };
     // Rows beyond kMfExactLen events stay with the lane-per-row kernel, which keeps the reference's
     // sequential fp32 order: the reference's own rounding grows with the length of its chains
     // (1.7e-5 on a 3000-event row), and beyond ~1000 events sums that are more exact than the
     // reference's stop agreeing with it within the 1e-5 tolerance.
     int len_cap = h->max_row > 0 ? std::min(h->max_row, kMfExactLen) : 1;
     const size_t budget1 = ((size_t)smem_cap - 512) / 4;
-    while (len_cap > 1 && out_words + 4 * warp_words(len_cap) > budget1) len_cap = len_cap * 3 / 4;
-    if (out_words + 4 * warp_words(len_cap) > budget1) {  // T too large for the stage: everything falls back
-        cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
-        return XPCS_OK;
+    // A CTA works through its 32 rows in ceil(32 / warps) rounds: 16 warps (2 rounds) when the longest
+    // row leaves them at least 2 len bins each (rows with more than bin_cap / 4 events then start their
+    // dense levels one level later), else 11 warps (3 rounds) with the full 4 len, else what fits.
+    int warps = 0, bin_cap = 4 * len_cap;
+    if (out_words + 16 * warp_words(len_cap, 2 * len_cap) <= budget1) {
+        warps = 16;
+        const size_t area = ((budget1 - out_words) / 16) & ~(size_t)1;           // words per warp
+        const size_t u = area - ((size_t)2 * m.T + 64 + 160 + (size_t)2 * len_cap);  // prefix sums / bins
+        bin_cap = (int)(std::min((size_t)4 * len_cap, u - 64) & ~(size_t)1);
+    } else if (out_words + 11 * warp_words(len_cap, 4 * len_cap) <= budget1) {
+        warps = 11;
+    } else {
+        while (len_cap > 1 && out_words + 4 * warp_words(len_cap, 4 * len_cap) > budget1) len_cap = len_cap * 3 / 4;
+        if (out_words + 4 * warp_words(len_cap, 4 * len_cap) > budget1) {  // T too large for the stage: everything falls back
+            cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
+            return XPCS_OK;
+        }
+        bin_cap = 4 * len_cap;
+        warps = (int)((budget1 - out_words) / warp_words(len_cap, bin_cap));
+        if (warps > kMfMaxWarps) warps = kMfMaxWarps;
     }
-    int warps = (int)((budget1 - out_words) / warp_words(len_cap));
-    if (warps > kMfMaxWarps) warps = kMfMaxWarps;
     m.len_cap = len_cap;
-    m.warp_words = (int)warp_words(len_cap);
+    m.bin_cap = bin_cap;
+    m.warp_words = (int)warp_words(len_cap, bin_cap);
     const size_t bytes = 4 * (out_words + (size_t)warps * m.warp_words);
     const bool compat = a.compat != 0;
     const int dpl = h->prm.delays_per_level;
