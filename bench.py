@@ -240,7 +240,7 @@ def run_reference_arm(args, wl, wl_key):
 KERNEL_GROUP = {  # kernel name -> stage of SURVEY.md 8(d)
     "k_block_frames": "K1", "k_hist": "K1", "k_slice_len": "K1", "k_slice_scan": "K1", "k_scatter": "K1",
     "k_finalize": "K1", "k_frame_scale": "K1", "k_hist_dense": "K1", "k_scatter_dense": "K1",
-    "k_finalize_warp": "K1", "k_dense_bounds": "K2",
+    "k_finalize_warp": "K1", "k_scatter_rec": "K1", "k_scatter_rec_dense": "K1", "k_place": "K1", "k_dense_bounds": "K2",
     "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_multitau_warp": "K4", "k_multitau_warpf": "K4",
     "k_unpermute": "K4",
     "k_segment_reduce": "K6", "k_normalize_finish": "K6",
@@ -253,6 +253,8 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
     tbl = {
         "k_hist": 6 * E,                       # one read of the frame-major events
         "k_scatter": 12 * E,                   # read frame-major, write pixel-major
+        "k_scatter_rec": 12 * E,               # read frame-major, append to the slice streams (8 B records move)
+        "k_place": 12 * E,                     # read the slice streams, write the rows (same 6 B/event accounting)
         "k_finalize": 12 * E,                  # read + write the pixel-major rows once
         "k_multitau": 6 * E + 12 * T * R,      # read each event once, write G2/IP/IF once
         "k_multitau_warp": 6 * E + 12 * T * R,

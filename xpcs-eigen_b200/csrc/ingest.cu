@@ -61,6 +61,10 @@ struct IngestArgs {
     // dense source (explicit frame id + float value per event)
     const int32_t *evt;
     const float *valf;
+    // stream scatter: slice-ordered records
+    int *slice_cur;
+    const int64_t *slice_rec;
+    unsigned long long *rec;
 };
 
 // summary slots
@@ -168,7 +172,8 @@ __global__ void __launch_bounds__(kIngestThreads) k_hist(IngestArgs a)
 
 // slice length = longest row of the slice; also copies the histogram to row_len.
 __global__ void k_slice_len(const int *__restrict__ row_count, int *__restrict__ row_len,
-                            int *__restrict__ slice_len, int n_slices, long long *summary)
+                            int *__restrict__ slice_len, int *__restrict__ slice_cur, int n_slices,
+                            long long *summary)
 {
     int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -179,20 +184,43 @@ __global__ void k_slice_len(const int *__restrict__ row_count, int *__restrict__
     int tot = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) {
         slice_len[s] = m;
+        slice_cur[s] = tot;
         atomicMax(summary + kSumMaxLen, (long long)m);
         atomicAdd((unsigned long long *)summary + kSumEvents, (unsigned long long)tot);
     }
 }
 
 // exclusive scan of slice_len*32 over all slices (single CTA; a few 10^4..10^5 entries)
+// blockIdx.x == 1: the same scan over the slices' event totals -> first record of every slice
 __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ slice_len,
                                                      int64_t *__restrict__ slice_base,
+                                                     const int *__restrict__ slice_tot,
+                                                     int64_t *__restrict__ slice_rec,
                                                      int n_slices, long long *summary)
 {
     __shared__ long long part[1024];
     const int tid = threadIdx.x;
     const int per = (n_slices + 1023) / 1024;
     const int a = tid * per, b = min(n_slices, a + per);
+    if (blockIdx.x == 1) {
+        long long s = 0;
+        for (int i = a; i < b; i++) s += (long long)slice_tot[i];
+        part[tid] = s;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            long long x = tid >= o ? part[tid - o] : 0;
+            __syncthreads();
+            part[tid] += x;
+            __syncthreads();
+        }
+        long long run = part[tid] - s;
+        for (int i = a; i < b; i++) {
+            slice_rec[i] = run;
+            run += (long long)slice_tot[i];
+        }
+        if (tid == 1023) slice_rec[n_slices] = part[1023];
+        return;
+    }
     long long s = 0;
     for (int i = a; i < b; i++) s += (long long)slice_len[i] * kSlice;
     part[tid] = s;
@@ -278,6 +306,143 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter(IngestArgs a)
     }
 }
 
+template <int KIND>
+struct WordT;
+template <>
+struct WordT<kPacked> {
+    typedef uint32_t type;
+};
+template <>
+struct WordT<kFloat> {
+    typedef unsigned long long type;
+};
+
+// Stream scatter (the default): the direct scatter above writes 4- or 8-byte words 128 bytes apart,
+// and a 128-byte line of the store is complete only when all 32 rows of the slice have received that
+// event rank -- with ~10^5 slices the open lines outgrow the L2 and DRAM sees partial-sector
+// traffic (3.5x the algorithmic bytes measured).  Here an event is appended to the record stream
+// of its SLICE instead (one open line per slice), and k_place -- one CTA per slice, the slice's
+// region of the store hot in L2 -- moves the records to their rows.
+// Record: kPacked  lane << 32 | word;  kFloat  lane << 59 | frame << 32 | float bits (frames < 2^27).
+constexpr int kRecLaneShiftF = 59;
+
+template <int KIND, bool DENSE_SRC>
+__global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
+{
+    const int64_t base = (int64_t)blockIdx.x * kEvPerBlock;
+    int f = DENSE_SRC ? 0 : a.block_first[blockIdx.x];
+    constexpr int kIter = kEvPerBlock / (kIngestThreads * 4);
+#pragma unroll 1
+    for (int k = 0; k < kIter; k++) {
+        const int64_t e0 = base + ((int64_t)k * kIngestThreads + threadIdx.x) * 4;
+        int nv = 0;
+        if (e0 < a.E) nv = (a.E - e0) >= 4 ? 4 : (int)(a.E - e0);
+        int pix[4], t[4];
+        int16_t raw[4] = {0, 0, 0, 0};
+        float rawf[4] = {0.f, 0.f, 0.f, 0.f};
+        if (nv == 4) {
+            int4 p4 = *reinterpret_cast<const int4 *>(a.idx + e0);
+            pix[0] = p4.x; pix[1] = p4.y; pix[2] = p4.z; pix[3] = p4.w;
+            if (DENSE_SRC) {
+                int4 t4 = *reinterpret_cast<const int4 *>(a.evt + e0);
+                t[0] = t4.x; t[1] = t4.y; t[2] = t4.z; t[3] = t4.w;
+                float4 f4 = *reinterpret_cast<const float4 *>(a.valf + e0);
+                rawf[0] = f4.x; rawf[1] = f4.y; rawf[2] = f4.z; rawf[3] = f4.w;
+            } else {
+                short4 s4 = *reinterpret_cast<const short4 *>(a.val + e0);
+                raw[0] = s4.x; raw[1] = s4.y; raw[2] = s4.z; raw[3] = s4.w;
+            }
+        } else {
+            for (int j = 0; j < nv; j++) {
+                pix[j] = a.idx[e0 + j];
+                if (DENSE_SRC) { t[j] = a.evt[e0 + j]; rawf[j] = a.valf[e0 + j]; }
+                else raw[j] = a.val[e0 + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j >= nv) continue;
+            int tj;
+            if (DENSE_SRC) tj = t[j];
+            else {
+                const int64_t e = e0 + j;
+                while (f + 1 < a.nraw && e >= __ldg(a.off + f + 1)) f++;
+                tj = out_frame(f, a.rawblock, a.stride, a.F);
+            }
+            if (tj < 0 || (unsigned)pix[j] >= (unsigned)a.P) continue;
+            const int r = __ldg(a.row_of_pixel + pix[j]);
+            if (r < 0) continue;
+            const int sl = r >> 5;
+            const int pos = atomicSub(a.slice_cur + sl, 1) - 1;
+            unsigned long long rec;
+            if (KIND == kPacked) {
+                rec = ((unsigned long long)(r & 31) << 32) |
+                      (unsigned long long)(((uint32_t)tj << kCountBits) | (uint32_t)(raw[j] & ((1 << kCountBits) - 1)));
+            } else {
+                float v = DENSE_SRC ? rawf[j]
+                                    : (float)((double)(float)raw[j] * __ldg(a.flat + pix[j]));
+                rec = ((unsigned long long)(r & 31) << kRecLaneShiftF) | ((unsigned long long)(uint32_t)tj << 32) |
+                      (unsigned long long)__float_as_uint(v);
+            }
+            a.rec[__ldg(a.slice_rec + sl) + pos] = rec;
+        }
+    }
+}
+
+// One warp per slice: records -> rows, in stream order (a stable placement: the rank of a record is
+// the number of earlier records of the same row, from 32 shared-memory cursors plus a match inside
+// the 32-record step).  The stream was filled from its end, so reading it forwards fills the rows
+// latest-first and nearly sorted, which is what the finalisation kernels expect from the scatter.
+constexpr int kPlaceWarps = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(kPlaceWarps * 32) k_place(const unsigned long long *__restrict__ rec,
+                                                            const int64_t *__restrict__ slice_rec,
+                                                            const int64_t *__restrict__ slice_base, void *store,
+                                                            int n_slices)
+{
+    typedef typename WordT<KIND>::type W;
+    __shared__ int cur_all[kPlaceWarps][kSlice];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kPlaceWarps + warp;
+    if (s >= n_slices) return;
+    int *cur = cur_all[warp];
+    cur[lane] = 0;
+    __syncwarp();
+    const int64_t r0 = slice_rec[s];
+    const int n = (int)(slice_rec[s + 1] - r0);
+    W *dst = reinterpret_cast<W *>(store) + slice_base[s];
+    // two steps of records in flight ahead of the one being placed
+    unsigned long long x1 = lane < n ? rec[r0 + lane] : 0ull;
+    unsigned long long x2 = 32 + lane < n ? rec[r0 + 32 + lane] : 0ull;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        const bool ok = e < n;
+        const unsigned long long x = x1;
+        x1 = x2;
+        x2 = e + 64 < n ? rec[r0 + e + 64] : 0ull;
+        int row = 32 + lane;  // idle lanes match nobody
+        W w = 0;
+        if (ok) {
+            if (KIND == kPacked) {
+                row = (int)(x >> 32);
+                w = (W)(uint32_t)x;
+            } else {
+                row = (int)(x >> kRecLaneShiftF);
+                w = (W)(x & ((1ull << kRecLaneShiftF) - 1ull));
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, row);
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        int rank = 0;
+        if (ok) rank = cur[row] + before;
+        __syncwarp();
+        if (ok && before == 0) cur[row] += __popc(peers);
+        __syncwarp();
+        if (ok) dst[(int64_t)rank * kSlice + row] = w;
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Row finalisation: one warp per slice, one lane per row.  Sorts the row by frame, merges
 // events that fell on the same output frame (duplicates, stride/average blocks), applies
@@ -298,17 +463,10 @@ struct FinalizeArgs {
     int n_slices, S, swindow, avg, smem_len;
     unsigned char *flagged;  // warp-per-row kernel: slices it leaves; lane-per-row kernel: only those (nullptr = all)
     int row_cap, window;     // warp-per-row kernel: longest row it takes, first ranking window
-};
-
-template <int KIND>
-struct WordT;
-template <>
-struct WordT<kPacked> {
-    typedef uint32_t type;
-};
-template <>
-struct WordT<kFloat> {
-    typedef unsigned long long type;
+    // lane-per-row kernel, every slice in shared memory: the rows are taken straight from the slice's
+    // record stream (stream scatter), k_place is skipped
+    const unsigned long long *rec;
+    const int64_t *slice_rec;
 };
 
 template <int KIND>
@@ -316,6 +474,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
 {
     typedef typename WordT<KIND>::type W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int curS[kSlice];
     const int s = blockIdx.x;
     const int lane = threadIdx.x;
     const int r = s * kSlice + lane;
@@ -329,7 +488,46 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     const int n = a.row_len[r];
     const bool in_smem = len <= a.smem_len;
     W *col;
-    if (in_smem) {
+    if (in_smem && a.rec) {
+        // stable placement of the slice's records (see k_place); the stream runs latest-first, so a
+        // record of rank k goes to position n - 1 - k of its row and the column is close to ascending
+        W *tile = reinterpret_cast<W *>(smem_raw);
+        col = tile + lane;
+        const int64_t r0 = a.slice_rec[s];
+        const int nrec = (int)(a.slice_rec[s + 1] - r0);
+        curS[lane] = 0;  // records of every row placed so far
+        __syncwarp();
+        unsigned long long x1 = lane < nrec ? a.rec[r0 + lane] : 0ull;
+        unsigned long long x2 = 32 + lane < nrec ? a.rec[r0 + 32 + lane] : 0ull;
+        for (int e0 = 0; e0 < nrec; e0 += 32) {
+            const int e = e0 + lane;
+            const bool ok = e < nrec;
+            const unsigned long long x = x1;
+            x1 = x2;
+            x2 = e + 64 < nrec ? a.rec[r0 + e + 64] : 0ull;
+            int row = 32 + lane;  // idle lanes match nobody
+            W w = 0;
+            if (ok) {
+                if (KIND == kPacked) {
+                    row = (int)(x >> 32);
+                    w = (W)(uint32_t)x;
+                } else {
+                    row = (int)(x >> kRecLaneShiftF);
+                    w = (W)(x & ((1ull << kRecLaneShiftF) - 1ull));
+                }
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, row);
+            const int before = __popc(peers & ((1u << lane) - 1u));
+            int rank = 0;
+            if (ok) rank = curS[row] + before;
+            __syncwarp();
+            if (ok && before == 0) curS[row] += __popc(peers);
+            __syncwarp();
+            const int nrow = __shfl_sync(0xffffffffu, n, row & 31);
+            if (ok) tile[(nrow - 1 - rank) * kSlice + row] = w;
+        }
+        __syncwarp();
+    } else if (in_smem) {
         col = reinterpret_cast<W *>(smem_raw) + lane;
         // the scatter filled the row from the top down: reverse while loading so that the
         // column is close to ascending already
@@ -1078,12 +1276,12 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         LaunchScope ls(h, "k_slice_len");
         int threads = 256, warps = h->n_slices;
         k_slice_len<<<(warps * 32 + threads - 1) / threads, threads, 0, h->stream>>>(
-            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->n_slices, h->d_summary.p);
+            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p);
     }
     {
         LaunchScope ls(h, "k_slice_scan");
-        k_slice_scan<<<1, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->n_slices,
-                                                h->d_summary.p);
+        k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
+                                                h->d_slice_rec.p, h->n_slices, h->d_summary.p);
     }
     long long sum[kSumSlots];
     int rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream),
@@ -1099,10 +1297,36 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     if (rc) return rc;
     ia.slice_base = h->d_slice_base.p;
     ia.store = h->d_store.p;
-    if (nblocks > 0) {
+    // stream scatter + placement unless the frames do not fit the float record (or XPCS_SCATTER_DIRECT)
+    const bool direct = (KIND == kFloat && h->prm.frames > (1 << 27)) || getenv("XPCS_SCATTER_DIRECT");
+    // Short rows (a slice fits 24 KB): one lane per row, the whole slice in shared memory -- the
+    // finalisation then takes the rows straight from the record streams.  Longer rows: one warp
+    // per row; slices beyond its buffers are flagged and left to the lane-per-row kernel, which
+    // then works in global memory.
+    const int smem_cap = max_dyn_smem(h->device) - 1024;
+    const size_t lane_bytes_all = (size_t)h->max_row * kSlice * sizeof(W);
+    const bool use_warp = lane_bytes_all > 24 * 1024 && !getenv("XPCS_FIN_LANE");
+    const bool fused_place = !direct && !use_warp && (long long)lane_bytes_all <= smem_cap && !getenv("XPCS_PLACE_KERNEL");
+    if (nblocks > 0 && direct) {
         LaunchScope ls(h, dense ? "k_scatter_dense" : "k_scatter");
         if (dense) k_scatter<KIND, true><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
         else k_scatter<KIND, false><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
+    } else if (nblocks > 0) {
+        rc = ensure(h, h->d_rec, (size_t)sum[kSumEvents] + 1, "event records");
+        if (rc) return rc;
+        ia.slice_cur = h->d_slice_cur.p;
+        ia.slice_rec = h->d_slice_rec.p;
+        ia.rec = h->d_rec.p;
+        {
+            LaunchScope ls(h, dense ? "k_scatter_rec_dense" : "k_scatter_rec");
+            if (dense) k_scatter_rec<KIND, true><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
+            else k_scatter_rec<KIND, false><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
+        }
+        if (!fused_place) {
+            LaunchScope ls(h, "k_place");
+            k_place<KIND><<<(h->n_slices + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, 0, h->stream>>>(
+                h->d_rec.p, h->d_slice_rec.p, h->d_slice_base.p, h->d_store.p, h->n_slices);
+        }
     }
     // finalize
     const int F = h->prm.frames;
@@ -1131,12 +1355,8 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         k_frame_scale<<<1, 256, 0, h->stream>>>(h->d_frame_acc.p, h->d_frame_scale.p, F, h->P);
         fa.frame_scale = h->d_frame_scale.p;
     }
-    const int smem_cap = max_dyn_smem(h->device) - 1024;
-    // Short rows (a slice fits 24 KB): one lane per row, the whole slice in shared memory.  Longer
-    // rows: one warp per row; slices beyond its buffers are flagged and left to the lane-per-row
-    // kernel, which then works in global memory.
-    const size_t lane_bytes_all = (size_t)h->max_row * kSlice * sizeof(W);
-    const bool use_warp = lane_bytes_all > 24 * 1024 && !getenv("XPCS_FIN_LANE");
+    fa.rec = (fused_place && nblocks > 0) ? h->d_rec.p : nullptr;
+    fa.slice_rec = h->d_slice_rec.p;
     fa.flagged = nullptr;
     if (use_warp && h->n_slices > 0) {
         rc = ensure(h, h->d_mt_fallback, (size_t)h->n_slices, "finalize flags");

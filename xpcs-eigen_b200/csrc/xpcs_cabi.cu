@@ -253,6 +253,8 @@ static int build_maps(xpcs_handle_s *h)
     if ((rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths"))) return rc;
     if ((rc = ensure(h, h->d_slice_len, (size_t)h->n_slices, "slice lengths"))) return rc;
     if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
+    if ((rc = ensure(h, h->d_slice_cur, (size_t)h->n_slices + 1, "slice cursors"))) return rc;
+    if ((rc = ensure(h, h->d_slice_rec, (size_t)h->n_slices + 1, "slice record offsets"))) return rc;
     cudaMemcpy(h->d_row_of_pixel.p, row_of_pixel.data(), sizeof(int) * P, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_pixel_of_row.p, pix_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_sbin_of_row.p, sbin_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
@@ -413,6 +415,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
     release(h->d_dense_counter);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
+    release(h->d_slice_cur); release(h->d_slice_rec); release(h->d_rec);
     release(h->d_block_first); release(h->d_store); release(h->d_summary); release(h->d_frame_acc);
     release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
     release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch); release(h->d_mt_fallback);
