@@ -29,11 +29,11 @@ namespace xpcs {
 
 // first raw frame of every block of kEvPerBlock events: largest f with off[f] <= e
 __global__ void k_block_frames(const int64_t *__restrict__ off, int nraw, int64_t E,
-                               int *__restrict__ first, int nblocks)
+                               int *__restrict__ first, int nblocks, int64_t ev_begin)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    int64_t e = (int64_t)b * kEvPerBlock;
+    int64_t e = (int64_t)b * kEvPerBlock + (ev_begin & ~3LL);
     int lo = 0, hi = nraw;  // invariant: off[lo] <= e, answer in [lo, hi)
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -65,6 +65,9 @@ struct IngestArgs {
     int *slice_cur;
     const int64_t *slice_rec;
     unsigned long long *rec;
+    // chunked ingest: the events [ev_begin, E) of idx/val, off points at the chunk's first frame
+    int64_t ev_begin;  // first event of the chunk (the blocks start at ev_begin & ~3: aligned vector loads)
+    int frame_base;    // raw frame number of off[0]
 };
 
 // summary slots
@@ -92,7 +95,7 @@ __device__ __forceinline__ int out_frame(int raw, int rawblock, int stride, int 
 template <int KIND, bool DENSE_SRC>
 __global__ void __launch_bounds__(kIngestThreads) k_hist(IngestArgs a)
 {
-    const int64_t base = (int64_t)blockIdx.x * kEvPerBlock;
+    const int64_t base = (a.ev_begin & ~3LL) + (int64_t)blockIdx.x * kEvPerBlock;
     int f = DENSE_SRC ? 0 : a.block_first[blockIdx.x];
     constexpr int kIter = kEvPerBlock / (kIngestThreads * 4);
 #pragma unroll 1
@@ -126,11 +129,11 @@ __global__ void __launch_bounds__(kIngestThreads) k_hist(IngestArgs a)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             v[j] = 0.0;
-            if (j >= nv) { t[j] = -1; continue; }
+            if (j >= nv || e0 + j < a.ev_begin) { t[j] = -1; continue; }
             if (!DENSE_SRC) {
                 const int64_t e = e0 + j;
                 while (f + 1 < a.nraw && e >= __ldg(a.off + f + 1)) f++;
-                t[j] = out_frame(f, a.rawblock, a.stride, a.F);
+                t[j] = out_frame(f + a.frame_base, a.rawblock, a.stride, a.F);
             }
             int r = -1;
             if (t[j] >= 0 && (unsigned)pix[j] < (unsigned)a.P) r = __ldg(a.row_of_pixel + pix[j]);
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ sli
 template <int KIND, bool DENSE_SRC>
 __global__ void __launch_bounds__(kIngestThreads) k_scatter(IngestArgs a)
 {
-    const int64_t base = (int64_t)blockIdx.x * kEvPerBlock;
+    const int64_t base = (a.ev_begin & ~3LL) + (int64_t)blockIdx.x * kEvPerBlock;
     int f = DENSE_SRC ? 0 : a.block_first[blockIdx.x];
     constexpr int kIter = kEvPerBlock / (kIngestThreads * 4);
 #pragma unroll 1
@@ -280,13 +283,13 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter(IngestArgs a)
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (j >= nv) continue;
+            if (j >= nv || e0 + j < a.ev_begin) continue;
             int tj;
             if (DENSE_SRC) tj = t[j];
             else {
                 const int64_t e = e0 + j;
                 while (f + 1 < a.nraw && e >= __ldg(a.off + f + 1)) f++;
-                tj = out_frame(f, a.rawblock, a.stride, a.F);
+                tj = out_frame(f + a.frame_base, a.rawblock, a.stride, a.F);
             }
             if (tj < 0 || (unsigned)pix[j] >= (unsigned)a.P) continue;
             const int r = __ldg(a.row_of_pixel + pix[j]);
@@ -329,7 +332,7 @@ constexpr int kRecLaneShiftF = 59;
 template <int KIND, bool DENSE_SRC>
 __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
 {
-    const int64_t base = (int64_t)blockIdx.x * kEvPerBlock;
+    const int64_t base = (a.ev_begin & ~3LL) + (int64_t)blockIdx.x * kEvPerBlock;
     int f = DENSE_SRC ? 0 : a.block_first[blockIdx.x];
     constexpr int kIter = kEvPerBlock / (kIngestThreads * 4);
 #pragma unroll 1
@@ -361,13 +364,13 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (j >= nv) continue;
+            if (j >= nv || e0 + j < a.ev_begin) continue;
             int tj;
             if (DENSE_SRC) tj = t[j];
             else {
                 const int64_t e = e0 + j;
                 while (f + 1 < a.nraw && e >= __ldg(a.off + f + 1)) f++;
-                tj = out_frame(f, a.rawblock, a.stride, a.F);
+                tj = out_frame(f + a.frame_base, a.rawblock, a.stride, a.F);
             }
             if (tj < 0 || (unsigned)pix[j] >= (unsigned)a.P) continue;
             const int r = __ldg(a.row_of_pixel + pix[j]);
@@ -467,6 +470,7 @@ struct FinalizeArgs {
     // record stream (stream scatter), k_place is skipped
     const unsigned long long *rec;
     const int64_t *slice_rec;
+    int accumulate;          // chunked ingest: row_sum += instead of =
 };
 
 template <int KIND>
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     if (a.flagged && !a.flagged[s]) return;  // done by k_finalize_warp
     const int len = a.slice_len[s];
     if (len == 0) {
-        a.row_sum[r] = 0.0;
+        if (!a.accumulate) a.row_sum[r] = 0.0;
         return;
     }
     W *g = reinterpret_cast<W *>(a.store) + a.slice_base[s] + lane;
@@ -625,7 +629,8 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
         if (win >= 0 && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
         total = (KIND == kPacked) ? (double)isum : (double)fsum;
     }
-    a.row_sum[r] = total;
+    if (a.accumulate) a.row_sum[r] += total;
+    else a.row_sum[r] = total;
     if (sb >= 0 && m > 0) atomicAdd(a.part_total + sb, total);
     a.row_len[r] = m;
     if (in_smem) {
@@ -661,7 +666,7 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
         return;
     }
     if (len == 0) {
-        if (tid < kSlice) a.row_sum[s * kSlice + tid] = 0.0;
+        if (tid < kSlice && !a.accumulate) a.row_sum[s * kSlice + tid] = 0.0;
         return;
     }
     const W kMaxW = ~(W)0;
@@ -770,7 +775,8 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
             total = (double)(float)total;
         }
         if (lane == 0) {
-            a.row_sum[r] = total;
+            if (a.accumulate) a.row_sum[r] += total;
+            else a.row_sum[r] = total;
             a.row_len[r] = m_base;
             if (sb >= 0 && m_base > 0) atomicAdd(a.part_total + sb, total);
         }
@@ -1267,8 +1273,9 @@ static int max_dyn_smem(int device)
     return v;
 }
 
+// chunk: -1 = whole ingest; k >= 0 = chunk k of a pipelined ingest (sums accumulate from k = 1 on)
 template <int KIND>
-static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool dense)
+static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool dense, int chunk = -1)
 {
     typedef typename WordT<KIND>::type W;
     // slice geometry from the histogram
@@ -1293,7 +1300,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     h->max_row = (int)sum[kSumMaxLen];
     h->store_words = sum[kSumWords];
     size_t need32 = (size_t)h->store_words * (sizeof(W) / 4);
-    rc = ensure(h, h->d_store, need32 + 32, "event store");
+    rc = ensure(h, h->d_store, chunk >= 0 ? need32 + need32 / 8 + 32 : need32 + 32, "event store");
     if (rc) return rc;
     ia.slice_base = h->d_slice_base.p;
     ia.store = h->d_store.p;
@@ -1312,7 +1319,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         if (dense) k_scatter<KIND, true><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
         else k_scatter<KIND, false><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
     } else if (nblocks > 0) {
-        rc = ensure(h, h->d_rec, (size_t)sum[kSumEvents] + 1, "event records");
+        rc = ensure(h, h->d_rec, (size_t)sum[kSumEvents] + (chunk >= 0 ? (size_t)sum[kSumEvents] / 8 : 0) + 1, "event records");
         if (rc) return rc;
         ia.slice_cur = h->d_slice_cur.p;
         ia.slice_rec = h->d_slice_rec.p;
@@ -1331,9 +1338,12 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     // finalize
     const int F = h->prm.frames;
     const int windows = (F + h->prm.static_window - 1) / h->prm.static_window;
-    cudaMemsetAsync(h->d_part_total.p, 0, sizeof(double) * (size_t)h->S, h->stream);
-    cudaMemsetAsync(h->d_part_partial.p, 0, sizeof(double) * (size_t)windows * h->S, h->stream);
+    if (chunk <= 0) {
+        cudaMemsetAsync(h->d_part_total.p, 0, sizeof(double) * (size_t)h->S, h->stream);
+        cudaMemsetAsync(h->d_part_partial.p, 0, sizeof(double) * (size_t)windows * h->S, h->stream);
+    }
     FinalizeArgs fa{};
+    fa.accumulate = chunk > 0 ? 1 : 0;
     fa.store = h->d_store.p;
     fa.slice_base = h->d_slice_base.p;
     fa.slice_len = h->d_slice_len.p;
@@ -1413,6 +1423,9 @@ int launch_ingest(xpcs_handle_s *h)
     if ((rc = ensure(h, h->d_row_sum, (size_t)h->R_pad, "row sums"))) return rc;
     if ((rc = ensure(h, h->d_part_total, (size_t)h->S, "partition sums"))) return rc;
     if ((rc = ensure(h, h->d_part_partial, (size_t)windows * h->S, "partition window sums"))) return rc;
+    // (a pipelined ingest that had to be abandoned may have handed these to a chunk store)
+    if ((rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths"))) return rc;
+    if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
 
     IngestArgs ia{};
     int64_t E = h->E;
@@ -1452,7 +1465,7 @@ int launch_ingest(xpcs_handle_s *h)
         if (nblocks > 0) {
             LaunchScope ls(h, "k_block_frames");
             k_block_frames<<<(nblocks + 255) / 256, 256, 0, h->stream>>>(ia.off, ia.nraw, E, h->d_block_first.p,
-                                                                       nblocks);
+                                                                       nblocks, 0);
         }
     }
     // exact integer path only for plain photon counts
@@ -1480,6 +1493,179 @@ int launch_ingest(xpcs_handle_s *h)
         break;
     }
     return check_cuda(h, cudaGetLastError(), "ingest kernels");
+}
+
+// ---- pipelined sparse ingest ------------------------------------------------------------------
+// Raw frames [f0, f1) -> chunk store h->chunk[h->pipe_chunks] (integer counts only: every sum the
+// Filter stage produces is then an exact integer, so the chunk order cannot change a result).
+int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1)
+{
+    const int F = h->prm.frames;
+    const int k = h->pipe_chunks;
+    if (k >= kMaxChunks) return 1;
+    int rc;
+    const int windows = (F + h->prm.static_window - 1) / h->prm.static_window;
+    if ((rc = ensure(h, h->d_summary, kSumSlots, "summary"))) return rc;
+    if ((rc = ensure(h, h->d_frame_acc, (size_t)F, "frame sums"))) return rc;
+    if ((rc = ensure(h, h->d_row_sum, (size_t)h->R_pad, "row sums"))) return rc;
+    if ((rc = ensure(h, h->d_part_total, (size_t)h->S, "partition sums"))) return rc;
+    if ((rc = ensure(h, h->d_part_partial, (size_t)windows * h->S, "partition window sums"))) return rc;
+    const int64_t e0 = h->frame_off_host[f0], e1 = h->frame_off_host[f1];
+    IngestArgs ia{};
+    ia.idx = h->d_idx.p;
+    ia.val = h->d_val.p;
+    ia.off = h->d_frame_off.p + f0;
+    ia.ev_begin = e0;
+    ia.frame_base = f0;
+    ia.nraw = f1 - f0;
+    ia.E = e1;
+    ia.row_of_pixel = h->d_row_of_pixel.p;
+    ia.flat = h->d_flat.p;
+    ia.row_count = h->d_row_count.p;
+    ia.frame_acc = h->d_frame_acc.p;
+    ia.summary = h->d_summary.p;
+    ia.F = F;
+    ia.stride = 1;
+    ia.rawblock = 1;
+    ia.P = h->P;
+    const int nblocks = (int)((e1 - (e0 & ~3LL) + kEvPerBlock - 1) / kEvPerBlock);
+    if ((rc = ensure(h, h->d_block_first, (size_t)nblocks + 1, "block frames"))) return rc;
+    ia.block_first = h->d_block_first.p;
+    h->kind = kPacked;
+    cudaMemsetAsync(h->d_summary.p, 0, sizeof(long long) * kSumSlots, h->stream);
+    cudaMemsetAsync(h->d_row_count.p, 0, sizeof(int) * (size_t)h->R_pad, h->stream);
+    if (k == 0) cudaMemsetAsync(h->d_frame_acc.p, 0, sizeof(double) * (size_t)F, h->stream);
+    if (nblocks > 0) {
+        {
+            LaunchScope ls(h, "k_block_frames");
+            k_block_frames<<<(nblocks + 255) / 256, 256, 0, h->stream>>>(ia.off, ia.nraw, ia.E, h->d_block_first.p,
+                                                                       nblocks, ia.ev_begin);
+        }
+        LaunchScope ls(h, "k_hist");
+        k_hist<kPacked, false><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
+    }
+    // the chunk's own buffers stand in for the handle's while it is built (same sizes from one ingest
+    // to the next: no reallocation, which would synchronise the device and stall the copy stream)
+    ChunkStore &c = h->chunk[k];
+    std::swap(c.store, h->d_store);
+    std::swap(c.slice_base, h->d_slice_base);
+    std::swap(c.row_len, h->d_row_len);
+    rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths");
+    if (!rc) rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets");
+    if (!rc) rc = run_store_build<kPacked>(h, ia, nblocks, false, k);
+    std::swap(c.store, h->d_store);
+    std::swap(c.slice_base, h->d_slice_base);
+    std::swap(c.row_len, h->d_row_len);
+    if (rc) return rc;  // 1: a count does not fit the packed word
+    h->pipe_chunks = k + 1;
+    return check_cuda(h, cudaGetLastError(), "chunk ingest kernels");
+}
+
+struct ConcatArgs {
+    const uint32_t *store[kMaxChunks];
+    const int64_t *slice_base[kMaxChunks];
+    const int *row_len[kMaxChunks];
+    int K;
+};
+
+__global__ void k_chunk_rows(ConcatArgs c, int *__restrict__ row_count, int R_pad)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R_pad) return;
+    int n = 0;
+    for (int k = 0; k < c.K; k++) n += c.row_len[k][r];
+    row_count[r] = n;
+}
+
+// One warp per slice, one lane per row: the chunk rows (sorted, chunks in frame order) one after
+// the other; the slice is assembled in shared memory and leaves as full 128-byte lines.
+__global__ void __launch_bounds__(32) k_concat(ConcatArgs c, uint32_t *__restrict__ store,
+                                               const int64_t *__restrict__ slice_base,
+                                               const int *__restrict__ slice_len, const int *__restrict__ row_len,
+                                               int smem_len)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int r = s * kSlice + lane;
+    const int len = slice_len[s];
+    if (len == 0) return;
+    const int n = row_len[r];
+    uint32_t *g = store + slice_base[s] + lane;
+    const bool in_smem = len <= smem_len;
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw) + lane;
+    int off = 0;
+    for (int k = 0; k < c.K; k++) {
+        const int nk = c.row_len[k][r];
+        const int lenk = __reduce_max_sync(0xffffffffu, nk);
+        const uint32_t *src = c.store[k] + c.slice_base[k][s] + lane;
+        for (int j = 0; j < lenk; j++)
+            if (j < nk) {
+                const uint32_t w = src[(int64_t)j * kSlice];
+                if (in_smem) tile[(off + j) * kSlice] = w;
+                else g[(int64_t)(off + j) * kSlice] = w;
+            }
+        off += nk;
+    }
+    if (in_smem) {
+        __syncwarp();
+        for (int j = 0; j < len; j++)
+            if (j < n) g[(int64_t)j * kSlice] = tile[j * kSlice];
+    }
+}
+
+int launch_ingest_concat(xpcs_handle_s *h)
+{
+    int rc;
+    ConcatArgs c{};
+    c.K = h->pipe_chunks;
+    for (int k = 0; k < c.K; k++) {
+        c.store[k] = h->chunk[k].store.p;
+        c.slice_base[k] = h->chunk[k].slice_base.p;
+        c.row_len[k] = h->chunk[k].row_len.p;
+    }
+    if ((rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths"))) return rc;
+    if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
+    cudaMemsetAsync(h->d_summary.p, 0, sizeof(long long) * kSumSlots, h->stream);
+    {
+        LaunchScope ls(h, "k_chunk_rows");
+        k_chunk_rows<<<(h->R_pad + 255) / 256, 256, 0, h->stream>>>(c, h->d_row_count.p, h->R_pad);
+    }
+    {
+        LaunchScope ls(h, "k_slice_len");
+        int threads = 256, warps = h->n_slices;
+        k_slice_len<<<(warps * 32 + threads - 1) / threads, threads, 0, h->stream>>>(
+            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p);
+    }
+    {
+        LaunchScope ls(h, "k_slice_scan");
+        k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
+                                                h->d_slice_rec.p, h->n_slices, h->d_summary.p);
+    }
+    long long sum[kSumSlots];
+    rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream), "summary D2H");
+    if (rc) return rc;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "chunk totals"))) return rc;
+    h->max_row = (int)sum[kSumMaxLen];
+    h->store_words = sum[kSumWords];
+    h->events_stored = sum[kSumEvents];
+    h->kind = kPacked;
+    if ((rc = ensure(h, h->d_store, (size_t)h->store_words + 32, "event store"))) return rc;
+    const int smem_cap = max_dyn_smem(h->device) - 1024;
+    int smem_len = h->max_row;
+    size_t bytes = (size_t)smem_len * kSlice * sizeof(uint32_t);
+    if ((long long)bytes > smem_cap) {
+        smem_len = 0;  // very long rows: straight to global memory
+        bytes = 0;
+    }
+    if ((rc = check_cuda(h, cudaFuncSetAttribute(k_concat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                         "concat smem attr")))
+        return rc;
+    if (h->n_slices > 0) {
+        LaunchScope ls(h, "k_concat");
+        k_concat<<<h->n_slices, 32, bytes, h->stream>>>(c, h->d_store.p, h->d_slice_base.p, h->d_slice_len.p,
+                                                         h->d_row_len.p, smem_len);
+    }
+    return check_cuda(h, cudaGetLastError(), "concat kernels");
 }
 
 int launch_dark(xpcs_handle_s *h, const int16_t *d_frames, int n)

@@ -55,6 +55,14 @@ struct DevBuf {
     size_t n = 0;  // capacity in elements
 };
 
+// Pipelined sparse ingest: the finished pixel-major store of one chunk of frames.
+constexpr int kMaxChunks = 16;
+struct ChunkStore {
+    DevBuf<uint32_t> store;
+    DevBuf<int64_t> slice_base;
+    DevBuf<int> row_len;
+};
+
 }  // namespace xpcs
 
 struct xpcs_handle_s {
@@ -147,6 +155,14 @@ struct xpcs_handle_s {
     xpcs::DevBuf<double> d_part_total;    // [S]
     xpcs::DevBuf<double> d_part_partial;  // [windows * S]
     xpcs::DevBuf<float> d_frame_scale;    // [F] normalize_by_framesum divisors
+    // pipelined sparse ingest (xpcs_push_sparse with host buffers, integer counts): every chunk of
+    // frames is ingested on the handle's stream while the next one crosses PCIe on the copy stream;
+    // xpcs_finish_ingest concatenates the chunk stores
+    bool pipe_on = false, pipe_broken = false;
+    int pipe_chunks = 0;                  // chunk stores filled in this ingest
+    xpcs::ChunkStore chunk[xpcs::kMaxChunks];
+    cudaEvent_t ev_chunk[xpcs::kMaxChunks] = {};
+    int64_t frame_off_uploaded = 0;       // entries of frame_off_host already in d_frame_off
     std::vector<float> frame_sum_host;    // [2F]
 
     // ---- results ----
@@ -212,6 +228,8 @@ void release(DevBuf<T> &b)
 
 // ---- launchers (ingest.cu) ----
 int launch_ingest(xpcs_handle_s *h);             // histogram -> slices -> scatter -> finalize
+int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1);  // same for raw frames [f0, f1) into the next chunk store; 1 = not representable
+int launch_ingest_concat(xpcs_handle_s *h);      // chunk stores -> the store
 int launch_dark(xpcs_handle_s *h, const int16_t *d_frames, int n);
 int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw, int nframes);
 // ---- launchers (multitau.cu) ----

@@ -306,6 +306,10 @@ static void reset_ingest(xpcs_handle_s *h)
     h->events_stored = 0;
     h->store_words = 0;
     h->max_row = 0;
+    h->pipe_on = false;
+    h->pipe_broken = false;
+    h->pipe_chunks = 0;
+    h->frame_off_uploaded = 0;
 }
 
 static int check_params(const XpcsParams *prm)
@@ -416,6 +420,10 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_dense_counter);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
     release(h->d_slice_cur); release(h->d_slice_rec); release(h->d_rec);
+    for (int k = 0; k < kMaxChunks; k++) {
+        release(h->chunk[k].store); release(h->chunk[k].slice_base); release(h->chunk[k].row_len);
+        if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
+    }
     release(h->d_block_first); release(h->d_store); release(h->d_summary); release(h->d_frame_acc);
     release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
     release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch); release(h->d_mt_fallback);
@@ -557,19 +565,99 @@ extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t
     int rc;
     if ((rc = grow(h, h->d_idx, (size_t)h->E, need + 8, "event indices"))) return rc;
     if ((rc = grow(h, h->d_val, (size_t)h->E, need + 8, "event values"))) return rc;
-    if (n > 0) {
-        rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p + h->E, idx + frame_offsets[0], sizeof(int32_t) * n,
-                                           cudaMemcpyHostToDevice, h->stream), "idx H2D");
-        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p + h->E, val + frame_offsets[0], sizeof(int16_t) * n,
-                                                    cudaMemcpyHostToDevice, h->stream), "val H2D");
-        if (rc) return rc;
-    }
+    const int raw0 = h->raw_frames;
+    const int64_t E0 = h->E;
+    h->frame_off_host.reserve(h->frame_off_host.size() + (size_t)nframes);
     for (int i = 0; i < nframes; i++)
-        h->frame_off_host.push_back(h->E + (frame_offsets[i + 1] - frame_offsets[0]));
-    push_timestamps(h, clock, ticks, nframes);
-    h->E += n;
-    h->raw_frames += nframes;
-    return XPCS_OK;
+        h->frame_off_host.push_back(E0 + (frame_offsets[i + 1] - frame_offsets[0]));
+    // rest of the host bookkeeping of a push (done while the copies are already under way when pipelined)
+    auto bookkeeping = [&]() {
+        push_timestamps(h, clock, ticks, nframes);
+        h->E += n;
+        h->raw_frames += nframes;
+    };
+
+    // Pipelined ingest (decided at the first push of an ingest): integer photon counts, no
+    // stride/average/frame-sum normalisation, a push large enough to be worth cutting up.
+    if (raw0 == 0) {
+        int64_t min_events = 4 << 20;
+        if (const char *e = getenv("XPCS_PIPELINE_MIN_EVENTS")) min_events = atoll(e);
+        h->pipe_on = !getenv("XPCS_NO_PIPELINE") && h->flat_is_one && h->prm.avg_frames == 1 &&
+                     h->prm.stride_frames == 1 && !h->prm.normalize_by_framesum &&
+                     h->prm.frames <= (1 << (32 - kCountBits)) && n >= min_events;
+    }
+    if (h->pipe_on && !h->pipe_broken && h->pipe_chunks >= kMaxChunks) h->pipe_broken = true;  // chunk table full
+    if (!h->pipe_on || h->pipe_broken) {
+        if (n > 0) {
+            rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p + E0, idx + frame_offsets[0], sizeof(int32_t) * n,
+                                               cudaMemcpyHostToDevice, h->stream), "idx H2D");
+            if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p + E0, val + frame_offsets[0], sizeof(int16_t) * n,
+                                                        cudaMemcpyHostToDevice, h->stream), "val H2D");
+            if (rc) return rc;
+        }
+        bookkeeping();
+        return XPCS_OK;
+    }
+
+    // chunks of about n / K events, cut at frame boundaries
+    int K = (int)std::min<int64_t>(8, std::max<int64_t>(1, n / (8 << 20)));
+    if (const char *e = getenv("XPCS_PIPELINE_CHUNKS")) K = std::max(1, atoi(e));
+    K = std::min(K, kMaxChunks - h->pipe_chunks);
+    if (!h->copy_stream) {
+        if ((rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream"))) return rc;
+    }
+    // frame offsets of this push (absolute event indices) behind the ones already on the device; they
+    // go first: a small copy queued behind the chunk copies would wait for all of them
+    {
+        const size_t have = (size_t)h->frame_off_uploaded, want = h->frame_off_host.size();
+        rc = grow(h, h->d_frame_off, have, want, "frame offsets");
+        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p + have, h->frame_off_host.data() + have,
+                                                    sizeof(int64_t) * (want - have), cudaMemcpyHostToDevice, h->stream),
+                                 "frame offsets H2D");
+        if (rc) return rc;
+        h->frame_off_uploaded = (int64_t)want;
+    }
+    std::vector<int> cut(1, 0);  // frame cuts relative to this push
+    for (int k = 1; k < K; k++) {
+        const int64_t target = frame_offsets[0] + n * k / K;
+        int f = (int)(std::lower_bound(frame_offsets, frame_offsets + nframes + 1, target) - frame_offsets);
+        f = std::min(std::max(f, cut.back()), nframes);
+        if (f > cut.back() && f < nframes) cut.push_back(f);
+    }
+    cut.push_back(nframes);
+    const int nc = (int)cut.size() - 1;
+    const int base_chunk = h->pipe_chunks;
+    // every chunk's copy is queued up front on the copy stream (which starts behind whatever the
+    // handle's stream has queued: buffer growth, earlier chunks) ...
+    cudaEvent_t ev_start = nullptr;
+    for (int k = 0; k < nc; k++) {
+        cudaEvent_t &ev = h->ev_chunk[base_chunk + k];
+        if (!ev && (rc = check_cuda(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "chunk event"))) return rc;
+    }
+    if ((rc = check_cuda(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming), "event"))) return rc;
+    cudaEventRecord(ev_start, h->stream);
+    cudaStreamWaitEvent(h->copy_stream, ev_start, 0);
+    for (int k = 0; k < nc && !rc; k++) {
+        const int64_t a = frame_offsets[cut[k]] - frame_offsets[0], b = frame_offsets[cut[k + 1]] - frame_offsets[0];
+        if (b > a) {
+            rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p + E0 + a, idx + frame_offsets[0] + a, sizeof(int32_t) * (b - a),
+                                               cudaMemcpyHostToDevice, h->copy_stream), "idx H2D");
+            if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p + E0 + a, val + frame_offsets[0] + a, sizeof(int16_t) * (b - a),
+                                                        cudaMemcpyHostToDevice, h->copy_stream), "val H2D");
+        }
+        cudaEventRecord(h->ev_chunk[base_chunk + k], h->copy_stream);
+    }
+    bookkeeping();
+    // ... and each chunk is ingested on the handle's stream as soon as it has arrived
+    for (int k = 0; k < nc && !rc && !h->pipe_broken; k++) {
+        cudaStreamWaitEvent(h->stream, h->ev_chunk[base_chunk + k], 0);
+        const int r2 = launch_ingest_chunk(h, raw0 + cut[k], raw0 + cut[k + 1]);
+        if (r2 == 1) h->pipe_broken = true;  // counts beyond the packed word: classic ingest at finish
+        else rc = r2;
+    }
+    cudaStreamSynchronize(h->copy_stream);  // the caller may reuse its buffers on return
+    cudaEventDestroy(ev_start);
+    return rc;
 }
 
 extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
@@ -675,6 +763,25 @@ extern "C" int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const doubl
     return XPCS_OK;
 }
 
+// Filter getters (main.cpp:339-343, sparse_filter.cpp:190) in the reference's fp32 operations
+__global__ void k_get_frame_sum(const double *__restrict__ facc, float *__restrict__ out, int F, int avg, int P)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    out[f] = (float)(f + 1.0);
+    float fs = (float)facc[f];
+    if (avg > 1) fs = __fdiv_rn(fs, (float)avg);
+    out[F + f] = __fdiv_rn(fs, (float)P);
+}
+
+__global__ void k_get_pixel_sum(const double *__restrict__ row_sum, const int *__restrict__ pixel_of_row,
+                                float *__restrict__ out, int R, int F)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    out[pixel_of_row[r]] = __fdiv_rn((float)row_sum[r], (float)F);
+}
+
 extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total,
                                   float *part_partial)
 {
@@ -696,37 +803,40 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     if (h->dense_source) {
         if ((rc = ensure(h, h->d_summary, 8, "summary"))) return rc;
     }
-    if ((rc = launch_ingest(h))) return rc;
+    if (h->pipe_on && !h->pipe_broken && h->pipe_chunks > 0) rc = launch_ingest_concat(h);
+    else rc = launch_ingest(h);
+    if (rc) return rc;
     h->ingest_done = true;
 
     // ---- Filter getters, post-scaled as in main.cpp:339-343 and :360-378 ----
+    // pixelSum and frameSum are formed on the device (same fp32 operations) and land in the caller's
+    // arrays directly; the small partition sums are finished on the host
     const int S = h->S;
     const int windows_all = (F + h->prm.static_window - 1) / h->prm.static_window;
     const int windows = F / h->prm.static_window;
-    std::vector<double> facc(F), racc, ptot(S), ppart((size_t)windows_all * S);
-    cudaMemcpyAsync(facc.data(), h->d_frame_acc.p, sizeof(double) * F, cudaMemcpyDeviceToHost, h->stream);
-    if (pixel_sum) {
-        racc.resize(h->R_pad);
-        cudaMemcpyAsync(racc.data(), h->d_row_sum.p, sizeof(double) * h->R_pad, cudaMemcpyDeviceToHost, h->stream);
+    std::vector<double> ptot(S), ppart((size_t)windows_all * S);
+    if (pixel_sum || frame_sum) {
+        if ((rc = ensure(h, h->d_scratch, (size_t)h->P + 2 * (size_t)F, "filter getters"))) return rc;
+        float *d_ps = h->d_scratch.p, *d_fs = h->d_scratch.p + h->P;
+        if (frame_sum) {
+            LaunchScope ls(h, "k_get_frame_sum");
+            k_get_frame_sum<<<(F + 255) / 256, 256, 0, h->stream>>>(h->d_frame_acc.p, d_fs, F, h->prm.avg_frames, h->P);
+        }
+        if (pixel_sum) {
+            cudaMemsetAsync(d_ps, 0, sizeof(float) * (size_t)h->P, h->stream);
+            if (h->R > 0) {
+                LaunchScope ls(h, "k_get_pixel_sum");
+                k_get_pixel_sum<<<(h->R + 255) / 256, 256, 0, h->stream>>>(h->d_row_sum.p, h->d_pixel_of_row.p, d_ps, h->R, F);
+            }
+            cudaMemcpyAsync(pixel_sum, d_ps, sizeof(float) * (size_t)h->P, cudaMemcpyDeviceToHost, h->stream);
+        }
+        if (frame_sum) cudaMemcpyAsync(frame_sum, d_fs, sizeof(float) * 2 * (size_t)F, cudaMemcpyDeviceToHost, h->stream);
     }
     if (S > 0) {
         cudaMemcpyAsync(ptot.data(), h->d_part_total.p, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream);
         cudaMemcpyAsync(ppart.data(), h->d_part_partial.p, sizeof(double) * (size_t)windows_all * S, cudaMemcpyDeviceToHost, h->stream);
     }
     if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "filter sums D2H"))) return rc;
-    h->frame_sum_host.assign(2 * (size_t)F, 0.0f);
-    const float avg = (float)h->prm.avg_frames;
-    for (int f = 0; f < F; f++) {
-        h->frame_sum_host[f] = (float)(f + 1.0);
-        float fs = (float)facc[f];
-        if (h->prm.avg_frames > 1) fs = fs / avg;
-        h->frame_sum_host[F + f] = fs / (float)h->P;  // sparse_filter.cpp:190
-    }
-    if (frame_sum) memcpy(frame_sum, h->frame_sum_host.data(), sizeof(float) * 2 * (size_t)F);
-    if (pixel_sum) {
-        for (int i = 0; i < h->P; i++) pixel_sum[i] = 0.0f;
-        for (int r = 0; r < h->R; r++) pixel_sum[h->pixel_of_row[r]] = (float)racc[r] / F;  // main.cpp:339-343
-    }
     if (part_total)
         for (int i = 0; i < S; i++) {
             const float denom = (float)h->pixels_per_sbin[i] * F;  // main.cpp:375-378
