@@ -173,7 +173,11 @@ def cpu_sample_job(pkg, O, wl, F_s, seed=1234):
             ref = refdrv
     except Exception:
         ref = None
-    threads = O.max_threads()
+    # all the host cores this process may use; not OMP_NUM_THREADS, which torchrun pins to 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     if ref is not None:
         job = ref.SparseJob(dq, sq, F_s, off, idx, val, dpl=8, swindow=max(1, F_s // 10))
 
@@ -399,8 +403,9 @@ def bench_dense(args, wl):
                 fr = gen_dense_device(torch, P, F_s, d_s, mu, dev, seed=7).cpu().numpy()
                 job = refdrv.SparseJob(dq, sq, F_s, dense=fr, dpl=8, swindow=max(1, F_s // 10), darks=d_s, lld=lld,
                                        sigma=sigma, flatfield=flat)
-                st = job.run(threads=os.cpu_count())
-                line["cpu_baseline"] = {"value": F_s / st["total_s"], "unit": UNIT, "cores": os.cpu_count(),
+                ncores = len(os.sched_getaffinity(0))
+                st = job.run(threads=ncores)
+                line["cpu_baseline"] = {"value": F_s / st["total_s"], "unit": UNIT, "cores": ncores,
                                         "kind": "reference", "seconds": st["total_s"], "stages_s": st,
                                         "sample": "%d of %d frames (+%d darks), same detector, flat-field and threshold" % (F_s, F, d_s)}
         except Exception as ex:  # the bench line must still be printed
@@ -515,6 +520,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) and any other NCCL
+        # log go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = entry.load_package()
