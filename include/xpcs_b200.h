@@ -133,7 +133,13 @@ int xpcs_get_dark(xpcs_handle h, double *avg, double *std);
  * idx/val = the concatenated payloads (int32 pixel index, int16 value) of those frames,
  * frame_offsets[nframes+1] = event offsets of each frame relative to idx/val,
  * clock/ticks = Header::elapsed / Header::corecotick per raw frame (nullable).
- * Host pointers (pinned memory makes the copies asynchronous). */
+ * Host pointers; idx/val must stay valid and unmodified until xpcs_finish_ingest returns
+ * unless the push was pipelined (then it has been consumed on return).  With pinned memory
+ * the copies are asynchronous, and a first push of >= 4 Mi events of plain photon counts
+ * (no flat-field, stride, averaging or frame-sum normalisation) is PIPELINED: cut into up to
+ * 8 chunks of frames, chunk k ingested on the device while chunk k+1 crosses PCIe; the
+ * results are bit-identical to the one-pass ingest.  Environment knobs read at push time:
+ * XPCS_NO_PIPELINE, XPCS_PIPELINE_MIN_EVENTS, XPCS_PIPELINE_CHUNKS. */
 int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val,
                      const int64_t *frame_offsets, const double *clock, const double *ticks,
                      int nframes);
