@@ -165,6 +165,11 @@ int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float 
                        float *part_partial);
 /* TimestampClock()/TimestampTicks(): [2][raw frames] each (sparse_filter.cpp:134-140) */
 int xpcs_get_timestamps(xpcs_handle h, double *clock, double *ticks);
+/* replaces the --frameout=N block of main.cpp:276-310: the first `nframes` post-filter frames,
+ * out[f * P + pixel] (zeros where a pixel has no event), read back from the pixel-major store.
+ * Call between xpcs_finish_ingest and xpcs_multitau.  (With normalize_by_framesum the store
+ * already carries the frame-sum scaling, which the reference applies after this dump.) */
+int xpcs_get_frames(xpcs_handle h, int nframes, float *out);
 
 /* ---- Correlation ---- */
 /* replaces: Corr::multiTau2(SparseData*, float* G2, float* IP, float* IF) (corr.cpp:315-431).

@@ -80,3 +80,23 @@ def test_corr_positional_imm_and_no_compat(pkg, tmp_path):
     k = list(c.ref["tau"].ravel()).index(40.0)
     assert c.ref["G2"][k, 0] == 0.0                                  # the reference drops the pair
     assert res["G2"][k, 0] == np.float32(0.0625) / np.float32(118)   # the exact value
+
+
+def test_corr_frameout(pkg, tmp_path):
+    """--frameout=N (main.cpp:276-310): the first N post-filter frames as dataset frames_out, declared
+    (height, width, N) and filled [N][pixels] like the reference's buffer."""
+    c = G.Case("sparse_staletail_32x32")
+    N = 7
+    res, _ = _run_corr(pkg, c, tmp_path, extra=["--frameout=%d" % N])
+    h, w = c.dq.shape
+    fo = res["frames_out"]
+    assert fo.shape == (h, w, N) and fo.dtype == np.float32
+    got = fo.ravel().reshape(N, h * w)
+    off, idx, val = c.inp["off"], c.inp["idx"], c.inp["val"]
+    valid = ((c.dq.ravel() > 0) & (c.sq.ravel() > 0))
+    want = np.zeros((N, h * w), np.float32)
+    for f in range(N):
+        sl = slice(int(off[f]), int(off[f + 1]))
+        np.add.at(want[f], idx[sl], val[sl].astype(np.float32))
+    want *= valid[None, :]
+    assert np.array_equal(got, want)

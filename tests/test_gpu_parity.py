@@ -260,3 +260,32 @@ def test_shards_sum_to_single_gpu_partials(pkg):
     assert sum(p[3] for p in parts) == rows
     total = parts[0][0] + parts[1][0] + parts[2][0]
     assert_exact(total, full, "sum of shard partials")
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_frame_dump_matches_filter_rows(pkg, oracle, flat):
+    """xpcs_get_frames (the --frameout dump, main.cpp:276-310) against the oracle's filtered rows: integer
+    store exactly, float store (flat-field) within 1e-5."""
+    h, w, F, N = 40, 48, 300, 25
+    dq, sq, off, idx, val = make_case(pkg, h, w, F, 0.03, 21)
+    ff = None
+    if flat:
+        ff = (1.0 + 0.05 * np.random.default_rng(5).standard_normal(h * w)).astype(np.float64)
+    kw = dict(flatfield=ff) if flat else {}
+    c = pkg.Correlator(dq, sq, F, dpl=8, **kw)
+    c.push_sparse(idx, val, off)
+    c.finish_ingest()
+    got = c.frames(N)
+    c.close()
+    qm = oracle.QMap(dq, sq)
+    fo = oracle.sparse_filter(qm, F, off, idx, val, flat=ff, stride=1, avg=1, swindow=F // 10)
+    want = np.zeros((N, h * w), np.float32)
+    ptr, t, v = fo.rows.row_ptr, fo.rows.t, fo.rows.v
+    for p in range(h * w):
+        for k in range(int(ptr[p]), int(ptr[p + 1])):
+            if t[k] < N:
+                want[t[k], p] = v[k]
+    if flat:
+        assert_close(got, want, "frames_out")
+    else:
+        assert_exact(got, want, "frames_out")

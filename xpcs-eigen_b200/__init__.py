@@ -195,6 +195,12 @@ class Correlator:
         return dict(pixel_sum=ps.reshape(self.height, self.width), frame_sum=fs.reshape(2, F),
                     part_total=pt[:S], part_partial=pp[: (F // self.static_window) * S].reshape(-1, S))
 
+    def frames(self, n):
+        """First n post-filter frames, (n, P) float32 (the --frameout dump, main.cpp:276-310)."""
+        out = np.zeros((n, self.P), np.float32)
+        self._check(self._lib.xpcs_get_frames(self._h, n, out.ctypes.data))
+        return out
+
     def timestamps(self):
         n = self.info().raw_frames_seen
         ck = np.zeros(2 * n, np.float64)

@@ -76,6 +76,7 @@ SYMBOLS = {
     "xpcs_push_dense_device": (_i, [_vp, _vp, _i]),
     "xpcs_finish_ingest": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "xpcs_get_timestamps": (_i, [_vp, _vp, _vp]),
+    "xpcs_get_frames": (_i, [_vp, C.c_int, _vp]),
     "xpcs_multitau": (_i, [_vp, _vp, _vp, _vp]),
     "xpcs_normalize": (_i, [_vp, _vp, _vp]),
     "xpcs_normalize_partials": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),

@@ -851,6 +851,61 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     return XPCS_OK;
 }
 
+// --frameout (main.cpp:276-310): one lane per row walks its column while the frame is below nframes
+template <int KIND>
+__global__ void __launch_bounds__(32) k_get_frames(const void *store, const int64_t *__restrict__ slice_base,
+                                                    const int *__restrict__ row_len, const int *__restrict__ pixel_of_row,
+                                                    float *__restrict__ out, int nframes, int P, int R)
+{
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int r = s * kSlice + lane;
+    if (r >= R) return;
+    const int n = row_len[r];
+    const int pix = pixel_of_row[r];
+    if (KIND == kPacked) {
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(store) + slice_base[s] + lane;
+        for (int j = 0; j < n; j++) {
+            const uint32_t w = col[(int64_t)j * kSlice];
+            const int f = (int)(w >> kCountBits);
+            if (f >= nframes) break;
+            out[(int64_t)f * P + pix] = (float)(w & ((1u << kCountBits) - 1u));
+        }
+    } else {
+        const unsigned long long *col = reinterpret_cast<const unsigned long long *>(store) + slice_base[s] + lane;
+        for (int j = 0; j < n; j++) {
+            const unsigned long long w = col[(int64_t)j * kSlice];
+            const int f = (int)(w >> 32);
+            if (f >= nframes) break;
+            out[(int64_t)f * P + pix] = __uint_as_float((uint32_t)w);
+        }
+    }
+}
+
+extern "C" int xpcs_get_frames(xpcs_handle h, int nframes, float *out)
+{
+    if (!h || !out || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "get_frames: bad arguments") : XPCS_E_ARG;
+    if (!h->ingest_done) return fail(h, XPCS_E_STATE, "get_frames before finish_ingest");
+    if (h->rows_consumed) return fail(h, XPCS_E_STATE, "the event rows were consumed by multitau; call get_frames before it");
+    if (nframes > h->prm.frames) nframes = h->prm.frames;
+    cudaSetDevice(h->device);
+    const size_t n = (size_t)nframes * h->P;
+    int rc = ensure(h, h->d_scratch, n, "frame dump");
+    if (rc) return rc;
+    cudaMemsetAsync(h->d_scratch.p, 0, sizeof(float) * n, h->stream);
+    if (h->n_slices > 0) {
+        LaunchScope ls(h, "k_get_frames");
+        if (h->kind == kPacked)
+            k_get_frames<kPacked><<<h->n_slices, 32, 0, h->stream>>>(h->d_store.p, h->d_slice_base.p, h->d_row_len.p,
+                                                                     h->d_pixel_of_row.p, h->d_scratch.p, nframes, h->P, h->R);
+        else
+            k_get_frames<kFloat><<<h->n_slices, 32, 0, h->stream>>>(h->d_store.p, h->d_slice_base.p, h->d_row_len.p,
+                                                                    h->d_pixel_of_row.p, h->d_scratch.p, nframes, h->P, h->R);
+    }
+    rc = check_cuda(h, cudaMemcpyAsync(out, h->d_scratch.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream), "frames D2H");
+    if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "frames D2H");
+    return rc;
+}
+
 extern "C" int xpcs_get_timestamps(xpcs_handle h, double *clock, double *ticks)
 {
     if (!h) return XPCS_E_ARG;

@@ -1,7 +1,7 @@
 // corr -- the reference's entry point `corr configuration.hdf5 [data.imm]` on the B200 library.
 //
 // Mirrors main() of the reference (src/xpcs/main.cpp:100-479): same positional argument, same
-// flags (--g2out --darkout --imm= --inpath= --outpath= --exchange= --entry=, main.cpp:86-98), same
+// flags (--g2out --darkout --frameout= --imm= --inpath= --outpath= --exchange= --entry=, main.cpp:86-98), same
 // HDF5 configuration keys (configuration.cpp:80-242), same result datasets written back into
 // the configuration file (main.cpp:345-457, corr.cpp:883-923, :1089-1090), same stage names in
 // the log ("Loading data", "Computing G2 MultiTau", "Normalizing Data", "Total";
@@ -61,9 +61,9 @@ struct Flags {
     bool g2out = false, darkout = false, no_compat = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     int device = 0;
+    int frameout = 0;
 };
 
-static bool starts(const std::string &s, const char *p) { return s.compare(0, strlen(p), p) == 0; }
 
 static int parse_flags(int argc, char **argv, Flags &f)
 {
@@ -98,7 +98,8 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "no_compat") f.no_compat = true;
             else if (name == "frame_threading" || name == "noframe_threading") {
             }  // the two-time contraction has one (tensor-core) path
-            else if (name == "ufxc" || name == "rigaku" || name == "hdf5" || name == "transposed" || starts(name, "frameout")) {
+            else if (name == "frameout") f.frameout = atoi(need().c_str());
+            else if (name == "ufxc" || name == "rigaku" || name == "hdf5" || name == "transposed") {
                 fprintf(stderr, "corr: --%s is outside the scope of this build (IMM input only)\n", name.c_str());
                 return 2;
             } else {
@@ -364,6 +365,12 @@ int main(int argc, char **argv)
             CHECK(xpcs_get_dark(h, avg.data(), sd.data()));
             file.put(out + "/DarkAvg", Type::F64, {uy, ux}, avg.data());
             file.put(out + "/DarkStd", Type::F64, {uy, ux}, sd.data());
+        }
+        if (fl.frameout > 0 && fl.frameout < frames) {  // main.cpp:276-310
+            std::vector<float> fr((size_t)fl.frameout * pixels);
+            CHECK(xpcs_get_frames(h, fl.frameout, fr.data()));
+            // the reference declares (height, width, N) for a buffer it fills as [N][pixels] (h5_result.cpp:169-226)
+            file.put(out + "/frames_out", Type::F32, {uy, ux, (uint64_t)fl.frameout}, fr.data());
         }
         if (conf.twotime) {
             Scope sc("Computing G2 TwoTimes");
