@@ -1,5 +1,5 @@
 """Wall-clock split of the host-buffer (e2e) path of the C3 workload: push / finish_ingest / multitau /
-normalize, with and without the pipelined ingest.  usage: python profiles/diag_e2e.py [frames]"""
+normalize, with and without the pipelined ingest.  usage: python profiles/diag_e2e.py [c3|c5] [frames]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,8 +7,10 @@ import torch
 import __graft_entry__ as entry
 import bench
 
-F = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-wl = dict(bench.WORKLOADS["c3"]); wl["F"] = F
+WL = sys.argv[1] if len(sys.argv) > 1 else "c3"
+wl = dict(bench.WORKLOADS[WL])
+F = int(sys.argv[2]) if len(sys.argv) > 2 else wl["F"]
+wl["F"] = F
 pkg = entry.load_package()
 dev = torch.device("cuda", 0)
 dq, sq = bench.module_maps(pkg, wl, 1)

@@ -185,8 +185,8 @@ class Correlator:
             self._keep = []
             return None
         F, S = self.F, self.S
-        ps = np.zeros(self.P, np.float32)
-        fs = np.zeros(2 * F, np.float32)
+        ps = np.empty(self.P, np.float32)   # fully written by the library
+        fs = np.empty(2 * F, np.float32)
         pt = np.zeros(max(S, 1), np.float32)
         pp = np.zeros(max((F // self.static_window) * S, 1), np.float32)
         self._check(self._lib.xpcs_finish_ingest(self._h, ps.ctypes.data, fs.ctypes.data, pt.ctypes.data,

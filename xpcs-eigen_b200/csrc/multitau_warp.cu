@@ -394,7 +394,8 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
                     // B_l[t] = B_{l-1}[2t] + B_{l-1}[2t+1]; the key of the occupied level-(l-1) bin of rank
                     // n_l is the first stale slot this level leaves behind (compat)
                     const int want = COMPAT ? (int)nlive[l] : 0;
-                    const bool track = COMPAT && nlive[l] < nlive[l - 1];
+                    // (a level whose bins are all occupied cannot leave a stale slot below L_l: its key is >= n_l)
+                    const bool track = COMPAT && nlive[l] < nlive[l - 1] && (int)nlive[l] < Ll;
                     int base = 0, cand = kInf;
                     for (int t0 = 0; t0 < Ll + 48; t0 += 32) {
                         const int t = t0 + lane;

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
                         bh[t] = v;
                         __syncwarp();
                     }
-                    if (COMPAT && nlive[l] < nlive[l - 1]) {
+                    if (COMPAT && nlive[l] < nlive[l - 1] && (int)nlive[l] < Ll) {  // all bins occupied: key >= n_l = L_l
                         // first stale slot this level leaves behind: the level-(l-1) bin of rank n_l
                         const int i = mf_select_head(fr, n, l - 1, (int)nlive[l], lane);
                         smin_run = min(smin_run, (int)(fr[i] >> (l - 1)));

@@ -521,6 +521,12 @@ extern "C" int xpcs_get_dark(xpcs_handle h, double *avg, double *sd)
     return check_cuda(h, cudaStreamSynchronize(h->stream), "dark D2H");
 }
 
+__global__ void k_rebase_offsets(int64_t *off, int n, int64_t delta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] += delta;
+}
+
 template <typename T>
 static int grow(xpcs_handle_s *h, DevBuf<T> &b, size_t used, size_t need, const char *what)
 {
@@ -567,11 +573,11 @@ extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t
     if ((rc = grow(h, h->d_val, (size_t)h->E, need + 8, "event values"))) return rc;
     const int raw0 = h->raw_frames;
     const int64_t E0 = h->E;
-    h->frame_off_host.reserve(h->frame_off_host.size() + (size_t)nframes);
-    for (int i = 0; i < nframes; i++)
-        h->frame_off_host.push_back(E0 + (frame_offsets[i + 1] - frame_offsets[0]));
-    // rest of the host bookkeeping of a push (done while the copies are already under way when pipelined)
+    // host bookkeeping of a push (done while the copies are already under way when pipelined)
     auto bookkeeping = [&]() {
+        h->frame_off_host.reserve(h->frame_off_host.size() + (size_t)nframes);
+        for (int i = 0; i < nframes; i++)
+            h->frame_off_host.push_back(E0 + (frame_offsets[i + 1] - frame_offsets[0]));
         push_timestamps(h, clock, ticks, nframes);
         h->E += n;
         h->raw_frames += nframes;
@@ -606,20 +612,14 @@ extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t
     if (!h->copy_stream) {
         if ((rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream"))) return rc;
     }
-    // frame offsets of this push (absolute event indices) behind the ones already on the device; they
-    // go first: a small copy queued behind the chunk copies would wait for all of them
-    {
-        const size_t have = (size_t)h->frame_off_uploaded, want = h->frame_off_host.size();
-        rc = grow(h, h->d_frame_off, have, want, "frame offsets");
-        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p + have, h->frame_off_host.data() + have,
-                                                    sizeof(int64_t) * (want - have), cudaMemcpyHostToDevice, h->stream),
-                                 "frame offsets H2D");
-        if (rc) return rc;
-        h->frame_off_uploaded = (int64_t)want;
-    }
+    // frame offsets of this push: the caller's array goes first on the copy stream (a small copy queued
+    // behind the chunk copies would wait for all of them) and is rebased to absolute event indices on
+    // the device
+    if ((rc = grow(h, h->d_frame_off, (size_t)h->frame_off_uploaded, (size_t)raw0 + nframes + 1, "frame offsets"))) return rc;
     std::vector<int> cut(1, 0);  // frame cuts relative to this push
     for (int k = 1; k < K; k++) {
-        const int64_t target = frame_offsets[0] + n * k / K;
+        // the last chunk is half the size of the others: its ingest is the only one nothing hides
+        const int64_t target = frame_offsets[0] + n * (2 * k) / (2 * K - 1);
         int f = (int)(std::lower_bound(frame_offsets, frame_offsets + nframes + 1, target) - frame_offsets);
         f = std::min(std::max(f, cut.back()), nframes);
         if (f > cut.back() && f < nframes) cut.push_back(f);
@@ -637,6 +637,16 @@ extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t
     if ((rc = check_cuda(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming), "event"))) return rc;
     cudaEventRecord(ev_start, h->stream);
     cudaStreamWaitEvent(h->copy_stream, ev_start, 0);
+    rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p + raw0, frame_offsets, sizeof(int64_t) * ((size_t)nframes + 1),
+                                       cudaMemcpyHostToDevice, h->copy_stream), "frame offsets H2D");
+    if (rc) return rc;
+    cudaEventRecord(ev_start, h->copy_stream);
+    cudaStreamWaitEvent(h->stream, ev_start, 0);
+    if (E0 != frame_offsets[0]) {
+        LaunchScope ls(h, "k_rebase_offsets");
+        k_rebase_offsets<<<(nframes + 256) / 256, 256, 0, h->stream>>>(h->d_frame_off.p + raw0, nframes + 1, E0 - frame_offsets[0]);
+    }
+    h->frame_off_uploaded = (int64_t)raw0 + nframes + 1;
     for (int k = 0; k < nc && !rc; k++) {
         const int64_t a = frame_offsets[cut[k]] - frame_offsets[0], b = frame_offsets[cut[k + 1]] - frame_offsets[0];
         if (b > a) {
@@ -790,7 +800,8 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     cudaSetDevice(h->device);
     const int F = h->prm.frames;
     int rc;
-    if (!h->dense_source && !h->external_events) {
+    const bool piped = h->pipe_on && !h->pipe_broken && h->pipe_chunks > 0;
+    if (!h->dense_source && !h->external_events && !piped) {
         if ((rc = ensure(h, h->d_frame_off, h->frame_off_host.size(), "frame offsets"))) return rc;
         rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p, h->frame_off_host.data(),
                                            sizeof(int64_t) * h->frame_off_host.size(), cudaMemcpyHostToDevice, h->stream),
@@ -803,7 +814,7 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     if (h->dense_source) {
         if ((rc = ensure(h, h->d_summary, 8, "summary"))) return rc;
     }
-    if (h->pipe_on && !h->pipe_broken && h->pipe_chunks > 0) rc = launch_ingest_concat(h);
+    if (piped) rc = launch_ingest_concat(h);
     else rc = launch_ingest(h);
     if (rc) return rc;
     h->ingest_done = true;
