@@ -392,38 +392,32 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
     }
 }
 
-// One warp per slice: records -> rows, in stream order (a stable placement: the rank of a record is
-// the number of earlier records of the same row, from 32 shared-memory cursors plus a match inside
-// the 32-record step).  The stream was filled from its end, so reading it forwards fills the rows
-// latest-first and nearly sorted, which is what the finalisation kernels expect from the scatter.
-constexpr int kPlaceWarps = 8;
+// One CTA per slice: records -> rows, in stream order (a stable placement: the rank of a record is the
+// number of earlier records of the same row -- 32 running cursors, plus the records of the row in the
+// warps before this one in the 512-record step, plus a match inside the warp).  The stream was filled
+// from its end, so reading it forwards fills the rows latest-first and nearly sorted, which is what the
+// finalisation kernels expect from the scatter.  A whole CTA per slice keeps the number of slices in
+// flight (and with it the partially written lines of the store) within the L2.
+constexpr int kPlaceWarps = 16;
 
 template <int KIND>
 __global__ void __launch_bounds__(kPlaceWarps * 32) k_place(const unsigned long long *__restrict__ rec,
                                                             const int64_t *__restrict__ slice_rec,
-                                                            const int64_t *__restrict__ slice_base, void *store,
-                                                            int n_slices)
+                                                            const int64_t *__restrict__ slice_base, void *store)
 {
     typedef typename WordT<KIND>::type W;
-    __shared__ int cur_all[kPlaceWarps][kSlice];
+    __shared__ int cur[kSlice];
+    __shared__ int wcnt[kPlaceWarps][kSlice];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kPlaceWarps + warp;
-    if (s >= n_slices) return;
-    int *cur = cur_all[warp];
-    cur[lane] = 0;
-    __syncwarp();
+    const int s = blockIdx.x;
+    if (warp == 0) cur[lane] = 0;
     const int64_t r0 = slice_rec[s];
     const int n = (int)(slice_rec[s + 1] - r0);
     W *dst = reinterpret_cast<W *>(store) + slice_base[s];
-    // two steps of records in flight ahead of the one being placed
-    unsigned long long x1 = lane < n ? rec[r0 + lane] : 0ull;
-    unsigned long long x2 = 32 + lane < n ? rec[r0 + 32 + lane] : 0ull;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-        const int e = e0 + lane;
+    for (int e0 = 0; e0 < n; e0 += kPlaceWarps * 32) {
+        const int e = e0 + (int)threadIdx.x;
         const bool ok = e < n;
-        const unsigned long long x = x1;
-        x1 = x2;
-        x2 = e + 64 < n ? rec[r0 + e + 64] : 0ull;
+        const unsigned long long x = ok ? rec[r0 + e] : 0ull;
         int row = 32 + lane;  // idle lanes match nobody
         W w = 0;
         if (ok) {
@@ -435,14 +429,25 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) k_place(const unsigned long 
                 w = (W)(x & ((1ull << kRecLaneShiftF) - 1ull));
             }
         }
+        wcnt[warp][lane] = 0;
+        __syncwarp();
         const unsigned peers = __match_any_sync(0xffffffffu, row);
         const int before = __popc(peers & ((1u << lane) - 1u));
-        int rank = 0;
-        if (ok) rank = cur[row] + before;
-        __syncwarp();
-        if (ok && before == 0) cur[row] += __popc(peers);
-        __syncwarp();
-        if (ok) dst[(int64_t)rank * kSlice + row] = w;
+        if (ok && before == 0) wcnt[warp][row] = __popc(peers);
+        __syncthreads();
+        if (warp == 0) {  // exclusive prefix over the warps, per row; the cursors move on
+            int run = cur[lane];
+#pragma unroll
+            for (int k = 0; k < kPlaceWarps; k++) {
+                const int c = wcnt[k][lane];
+                wcnt[k][lane] = run;
+                run += c;
+            }
+            cur[lane] = run;
+        }
+        __syncthreads();
+        if (ok) dst[(int64_t)(wcnt[warp][row] + before) * kSlice + row] = w;
+        __syncthreads();
     }
 }
 
@@ -1331,8 +1336,8 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         }
         if (!fused_place) {
             LaunchScope ls(h, "k_place");
-            k_place<KIND><<<(h->n_slices + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, 0, h->stream>>>(
-                h->d_rec.p, h->d_slice_rec.p, h->d_slice_base.p, h->d_store.p, h->n_slices);
+            k_place<KIND><<<h->n_slices, kPlaceWarps * 32, 0, h->stream>>>(h->d_rec.p, h->d_slice_rec.p,
+                                                                          h->d_slice_base.p, h->d_store.p);
         }
     }
     // finalize
