@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     {
         float fsum = 0.0f;
         long long isum = 0;
-        int win = -1;
+        int win = -1, wend = 0;  // current static window and its first frame beyond
         double wacc = 0.0;
         for (int i = 0; i < m; i++) {
             int t;
@@ -623,10 +623,10 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
                 if (a.frame_scale) x = __fdiv_rn(x, a.frame_scale[t]);
                 col[(int64_t)i * kSlice] = (W)(((unsigned long long)(uint32_t)t << 32) | __float_as_uint(x));
             }
-            int wi = t / a.swindow;
-            if (wi != win) {
+            if (t >= wend) {  // frames ascend: a division only when the static window changes
                 if (win >= 0 && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
-                win = wi;
+                win = t / a.swindow;
+                wend = (win + 1) * a.swindow;
                 wacc = 0.0;
             }
             wacc += v;
