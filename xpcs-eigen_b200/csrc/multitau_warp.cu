@@ -30,6 +30,8 @@
 // search wrong) is bounded from below on the sparse levels and tracked exactly on the dense
 // ones; only when it drops below L_l is the boundary walk of multitau.cu replayed, with
 // rank/select over the events instead of a materialised array.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace xpcs {
@@ -47,6 +49,7 @@ struct MwArgs {
     int warp_words;            // per-warp shared words
     int T;
     int lastl, cnt_last;       // last level >= 1 with delays (0 = none) and its delay count
+    int parts;                 // CTAs per slice (1, 2 or 4): a CTA stages 32 / parts rows
 };
 
 __device__ __forceinline__ float mw_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
@@ -121,23 +124,29 @@ __device__ __forceinline__ int mw_stale_threshold(const uint32_t *ev, int n, con
     return kInf;
 }
 
-template <int DPL, bool COMPAT>
-__global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArgs m)
+// MINB = CTAs per SM the register allocation must allow: 2 (<= 64 registers) for whole-slice CTAs, 3
+// (<= 42) for half-slice CTAs, whose shared memory lets three of them share an SM
+template <int DPL, bool COMPAT, int MINB>
+__global__ void __launch_bounds__(kMwWarps * 32, MINB) k_multitau_warp(MtArgs a, MwArgs m)
 {
     constexpr int LG = DPL == 8 ? 3 : 2;
     constexpr int LO = DPL + 1;
     extern __shared__ __align__(16) uint32_t mw_smem[];
-    const int s = blockIdx.x;
+    // a CTA owns nrows = 32 / parts consecutive rows of slice s (fewer rows: a smaller stage, more CTAs
+    // per SM); a warp-wide access then covers jstep = parts consecutive event ranks / delays
+    const int s = blockIdx.x / m.parts;
+    const int nrows = kSlice / m.parts, rbase = (blockIdx.x % m.parts) * nrows, jstep = m.parts;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rl = lane % nrows, jsub = lane / nrows;
     const int nwarps = blockDim.x >> 5;
     const int len = a.slice_len[s];
     if (len > m.len_cap) {  // CTA-uniform
         if (tid == 0) m.fallback[s] = 1;
         return;
     }
-    uint32_t *evT = mw_smem;                              // [32][pitch_e]
-    uint32_t *outS = evT + 32 * m.pitch_e;                // [3][32][pitch_t]
-    uint32_t *wsm = outS + 3 * 32 * m.pitch_t + warp * m.warp_words;
+    uint32_t *evT = mw_smem;                              // [nrows][pitch_e]
+    uint32_t *outS = evT + nrows * m.pitch_e;             // [3][nrows][pitch_t]
+    uint32_t *wsm = outS + 3 * nrows * m.pitch_t + warp * m.warp_words;
     uint32_t *bw = wsm;                                   // [2 * len_cap + 64] words = 16-bit bins
     unsigned short *bh = reinterpret_cast<unsigned short *>(bw);
     uint32_t *tb = bw + 2 * m.len_cap + 64;
@@ -151,22 +160,22 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
     const int cumlast = m.lastl >= 1 ? DPL * (m.lastl - 1) + m.cnt_last : 0;
 
     // ---- phase 0: slice tile -> row-major shared memory (lane = row on the way in)
-    const int my_len = a.row_len[s * kSlice + lane];
+    const int my_len = a.row_len[s * kSlice + rbase + rl];
     {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane;
-        uint32_t *dst = evT + lane * m.pitch_e;
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + rbase + rl;
+        uint32_t *dst = evT + rl * m.pitch_e;
 #pragma unroll 4
-        for (int j = warp; j < len; j += nwarps)
+        for (int j = warp * jstep + jsub; j < len; j += nwarps * jstep)
             if (j < my_len) dst[j] = g[(int64_t)j * kSlice];
     }
     __syncthreads();
 
-    for (int rr = warp; rr < kSlice; rr += nwarps) {
+    for (int rr = warp; rr < nrows; rr += nwarps) {
         const int n = __shfl_sync(kFull, my_len, rr);
         const uint32_t *ev = evT + rr * m.pitch_e;
         uint32_t *H = outS + rr * m.pitch_t;              // G2 numerators, later the G2 floats
-        uint32_t *oIP = H + 32 * m.pitch_t;
-        uint32_t *oIF = oIP + 32 * m.pitch_t;
+        uint32_t *oIP = H + nrows * m.pitch_t;
+        uint32_t *oIF = oIP + nrows * m.pitch_t;
 
         // ---- phase 1: count total, merge-level histogram, dead-level and IP / IF threshold histograms.
         // The IF thresholds t' << l ascend with the delay index and the IP thresholds (L_l - t') << l
@@ -492,15 +501,15 @@ __global__ void __launch_bounds__(kMwWarps * 32) k_multitau_warp(MtArgs a, MwArg
     }
     __syncthreads();
 
-    // ---- results: [3][32 rows][T] stage -> [T][R_pad], one 128-byte line per (array, delay)
+    // ---- results: [3][nrows][T] stage -> [T][R_pad], 128 / parts contiguous bytes per (array, delay)
     {
         float *dst[3] = {a.G2, a.IP, a.IF};
-        const int64_t r0 = (int64_t)s * kSlice + lane;
+        const int64_t r0 = (int64_t)s * kSlice + rbase + rl;
 #pragma unroll
         for (int arr = 0; arr < 3; arr++) {
-            const uint32_t *src = outS + arr * 32 * m.pitch_t + lane * m.pitch_t;
+            const uint32_t *src = outS + arr * nrows * m.pitch_t + rl * m.pitch_t;
             float *d = dst[arr] + r0;
-            for (int t = warp; t < T; t += nwarps) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
+            for (int t = warp * jstep + jsub; t < T; t += nwarps * jstep) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
         }
     }
 }
@@ -528,15 +537,21 @@ bool multitau_warp_eligible(const xpcs_handle_s *h)
     return true;
 }
 
-template <int DPL, bool COMPAT>
-static int run_warp(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes, int warps)
+template <int DPL, bool COMPAT, int MINB>
+static int run_warp_b(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes, int warps)
 {
-    int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau_warp<DPL, COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = check_cuda(h, cudaFuncSetAttribute(k_multitau_warp<DPL, COMPAT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)bytes), "multitau_warp smem attr");
     if (rc) return rc;
     LaunchScope ls(h, "k_multitau_warp");
-    k_multitau_warp<DPL, COMPAT><<<h->n_slices, warps * 32, bytes, h->stream>>>(a, m);
+    k_multitau_warp<DPL, COMPAT, MINB><<<h->n_slices * m.parts, warps * 32, bytes, h->stream>>>(a, m);
     return XPCS_OK;
+}
+
+template <int DPL, bool COMPAT>
+static int run_warp(xpcs_handle_s *h, MtArgs &a, MwArgs &m, size_t bytes, int warps)
+{
+    return m.parts >= 2 ? run_warp_b<DPL, COMPAT, 3>(h, a, m, bytes, warps) : run_warp_b<DPL, COMPAT, 2>(h, a, m, bytes, warps);
 }
 
 int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
@@ -556,17 +571,22 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
             m.lastl = l;
             m.cnt_last = h->sched.count[l];
         }
-    const size_t out_bytes = (size_t)3 * 32 * m.pitch_t * 4;
-    // bytes(len, warps) = out + 4 * (32 * (len | 1) + warps * (2 len + 64 + tables)).  Two CTAs per SM when
-    // the longest row allows it -- with 16 warps each, else with 12 or 8 (a long delay schedule makes the
-    // result stage large) -- one CTA of 16 warps otherwise; longer slices go to the lane-per-row kernel
-    auto bytes_for = [&](int len, int warps) {
-        return out_bytes + 4 * ((size_t)32 * (len | 1) + (size_t)warps * (2 * (size_t)len + 64 + kMwTables));
+    // bytes(len, warps, parts) = 4 * ((3 pitch_t + (len | 1)) * 32 / parts + warps * (2 len + 64 + tables)).
+    // Occupancy decides (measured on C3: 16 / 24 / 32 / 48 warps per SM -> 6.3 / 5.1 / 4.2 / 4.1 ms; the
+    // last step pays for its 42-register budget with ~10 % more instructions): three CTAs of
+    // 16 warps per SM when half a slice per CTA makes them fit, else two CTAs of a whole slice -- with 16
+    // warps each, or with 12 or 8 (a long delay schedule makes the result stage large) -- else one CTA
+    // of 16 warps; longer slices go to the lane-per-row kernel
+    auto bytes_for = [&](int len, int warps, int parts = 1) {
+        return 4 * (((size_t)3 * m.pitch_t + (len | 1)) * (32 / parts) + (size_t)warps * (2 * (size_t)len + 64 + kMwTables));
     };
     const size_t budget2 = (size_t)(smem_cap + 1024) / 2 - 1024 - 512;  // two resident CTAs (1 KB reserved each)
+    const size_t budget3 = (size_t)(smem_cap + 1024) / 3 - 1024 - 512;  // three
     int len_cap = h->max_row > 0 ? h->max_row : 1;
     int warps = kMwWarps;
-    if (bytes_for(len_cap, 16) > budget2) {
+    m.parts = 1;
+    if (bytes_for(len_cap, 16, 2) <= budget3) m.parts = 2;
+    else if (bytes_for(len_cap, 16) > budget2) {
         if (bytes_for(len_cap, 12) <= budget2) warps = 12;
         else if (bytes_for(len_cap, 8) <= budget2) warps = 8;
         else {
@@ -574,14 +594,22 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
             while (len_cap > 1 && bytes_for(len_cap, 16) > budget1) len_cap = len_cap * 3 / 4;
         }
     }
-    if (bytes_for(len_cap, warps) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
+    if (const char *e = getenv("XPCS_MW_WARPS")) {  // diagnostics: warps per CTA (4..16)
+        const int w = atoi(e);
+        if (w >= 4 && w <= kMwWarps) warps = w;
+    }
+    if (const char *e = getenv("XPCS_MW_PARTS")) {  // diagnostics: CTAs per slice (1, 2, 4)
+        const int q = atoi(e);
+        if (q == 1 || q == 2 || q == 4) m.parts = q;
+    }
+    if (bytes_for(len_cap, warps, m.parts) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
         return XPCS_OK;
     }
     m.len_cap = len_cap;
     m.pitch_e = len_cap | 1;
     m.warp_words = 2 * len_cap + 64 + kMwTables;
-    const size_t bytes = bytes_for(len_cap, warps);
+    const size_t bytes = bytes_for(len_cap, warps, m.parts);
     const bool compat = a.compat != 0;
     const int dpl = h->prm.delays_per_level;
     if (dpl == 8) rc = compat ? run_warp<8, true>(h, a, m, bytes, warps) : run_warp<8, false>(h, a, m, bytes, warps);
