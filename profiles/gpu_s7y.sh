@@ -1,5 +1,5 @@
 # session 7 state: parity suite, all bench legs (c3 default with cpu baseline, c2, c4, c5), reference arm, launch list, ncu full
-TAG=${1:-s7z}
+TAG=${1:-s7y}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
