@@ -80,3 +80,80 @@ def test_pipeline_abandoned_on_large_counts(pkg, oracle):
     for key in ("frame_sum", "pixel_sum", "part_total", "part_partial"):
         assert_exact(piped[0][key], plain[0][key], key)
     assert_exact(piped[2], plain[2], "norm-0-g2")
+
+
+def test_pipelined_shards_sum_to_single_gpu_partials(pkg):
+    """Pixel shards each running the pipelined ingest over the full event stream (foreign pixels
+    skipped): the sum of their normalisation partials is the unsharded one-pass buffer bit for bit."""
+    import torch
+    dq, sq, off, idx, val = make_case(pkg, 64, 64, 700, 0.02, 61, n_dynamic=5, static_per_dynamic=4)
+    F = 700
+
+    def partials(k, K, env):
+        old = {n: os.environ.get(n) for n in ("XPCS_PIPELINE_MIN_EVENTS", "XPCS_PIPELINE_CHUNKS", "XPCS_NO_PIPELINE")}
+        for n in old:
+            os.environ.pop(n, None)
+        os.environ.update(env)
+        try:
+            c = pkg.Correlator(dq, sq, F, shard_index=k, shard_count=K)
+            c.push_sparse(idx, val, off)
+            c.finish_ingest(want=False)
+            c.multitau(want=False)
+            ptr, n = c.normalize_partials()
+            torch.cuda.synchronize()
+            host = pkg.torchio.device_view(ptr, n, "float64", "cuda:0").cpu().numpy().copy()
+            c.normalize_finish()
+            c.close()
+        finally:
+            for n, v in old.items():
+                os.environ.pop(n, None)
+                if v is not None:
+                    os.environ[n] = v
+        return host
+
+    full = partials(0, 1, {"XPCS_NO_PIPELINE": "1"})
+    total = sum(partials(k, 3, {"XPCS_PIPELINE_MIN_EVENTS": "1", "XPCS_PIPELINE_CHUNKS": "5"}) for k in range(3))
+    assert_exact(total, full, "sum of pipelined shard partials")
+
+
+def test_pipelined_ingest_with_empty_frames_and_reset(pkg, oracle):
+    """Frames without events at chunk boundaries, an empty trailing push, and a second ingest on the same
+    handle after xpcs_reset (the chunk stores are reused)."""
+    dq, sq, off, idx, val = make_case(pkg, 32, 32, 240, 0.04, 17)
+    # empty out frames 58..63 and 119..121 (chunk cuts of a 4-chunk split fall near 60, 120, 180)
+    keep = np.ones(idx.size, bool)
+    for a, b in ((58, 64), (119, 122)):
+        keep[int(off[a]):int(off[b])] = False
+    cnt = np.diff(off)
+    for a, b in ((58, 64), (119, 122)):
+        cnt[a:b] = 0
+    idx2, val2 = idx[keep], val[keep]
+    off2 = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    old = {n: os.environ.get(n) for n in ("XPCS_PIPELINE_MIN_EVENTS", "XPCS_PIPELINE_CHUNKS", "XPCS_NO_PIPELINE")}
+    os.environ.pop("XPCS_NO_PIPELINE", None)
+    os.environ.update({"XPCS_PIPELINE_MIN_EVENTS": "1", "XPCS_PIPELINE_CHUNKS": "4"})
+    try:
+        c = pkg.Correlator(dq, sq, 240, dpl=8, compat=True)
+        outs = []
+        for it in range(2):
+            if it:
+                c.reset()
+            c.push_sparse(idx2, val2, off2)
+            c.push_sparse(idx2[:0], val2[:0], np.zeros(1, np.int64))  # a push of zero frames
+            sums = c.finish_ingest()
+            G = c.multitau(want=True)
+            g2, se = c.normalize()
+            outs.append((sums, G, g2))
+        c.close()
+    finally:
+        for n, v in old.items():
+            os.environ.pop(n, None)
+            if v is not None:
+                os.environ[n] = v
+    rs, rG, rg2, rse = run_oracle(oracle, dq, sq, 240, off2, idx2, val2, dpl=8, compat=True)
+    for sums, G, g2 in outs:
+        for k, name in enumerate(("G2", "IP", "IF")):
+            assert_exact(G[k], rG[k], name)
+        for key in ("frame_sum", "pixel_sum", "part_total", "part_partial"):
+            assert_exact(sums[key], rs[key], key)
+        assert_exact(g2, rg2, "norm-0-g2")
