@@ -825,6 +825,7 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     const int S = h->S;
     const int windows_all = (F + h->prm.static_window - 1) / h->prm.static_window;
     const int windows = F / h->prm.static_window;
+    if (!pixel_sum && !frame_sum && !part_total && !part_partial) return XPCS_OK;  // nothing to read back
     std::vector<double> ptot(S), ppart((size_t)windows_all * S);
     if (pixel_sum || frame_sum) {
         if ((rc = ensure(h, h->d_scratch, (size_t)h->P + 2 * (size_t)F, "filter getters"))) return rc;
