@@ -3,7 +3,7 @@
 //
 // Rows are stored in (dq, sq, pixel) order, so every static segment is a contiguous row
 // range of the [T][R_pad] correlator arrays.
-//  k_segment_reduce  one CTA per (segment, chunk of dt <= 32 delays); tiles of 32 rows stream through
+//  k_segment_reduce  one CTA per (segment, chunk of 32 delays); tiles of 32 rows stream through
 //                    a cp.async ring; warp 0 (lane = delay) folds them in row order, so the three
 //                    fp32 sums run in exactly the reference's order (corr.cpp:966-991: sequential
 //                    += over the pixels of a static bin); warps 1..3 accumulate, in fp64, the sum
@@ -24,13 +24,13 @@ constexpr int kSegWarps = 4;            // warp 0: ordered fp32 sums; warps 1..3
 constexpr int kSegTile = 32;            // rows per tile
 constexpr int kSegStages = 3;           // cp.async ring depth
 constexpr int kSegPitch = kSegTile + 1; // padded: lane = delay reads down a row conflict free
+constexpr int kSegTileFloats = 3 * 32 * kSegPitch;
 
 struct SegArgs {
     const float *G2, *IP, *IF;
     const int *lseg_row_start;
     double *partials;
     int R_pad, T, nseg_local, seg_first, nseg_total;
-    int dt;  // delays per CTA (32, 16, 8 or 4): fewer when a shard owns few segments, so that the grid still fills the GPU
 };
 
 __device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gsrc)
@@ -42,7 +42,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// One CTA per (static segment, chunk of dt delays).  The [dt delays][32 rows] tiles of G2, IP
+// One CTA per (static segment, chunk of 32 delays).  The [32 delays][32 rows] tiles of G2, IP
 // and IF stream through a 3-deep cp.async ring (coalesced 128-byte row pieces in, padded pitch
 // in shared memory).  Warp 0, lane = delay, folds every tile in row order: the three fp32 sums
 // run in exactly the reference's order (corr.cpp:966-991).  Warps 1..3 accumulate, in fp64 and
@@ -54,24 +54,23 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_segment_reduce(SegArgs a)
     extern __shared__ __align__(16) float seg_smem[];
     __shared__ double xs[kSegWarps - 1][2][32];
     const int seg = blockIdx.x;
-    const int t0 = blockIdx.y * a.dt;
+    const int t0 = blockIdx.y * 32;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int r0 = a.lseg_row_start[seg], r1 = a.lseg_row_start[seg + 1];
-    const int nt = min(a.dt, a.T - t0);
-    const int stage_floats = 3 * a.dt * kSegPitch;
+    const int nt = min(32, a.T - t0);
     const int ntiles = (r1 - r0 + kSegTile - 1) / kSegTile;
 
     auto issue = [&](int tile) {
         if (tile < ntiles) {
-            float *st = seg_smem + (size_t)(tile % kSegStages) * stage_floats;
+            float *st = seg_smem + (size_t)(tile % kSegStages) * kSegTileFloats;
             const int base = r0 + tile * kSegTile;
             if (base + lane < r1) {
                 for (int t = warp; t < nt; t += kSegWarps) {
                     const int64_t o = (int64_t)(t0 + t) * a.R_pad + base + lane;
-                    cp_async_4(st + (0 * a.dt + t) * kSegPitch + lane, a.G2 + o);
-                    cp_async_4(st + (1 * a.dt + t) * kSegPitch + lane, a.IP + o);
-                    cp_async_4(st + (2 * a.dt + t) * kSegPitch + lane, a.IF + o);
+                    cp_async_4(st + (0 * 32 + t) * kSegPitch + lane, a.G2 + o);
+                    cp_async_4(st + (1 * 32 + t) * kSegPitch + lane, a.IP + o);
+                    cp_async_4(st + (2 * 32 + t) * kSegPitch + lane, a.IF + o);
                 }
             }
         }
@@ -85,12 +84,12 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_segment_reduce(SegArgs a)
         issue(tile + kSegStages - 1);
         cp_async_wait<kSegStages - 1>();
         __syncthreads();
-        const float *st = seg_smem + (size_t)(tile % kSegStages) * stage_floats;
+        const float *st = seg_smem + (size_t)(tile % kSegStages) * kSegTileFloats;
         const int rows = min(kSegTile, r1 - r0 - tile * kSegTile);
         if (lane < nt) {
-            const float *tg = st + (0 * a.dt + lane) * kSegPitch;
-            const float *tp = st + (1 * a.dt + lane) * kSegPitch;
-            const float *tf = st + (2 * a.dt + lane) * kSegPitch;
+            const float *tg = st + (0 * 32 + lane) * kSegPitch;
+            const float *tp = st + (1 * 32 + lane) * kSegPitch;
+            const float *tf = st + (2 * 32 + lane) * kSegPitch;
             if (warp == 0) {
                 for (int rr = 0; rr < rows; rr++) {
                     sg = __fadd_rn(sg, tg[rr]);
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_segment_reduce(SegArgs a)
         sp = __fdiv_rn(sp, cnt);
         sf = __fdiv_rn(sf, cnt);
         const float g2 = __fdiv_rn(sg, __fmul_rn(sp, sf));
-        const int64_t o = (int64_t)(a.seg_first + seg) * a.T + t0 + lane;  // lane < nt <= dt
+        const int64_t o = (int64_t)(a.seg_first + seg) * a.T + t0 + lane;
         const int64_t plane = (int64_t)a.nseg_total * a.T;
         a.partials[o] = (double)g2;
         a.partials[plane + o] = (xs[0][0][lane] + xs[1][0][lane]) + xs[2][0][lane];
@@ -186,10 +185,8 @@ int launch_normalize_partials(xpcs_handle_s *h)
         a.nseg_local = nseg_local;
         a.seg_first = h->seg_first;
         a.nseg_total = h->nseg_total;
-        a.dt = 32;
-        while (a.dt > 4 && (long long)nseg_local * ((h->T + a.dt - 1) / a.dt) < 4 * 148) a.dt >>= 1;
-        dim3 grid(nseg_local, (h->T + a.dt - 1) / a.dt);
-        const size_t smem = sizeof(float) * (size_t)kSegStages * 3 * a.dt * kSegPitch;
+        dim3 grid(nseg_local, (h->T + 31) / 32);
+        const size_t smem = sizeof(float) * (size_t)kSegStages * kSegTileFloats;
         rc = check_cuda(h, cudaFuncSetAttribute(k_segment_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "segment reduce smem attr");
         if (rc) return rc;
