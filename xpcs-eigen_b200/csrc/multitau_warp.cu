@@ -1,10 +1,11 @@
 // multitau_warp.cu -- multi-tau correlator, one WARP per pixel row (integer photon counts).
 //
 // Replaces Corr::multiTau2 (reference corr.cpp:315-431) for the packed store
-// (word = frame << 12 | count).  One CTA owns one slice of 32 rows: the slice tile is read
-// once with coalesced 128-byte lines and transposed into shared memory (row-major, odd pitch),
-// then each warp works through its rows with lanes over events / bins / delays, and the
-// 32 x T x 3 results leave through a shared-memory stage as full 128-byte lines.
+// (word = frame << 12 | count).  One CTA owns one slice of 32 rows -- or half of one, 16 rows, when
+// that makes three CTAs fit an SM: the tile is read once with coalesced 128-byte (64-byte) lines and
+// transposed into shared memory (row-major, odd pitch), then each warp works through its rows with
+// lanes over events / bins / delays, and the rows x T x 3 results leave through a shared-memory stage
+// as full 128-byte (64-byte) lines.
 //
 // Nothing is compacted level by level.  Every quantity is a function of the level-0 events
 // (f_i, c_i) of the row (tests/multitau_model.py restates this on the CPU and is checked bit
