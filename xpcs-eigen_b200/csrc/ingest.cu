@@ -1562,6 +1562,7 @@ int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1)
     std::swap(c.slice_base, h->d_slice_base);
     std::swap(c.row_len, h->d_row_len);
     if (rc) return rc;  // 1: a count does not fit the packed word
+    h->pipe_events = (k == 0 ? 0 : h->pipe_events) + h->events_stored;
     h->pipe_chunks = k + 1;
     return check_cuda(h, cudaGetLastError(), "chunk ingest kernels");
 }
@@ -1652,7 +1653,7 @@ int launch_ingest_concat(xpcs_handle_s *h)
     if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "chunk totals"))) return rc;
     h->max_row = (int)sum[kSumMaxLen];
     h->store_words = sum[kSumWords];
-    h->events_stored = sum[kSumEvents];
+    h->events_stored = h->pipe_events;  // as the one-pass ingest counts them: before duplicates merge
     h->kind = kPacked;
     if ((rc = ensure(h, h->d_store, (size_t)h->store_words + 32, "event store"))) return rc;
     const int smem_cap = max_dyn_smem(h->device) - 1024;

@@ -160,6 +160,7 @@ struct xpcs_handle_s {
     // xpcs_finish_ingest concatenates the chunk stores
     bool pipe_on = false, pipe_broken = false;
     int pipe_chunks = 0;                  // chunk stores filled in this ingest
+    int64_t pipe_events = 0;              // events the chunk ingests stored (before merging duplicates)
     xpcs::ChunkStore chunk[xpcs::kMaxChunks];
     cudaEvent_t ev_chunk[xpcs::kMaxChunks] = {};
     int64_t frame_off_uploaded = 0;       // entries of frame_off_host already in d_frame_off
