@@ -182,20 +182,24 @@ def scratch_dir():
 
 
 def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout=False, threads=None, keep=False,
-             **cfg):
+             ufxc=None, **cfg):
     """Write IMM + config, run the reference, return (results dict of the output group, run info).
     sparse = (frame_off, idx, val); dense = int16 frames [darks + frames][P]."""
     d = scratch_dir()
     try:
         imm = os.path.join(d, "data.imm")
         h, w = np.asarray(dq).shape
-        if sparse is not None:
+        extra = ()
+        if ufxc is not None:  # raw 32-bit words of a UFXC file, read through --ufxc
+            np.asarray(ufxc, "<u4").tofile(imm)
+            extra = ("--ufxc",)
+        elif sparse is not None:
             synth.write_imm_sparse(imm, h, w, *sparse)
         else:
             synth.write_imm_dense(imm, h, w, dense)
         root = os.path.join(d, "case.h5dir")
         write_config(root, dq, sq, frames, imm, **cfg)
-        info = run(root, imm, g2out=g2out, darkout=darkout, threads=threads, cwd=d)
+        info = run(root, imm, g2out=g2out, darkout=darkout, threads=threads, extra=extra, cwd=d)
         res = listing(root, cfg.get("output", "/exchange"))
         return res, info
     finally:

@@ -49,6 +49,35 @@ def sparse_case(name, h, w, F_raw, occ, seed, dpl=8, nd=4, spd=3, r_min=2.0, fla
                     params=np.array([F_raw, dpl, stride, avg, sw, int(norm)], np.int64)), res, info)
 
 
+def ufxc_case(name, h, w, F, occ, seed, f0=1900):
+    """--ufxc (io/ufxc.cpp): the event words go through the reader's frame-counter unwrapping (the counter
+    wraps at 2048: f0 = 1900 puts the wrap inside the run), empty frames, a pixel hit twice in a frame, a
+    zero count.  The fixture is a "sparse" one (the decoded events in file order) that also carries the raw
+    words the reference read."""
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=4, static_per_dynamic=3, r_min=2.0)
+    off, idx, val = S.sparse_frames(h * w, F, occ, seed=seed)
+    val = np.minimum(val, 3).astype(np.int16)
+    cnt = np.diff(off)
+    keep = np.ones(idx.size, bool)
+    for f in (10, 11, 200):                       # empty frames (the first frame must have events)
+        keep[int(off[f]):int(off[f + 1])] = False
+        cnt[f] = 0
+    idx, val = idx[keep], val[keep]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    val[int(off[5])] = 0                           # an event with count 0
+    # frame 7: its first pixel once more at the end of the frame (duplicate, not adjacent in the file)
+    a, b = int(off[7]), int(off[8])
+    idx = np.concatenate([idx[:b], idx[a:a + 1], idx[b:]])
+    val = np.concatenate([val[:b], np.array([2], np.int16), val[b:]])
+    off = off.copy()
+    off[8:] += 1
+    words = S.ufxc_words(h, w, off, idx, val, f0=f0)
+    sw = max(1, F // 10)
+    res, info = refdrv.run_case(S, dq, sq, F, ufxc=words, g2out=True, dpl=8, static_window=sw)
+    save(name, dict(kind=np.array("sparse"), fmt=np.array("ufxc"), words=words, dq=dq, sq=sq, off=off,
+                    idx=idx.astype(np.int32), val=val, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
+
+
 def main():
     if not refdrv.available():
         raise SystemExit("oracle/_ref/corr_ref missing: run `make -C oracle ref` (needs /root/reference)")
@@ -67,6 +96,7 @@ def main():
     sparse_case("sparse_flat_stride2_avg2", 24, 24, 1200, 0.03, 5, flat=True, stride=2, avg=2)
     sparse_case("sparse_flat_avg3", 24, 24, 900, 0.03, 6, flat=True, avg=3)
     sparse_case("sparse_framesum_norm", 24, 24, 500, 0.04, 7, norm=True)
+    ufxc_case("ufxc_wrap_48x40", 48, 40, 400, 0.02, 9)
 
     # dense int16 source with dark frames, flat-field and threshold (DenseFilter + DarkImage)
     h = w = 16

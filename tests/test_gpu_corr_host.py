@@ -1,5 +1,5 @@
-"""End to end through the host program: `corr config.hdf5 --imm data.imm [--g2out] [--darkout]`
-(the reference's entry point) on the inputs of every golden fixture, results read back from the
+"""End to end through the host program: `corr config.hdf5 --imm data.imm [--g2out] [--darkout] [--ufxc]`
+(the reference's entry point) on the inputs of every golden fixture (IMM sparse / dense, UFXC event words), results read back from the
 configuration HDF5 file and compared dataset by dataset -- name, shape, dtype, values -- with
 what the unmodified reference binary wrote (tests/golden/make_golden.py)."""
 import os
@@ -29,6 +29,9 @@ def _run_corr(pkg, c, tmp_path, extra=()):
         kw.update(darks=c.darks)
         if "thresh" in c.inp:
             kw.update(lld=float(c.inp["thresh"][0]), sigma=float(c.inp["thresh"][1]))
+    elif "words" in c.inp:  # a UFXC event file (io/ufxc.cpp), read through --ufxc
+        np.asarray(c.inp["words"], "<u4").tofile(imm)
+        extra = list(extra) + ["--ufxc"]
     else:
         pkg.synth.write_imm_sparse(imm, h, w, c.inp["off"], c.inp["idx"], c.inp["val"])
     if c.kind == "twotime":

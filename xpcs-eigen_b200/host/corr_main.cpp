@@ -7,8 +7,9 @@
 // the log ("Loading data", "Computing G2 MultiTau", "Normalizing Data", "Total";
 // benchmark.h:56-86).  Everything between the IMM reader and the result writer runs on the GPU
 // through the C-ABI of include/xpcs_b200.h; there is no CPU compute path.
-// HDF5 I/O is h5lite (the image has no libhdf5); the UFXC / Rigaku / HDF5-frame readers of the
-// reference are out of scope and their flags are rejected.
+// HDF5 I/O is h5lite (the image has no libhdf5).  Inputs: IMM (sparse and dense) and, with --ufxc, the
+// UFXC event stream (io/ufxc.cpp); the Rigaku and HDF5-frame readers of the reference are out of
+// scope and their flags are rejected.
 #include <sys/stat.h>
 
 #include <chrono>
@@ -58,7 +59,7 @@ struct Scope {
 };
 
 struct Flags {
-    bool g2out = false, darkout = false, no_compat = false;
+    bool g2out = false, darkout = false, no_compat = false, ufxc = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     int device = 0;
     int frameout = 0;
@@ -99,8 +100,9 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "frame_threading" || name == "noframe_threading") {
             }  // the two-time contraction has one (tensor-core) path
             else if (name == "frameout") f.frameout = atoi(need().c_str());
-            else if (name == "ufxc" || name == "rigaku" || name == "hdf5" || name == "transposed") {
-                fprintf(stderr, "corr: --%s is outside the scope of this build (IMM input only)\n", name.c_str());
+            else if (name == "ufxc") f.ufxc = !has_val || val == "true" || val == "1";
+            else if (name == "rigaku" || name == "hdf5" || name == "transposed") {
+                fprintf(stderr, "corr: --%s is outside the scope of this build (IMM and UFXC input only)\n", name.c_str());
                 return 2;
             } else {
                 fprintf(stderr, "corr: unknown flag --%s\n", name.c_str());
@@ -312,28 +314,85 @@ int main(int argc, char **argv)
         bool had_dark = false;
         {
             Scope sc("Loading data");
-            xpcs_host::ImmReader reader(conf.imm_path);
-            xpcs_host::ImmBatch b;
-            int r = 0;
-            if (!reader.sparse() && conf.darks > 0) {  // main.cpp:227-239: darks come from the file start
-                reader.next(conf.darks, b, pixels);
-                CHECK(xpcs_set_dark(h, b.val.data(), conf.darks));
-                had_dark = true;
-                r += conf.darks;
-            }
-            const int frame_from = conf.frame_start_todo - 1;
-            if (frame_from > 0 && r < frame_from) reader.skip(frame_from - r);  // main.cpp:241-245
-            int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
-            if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
-            const int64_t raw_todo = (int64_t)frames * block;
-            const int chunk = reader.sparse() ? 4096 : std::max(1, (int)((256ll << 20) / ((int64_t)pixels * 2)));
-            for (int64_t done = 0; done < raw_todo;) {
-                const int n = (int)std::min<int64_t>(chunk, raw_todo - done);
-                reader.next(n, b, pixels);
-                if (reader.sparse())
-                    CHECK(xpcs_push_sparse(h, b.idx.data(), b.val.data(), b.offsets.data(), b.clock.data(), b.ticks.data(), n));
-                else CHECK(xpcs_push_dense(h, b.val.data(), b.clock.data(), b.ticks.data(), n));
-                done += n;
+            if (fl.ufxc) {
+                // --ufxc (main.cpp:206-207; io/ufxc.cpp:59-153): a stream of 32-bit event words -- frame counter
+                // in bits 31..21 (11 bits, unwrapped by +-2048 when it jumps by more than 2000; the first word
+                // is frame 0), count in bits 16..15, column-major pixel in bits 14..0.  Frames come out in
+                // file order, a missing frame is an empty frame, the reader's SkipFrames does nothing (the
+                // frame range always starts at the first frame), clock = ticks = frame number.
+                FILE *fp = fopen(conf.imm_path.c_str(), "rb");
+                if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
+                std::vector<uint32_t> words;
+                {
+                    uint32_t buf[4096];
+                    size_t got;
+                    while ((got = fread(buf, sizeof(uint32_t), 4096, fp)) > 0) words.insert(words.end(), buf, buf + got);
+                    fclose(fp);
+                }
+                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
+                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
+                const int64_t raw_todo = (int64_t)frames * block;
+                std::vector<int64_t> count((size_t)raw_todo + 1, 0);
+                std::vector<int64_t> frame_of(words.size(), -1);
+                if (!words.empty()) {
+                    const long first = (long)(words[0] >> 21);
+                    long prev = first, wrap = 0;
+                    for (size_t i = 0; i < words.size(); i++) {
+                        const long c = (long)(words[i] >> 21);
+                        if (i > 0) {
+                            const long diff = c - prev;
+                            if (diff < -2000) wrap += 2048;
+                            else if (diff > 2000) wrap -= 2048;
+                        }
+                        const long ff = c + wrap - first;
+                        prev = c;
+                        if (ff >= 0 && ff < raw_todo) {
+                            frame_of[i] = ff;
+                            count[(size_t)ff + 1]++;
+                        }
+                    }
+                }
+                for (int64_t f = 0; f < raw_todo; f++) count[(size_t)f + 1] += count[(size_t)f];
+                std::vector<int32_t> idx((size_t)count[(size_t)raw_todo] + 1);
+                std::vector<int16_t> val((size_t)count[(size_t)raw_todo] + 1);
+                {
+                    std::vector<int64_t> cur(count.begin(), count.end() - 1);
+                    const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
+                    for (size_t i = 0; i < words.size(); i++) {
+                        if (frame_of[i] < 0) continue;
+                        const uint32_t pix = words[i] & 0x7fffu;
+                        const int64_t at = cur[(size_t)frame_of[i]]++;  // file order inside a frame
+                        idx[(size_t)at] = (int32_t)((pix % H) * W + pix / H);
+                        val[(size_t)at] = (int16_t)((words[i] >> 15) & 0x3u);
+                    }
+                }
+                std::vector<double> stamp((size_t)raw_todo);
+                for (int64_t f = 0; f < raw_todo; f++) stamp[(size_t)f] = (double)f;
+                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), count.data(), stamp.data(), stamp.data(), (int)raw_todo));
+            } else {
+                xpcs_host::ImmReader reader(conf.imm_path);
+                xpcs_host::ImmBatch b;
+                int r = 0;
+                if (!reader.sparse() && conf.darks > 0) {  // main.cpp:227-239: darks come from the file start
+                    reader.next(conf.darks, b, pixels);
+                    CHECK(xpcs_set_dark(h, b.val.data(), conf.darks));
+                    had_dark = true;
+                    r += conf.darks;
+                }
+                const int frame_from = conf.frame_start_todo - 1;
+                if (frame_from > 0 && r < frame_from) reader.skip(frame_from - r);  // main.cpp:241-245
+                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
+                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
+                const int64_t raw_todo = (int64_t)frames * block;
+                const int chunk = reader.sparse() ? 4096 : std::max(1, (int)((256ll << 20) / ((int64_t)pixels * 2)));
+                for (int64_t done = 0; done < raw_todo;) {
+                    const int n = (int)std::min<int64_t>(chunk, raw_todo - done);
+                    reader.next(n, b, pixels);
+                    if (reader.sparse())
+                        CHECK(xpcs_push_sparse(h, b.idx.data(), b.val.data(), b.offsets.data(), b.clock.data(), b.ticks.data(), n));
+                    else CHECK(xpcs_push_dense(h, b.val.data(), b.clock.data(), b.ticks.data(), n));
+                    done += n;
+                }
             }
             std::vector<float> pixel_sum(pixels), frame_sum(2 * (size_t)frames), pm_total(S > 0 ? S : 1);
             const int windows = frames / prm.static_window;

@@ -109,6 +109,23 @@ def write_imm_sparse(path, h, w, frame_off, idx, val, dt=1e-3):
             fh.write(np.ascontiguousarray(val[a:b], "<i2").tobytes())
 
 
+def ufxc_words(h, w, frame_off, idx, val, f0=0):
+    """Events -> the 32-bit words of a UFXC file (reference io/ufxc.cpp:59-99, 144-153): bits 31..21 the
+    frame counter (11 bits, wraps at 2048; the first word's counter is frame 0), bits 16..15 the count
+    (0..3), bits 14..0 the pixel in column-major order (index = (pix % h) * w + pix // h)."""
+    assert h * w <= 1 << 15
+    idx = np.asarray(idx, np.int64)
+    fr = np.repeat(np.arange(len(frame_off) - 1, dtype=np.int64), np.diff(frame_off))
+    pix = (idx % w) * h + idx // w
+    v = np.asarray(val, np.int64)
+    assert v.min(initial=0) >= 0 and v.max(initial=0) <= 3
+    return ((((f0 + fr) & 0x7FF) << 21) | (v << 15) | pix).astype("<u4")
+
+
+def write_ufxc(path, h, w, frame_off, idx, val, f0=0):
+    ufxc_words(h, w, frame_off, idx, val, f0).tofile(path)
+
+
 def write_imm_dense(path, h, w, frames, dt=1e-3):
     frames = np.asarray(frames).reshape(-1, h * w)
     elapsed, tick = frame_clock(frames.shape[0], dt)
