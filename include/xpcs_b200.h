@@ -38,6 +38,11 @@ extern "C" {
 #define XPCS_COMPAT_STALE_TAIL 1u /* reproduce the reference's dropped G2 pairs: the binary
                                      search of corr.cpp:406 runs over the un-shrunk index
                                      vector.  Off = exact sums.            */
+#define XPCS_COMPAT_LATE_WINDOW 2u /* static windows as the Rigaku reader counts them
+                                     (io/rigaku.cpp:190-193: the window number moves on AFTER the
+                                     frames 1w, 2w, ...), not as the Filter stage does
+                                     (sparse_filter.cpp:160-162: before them): frame t > 0
+                                     belongs to window (t-1)/w.                             */
 #define XPCS_FLAG_LANE_MULTITAU 0x100u /* diagnostics: run the lane-per-row multi-tau kernel on
                                           every slice instead of the warp-per-row one (both are
                                           exact on integer counts; used by the parity tests to

@@ -46,6 +46,8 @@ def lib():
     L.xo_sparse_filter.argtypes = [C.c_int] * 6 + [_i16p, _i32p, _f64p, _i64p, _i32p, _i16p, C.c_int64,
                                                    _i64p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p]
     L.xo_sparse_filter.restype = C.c_int64
+    L.xo_set_late_window.argtypes = [C.c_int]
+    L.xo_set_late_window.restype = None
     L.xo_dense_filter.argtypes = [C.c_int] * 6 + [_i16p, _i32p, _f64p, C.c_void_p, C.c_void_p, C.c_float,
                                                   C.c_float, _i16p, C.c_int64, _i64p, _i32p, _f32p, _f32p,
                                                   _f32p, _f32p, _f32p]
@@ -135,8 +137,53 @@ def _filter_alloc(P, F, S, swindow, cap):
     return o
 
 
-def sparse_filter(qm, F, frame_off, idx, val, flat=None, stride=1, avg=1, swindow=1):
-    """filter/sparse_filter.cpp:115-193 over the ingest loop main.cpp:258-268."""
+def rigaku_frames(words, h, w, frame_start_todo, frames, mask):
+    """The event stream the Rigaku reader (io/rigaku.cpp:139-267, stride = average = 1) turns into output
+    frames.  A 64-bit word carries the frame in bits 63..40, the column-major pixel in bits 35..16 and the
+    count in bits 10..0.  Words of frames <= frame_start_todo are skipped; an output frame ends when the frame
+    number of a word differs from the previous one (so frames without events vanish, except that a run not
+    starting at frame_start_todo + 1 opens with an empty output frame); reading stops once `frames` output
+    frames are complete; events on masked pixels are dropped after the frame bookkeeping; the frame still
+    open at the end of the file is kept only if it holds more than one pixel.
+    -> (frame_off int64[frames + 1], idx int32, val int16) in file order, as for xpcs_push_sparse."""
+    words = np.asarray(words, np.uint64)
+    off, idx, val = [0], [], []
+    prev = frame_start_todo + 1
+    done = 0
+    cur_idx, cur_val = [], []
+
+    def flush():
+        idx.extend(cur_idx)
+        val.extend(cur_val)
+        off.append(len(idx))
+        del cur_idx[:], cur_val[:]
+
+    for wd in words.tolist():
+        frame = (wd >> 40) & 0xFFFFFFFF
+        if frame <= frame_start_todo:
+            continue
+        if done >= frames:
+            break
+        if frame != prev:
+            flush()
+            prev = frame
+            done += 1
+        pix = (wd >> 16) & 0xFFFFF
+        pix = (pix % h) * w + pix // h
+        if not mask[pix]:
+            continue
+        cur_idx.append(pix)
+        cur_val.append(wd & 0x7FF)
+    if done < frames and len(set(cur_idx)) > 1:
+        flush()
+    while len(off) < frames + 1:
+        off.append(len(idx))
+    return np.asarray(off, np.int64), np.asarray(idx, np.int32), np.asarray(val, np.int16)
+
+
+def sparse_filter(qm, F, frame_off, idx, val, flat=None, stride=1, avg=1, swindow=1, late_window=False):
+    """filter/sparse_filter.cpp:115-193 over the ingest loop main.cpp:258-268.  late_window: the static-window
+    rule of the Rigaku reader (io/rigaku.cpp:190-193), whose per-frame sums are otherwise the same."""
     P = qm.P
     flat = np.ones(P, np.float64) if flat is None else np.ascontiguousarray(flat, np.float64).ravel()
     frame_off = np.ascontiguousarray(frame_off, np.int64)
@@ -144,10 +191,14 @@ def sparse_filter(qm, F, frame_off, idx, val, flat=None, stride=1, avg=1, swindo
     val = np.ascontiguousarray(val, np.int16)
     cap = int(idx.size)
     o = _filter_alloc(P, F, qm.S, swindow, cap)
-    n = lib().xo_sparse_filter(P, F, stride, avg, swindow, qm.S, qm.mask, qm.sbin_of_pixel, flat, frame_off,
-                               idx if idx.size else np.zeros(1, np.int32),
-                               val if val.size else np.zeros(1, np.int16), cap, o.row_ptr, o.t, o.v,
-                               o.pixel_sum, o.frame_sum, o.part_total, o.part_partial)
+    lib().xo_set_late_window(1 if late_window else 0)
+    try:
+        n = lib().xo_sparse_filter(P, F, stride, avg, swindow, qm.S, qm.mask, qm.sbin_of_pixel, flat, frame_off,
+                                   idx if idx.size else np.zeros(1, np.int32),
+                                   val if val.size else np.zeros(1, np.int16), cap, o.row_ptr, o.t, o.v,
+                                   o.pixel_sum, o.frame_sum, o.part_total, o.part_partial)
+    finally:
+        lib().xo_set_late_window(0)
     assert n >= 0
     o.rows = Rows(o.row_ptr, o.t[:n], o.v[:n])
     o.n = int(n)

@@ -182,7 +182,7 @@ def scratch_dir():
 
 
 def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout=False, threads=None, keep=False,
-             ufxc=None, **cfg):
+             ufxc=None, rigaku=None, **cfg):
     """Write IMM + config, run the reference, return (results dict of the output group, run info).
     sparse = (frame_off, idx, val); dense = int16 frames [darks + frames][P]."""
     d = scratch_dir()
@@ -193,6 +193,9 @@ def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout
         if ufxc is not None:  # raw 32-bit words of a UFXC file, read through --ufxc
             np.asarray(ufxc, "<u4").tofile(imm)
             extra = ("--ufxc",)
+        elif rigaku is not None:  # raw 64-bit words of a Rigaku file, read through --rigaku
+            np.asarray(rigaku, "<u8").tofile(imm)
+            extra = ("--rigaku",)
         elif sparse is not None:
             synth.write_imm_sparse(imm, h, w, *sparse)
         else:

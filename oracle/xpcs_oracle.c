@@ -197,13 +197,18 @@ static int cmp_int(const void *a, const void *b)
 /* Shared tail of SparseFilter::Apply (sparse_filter.cpp:164-191) and
  * DenseFilter::Apply (dense_filter.cpp:178-207): emit the touched pixels of one
  * output frame in ascending pixel order and update every accumulator. */
+/* io/rigaku.cpp:190-193 moves the static-window number on AFTER the frames 1w, 2w, ... (the
+ * Filter stage, sparse_filter.cpp:160-162, before them); the Rigaku restatement switches this on. */
+static int g_late_window = 0;
+void xo_set_late_window(int on) { g_late_window = on; }
+
 static void emit_frame(int P, int F, int S, int swindow, int frame, int *partition_no,
                        int *touched, int ntouched, float *pix_value, short *touched_map,
                        const int *sbin_of_pixel, float avg_div, float *pixel_sum,
                        float *frame_sum, float *part_total, float *part_partial,
                        xo_event **ev, int64_t *nev, int64_t *cap)
 {
-    if (frame > 0 && (frame % swindow) == 0) (*partition_no)++;
+    if (!g_late_window && frame > 0 && (frame % swindow) == 0) (*partition_no)++;
     qsort(touched, (size_t)ntouched, sizeof(int), cmp_int);
     float f_sum = 0.0f;
     for (int k = 0; k < ntouched; k++) {
@@ -227,6 +232,7 @@ static void emit_frame(int P, int F, int S, int swindow, int frame, int *partiti
     }
     frame_sum[frame] = (float)(frame + 1.0);
     frame_sum[frame + F] = f_sum / (float)P;
+    if (g_late_window && frame > 0 && (frame % swindow) == 0) (*partition_no)++;
 }
 
 /* Stable counting sort of the (frame-ascending, pixel-ascending) filtered events

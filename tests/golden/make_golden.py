@@ -78,6 +78,42 @@ def ufxc_case(name, h, w, F, occ, seed, f0=1900):
                     idx=idx.astype(np.int32), val=val, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
 
 
+def rigaku_case(name, h, w, F, occ, seed):
+    """--rigaku (io/rigaku.cpp): 64-bit event words; the reader itself plays the Filter stage.  Frames without
+    events vanish (the output frames are the non-empty ones, renumbered), events inside a frame come unsorted
+    and a pixel twice, the file holds more frames than are asked for, and the static windows follow the
+    reader's own rule (XPCS_COMPAT_LATE_WINDOW).  Stored as a "sparse" fixture: the events the reader's
+    restatement (oracle.rigaku_frames) delivers, plus the raw words the reference read."""
+    from oracle import oracle as O
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=4, static_per_dynamic=3, r_min=2.0)
+    n_file = F + 40
+    off, idx, val = S.sparse_frames(h * w, n_file, occ, seed=seed)
+    val = np.minimum(val, 7).astype(np.int16)
+    rng = np.random.default_rng(seed)
+    cnt = np.diff(off)
+    keep = np.ones(idx.size, bool)
+    for f in (3, 4, 57, 300):                     # file frames without events
+        keep[int(off[f]):int(off[f + 1])] = False
+        cnt[f] = 0
+    idx, val = idx[keep], val[keep]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    # shuffle the events inside every frame, and hit the first pixel of frame 9 twice
+    order = np.concatenate([a + rng.permutation(b - a) for a, b in zip(off[:-1], off[1:])]).astype(np.int64)
+    idx, val = idx[order], val[order]
+    a, b = int(off[9]), int(off[10])
+    idx = np.concatenate([idx[:b], idx[a:a + 1], idx[b:]])
+    val = np.concatenate([val[:b], np.array([3], np.int16), val[b:]])
+    off = off.copy()
+    off[10:] += 1
+    words = S.rigaku_words(h, w, np.arange(1, n_file + 1), off, idx, val)
+    sw = max(1, F // 10)
+    res, info = refdrv.run_case(S, dq, sq, F, rigaku=words, g2out=True, dpl=8, static_window=sw)
+    qm = O.QMap(dq, sq)
+    eoff, eidx, evalv = O.rigaku_frames(words, h, w, 0, F, qm.mask)
+    save(name, dict(kind=np.array("sparse"), fmt=np.array("rigaku"), words=words, dq=dq, sq=sq, off=eoff, idx=eidx,
+                    val=evalv, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
+
+
 def main():
     if not refdrv.available():
         raise SystemExit("oracle/_ref/corr_ref missing: run `make -C oracle ref` (needs /root/reference)")
@@ -97,6 +133,7 @@ def main():
     sparse_case("sparse_flat_avg3", 24, 24, 900, 0.03, 6, flat=True, avg=3)
     sparse_case("sparse_framesum_norm", 24, 24, 500, 0.04, 7, norm=True)
     ufxc_case("ufxc_wrap_48x40", 48, 40, 400, 0.02, 9)
+    rigaku_case("rigaku_compact_32x40", 32, 40, 400, 0.02, 10)
 
     # dense int16 source with dark frames, flat-field and threshold (DenseFilter + DarkImage)
     h = w = 16

@@ -31,6 +31,8 @@ class Case:
         self.F = self.F_raw // block
         self.dq, self.sq = self.inp["dq"], self.inp["sq"]
         self.flat = self.inp.get("flat")
+        self.fmt = str(self.inp["fmt"]) if "fmt" in self.inp else "imm"   # imm | ufxc | rigaku
+        self.late_window = self.fmt == "rigaku"                           # XPCS_COMPAT_LATE_WINDOW
 
 
 def rel_err(a, b):

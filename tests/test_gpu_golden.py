@@ -19,7 +19,7 @@ def _close(a, b, what, rtol=RTOL):
 
 def _run(pkg, c):
     kw = dict(dpl=c.dpl, flatfield=c.flat, stride=c.stride, avg=c.avg, static_window=c.swindow,
-              normalize_by_framesum=bool(c.norm), compat=True)
+              normalize_by_framesum=bool(c.norm), compat=True, late_window=c.late_window)
     if c.kind == "dense" and "thresh" in c.inp:
         kw.update(lld=float(c.inp["thresh"][0]), sigma=float(c.inp["thresh"][1]))
     cor = pkg.Correlator(c.dq, c.sq, c.F, **kw)

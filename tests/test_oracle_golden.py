@@ -13,8 +13,13 @@ def _filter(O, c):
     qm = O.QMap(c.dq, c.sq)
     dark = None
     if c.kind in ("sparse", "twotime"):
-        fo = O.sparse_filter(qm, c.F, c.inp["off"], c.inp["idx"], c.inp["val"], flat=c.flat, stride=c.stride,
-                             avg=c.avg, swindow=c.swindow)
+        off, idx, val = c.inp["off"], c.inp["idx"], c.inp["val"]
+        if c.fmt == "rigaku":  # the reader's restatement must deliver the stored events from the raw words
+            h, w = c.dq.shape
+            off, idx, val = O.rigaku_frames(c.inp["words"], h, w, 0, c.F, qm.mask)
+            assert np.array_equal(off, c.inp["off"]) and np.array_equal(idx, c.inp["idx"]) and np.array_equal(val, c.inp["val"])
+        fo = O.sparse_filter(qm, c.F, off, idx, val, flat=c.flat, stride=c.stride, avg=c.avg, swindow=c.swindow,
+                             late_window=c.late_window)
     else:
         fr = c.inp["frames"]
         if c.darks:

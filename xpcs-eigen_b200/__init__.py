@@ -17,7 +17,7 @@ from .cabi import XPCS_COMPAT_STALE_TAIL, XpcsError, XpcsInfo, XpcsParams, XpcsS
 
 
 def make_params(dqmap, sqmap, frames, dpl=8, flatfield=None, stride=1, avg=1, static_window=None,
-                normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, shard_index=0, shard_count=1,
+                normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, shard_index=0, shard_count=1, late_window=False,
                 reserve_events=0, lane_multitau=False, scalar_dense=False):
     """XpcsParams from numpy maps; returns (params, keepalive list)."""
     dq = np.ascontiguousarray(dqmap, np.int32)
@@ -33,6 +33,7 @@ def make_params(dqmap, sqmap, frames, dpl=8, flatfield=None, stride=1, avg=1, st
     p.static_window = int(static_window) if static_window else max(1, int(frames) // 10)
     p.normalize_by_framesum = int(bool(normalize_by_framesum))
     p.compat_flags = (XPCS_COMPAT_STALE_TAIL if compat else 0) | (cabi.XPCS_FLAG_LANE_MULTITAU if lane_multitau else 0) | \
+        (cabi.XPCS_COMPAT_LATE_WINDOW if late_window else 0) | \
         (cabi.XPCS_FLAG_SCALAR_DENSE if scalar_dense else 0)
     p.lld, p.sigma = float(lld), float(sigma)
     p.dqmap, p.sqmap = dq.ctypes.data, sq.ctypes.data
@@ -82,13 +83,13 @@ class Correlator:
 
     def __init__(self, dqmap, sqmap, frames, dpl=8, flatfield=None, stride=1, avg=1, static_window=None,
                  normalize_by_framesum=False, compat=True, lld=0.0, sigma=0.0, device=0, shard_index=0,
-                 shard_count=1, reserve_events=0, lane_multitau=False, scalar_dense=False):
+                 shard_count=1, reserve_events=0, lane_multitau=False, scalar_dense=False, late_window=False):
         self._lib = cabi.load()
         p, self._maps = make_params(dqmap, sqmap, frames, dpl=dpl, flatfield=flatfield, stride=stride, avg=avg,
                                     static_window=static_window, normalize_by_framesum=normalize_by_framesum,
                                     compat=compat, lld=lld, sigma=sigma, shard_index=shard_index,
                                     shard_count=shard_count, reserve_events=reserve_events,
-                                    lane_multitau=lane_multitau, scalar_dense=scalar_dense)
+                                    lane_multitau=lane_multitau, scalar_dense=scalar_dense, late_window=late_window)
         self.height, self.width = p.height, p.width
         self.P = p.width * p.height
         self.F = int(frames)

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxpcs_b200.so")
 
 XPCS_COMPAT_STALE_TAIL = 1
+XPCS_COMPAT_LATE_WINDOW = 2
 XPCS_FLAG_LANE_MULTITAU = 0x100
 XPCS_FLAG_SCALAR_DENSE = 0x200
 

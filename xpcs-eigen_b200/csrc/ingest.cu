@@ -476,6 +476,7 @@ struct FinalizeArgs {
     const unsigned long long *rec;
     const int64_t *slice_rec;
     int accumulate;          // chunked ingest: row_sum += instead of =
+    int late_window;         // XPCS_COMPAT_LATE_WINDOW: frame t > 0 belongs to static window (t - 1) / swindow
 };
 
 template <int KIND>
@@ -625,8 +626,8 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
             }
             if (t >= wend) {  // frames ascend: a division only when the static window changes
                 if (win >= 0 && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
-                win = t / a.swindow;
-                wend = (win + 1) * a.swindow;
+                win = a.late_window ? (t > 0 ? (t - 1) / a.swindow : 0) : t / a.swindow;
+                wend = (win + 1) * a.swindow + (a.late_window ? 1 : 0);
                 wacc = 0.0;
             }
             wacc += v;
@@ -756,7 +757,8 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
             if (head) B[m_base + __popc(mk & ((1u << lane) - 1u))] = outw;
             m_base += __popc(mk);
             // per-static-window sums: the frames ascend, so a window is a run of lanes
-            int wi = valid ? (int)(key / (uint32_t)a.swindow) : 0x7fffffff;
+            int wi = 0x7fffffff;
+            if (valid) wi = a.late_window ? (key > 0u ? (int)((key - 1u) / (uint32_t)a.swindow) : 0) : (int)(key / (uint32_t)a.swindow);
             double x = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1349,6 +1351,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     }
     FinalizeArgs fa{};
     fa.accumulate = chunk > 0 ? 1 : 0;
+    fa.late_window = (h->prm.compat_flags & XPCS_COMPAT_LATE_WINDOW) ? 1 : 0;
     fa.store = h->d_store.p;
     fa.slice_base = h->d_slice_base.p;
     fa.slice_len = h->d_slice_len.p;

@@ -7,9 +7,9 @@
 // the log ("Loading data", "Computing G2 MultiTau", "Normalizing Data", "Total";
 // benchmark.h:56-86).  Everything between the IMM reader and the result writer runs on the GPU
 // through the C-ABI of include/xpcs_b200.h; there is no CPU compute path.
-// HDF5 I/O is h5lite (the image has no libhdf5).  Inputs: IMM (sparse and dense) and, with --ufxc, the
-// UFXC event stream (io/ufxc.cpp); the Rigaku and HDF5-frame readers of the reference are out of
-// scope and their flags are rejected.
+// HDF5 I/O is h5lite (the image has no libhdf5).  Inputs: IMM (sparse and dense), with --ufxc the UFXC
+// event stream (io/ufxc.cpp) and with --rigaku the Rigaku one (io/rigaku.cpp, stride = average = 1);
+// the HDF5-frame reader of the reference is out of scope and its flags are rejected.
 #include <sys/stat.h>
 
 #include <chrono>
@@ -59,7 +59,7 @@ struct Scope {
 };
 
 struct Flags {
-    bool g2out = false, darkout = false, no_compat = false, ufxc = false;
+    bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     int device = 0;
     int frameout = 0;
@@ -101,8 +101,9 @@ static int parse_flags(int argc, char **argv, Flags &f)
             }  // the two-time contraction has one (tensor-core) path
             else if (name == "frameout") f.frameout = atoi(need().c_str());
             else if (name == "ufxc") f.ufxc = !has_val || val == "true" || val == "1";
-            else if (name == "rigaku" || name == "hdf5" || name == "transposed") {
-                fprintf(stderr, "corr: --%s is outside the scope of this build (IMM and UFXC input only)\n", name.c_str());
+            else if (name == "rigaku") f.rigaku = !has_val || val == "true" || val == "1";
+            else if (name == "hdf5" || name == "transposed") {
+                fprintf(stderr, "corr: --%s is outside the scope of this build (IMM, UFXC and Rigaku input only)\n", name.c_str());
                 return 2;
             } else {
                 fprintf(stderr, "corr: unknown flag --%s\n", name.c_str());
@@ -292,6 +293,15 @@ int main(int argc, char **argv)
     prm.static_window = conf.static_window > 0 ? conf.static_window : 1;
     prm.normalize_by_framesum = conf.normalize_by_framesum;
     prm.compat_flags = fl.no_compat ? 0u : XPCS_COMPAT_STALE_TAIL;
+    if (fl.rigaku) {
+        // the Rigaku reader plays the Filter stage itself and counts the static windows its own way
+        // (io/rigaku.cpp:190-193); its stride / average modes are not covered here
+        if (conf.stride > 1 || conf.avg > 1) {
+            fprintf(stderr, "corr: --rigaku with stride_frames / avg_frames > 1 is outside the scope of this build\n");
+            return 2;
+        }
+        prm.compat_flags |= XPCS_COMPAT_LATE_WINDOW;
+    }
     prm.lld = conf.lld;
     prm.sigma = conf.sigma;
     prm.dqmap = conf.dqmap.data();
@@ -369,6 +379,66 @@ int main(int argc, char **argv)
                 std::vector<double> stamp((size_t)raw_todo);
                 for (int64_t f = 0; f < raw_todo; f++) stamp[(size_t)f] = (double)f;
                 CHECK(xpcs_push_sparse(h, idx.data(), val.data(), count.data(), stamp.data(), stamp.data(), (int)raw_todo));
+            } else if (fl.rigaku) {
+                // --rigaku (main.cpp:208-210; io/rigaku.cpp:139-267, stride = average = 1): 64-bit event words,
+                // frame number in bits 63..40, column-major pixel in bits 35..16, count in bits 10..0.  Words of
+                // frames up to data_begin_todo - 1 are skipped; an output frame is closed when the frame number
+                // changes, so frames without events vanish (a run that does not start at data_begin_todo opens
+                // with an empty output frame); reading stops when `frames` output frames are closed; masked
+                // pixels are dropped after the frame bookkeeping; the frame still open at the end of the file
+                // counts only if it holds more than one pixel; clock = ticks = output frame number.
+                FILE *fp = fopen(conf.imm_path.c_str(), "rb");
+                if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
+                const uint64_t start = (uint64_t)(conf.frame_start_todo > 0 ? conf.frame_start_todo - 1 : 0);
+                const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
+                std::vector<int32_t> idx;
+                std::vector<int16_t> val;
+                std::vector<int64_t> offs(1, 0);
+                uint64_t open_frame = start + 1;
+                size_t open_at = 0;  // first event of the frame still open
+                bool stop = false;
+                std::vector<uint64_t> buf(1 << 15);
+                size_t got;
+                while (!stop && (got = fread(buf.data(), sizeof(uint64_t), buf.size(), fp)) > 0) {
+                    for (size_t i = 0; i < got; i++) {
+                        const uint64_t wd = buf[i];
+                        const uint64_t fr = (wd >> 40) & 0xffffffffull;
+                        if (fr <= start) continue;
+                        if ((int64_t)offs.size() - 1 >= frames) {
+                            stop = true;
+                            break;
+                        }
+                        if (fr != open_frame) {
+                            offs.push_back((int64_t)idx.size());
+                            open_frame = fr;
+                            open_at = idx.size();
+                        }
+                        uint32_t pix = (uint32_t)((wd >> 16) & 0xfffffu);
+                        pix = (pix % H) * W + pix / H;
+                        if (pix >= (uint32_t)pixels || conf.dqmap[pix] < 1 || conf.sqmap[pix] < 1) continue;
+                        idx.push_back((int32_t)pix);
+                        val.push_back((int16_t)(wd & 0x7ffu));
+                    }
+                }
+                fclose(fp);
+                if ((int64_t)offs.size() - 1 < frames) {  // the open frame: kept if it has more than one distinct pixel
+                    bool two = false;
+                    for (size_t k = open_at + 1; k < idx.size() && !two; k++) two = idx[k] != idx[open_at];
+                    if (two) offs.push_back((int64_t)idx.size());
+                    else {
+                        idx.resize(open_at);
+                        val.resize(open_at);
+                    }
+                } else {  // `frames` closed: whatever was collected for the next one is dropped
+                    idx.resize((size_t)offs.back());
+                    val.resize((size_t)offs.back());
+                }
+                while ((int64_t)offs.size() - 1 < frames) offs.push_back((int64_t)idx.size());
+                std::vector<double> stamp((size_t)frames);
+                for (int f = 0; f < frames; f++) stamp[(size_t)f] = (double)f;
+                idx.push_back(0);
+                val.push_back(0);
+                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), offs.data(), stamp.data(), stamp.data(), frames));
             } else {
                 xpcs_host::ImmReader reader(conf.imm_path);
                 xpcs_host::ImmBatch b;
@@ -415,6 +485,15 @@ int main(int argc, char **argv)
                 ck[real_frames + i] = clock[raw_seen + i];
                 tk[i] = ticks[i];
                 tk[real_frames + i] = ticks[raw_seen + i];
+            }
+            if (fl.rigaku) {
+                // the Rigaku reader hands main() arrays of `frames` doubles (io/rigaku.cpp:91-92, 184-185: the
+                // output frame number), which main() writes as [2][frames] (main.cpp:399-411): the first row is
+                // 0 .. frames-1, the second is whatever lies behind the array.  Row 0 as the reference, row 1 zero.
+                for (int i = 0; i < real_frames; i++) {
+                    ck[i] = tk[i] = (double)i;
+                    ck[real_frames + i] = tk[real_frames + i] = 0.0;
+                }
             }
             file.put(out + "/timestamp_clock", Type::F64, {2, (uint64_t)real_frames}, ck.data());
             file.put(out + "/timestamp_tick", Type::F64, {2, (uint64_t)real_frames}, tk.data());

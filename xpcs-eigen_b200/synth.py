@@ -122,6 +122,18 @@ def ufxc_words(h, w, frame_off, idx, val, f0=0):
     return ((((f0 + fr) & 0x7FF) << 21) | (v << 15) | pix).astype("<u4")
 
 
+def rigaku_words(h, w, frame_ids, frame_off, idx, val):
+    """Events -> the 64-bit words of a Rigaku file (reference io/rigaku.cpp:143, 210-217): frame number in
+    bits 63..40 (frame_ids[f] for the events of frame f), column-major pixel in bits 35..16, count (0..2047)
+    in bits 10..0."""
+    idx = np.asarray(idx, np.int64)
+    fr = np.repeat(np.asarray(frame_ids, np.int64), np.diff(frame_off))
+    pix = (idx % w) * h + idx // w
+    v = np.asarray(val, np.int64)
+    assert v.min(initial=0) >= 0 and v.max(initial=0) <= 0x7FF and h * w <= 1 << 20
+    return ((fr.astype(np.uint64) << np.uint64(40)) | (pix.astype(np.uint64) << np.uint64(16)) | v.astype(np.uint64)).astype("<u8")
+
+
 def write_ufxc(path, h, w, frame_off, idx, val, f0=0):
     ufxc_words(h, w, frame_off, idx, val, f0).tofile(path)
 
