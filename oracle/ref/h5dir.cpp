@@ -32,6 +32,7 @@ struct Obj {
     int rank = 0;
     hsize_t dims[4] = {0, 0, 0, 0};
     bool selected = false;
+    hsize_t sel_start[4] = {0, 0, 0, 0}, sel_count[4] = {0, 0, 0, 0};  // hyperslab (unit stride) when selected
 };
 
 std::mutex g_mu;
@@ -335,13 +336,44 @@ herr_t H5Dread(hid_t d, hid_t mem_type, hid_t, hid_t file_space, hid_t, void *bu
 {
     Obj o;
     if (!get(d, o) || o.kind != K_DSET || !buf) return -1;
-    if (file_space != H5S_ALL) {
-        Obj fs;
-        if (get(file_space, fs) && fs.selected) return -1;  // hyperslab reads: not needed on this path
-    }
     int mtc;
     size_t mes;
     if (!resolve_type(mem_type, mtc, mes)) return -1;
+    if (file_space != H5S_ALL) {
+        Obj fs;
+        if (get(file_space, fs) && fs.selected) {
+            // unit-stride hyperslab (io/hdf5.cpp:141-149 reads one frame of a stack): the selected elements,
+            // row-major, packed into buf
+            if (fs.rank != o.rank || o.rank > 4) return -1;
+            hsize_t st[4] = {0, 0, 0, 0}, ct[4] = {1, 1, 1, 1}, dm[4] = {1, 1, 1, 1};
+            const int pad = 4 - o.rank;
+            for (int i = 0; i < o.rank; i++) {
+                st[pad + i] = fs.sel_start[i];
+                ct[pad + i] = fs.sel_count[i];
+                dm[pad + i] = o.dims[i];
+                if (fs.sel_start[i] + fs.sel_count[i] > o.dims[i]) return -1;
+            }
+            FILE *f = fopen(o.path.c_str(), "rb");
+            if (!f) return -1;
+            std::vector<unsigned char> row((size_t)ct[3] * o.esize ? (size_t)ct[3] * o.esize : 1);
+            unsigned char *out = (unsigned char *)buf;
+            for (hsize_t a = 0; a < ct[0]; a++)
+                for (hsize_t b = 0; b < ct[1]; b++)
+                    for (hsize_t c = 0; c < ct[2]; c++) {
+                        const hsize_t lin = (((st[0] + a) * dm[1] + (st[1] + b)) * dm[2] + (st[2] + c)) * dm[3] + st[3];
+                        fseek(f, (long)(sizeof(Header) + lin * o.esize), SEEK_SET);
+                        if (fread(row.data(), o.esize, (size_t)ct[3], f) != (size_t)ct[3]) {
+                            fclose(f);
+                            return -1;
+                        }
+                        if (mtc == o.tcode) memcpy(out, row.data(), (size_t)ct[3] * o.esize);
+                        else convert(row.data(), o.tcode, out, mtc, (size_t)ct[3]);
+                        out += (size_t)ct[3] * mes;
+                    }
+            fclose(f);
+            return 0;
+        }
+    }
     size_t n = 1;
     for (int i = 0; i < o.rank; i++) n *= (size_t)o.dims[i];
     const size_t bytes = n * o.esize;
@@ -419,6 +451,10 @@ herr_t H5Sselect_hyperslab(hid_t s, H5S_seloper_t, const hsize_t *start, const h
     for (int i = 0; i < o.rank; i++)
         if (start[i] != 0 || count[i] != o.dims[i]) whole = false;
     o.selected = !whole;
+    for (int i = 0; i < o.rank; i++) {
+        o.sel_start[i] = start[i];
+        o.sel_count[i] = count[i];
+    }
     return 0;
 }
 

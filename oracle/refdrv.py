@@ -182,7 +182,7 @@ def scratch_dir():
 
 
 def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout=False, threads=None, keep=False,
-             ufxc=None, rigaku=None, **cfg):
+             ufxc=None, rigaku=None, hdf5=None, **cfg):
     """Write IMM + config, run the reference, return (results dict of the output group, run info).
     sparse = (frame_off, idx, val); dense = int16 frames [darks + frames][P]."""
     d = scratch_dir()
@@ -193,6 +193,9 @@ def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout
         if ufxc is not None:  # raw 32-bit words of a UFXC file, read through --ufxc
             np.asarray(ufxc, "<u4").tofile(imm)
             extra = ("--ufxc",)
+        elif hdf5 is not None:  # frame stack [frames][h][w] (uint16 / uint32) at /entry/data/data, read through --hdf5
+            put(imm, "/entry/data/data", np.ascontiguousarray(hdf5))
+            extra = ("--hdf5",)
         elif rigaku is not None:  # raw 64-bit words of a Rigaku file, read through --rigaku
             np.asarray(rigaku, "<u8").tofile(imm)
             extra = ("--rigaku",)

@@ -114,6 +114,25 @@ def rigaku_case(name, h, w, F, occ, seed):
                     val=evalv, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
 
 
+def hdf5_case(name, h, w, F, occ, seed, begin=4, dtype=np.uint16):
+    """--hdf5 (io/hdf5.cpp): a dense frame stack /entry/data/data; every non-zero sample is an event, the frames
+    before data_begin_todo are skipped.  Stored as a "sparse" fixture (the events of the frames that are read)
+    plus the stack itself."""
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=4, static_per_dynamic=3, r_min=2.0)
+    n_file = F + begin - 1 + 5
+    off, idx, val = S.sparse_frames(h * w, n_file, occ, seed=seed)
+    stack = np.zeros((n_file, h * w), dtype)
+    fr = np.repeat(np.arange(n_file), np.diff(off))
+    stack[fr, idx] = val
+    stack = stack.reshape(n_file, h, w)
+    sw = max(1, F // 10)
+    res, info = refdrv.run_case(S, dq, sq, F, hdf5=stack, g2out=True, dpl=8, static_window=sw, begin=begin)
+    a, b = int(off[begin - 1]), int(off[begin - 1 + F])
+    save(name, dict(kind=np.array("sparse"), fmt=np.array("hdf5"), stack=stack, dq=dq, sq=sq,
+                    off=(off[begin - 1: begin + F] - a).astype(np.int64), idx=idx[a:b].astype(np.int32), val=val[a:b],
+                    begin=np.array(begin), params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
+
+
 def main():
     if not refdrv.available():
         raise SystemExit("oracle/_ref/corr_ref missing: run `make -C oracle ref` (needs /root/reference)")
@@ -134,6 +153,7 @@ def main():
     sparse_case("sparse_framesum_norm", 24, 24, 500, 0.04, 7, norm=True)
     ufxc_case("ufxc_wrap_48x40", 48, 40, 400, 0.02, 9)
     rigaku_case("rigaku_compact_32x40", 32, 40, 400, 0.02, 10)
+    hdf5_case("hdf5_stack_24x32", 24, 32, 300, 0.03, 11)
 
     # dense int16 source with dark frames, flat-field and threshold (DenseFilter + DarkImage)
     h = w = 16

@@ -1,5 +1,5 @@
-"""End to end through the host program: `corr config.hdf5 --imm data.imm [--g2out] [--darkout] [--ufxc | --rigaku]`
-(the reference's entry point) on the inputs of every golden fixture (IMM sparse / dense, UFXC and Rigaku event words), results read back from the
+"""End to end through the host program: `corr config.hdf5 --imm data.imm [--g2out] [--darkout] [--ufxc | --rigaku | --hdf5]`
+(the reference's entry point) on the inputs of every golden fixture (IMM sparse / dense, UFXC and Rigaku event words, an HDF5 frame stack), results read back from the
 configuration HDF5 file and compared dataset by dataset -- name, shape, dtype, values -- with
 what the unmodified reference binary wrote (tests/golden/make_golden.py)."""
 import os
@@ -29,6 +29,13 @@ def _run_corr(pkg, c, tmp_path, extra=()):
         kw.update(darks=c.darks)
         if "thresh" in c.inp:
             kw.update(lld=float(c.inp["thresh"][0]), sigma=float(c.inp["thresh"][1]))
+    elif c.fmt == "hdf5":  # a frame stack /entry/data/data (io/hdf5.cpp), read through --hdf5
+        st = pkg.h5lite.File()
+        st.put("/entry/data/data", c.inp["stack"])
+        st.save(imm)
+        st.close()
+        kw.update(begin=int(c.inp["begin"]))
+        extra = list(extra) + ["--hdf5"]
     elif c.fmt == "ufxc":  # a UFXC event file (io/ufxc.cpp), read through --ufxc
         np.asarray(c.inp["words"], "<u4").tofile(imm)
         extra = list(extra) + ["--ufxc"]

@@ -8,8 +8,8 @@
 // benchmark.h:56-86).  Everything between the IMM reader and the result writer runs on the GPU
 // through the C-ABI of include/xpcs_b200.h; there is no CPU compute path.
 // HDF5 I/O is h5lite (the image has no libhdf5).  Inputs: IMM (sparse and dense), with --ufxc the UFXC
-// event stream (io/ufxc.cpp) and with --rigaku the Rigaku one (io/rigaku.cpp, stride = average = 1);
-// the HDF5-frame reader of the reference is out of scope and its flags are rejected.
+// event stream (io/ufxc.cpp), with --rigaku the Rigaku one (io/rigaku.cpp, stride = average = 1) and with
+// --hdf5 a frame stack /entry/data/data (io/hdf5.cpp; contiguous uint16 / uint32, no chunk filters).
 #include <sys/stat.h>
 
 #include <chrono>
@@ -59,7 +59,7 @@ struct Scope {
 };
 
 struct Flags {
-    bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false;
+    bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false, hdf5 = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     int device = 0;
     int frameout = 0;
@@ -102,10 +102,10 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "frameout") f.frameout = atoi(need().c_str());
             else if (name == "ufxc") f.ufxc = !has_val || val == "true" || val == "1";
             else if (name == "rigaku") f.rigaku = !has_val || val == "true" || val == "1";
-            else if (name == "hdf5" || name == "transposed") {
-                fprintf(stderr, "corr: --%s is outside the scope of this build (IMM, UFXC and Rigaku input only)\n", name.c_str());
-                return 2;
-            } else {
+            else if (name == "hdf5") f.hdf5 = !has_val || val == "true" || val == "1";
+            else if (name == "transposed" || name == "notransposed") {
+            }  // the reference stores the flag and never uses it (io/hdf5.cpp:62, 121-228)
+            else {
                 fprintf(stderr, "corr: unknown flag --%s\n", name.c_str());
                 return 2;
             }
@@ -379,6 +379,41 @@ int main(int argc, char **argv)
                 std::vector<double> stamp((size_t)raw_todo);
                 for (int64_t f = 0; f < raw_todo; f++) stamp[(size_t)f] = (double)f;
                 CHECK(xpcs_push_sparse(h, idx.data(), val.data(), count.data(), stamp.data(), stamp.data(), (int)raw_todo));
+            } else if (fl.hdf5) {
+                // --hdf5 (main.cpp:211-216; io/hdf5.cpp:62-228): /entry/data/data, uint16 or uint32 [frames][.][.];
+                // every non-zero sample of a frame is an event at its linear index, the frames before
+                // data_begin_todo are skipped, clock = ticks = frame number in the stack.
+                const h5lite::File stack = h5lite::File::load(conf.imm_path);
+                const h5lite::Dataset &d = stack.dataset("/entry/data/data");
+                if (d.dims.size() != 3 || (d.type != Type::U16 && d.type != Type::U32))
+                    throw std::runtime_error("/entry/data/data must be a 3-d uint16 or uint32 dataset");
+                const uint64_t nfr = d.dims[0], per = d.dims[1] * d.dims[2];
+                if (per != (uint64_t)pixels) throw std::runtime_error("/entry/data/data: frame size differs from the detector");
+                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
+                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
+                const int64_t raw_todo = (int64_t)frames * block;
+                const int64_t first = conf.frame_start_todo > 1 ? conf.frame_start_todo - 1 : 0;  // main.cpp:241-245
+                if ((uint64_t)(first + raw_todo) > nfr) throw std::runtime_error("/entry/data/data holds too few frames");
+                std::vector<int32_t> idx;
+                std::vector<int16_t> val;
+                std::vector<int64_t> offs(1, 0);
+                std::vector<double> stamp;
+                const uint16_t *p16 = reinterpret_cast<const uint16_t *>(d.data.data());
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(d.data.data());
+                for (int64_t f = first; f < first + raw_todo; f++) {
+                    for (uint64_t i = 0; i < per; i++) {
+                        const uint32_t v = d.type == Type::U16 ? p16[(uint64_t)f * per + i] : p32[(uint64_t)f * per + i];
+                        if (v == 0) continue;
+                        if (v > 32767u) throw std::runtime_error("/entry/data/data: a sample above 32767 does not fit the int16 event payload");
+                        idx.push_back((int32_t)i);
+                        val.push_back((int16_t)v);
+                    }
+                    offs.push_back((int64_t)idx.size());
+                    stamp.push_back((double)f);
+                }
+                idx.push_back(0);
+                val.push_back(0);
+                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), offs.data(), stamp.data(), stamp.data(), (int)raw_todo));
             } else if (fl.rigaku) {
                 // --rigaku (main.cpp:208-210; io/rigaku.cpp:139-267, stride = average = 1): 64-bit event words,
                 // frame number in bits 63..40, column-major pixel in bits 35..16, count in bits 10..0.  Words of
