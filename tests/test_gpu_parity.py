@@ -289,3 +289,31 @@ def test_frame_dump_matches_filter_rows(pkg, oracle, flat):
         assert_close(got, want, "frames_out")
     else:
         assert_exact(got, want, "frames_out")
+
+
+@pytest.mark.parametrize("flat,F,sw", [(False, 400, 40), (True, 400, 40), (False, 333, 37), (True, 250, 1)])
+def test_late_window_partition_sums(pkg, oracle, flat, F, sw):
+    """XPCS_COMPAT_LATE_WINDOW (the Rigaku reader's static-window rule, io/rigaku.cpp:190-193): the partial
+    partition means of the integer and of the float store against the oracle's restatement; everything else
+    is unchanged by the flag."""
+    h, w = 32, 40
+    dq, sq, off, idx, val = make_case(pkg, h, w, F, 0.03, 31)
+    ff = (1.0 + 0.05 * np.random.default_rng(6).standard_normal(h * w)).astype(np.float64) if flat else None
+    kw = dict(flatfield=ff) if flat else {}
+    out = {}
+    for late in (False, True):
+        c = pkg.Correlator(dq, sq, F, dpl=8, static_window=sw, late_window=late, **kw)
+        c.push_sparse(idx, val, off)
+        out[late] = c.finish_ingest()
+        c.close()
+    qm = oracle.QMap(dq, sq)
+    fo = oracle.sparse_filter(qm, F, off, idx, val, flat=ff, stride=1, avg=1, swindow=sw, late_window=True)
+    oracle.post_scale(qm, F, sw, fo)
+    W = F // sw
+    want = fo.part_partial[: W * qm.S].reshape(W, qm.S)
+    chk = assert_close if flat else assert_exact
+    chk(out[True]["part_partial"], want, "partition-mean-partial (late windows)")
+    for key in ("pixel_sum", "frame_sum", "part_total"):
+        assert_exact(out[True][key], out[False][key], key)
+    if sw > 1:
+        assert np.any(out[True]["part_partial"] != out[False]["part_partial"])
