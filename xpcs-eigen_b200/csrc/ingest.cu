@@ -62,8 +62,7 @@ struct IngestArgs {
     const int32_t *evt;
     const float *valf;
     // stream scatter: slice-ordered records
-    int *slice_cur;
-    const int64_t *slice_rec;
+    unsigned long long *slice_end;  // per slice: end of its record stream, counted down (one atomic gives the position)
     unsigned long long *rec;
     // chunked ingest: the events [ev_begin, E) of idx/val, off points at the chunk's first frame
     int64_t ev_begin;  // first event of the chunk (the blocks start at ev_begin & ~3: aligned vector loads)
@@ -199,6 +198,7 @@ __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ sli
                                                      int64_t *__restrict__ slice_base,
                                                      const int *__restrict__ slice_tot,
                                                      int64_t *__restrict__ slice_rec,
+                                                     unsigned long long *__restrict__ slice_end,
                                                      int n_slices, long long *summary)
 {
     __shared__ long long part[1024];
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ sli
         for (int i = a; i < b; i++) {
             slice_rec[i] = run;
             run += (long long)slice_tot[i];
+            slice_end[i] = (unsigned long long)run;
         }
         if (tid == 1023) slice_rec[n_slices] = part[1023];
         return;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
             const int r = __ldg(a.row_of_pixel + pix[j]);
             if (r < 0) continue;
             const int sl = r >> 5;
-            const int pos = atomicSub(a.slice_cur + sl, 1) - 1;
+            const unsigned long long pos = atomicAdd(a.slice_end + sl, ~0ull) - 1ull;  // -1: the stream fills from its end
             unsigned long long rec;
             if (KIND == kPacked) {
                 rec = ((unsigned long long)(r & 31) << 32) |
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
                 rec = ((unsigned long long)(r & 31) << kRecLaneShiftF) | ((unsigned long long)(uint32_t)tj << 32) |
                       (unsigned long long)__float_as_uint(v);
             }
-            a.rec[__ldg(a.slice_rec + sl) + pos] = rec;
+            a.rec[pos] = rec;
         }
     }
 }
@@ -1295,7 +1296,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     {
         LaunchScope ls(h, "k_slice_scan");
         k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
-                                                h->d_slice_rec.p, h->n_slices, h->d_summary.p);
+                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p);
     }
     long long sum[kSumSlots];
     int rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream),
@@ -1328,8 +1329,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     } else if (nblocks > 0) {
         rc = ensure(h, h->d_rec, (size_t)sum[kSumEvents] + (chunk >= 0 ? (size_t)sum[kSumEvents] / 8 : 0) + 1, "event records");
         if (rc) return rc;
-        ia.slice_cur = h->d_slice_cur.p;
-        ia.slice_rec = h->d_slice_rec.p;
+        ia.slice_end = h->d_slice_end.p;
         ia.rec = h->d_rec.p;
         {
             LaunchScope ls(h, dense ? "k_scatter_rec_dense" : "k_scatter_rec");
@@ -1648,7 +1648,7 @@ int launch_ingest_concat(xpcs_handle_s *h)
     {
         LaunchScope ls(h, "k_slice_scan");
         k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
-                                                h->d_slice_rec.p, h->n_slices, h->d_summary.p);
+                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p);
     }
     long long sum[kSumSlots];
     rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream), "summary D2H");

@@ -143,6 +143,7 @@ struct xpcs_handle_s {
     xpcs::DevBuf<int64_t> d_slice_base;   // [n_slices + 1] in words
     xpcs::DevBuf<int> d_slice_cur;        // [n_slices] events of the slice, counted down by the stream scatter
     xpcs::DevBuf<int64_t> d_slice_rec;    // [n_slices + 1] first record of the slice in d_rec
+    xpcs::DevBuf<unsigned long long> d_slice_end;  // [n_slices] end of the slice's stream, counted down by the stream scatter
     xpcs::DevBuf<unsigned long long> d_rec;  // [E] slice-ordered event records (lane | word)
     xpcs::DevBuf<int> d_block_first;      // first raw frame of every event block
     xpcs::DevBuf<uint32_t> d_store;       // words (uint32 packed, or pairs for float values)

@@ -255,6 +255,7 @@ static int build_maps(xpcs_handle_s *h)
     if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
     if ((rc = ensure(h, h->d_slice_cur, (size_t)h->n_slices + 1, "slice cursors"))) return rc;
     if ((rc = ensure(h, h->d_slice_rec, (size_t)h->n_slices + 1, "slice record offsets"))) return rc;
+    if ((rc = ensure(h, h->d_slice_end, (size_t)h->n_slices + 1, "slice stream cursors"))) return rc;
     cudaMemcpy(h->d_row_of_pixel.p, row_of_pixel.data(), sizeof(int) * P, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_pixel_of_row.p, pix_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_sbin_of_row.p, sbin_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
@@ -419,7 +420,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
     release(h->d_dense_counter);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
-    release(h->d_slice_cur); release(h->d_slice_rec); release(h->d_rec);
+    release(h->d_slice_cur); release(h->d_slice_rec); release(h->d_slice_end); release(h->d_rec);
     for (int k = 0; k < kMaxChunks; k++) {
         release(h->chunk[k].store); release(h->chunk[k].slice_base); release(h->chunk[k].row_len);
         if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
