@@ -142,7 +142,7 @@ int xpcs_get_dark(xpcs_handle h, double *avg, double *std);
  * unless the push was pipelined (then it has been consumed on return).  With pinned memory
  * the copies are asynchronous, and a first push of >= 4 Mi events of plain photon counts
  * (no flat-field, stride, averaging or frame-sum normalisation) is PIPELINED: cut into up to
- * 8 chunks of frames, chunk k ingested on the device while chunk k+1 crosses PCIe; the
+ * 4 chunks of frames, chunk k ingested on the device while chunk k+1 crosses PCIe; the
  * results are bit-identical to the one-pass ingest.  Environment knobs read at push time:
  * XPCS_NO_PIPELINE, XPCS_PIPELINE_MIN_EVENTS, XPCS_PIPELINE_CHUNKS. */
 int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val,
