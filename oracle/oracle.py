@@ -137,6 +137,38 @@ def _filter_alloc(P, F, S, swindow, cap):
     return o
 
 
+def ufxc_frames(words, h, w, nraw):
+    """The frames the UFXC reader (io/ufxc.cpp:59-99, 144-153) delivers for raw frames 0 .. nraw-1: a 32-bit word
+    carries an 11-bit frame counter (bits 31..21; the first word is frame 0, a jump of more than 2000 between
+    consecutive words moves the counter's base by 2048), the count in bits 16..15 and the column-major pixel in
+    bits 14..0; events keep their file order inside a frame, a frame without words is empty.
+    -> (frame_off int64[nraw + 1], idx int32, val int16)."""
+    words = np.asarray(words, np.uint32).astype(np.int64)
+    per = [[] for _ in range(nraw)]
+    if words.size:
+        first = int(words[0] >> 21)
+        prev, base = first, 0
+        for k, wd in enumerate(words.tolist()):
+            c = wd >> 21
+            if k > 0:
+                d = c - prev
+                if d < -2000:
+                    base += 2048
+                elif d > 2000:
+                    base -= 2048
+            prev = c
+            ff = c + base - first
+            if 0 <= ff < nraw:
+                pix = wd & 0x7FFF
+                per[ff].append(((pix % h) * w + pix // h, (wd >> 15) & 3))
+    off = np.zeros(nraw + 1, np.int64)
+    off[1:] = np.cumsum([len(p) for p in per])
+    flat = [e for p in per for e in p]
+    idx = np.asarray([e[0] for e in flat], np.int32)
+    val = np.asarray([e[1] for e in flat], np.int16)
+    return off, idx, val
+
+
 def rigaku_frames(words, h, w, frame_start_todo, frames, mask):
     """The event stream the Rigaku reader (io/rigaku.cpp:139-267, stride = average = 1) turns into output
     frames.  A 64-bit word carries the frame in bits 63..40, the column-major pixel in bits 35..16 and the

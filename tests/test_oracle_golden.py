@@ -14,6 +14,10 @@ def _filter(O, c):
     dark = None
     if c.kind in ("sparse", "twotime"):
         off, idx, val = c.inp["off"], c.inp["idx"], c.inp["val"]
+        if c.fmt == "ufxc":  # the reader's restatement must deliver the stored events from the raw words
+            h, w = c.dq.shape
+            o2, i2, v2 = O.ufxc_frames(c.inp["words"], h, w, c.F_raw)
+            assert np.array_equal(o2, off) and np.array_equal(i2, idx) and np.array_equal(v2, val)
         if c.fmt == "rigaku":  # the reader's restatement must deliver the stored events from the raw words
             h, w = c.dq.shape
             off, idx, val = O.rigaku_frames(c.inp["words"], h, w, 0, c.F, qm.mask)
