@@ -6,13 +6,16 @@ One "step" = one whole correlation job over one batch of synthetic input:
     -> q-bin normalisation (norm-0-g2, norm-0-stderr)
 Workload (default `c3`): BASELINE.json configs[2], the configuration north_star's target is
 quoted on -- sparse 1 Mpixel detector (1024x1024), 100 000 frames, 0.1 % occupancy, dpl 8,
-36 dynamic / 360 static annular q-bins.  With N GPUs the detector has N such 1-Mpixel modules
-sharing the q-bins, pixel-sharded at static-bin boundaries: every rank owns ~1 Mpixel worth of
-rows and receives only its own (demultiplexed) events, so per-GPU work is fixed ("weak").
-`value` counts 1-Mpixel-detector frames per second: N * F / t (at N=1 plain frames/s).
+36 dynamic / 360 static annular q-bins.  With N GPUs it is the SAME job ("strong"): ONE 1-Mpixel
+detector, every GPU holds 1/N of the frames (its share of the file) and owns 1/N of the pixel rows
+(cut at static-bin boundaries); the library moves the events to their owners over NVLink and
+all-reduces the sums and normalisation partials (NCCL inside the C-ABI, csrc/comm.cu).  `value` =
+F / t.  The data is the same for every N (8 slabs seeded by slab number) and the run asserts that
+g2 / stderr equal a one-GPU run bit for bit, plus a sampled-row check against the oracle
+("parity").  `--scaling weak` keeps round 1's N-modules construction.
 `--workload c2` runs BASELINE.json configs[1] (dense 1024x1024 int16, dark/flat/threshold).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|c5]
 
 Contract keys: metric/value/unit/n_gpus/steps/warmup/ms_per_step/higher_is_better/scaling/
 vs_baseline/dtype/data/config + clocks, e2e, gpu_launches, roofline, cpu_baseline.
@@ -230,7 +233,9 @@ def run_reference_arm(args, wl, wl_key):
     if wl["kind"] != "sparse":
         wl = WORKLOADS["c3"]
         wl_key = "c3"
-    F_s = args.cpu_frames or 5000
+    # c1 (BASELINE configs[0], the reference's own CPU-runnable case) runs at its full size: a same-config pair;
+    # the larger workloads run a bounded sample (5 000 frames of the same detector, occupancy and q-maps)
+    F_s = args.cpu_frames or (wl["F"] if wl_key == "c1" else min(5000, wl["F"]))
     run, kind, threads, E = cpu_sample_job(pkg, O, wl, F_s)
     for _ in range(args.warmup):
         run()
@@ -245,8 +250,8 @@ def run_reference_arm(args, wl, wl_key):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "workload_key": wl_key, "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "workload_key": wl_key, "sample": sample, "same_config": F_s == wl["F"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "stages_s": stages},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -260,6 +265,8 @@ def run_reference_arm(args, wl, wl_key):
 # GPU arm
 # ----------------------------------------------------------------------------------------
 KERNEL_GROUP = {  # kernel name -> stage of SURVEY.md 8(d)
+    "k_demux_count": "K0", "k_demux_scan": "K0", "k_demux_scatter": "K0", "k_merge_offsets": "K0", "k_concat": "K1",
+    "k_chunk_rows": "K1",
     "k_block_frames": "K1", "k_hist": "K1", "k_slice_len": "K1", "k_slice_scan": "K1", "k_scatter": "K1",
     "k_finalize": "K1", "k_frame_scale": "K1", "k_hist_dense": "K1", "k_scatter_dense": "K1",
     "k_finalize_warp": "K1", "k_scatter_rec": "K1", "k_scatter_rec_dense": "K1", "k_place": "K1", "k_dense_bounds": "K2",
@@ -273,6 +280,8 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
     """Algorithmic bytes per launch of each kernel (DESIGN.md 'Kernels' table; SURVEY.md 8d:
     one event = 6 B, one correlator value = 4 B)."""
     tbl = {
+        "k_demux_count": 4 * E,                # multi-GPU slab partition: the pixel indices of the slab
+        "k_demux_scatter": 12 * E,             # read the slab, write the per-owner streams
         "k_hist": 6 * E,                       # one read of the frame-major events
         "k_scatter": 12 * E,                   # read frame-major, write pixel-major
         "k_scatter_rec": 12 * E,               # read frame-major, append to the slice streams (8 B records move)
@@ -495,37 +504,84 @@ def bench_twotime(args, wl):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
-    ap.add_argument("--occupancy", type=float, default=0.0, help="override the occupancy of a sparse workload (c5 sweep)")
-    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (c2: 42 GB pinned)")
-    ap.add_argument("--no-compat", action="store_true", help="exact sums instead of the reference's stale-tail behaviour")
-    args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.frames:
-        wl["F"] = args.frames
-    if args.occupancy and wl["kind"] == "sparse":
-        wl["occ"] = args.occupancy
-        wl["name"] += " [occupancy %g]" % args.occupancy
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 0)
+# ----------------------------------------------------------------------------------------
+# parity block of the sparse bench legs (the oracle as the checker, outside every timed region)
+# ----------------------------------------------------------------------------------------
+def rows_of_pixels(O, pix_sorted, ev_pix, ev_frame, ev_val):
+    """CSR rows (oracle.Rows) of the listed pixels from their events: row i = pixel pix_sorted[i], frames ascending."""
+    row = np.searchsorted(pix_sorted, ev_pix)
+    order = np.lexsort((ev_frame, row))
+    row, t, v = row[order], ev_frame[order].astype(np.int32), ev_val[order].astype(np.float32)
+    row_ptr = np.zeros(pix_sorted.size + 1, np.int64)
+    np.add.at(row_ptr, row + 1, 1)
+    return O.Rows(np.cumsum(row_ptr), t, v)
 
-    if args.impl == "reference":
-        return run_reference_arm(args, wl, args.workload)
 
-    if wl["kind"] == "dense":
-        return bench_dense(args, wl)
-    if wl["kind"] == "twotime":
-        return bench_twotime(args, wl)
+def parity_block(torch, pkg, O, c, dq, sq, F, dev_events, own_pixels, g2_dev, n_rows=2000, compat=True, seed=5):
+    """Bit-for-bit check of the timed configuration itself (not of a small stand-in):
+    (1) G2 / IP / IF of ~n_rows sampled pixel rows against oracle.multitau (corr.cpp:315-431) on those rows' events;
+    (2) norm-0-g2 of a few dynamic bins recomputed by oracle.normalize (corr.cpp:927-1091) from the device's
+        G2 / IP / IF of the bins' pixels.
+    dev_events = (idx, val, off) device tensors of ALL frames of the job (whole detector)."""
+    d_idx, d_val, d_off = dev_events
+    P = dq.size
+    dev = d_idx.device
+    rng = np.random.default_rng(seed)
+    valid = np.flatnonzero((dq.ravel() > 0) & (sq.ravel() > 0))
+    own = np.asarray(own_pixels, np.int64)
+    samp = np.sort(rng.choice(own, size=min(n_rows, own.size), replace=False)).astype(np.int32)
 
+    def events_of(pixels):
+        lut = torch.zeros(P, dtype=torch.bool, device=dev)
+        lut[torch.from_numpy(np.asarray(pixels, np.int64)).to(dev)] = True
+        m = lut[d_idx.long()]
+        e = torch.nonzero(m).squeeze(1)
+        fr = torch.searchsorted(d_off, e, right=True) - 1
+        return d_idx[e].cpu().numpy(), fr.cpu().numpy(), d_val[e].cpu().numpy()
+
+    T = c.T
+    out = {"rows": int(samp.size), "row_entries": int(3 * T * samp.size)}
+    ep, ef, ev = events_of(samp)
+    rows = rows_of_pixels(O, samp, ep, ef, ev)
+    rG2, rIP, rIF = O.multitau(samp.size, F, 8, rows, compat=compat)
+    G2, IP, IF = c.correlators(samp)
+    mism = int((G2 != rG2).sum() + (IP != rIP).sum() + (IF != rIF).sum())
+    out["mismatches"] = mism
+    out["row_events"] = int(ep.size)
+    out["nonzero_g2_entries"] = int((rG2 != 0).sum())
+
+    # (2) dynamic bins wholly owned by this rank: the first two and the last such
+    dqf, sqf = dq.ravel(), sq.ravel()
+    ownset = np.zeros(P, bool)
+    ownset[own] = True
+    bins = [q for q in range(1, int(dqf.max()) + 1) if ownset[valid[dqf[valid] == q]].all() and (dqf[valid] == q).any()]
+    pick = sorted(set(bins[:2] + bins[-1:]))
+    nm = 0
+    for q in pick:
+        pix = np.flatnonzero((dqf == q) & (sqf > 0)).astype(np.int32)   # ascending: the order inside a static bin
+        G2q, IPq, IFq = c.correlators(pix)
+        sq_local = np.unique(sqf[pix], return_inverse=True)[1].astype(np.int32) + 1
+        qm = O.QMap(np.ones((1, pix.size), np.int32), sq_local.reshape(1, -1))
+        rg2, _ = O.normalize(qm, G2q, IPq, IFq)
+        nm += int(G.n_diff_arrays(rg2[:, 0], g2_dev[:, q - 1]))
+    out["norm_bins"] = pick
+    out["norm_mismatches"] = nm
+    out["ok"] = mism == 0 and nm == 0
+    return out
+
+
+class G:  # tiny helper namespace (NaN-aware inequality count)
+    @staticmethod
+    def n_diff_arrays(a, b):
+        a = np.asarray(a).ravel()
+        b = np.asarray(b).ravel()
+        return int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+
+
+N_SLABS = 8  # the synthetic job is generated as 8 slabs of frames seeded by slab number: the same data for every GPU count
+
+
+def bench_sparse(args, wl):
     import torch
     import torch.distributed as dist
 
@@ -536,11 +592,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    weak = args.scaling == "weak" and world > 1
     if world > 1:
         bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) and any other NCCL
-        # log go to stderr
+        # stdout carries the one JSON line: NCCL's logs go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
@@ -548,53 +604,72 @@ def main():
 
     pkg = entry.load_package()
     F, occ = wl["F"], wl["occ"]
-    dq, sq = module_maps(pkg, wl, world)
+    dq, sq = module_maps(pkg, wl, world if weak else 1)
     P = dq.size
-    E_est = int(wl["h"] * wl["w"] * F * occ * 1.02) + 4096
+    E_est = int(wl["h"] * wl["w"] * F * occ * 1.02 / (1 if weak else world)) + (1 << 16)
     c = pkg.Correlator(dq, sq, F, dpl=8, compat=not args.no_compat, device=local, shard_index=rank,
                        shard_count=world, reserve_events=E_est)
+    if world > 1:  # the library's own communicator (NCCL bound at run time: the copy torch loaded)
+        uid = [pkg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        c.comm_init(world, rank, uid[0])
     info = c.info()
-    T, Q, R = c.T, c.Q, info.n_rows
+    T, Q, R, S = c.T, c.Q, info.n_rows, c.S
     stream = torch.cuda.Stream(device=dev)
     c.set_stream(stream.cuda_stream)
 
-    # this rank's demultiplexed pixel universe: its own rows + its share of the masked pixels
-    if world == 1:
-        pixels_dev, n_pix = None, P
-    else:
+    # ---- synthetic input, resident in HBM before any timed region ----
+    n_slabs = N_SLABS if N_SLABS % world == 0 else world
+    slab_frames = [F * (k + 1) // n_slabs - F * k // n_slabs for k in range(n_slabs)]
+    slab_first = [F * k // n_slabs for k in range(n_slabs)]
+
+    def gen_slabs(ks):
+        parts, base = [], 0
+        offs = [torch.zeros(1, dtype=torch.int64, device=dev)]
+        for k in ks:
+            i, v, o = gen_sparse_device(torch, None, wl["h"] * wl["w"], slab_frames[k], occ, 1234 + k, dev)
+            parts.append((i, v))
+            offs.append(o[1:] + base)
+            base += int(i.numel())
+        return (torch.cat([p[0] for p in parts]).contiguous(), torch.cat([p[1] for p in parts]).contiguous(),
+                torch.cat(offs).contiguous())
+
+    if weak:
+        # N modules of the detector sharing the q-bins, every rank fed its own (demultiplexed) pixels: per-GPU work fixed
         own = c.row_pixels()
         masked = np.nonzero((dq.ravel() < 1) | (sq.ravel() < 1))[0].astype(np.int32)[rank::world]
         uni = np.sort(np.concatenate([own, masked])).astype(np.int32)
-        pixels_dev, n_pix = torch.from_numpy(uni).to(dev), int(uni.size)
-    d_idx, d_val, d_off = gen_sparse_device(torch, pixels_dev, n_pix, F, occ, 1234 + rank, dev)
+        d_idx, d_val, d_off = gen_sparse_device(torch, torch.from_numpy(uni).to(dev), int(uni.size), F, occ, 1234 + rank, dev)
+        first, nfr = 0, F
+    else:
+        my = list(range(rank * n_slabs // world, (rank + 1) * n_slabs // world))
+        d_idx, d_val, d_off = gen_slabs(my)
+        first, nfr = slab_first[my[0]], sum(slab_frames[k] for k in my)
     E = int(d_idx.numel())
     h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
     h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
-    h_off = torch.empty(F + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
+    h_off = torch.empty(nfr + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
     torch.cuda.synchronize()
-
-    def allreduce_partials(ptr, n):
-        if world == 1:
-            return
-        t = pkg.torchio.device_view(ptr, n, "float64", "cuda:%d" % local)
-        with torch.cuda.stream(stream):
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     def step_device():
         c.reset()
-        c.push_sparse_device(d_idx.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), E, F)
+        if weak:
+            c.push_sparse_device(d_idx.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), E, F)
+        else:
+            c.push_sparse_slab_device(first, d_idx.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), E, nfr)
         c.finish_ingest(want=False)
         c.multitau(want=False)
-        allreduce_partials(*c.normalize_partials())
-        return c.normalize_finish()
+        return c.normalize()
 
     def step_e2e():
         c.reset()
-        c.push_sparse_raw(h_idx.data_ptr(), h_val.data_ptr(), h_off.data_ptr(), F)
+        if weak:
+            c.push_sparse_raw(h_idx.data_ptr(), h_val.data_ptr(), h_off.data_ptr(), F)
+        else:
+            c.push_sparse_slab_raw(first, h_idx.data_ptr(), h_val.data_ptr(), h_off.data_ptr(), nfr)
         sums = c.finish_ingest(want=True)
         c.multitau(want=False)
-        allreduce_partials(*c.normalize_partials())
-        g2, se = c.normalize_finish()
+        g2, se = c.normalize()
         return sums, g2, se
 
     def barrier():
@@ -603,18 +678,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_over_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
     # ---- device-resident timing (value) ----
@@ -628,16 +696,20 @@ def main():
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         g2, se = step_device()
     e1.record(stream)
     barrier()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = int(sum_over_ranks(c.launch_count()))
+    wall_dev = 1e3 * (time.perf_counter() - t0) / args.steps
+    ms_dev = reduce_over_ranks(e0.elapsed_time(e1) / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    launches = int(reduce_over_ranks(c.launch_count(), dist.ReduceOp.SUM if world > 1 else None))
     report = c.kernel_report(reset=True)
     c.kernel_timing(False)
     finite_g2 = bool(np.isfinite(g2).all())
+    g2_timed = g2.copy()
+    Es = int(c.info().events_stored)
 
     # ---- end-to-end timing through the public API with host buffers ----
     for _ in range(min(args.warmup, 3)):
@@ -650,30 +722,34 @@ def main():
     e1.record(stream)
     barrier()
     wall = (time.perf_counter() - t0) / args.steps
-    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, 1e3 * wall))
+    ms_e2e = reduce_over_ranks(max(e0.elapsed_time(e1) / args.steps, 1e3 * wall), dist.ReduceOp.MAX if world > 1 else None)
     clocks = sampler.stop() if rank == 0 else None
-    h2d = 4 * E + 2 * E + 8 * (F + 1)
-    S = c.S
+    h2d = 4 * E + 2 * E + 8 * (nfr + 1)
     d2h = 4 * (P + 2 * F + S + (F // c.static_window) * S) + 2 * 4 * T * Q
-    E_total = sum_over_ranks(E)
-    R_total = sum_over_ranks(R)
+    E_total = reduce_over_ranks(E, dist.ReduceOp.SUM if world > 1 else None)
+    R_total = reduce_over_ranks(R, dist.ReduceOp.SUM if world > 1 else None)
+    h2d_total = reduce_over_ranks(h2d, dist.ReduceOp.SUM if world > 1 else None)
+    e2e_identical = bool(np.array_equal(g2e, g2_timed, equal_nan=True))
 
-    value = world * F / (ms_dev * 1e-3)
-    e2e_value = world * F / (ms_e2e * 1e-3)
+    jobs = world if weak else 1
+    value = jobs * F / (ms_dev * 1e-3)
+    e2e_value = jobs * F / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (rank 0's launches) ----
+    # ---- roofline of the dominant kernel (rank 0's launches; library (NCCL) kernels listed but not ranked) ----
     peak, peak_src = peaks()
-    Es = int(c.info().events_stored)
     kern = {}
     for name, (ms, n) in report.items():
         if n <= 0:
             continue
         per = ms / n
-        b = algorithmic_bytes(name, Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_warpf") else E, T, R, Q, P)
+        Ek = Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_warpf") else \
+            (E if name.startswith("k_demux") else Es)
+        b = algorithmic_bytes(name, Ek, T, R, Q, P)
         kern[name] = {"ms_per_launch": per, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,
                       "algo_bytes": b, "gbs": (b / (per * 1e-3) / 1e9) if per > 0 and b else None,
-                      "stage": KERNEL_GROUP.get(name, "?")}
-    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+                      "stage": KERNEL_GROUP.get(name, "NCCL" if name.startswith("nccl_") else "?")}
+    own_k = [k for k in kern if not k.startswith("nccl_")]
+    dom = max(own_k, key=lambda k: kern[k]["ms_per_step"]) if own_k else None
     roof = None
     if dom:
         k = kern[dom]
@@ -684,46 +760,87 @@ def main():
         tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the ncu --set full capture
         if os.path.exists(tr):
             try:
-                roof["traffic"] = json.load(open(tr)).get(args.workload, {}).get(dom)
+                tj = json.load(open(tr))
+                roof["traffic"] = tj.get(args.workload, {}).get(dom)
+                roof["traffic_source"] = tj.get("_source", "profiles/traffic.json (ncu --set full capture of this command)")
             except Exception:
                 pass
-    pipeline_bytes = 18 * E + 12 * T * R
+    pipeline_bytes = 18 * Es + 12 * T * R
     kernels_ms = sum(k["ms_per_step"] for k in kern.values())
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int64 numerators / f32 quotients", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak" if weak else "strong",
+        "vs_baseline": None, "dtype": "u32 numerators / f32 quotients", "data": "synthetic",
         "config": {"workload": wl["name"], "workload_key": args.workload, "detector_pixels": int(P),
-                   "pixels_per_gpu_rows": int(R), "frames": F, "events_per_gpu": E, "delays": T, "q_bins": Q,
-                   "static_bins": S, "parallelism": "pixel-shard x%d (static-bin aligned, demultiplexed events)" % world,
-                   "value_definition": "1-Mpixel-detector frames/s = n_gpus*F/t (all stages: ingest, multi-tau, normalise)",
-                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (6 * E / 1e6),
+                   "rows_this_gpu": int(R), "rows_total": int(R_total), "frames": F, "events_this_gpu_slab": E,
+                   "events_total": int(E_total), "delays": T, "q_bins": Q, "static_bins": S,
+                   "parallelism": ("%d modules, one per GPU (weak)" % world) if weak else
+                   ("ONE detector: frame slabs in (1/%d of the frames per GPU), pixel rows out (static-bin aligned), "
+                    "events redistributed over NVLink by the library (ncclSend/ncclRecv), sums and normalisation "
+                    "partials all-reduced (NCCL inside the C-ABI)" % world) if world > 1 else "single GPU",
+                   "value_definition": "frames of the whole detector per second = F/t, all stages (exchange, ingest, multi-tau, normalise)"
+                   if not weak else "1-Mpixel-module frames/s = n_gpus*F/t",
+                   "l2": "inputs (%.0f MB/step per GPU) exceed the 126 MB L2; no flush needed" % (6 * E / 1e6)
+                   if 6 * E > 126e6 else "inputs %.0f MB/step per GPU; results %.0f MB/step written in between evict them" % (6 * E / 1e6, 12.0 * T * R / 1e6),
                    "compat_stale_tail": not args.no_compat},
         "pixel_frames_per_s": float(R_total) * F / (ms_dev * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "api": "Correlator.push_sparse/finish_ingest/multitau/normalize (C-ABI xpcs_*)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "h2d_bytes_per_step_per_gpu": h2d,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "g2_identical_to_device_resident_run": e2e_identical,
+                "api": "Correlator.push_sparse_slab/finish_ingest/multitau/normalize (C-ABI xpcs_*), pinned host buffers"},
         "gpu_launches": launches,
         "roofline": roof,
-        "pipeline": {"algo_bytes_per_step": pipeline_bytes, "formula": "18*E + 12*T*P_valid (SURVEY 8d PRIMARY)",
+        "pipeline": {"algo_bytes_per_step": pipeline_bytes, "formula": "18*E + 12*T*P_valid (SURVEY 8d PRIMARY), this GPU's share",
                      "kernel_ms_per_step": kernels_ms, "gbs_over_step": pipeline_bytes / (ms_dev * 1e-3) / 1e9,
                      "frac_of_peak_over_step": pipeline_bytes / (ms_dev * 1e-3) / 1e9 / peak,
-                     "gbs_over_kernel_time": pipeline_bytes / (kernels_ms * 1e-3) / 1e9 if kernels_ms else None},
+                     "host_wall_ms_per_step": wall_dev},
         "kernels": kern,
         "results_finite": finite_g2,
     }
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
+    # ---- parity of the timed configuration (rank 0; untimed; the oracle is the checker) ----
+    ok = True
+    if not args.no_parity and not weak:
+        c.kernel_timing(False)
+        g2p, sep = step_device()          # leaves G2 / IP / IF of this run on the device
+        par = {}
+        if rank == 0:
+            O = entry.load_oracle()
+            all_ev = (d_idx, d_val, d_off) if world == 1 else gen_slabs(range(n_slabs))
+            par = parity_block(torch, pkg, O, c, dq, sq, F, all_ev, c.row_pixels(), g2p, n_rows=args.parity_rows,
+                               compat=not args.no_compat)
+            if world > 1:
+                # the same job on ONE GPU (this one), same data: g2 / stderr must be bit-identical
+                c1 = pkg.Correlator(dq, sq, F, dpl=8, compat=not args.no_compat, device=local, reserve_events=int(all_ev[0].numel()))
+                c1.push_sparse_device(all_ev[0].data_ptr(), all_ev[1].data_ptr(), all_ev[2].data_ptr(), int(all_ev[0].numel()), F)
+                c1.finish_ingest(want=False)
+                c1.multitau(want=False)
+                g2_1, se_1 = c1.normalize()
+                c1.close()
+                par["single_gpu_g2_identical"] = bool(np.array_equal(g2_1, g2p, equal_nan=True))
+                par["single_gpu_stderr_identical"] = bool(np.array_equal(se_1, sep, equal_nan=True))
+                par["ok"] = par["ok"] and par["single_gpu_g2_identical"] and par["single_gpu_stderr_identical"]
+            ok = bool(par["ok"])
+        line["parity"] = par
+        barrier()
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference binary on a bounded sample of the same workload ----
     if rank == 0 and world == 1 and not args.no_cpu:
         O = entry.load_oracle()
-        F_s = args.cpu_frames or 5000
+        F_s = args.cpu_frames or min(5000, F)
         run, kind, threads, E_s = cpu_sample_job(pkg, O, wl, F_s)
         t, stages = run()
         line["cpu_baseline"] = {
-            "value": F_s / t, "unit": UNIT, "cores": threads, "kind": kind,
+            "value": F_s / t, "unit": UNIT, "cores": threads, "kind": kind, "same_config": F_s == F,
             "sample": "%d of %d frames, same detector/occupancy/q-maps (%d events), all stages, one pass" % (F_s, F, E_s),
             "seconds": t, "stages_s": stages}
+        fc = os.path.join(ROOT, "profiles", "ref_full_config.json")  # one full-F run of the reference per round
+        if os.path.exists(fc):
+            try:
+                line["cpu_baseline"]["full_config"] = json.load(open(fc)).get(args.workload)
+            except Exception:
+                pass
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
@@ -731,7 +848,40 @@ def main():
     c.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = ONE detector sharded over the GPUs (default); weak = N modules, one per GPU")
+    ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
+    ap.add_argument("--occupancy", type=float, default=0.0, help="override the occupancy of a sparse workload (c5 sweep)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (c2: 42 GB pinned)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (sampled rows against the oracle)")
+    ap.add_argument("--parity-rows", type=int, default=2000)
+    ap.add_argument("--no-compat", action="store_true", help="exact sums instead of the reference's stale-tail behaviour")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames:
+        wl["F"] = args.frames
+    if args.occupancy and wl["kind"] == "sparse":
+        wl["occ"] = args.occupancy
+        wl["name"] += " [occupancy %g]" % args.occupancy
+    if args.impl == "reference":
+        return run_reference_arm(args, wl, args.workload)
+    if wl["kind"] == "dense":
+        return bench_dense(args, wl)
+    if wl["kind"] == "twotime":
+        return bench_twotime(args, wl)
+    return bench_sparse(args, wl)
 
 
 if __name__ == "__main__":

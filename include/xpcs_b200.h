@@ -165,7 +165,8 @@ int xpcs_push_dense_device(xpcs_handle h, const int16_t *d_frames, int nframes);
  *   frame_sum[2F]       FramesSum()
  *   part_total[S]       PartitionsMean()/(pixels_per_sbin*F)
  *   part_partial[floor(F/window)*S]  PartialPartitionsMean()/(pixels_per_sbin*window)
- * all nullable.  With shard_count > 1 the sums cover this shard's pixels only. */
+ * all nullable.  With shard_count > 1 and no communicator the sums cover this shard's pixels only; with a
+ * communicator (xpcs_comm_init) they are all-reduced and cover the whole detector on every rank. */
 int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total,
                        float *part_partial);
 /* TimestampClock()/TimestampTicks(): [2][raw frames] each (sparse_filter.cpp:134-140) */
@@ -181,6 +182,10 @@ int xpcs_get_frames(xpcs_handle h, int nframes, float *out);
  * G2/IP/IF: host [T][P] tau-major, fully written (zeros for masked / event-less pixels);
  * all three NULL = keep the results on the device only (the normal path without --g2out). */
 int xpcs_multitau(xpcs_handle h, float *G2, float *IP, float *IF);
+/* The same G2 / IP / IF arrays restricted to `n` listed detector pixels: host [T][n] each (nullable); call
+ * after xpcs_multitau.  Pixels that are masked or owned by another shard come back as zeros.  What --g2out
+ * gives for a region of interest without moving T*P floats (a 1 Mpixel, 115-delay job is 3 x 483 MB). */
+int xpcs_get_correlators(xpcs_handle h, const int32_t *pixels, int n, float *G2, float *IP, float *IF);
 /* replaces: Corr::normalizeG2s (corr.cpp:927-1091): g2 and std-error, host (T, Q) each.
  * Equivalent to xpcs_normalize_partials + xpcs_normalize_finish. */
 int xpcs_normalize(xpcs_handle h, float *g2, float *stderr_out);
@@ -191,15 +196,55 @@ int xpcs_normalize(xpcs_handle h, float *g2, float *stderr_out);
  * of squares of the per-pixel G2/(IP*IF).  Summing the buffers of all shards element-wise
  * (ncclAllReduce / torch.distributed.all_reduce, SUM, float64, in place on *d_partials)
  * yields the single-GPU buffer bit for bit, because every segment is owned by exactly one
- * shard.  xpcs_normalize_finish then produces g2 / stderr from the (reduced) buffer. */
+ * shard.  xpcs_normalize_finish then produces g2 / stderr from the (reduced) buffer.  With a communicator
+ * (xpcs_comm_init) xpcs_normalize_partials performs that all-reduce itself (ncclAllReduce on the handle's
+ * stream) and the caller has nothing to exchange. */
 int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t *count);
 int xpcs_normalize_finish(xpcs_handle h, float *g2, float *stderr_out);
+
+/* ---- multi-GPU: one handle per GPU, pixel-sharded ----
+ * replaces: the OpenMP pixel loop of Corr::multiTau2 (corr.cpp:329-332) spread over GPUs.  The exchange
+ * quantities are the events themselves (below), the per-frame / per-static-bin sums of the Filter stage
+ * (sparse_filter.cpp:175,190; corr.cpp:966-1014) and the normalisation partials.  One NCCL communicator rank per
+ * handle; NCCL is bound at run time (libnccl.so.2).  Call sequence per rank (one process or one thread per GPU;
+ * with a communicator every rank must make the same calls with the same NULL-ness of output arguments, because
+ * xpcs_finish_ingest and xpcs_normalize[_partials] contain collectives):
+ *   rank 0: xpcs_comm_unique_id(id)  ->  hand the 128 bytes to every rank
+ *   all:    xpcs_create(shard_index = rank, shard_count = n)  ->  xpcs_comm_init(h, n, rank, id)
+ *   all:    xpcs_push_sparse_slab(h, first_frame_of_my_slab, ...)  ->  xpcs_finish_ingest  ->  xpcs_multitau
+ *           ->  xpcs_normalize
+ * With a communicator xpcs_finish_ingest returns WHOLE-DETECTOR sums on every rank (frame_sum, part_total,
+ * part_partial and pixel_sum are all-reduced; exact for integer counts), xpcs_normalize returns the same g2 /
+ * stderr on every rank, bit-identical to a single-GPU run, and normalize_by_framesum works sharded. */
+int xpcs_comm_unique_id(void *id128);                                    /* ncclGetUniqueId: 128 bytes out   */
+int xpcs_comm_init(xpcs_handle h, int nranks, int rank, const void *id128); /* collective: ncclCommInitRank  */
+int xpcs_comm_nccl_version(void);                                        /* 0 = NCCL not loadable            */
+/* Frame-slab ingest: this rank holds raw frames [first_raw_frame, first_raw_frame + nframes) of the WHOLE
+ * detector (all pixels) -- e.g. its 1/n of the IMM file, so a job's host->device traffic is the file once,
+ * spread over every GPU's PCIe link.  The slabs of ranks 0..n-1 must tile the job's raw frames in rank order.
+ * xpcs_finish_ingest then partitions the slab by pixel owner on the device and moves every partition to its
+ * owner (grouped ncclSend/ncclRecv over NVLink), after which each rank ingests the events of its own pixels
+ * for all frames.  One slab push per ingest.  Arguments as xpcs_push_sparse / xpcs_push_sparse_device
+ * (frame_offsets index the slab's own idx/val arrays).  With shard_count == 1 these are plain pushes. */
+int xpcs_push_sparse_slab(xpcs_handle h, int first_raw_frame, const int32_t *idx, const int16_t *val,
+                          const int64_t *frame_offsets, const double *clock, const double *ticks, int nframes);
+int xpcs_push_sparse_slab_device(xpcs_handle h, int first_raw_frame, const int32_t *d_idx, const int16_t *d_val,
+                                 const int64_t *d_frame_offsets, int64_t n_events, int nframes);
 
 /* replaces: Corr::twotime -> twotimeQBinThreading (corr.cpp:562-572, :781-924) including
  * Smoothing (:433-560, :1166-1305), for ONE dynamic bin `qbin`:
  *   C[F*F] row-major upper triangle (lower = 0), g2full[F], g2partials[wsize*partials]
- *   ([d][w]), sg[F] (or [1] when average) -- all host, nullable.
- * smoothing_method: 0 = none, 1 = symmetric; smoothing_average: "Average" filter. */
+ *   ([d][w]), sg[rows][F] (or [rows][1] when average) -- all host, nullable.
+ * smoothing_method: 0 = none, 1 = symmetric (one sg row: the bin's mean intensity per frame,
+ * ComputeSGSymmetric :1166-1226), 2 = StaticMap (one sg row per static partition of the bin, in the
+ * order of Configuration::getBinMaps(); every pixel is divided by the sg of its own static partition,
+ * SmoothingStaticMap :433-494, ComputeSGStaticMap :1228-1305; sg must hold n_static * F floats);
+ * smoothing_average: the "Average" filter.  *sg_rows (nullable) receives the number of sg rows.
+ * twotimeFrameThreading (corr.cpp:574-779, `corr --frame_threading`) computes the same C in another
+ * summation order on the CPU; there is one contraction here (tensor cores), equal to both within 1e-5. */
+int xpcs_twotime_sg(xpcs_handle h, int qbin, int wsize, int smoothing_method, int smoothing_average,
+                    float *C, float *g2full, float *g2partials, float *sg, int *sg_rows);
+/* the same without the row count (symmetric smoothing: sg[F] or sg[1]) */
 int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int smoothing_method, int smoothing_average,
                  float *C, float *g2full, float *g2partials, float *sg);
 

@@ -169,25 +169,31 @@ def ufxc_frames(words, h, w, nraw):
     return off, idx, val
 
 
-def rigaku_frames(words, h, w, frame_start_todo, frames, mask):
-    """The event stream the Rigaku reader (io/rigaku.cpp:139-267, stride = average = 1) turns into output
-    frames.  A 64-bit word carries the frame in bits 63..40, the column-major pixel in bits 35..16 and the
-    count in bits 10..0.  Words of frames <= frame_start_todo are skipped; an output frame ends when the frame
-    number of a word differs from the previous one (so frames without events vanish, except that a run not
-    starting at frame_start_todo + 1 opens with an empty output frame); reading stops once `frames` output
-    frames are complete; events on masked pixels are dropped after the frame bookkeeping; the frame still
-    open at the end of the file is kept only if it holds more than one pixel.
-    -> (frame_off int64[frames + 1], idx int32, val int16) in file order, as for xpcs_push_sparse."""
+def rigaku_frames(words, h, w, frame_start_todo, frames, mask, stride=1, avg=1):
+    """The event stream the Rigaku reader (io/rigaku.cpp:139-267) turns into `frames` output frames.  A 64-bit
+    word carries the frame in bits 63..40, the column-major pixel in bits 35..16 and the count in bits 10..0.
+    Words of frames <= frame_start_todo are skipped; with stride > 1 words of frames that are not a multiple of
+    the stride are skipped too (:161-162); an output frame ends when the frame number of a word differs from the
+    previous one (avg == 1) or passes the next boundary frame_start_todo + k * block (avg > 1) (:166-168) -- so
+    frames without events vanish, except that a run not starting where the reader expects opens with an empty
+    output frame; reading stops once `frames` output frames are complete; events on masked pixels are dropped
+    after the frame bookkeeping; what is still open at the end of the file is kept only if it holds more than one
+    pixel (:232).  The reader sums the words of an output frame per pixel and divides by avg, which is what the
+    Filter stage does with a block of `block` raw frames (sparse_filter.cpp:143-172): the output frames come
+    back as blocks of `block` = stride * avg (or max) raw frames whose first raw frame holds the words.
+    -> (frame_off int64[frames * block + 1], idx int32, val int16) in file order, as for xpcs_push_sparse."""
     words = np.asarray(words, np.uint64)
+    block = stride * avg if (stride > 1 and avg > 1) else max(stride, avg)
     off, idx, val = [0], [], []
     prev = frame_start_todo + 1
+    nxt = frame_start_todo + block
     done = 0
     cur_idx, cur_val = [], []
 
     def flush():
         idx.extend(cur_idx)
         val.extend(cur_val)
-        off.append(len(idx))
+        off.extend([len(idx)] * block)   # raw frame 0 of the block carries the words, the others are empty
         del cur_idx[:], cur_val[:]
 
     for wd in words.tolist():
@@ -196,10 +202,13 @@ def rigaku_frames(words, h, w, frame_start_todo, frames, mask):
             continue
         if done >= frames:
             break
-        if frame != prev:
+        if stride > 1 and frame != 0 and frame % stride != 0:
+            continue
+        if (avg > 1 and frame > nxt) or (avg == 1 and frame != prev):
             flush()
             prev = frame
             done += 1
+            nxt += block
         pix = (wd >> 16) & 0xFFFFF
         pix = (pix % h) * w + pix // h
         if not mask[pix]:
@@ -208,7 +217,7 @@ def rigaku_frames(words, h, w, frame_start_todo, frames, mask):
         cur_val.append(wd & 0x7FF)
     if done < frames and len(set(cur_idx)) > 1:
         flush()
-    while len(off) < frames + 1:
+    while len(off) < frames * block + 1:
         off.append(len(idx))
     return np.asarray(off, np.int64), np.asarray(idx, np.int32), np.asarray(val, np.int16)
 

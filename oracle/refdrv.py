@@ -182,7 +182,7 @@ def scratch_dir():
 
 
 def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout=False, threads=None, keep=False,
-             ufxc=None, rigaku=None, hdf5=None, **cfg):
+             ufxc=None, rigaku=None, hdf5=None, extra_args=(), **cfg):
     """Write IMM + config, run the reference, return (results dict of the output group, run info).
     sparse = (frame_off, idx, val); dense = int16 frames [darks + frames][P]."""
     d = scratch_dir()
@@ -205,7 +205,7 @@ def run_case(synth, dq, sq, frames, sparse=None, dense=None, g2out=True, darkout
             synth.write_imm_dense(imm, h, w, dense)
         root = os.path.join(d, "case.h5dir")
         write_config(root, dq, sq, frames, imm, **cfg)
-        info = run(root, imm, g2out=g2out, darkout=darkout, threads=threads, extra=extra, cwd=d)
+        info = run(root, imm, g2out=g2out, darkout=darkout, threads=threads, extra=tuple(extra) + tuple(extra_args), cwd=d)
         res = listing(root, cfg.get("output", "/exchange"))
         return res, info
     finally:

@@ -14,6 +14,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_present():
+    """A CUDA device node exists (no torch import, no CUDA context).  The product itself never falls back:
+    on a GPU box a missing library or device makes the gpu tests FAIL, they are only skipped where there
+    is no GPU at all (plain `pytest tests` in the build container)."""
+    if os.environ.get("XPCS_FORCE_GPU_TESTS"):
+        return True
+    if os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0"):
+        return True
+    try:  # the driver API without a context: cuInit + cuDeviceGetCount
+        import ctypes
+        cu = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        return cu.cuInit(0) == 0 and cu.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+    except OSError:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (gpu tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def pkg():
     return entry.load_package()

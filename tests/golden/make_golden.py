@@ -78,7 +78,7 @@ def ufxc_case(name, h, w, F, occ, seed, f0=1900):
                     idx=idx.astype(np.int32), val=val, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
 
 
-def rigaku_case(name, h, w, F, occ, seed):
+def rigaku_case(name, h, w, F, occ, seed, stride=1, avg=1, flat=False):
     """--rigaku (io/rigaku.cpp): 64-bit event words; the reader itself plays the Filter stage.  Frames without
     events vanish (the output frames are the non-empty ones, renumbered), events inside a frame come unsorted
     and a pixel twice, the file holds more frames than are asked for, and the static windows follow the
@@ -86,9 +86,11 @@ def rigaku_case(name, h, w, F, occ, seed):
     restatement (oracle.rigaku_frames) delivers, plus the raw words the reference read."""
     from oracle import oracle as O
     dq, sq = S.annular_qmaps(h, w, n_dynamic=4, static_per_dynamic=3, r_min=2.0)
-    n_file = F + 40
+    block = stride * avg if (stride > 1 and avg > 1) else max(stride, avg)
+    n_file = F + 40      # F = raw frames to do (the reader folds `block` of them into one output frame)
     off, idx, val = S.sparse_frames(h * w, n_file, occ, seed=seed)
     val = np.minimum(val, 7).astype(np.int16)
+    ff = S.flatfield(h * w, seed=seed + 100) if flat else None
     rng = np.random.default_rng(seed)
     cnt = np.diff(off)
     keep = np.ones(idx.size, bool)
@@ -106,12 +108,13 @@ def rigaku_case(name, h, w, F, occ, seed):
     off = off.copy()
     off[10:] += 1
     words = S.rigaku_words(h, w, np.arange(1, n_file + 1), off, idx, val)
-    sw = max(1, F // 10)
-    res, info = refdrv.run_case(S, dq, sq, F, rigaku=words, g2out=True, dpl=8, static_window=sw)
+    sw = max(1, (F // block) // 10)
+    res, info = refdrv.run_case(S, dq, sq, F, rigaku=words, g2out=True, dpl=8, static_window=sw, stride=stride, avg=avg,
+                                flatfield=ff)
     qm = O.QMap(dq, sq)
-    eoff, eidx, evalv = O.rigaku_frames(words, h, w, 0, F, qm.mask)
+    eoff, eidx, evalv = O.rigaku_frames(words, h, w, 0, F // block, qm.mask, stride=stride, avg=avg)
     save(name, dict(kind=np.array("sparse"), fmt=np.array("rigaku"), words=words, dq=dq, sq=sq, off=eoff, idx=eidx,
-                    val=evalv, params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
+                    val=evalv, flat=ff, params=np.array([F, 8, stride, avg, sw, 0], np.int64)), res, info)
 
 
 def hdf5_case(name, h, w, F, occ, seed, begin=4, dtype=np.uint16):
@@ -133,9 +136,47 @@ def hdf5_case(name, h, w, F, occ, seed, begin=4, dtype=np.uint16):
                     begin=np.array(begin), params=np.array([F, 8, 1, 1, sw, 0], np.int64)), res, info)
 
 
+def twotime_cases():
+    """two-time, symmetric smoothing, with and without the "Average" filter; round 2: StaticMap smoothing (both
+    filters) and one run of the reference's other summation order (--frame_threading, corr.cpp:574-779)."""
+    h = w = 16
+    F = 200
+    dq, sq = S.annular_qmaps(h, w, n_dynamic=3, static_per_dynamic=2, r_min=1.0)
+    off, idx, val = S.sparse_frames(h * w, F, 0.06, seed=10)
+    cases = [("twotime_symmetric_none", "symmetric", "None", ()), ("twotime_symmetric_average", "symmetric", "Average", ()),
+             ("twotime_staticmap_none", "StaticMap", "None", ()), ("twotime_staticmap_average", "StaticMap", "Average", ()),
+             ("twotime_symmetric_framethreading", "symmetric", "None", ("--frame_threading",))]
+    for name, method, filt, extra in cases:
+        if not wanted(name):
+            continue
+        res, info = refdrv.run_case(S, dq, sq, F, sparse=(off, idx, val), g2out=False, dpl=8, static_window=20,
+                                    twotime=dict(qbins=[1, 3], wsize=10, method=method, filter=filt), extra_args=extra)
+        save(name, dict(kind=np.array("twotime"), dq=dq, sq=sq, off=off, idx=idx, val=val,
+                        params=np.array([F, 8, 1, 1, 20, 0], np.int64), qbins=np.array([1, 3], np.int32),
+                        wsize=np.array(10), filt=np.array(filt), method=np.array(method.lower())), res, info)
+
+
+ONLY = set(sys.argv[1:])
+
+
+def wanted(name):
+    return not ONLY or name in ONLY
+
+
 def main():
     if not refdrv.available():
         raise SystemExit("oracle/_ref/corr_ref missing: run `make -C oracle ref` (needs /root/reference)")
+    if ONLY:   # python make_golden.py name [name ...]: only these fixtures (the others stay byte-identical)
+        twotime_cases()
+        if wanted("rigaku_stride2_32x40"):
+            rigaku_case("rigaku_stride2_32x40", 32, 40, 600, 0.02, 12, stride=2)
+        if wanted("rigaku_avg3_flat_32x40"):
+            rigaku_case("rigaku_avg3_flat_32x40", 32, 40, 600, 0.02, 13, avg=3, flat=True)
+        if wanted("rigaku_stride2_avg2_32x40"):
+            rigaku_case("rigaku_stride2_avg2_32x40", 32, 40, 800, 0.02, 14, stride=2, avg=2)
+        if wanted("hdf5_stack_u32_24x32"):
+            hdf5_case("hdf5_stack_u32_24x32", 24, 32, 200, 0.03, 15, begin=2, dtype=np.uint32)
+        return
     sparse_case("sparse_int_24x24", 24, 24, 600, 0.03, 1)
     sparse_case("sparse_odd_dpl4", 20, 28, 1001, 0.012, 2, dpl=4)
     sparse_case("sparse_staletail_32x32", 32, 32, 4000, 0.004, 3)   # rows hit the lower_bound quirk (SURVEY A.4)
@@ -173,18 +214,11 @@ def main():
     save("dense_nodark_16x16", dict(kind=np.array("dense"), dq=dq, sq=sq, frames=fr2,
                                     params=np.array([200, 8, 1, 1, 20, 0, 0], np.int64)), res, info)
 
-    # two-time, symmetric smoothing, with and without the "Average" filter
-    h = w = 16
-    F = 200
-    dq, sq = S.annular_qmaps(h, w, n_dynamic=3, static_per_dynamic=2, r_min=1.0)
-    off, idx, val = S.sparse_frames(h * w, F, 0.06, seed=10)
-    for tag, filt in (("none", "None"), ("average", "Average")):
-        res, info = refdrv.run_case(S, dq, sq, F, sparse=(off, idx, val), g2out=False, dpl=8, static_window=20,
-                                    twotime=dict(qbins=[1, 3], wsize=10, method="symmetric", filter=filt))
-        save("twotime_symmetric_" + tag, dict(kind=np.array("twotime"), dq=dq, sq=sq, off=off, idx=idx, val=val,
-                                              params=np.array([F, 8, 1, 1, 20, 0], np.int64),
-                                              qbins=np.array([1, 3], np.int32), wsize=np.array(10),
-                                              filt=np.array(filt)), res, info)
+    twotime_cases()
+    rigaku_case("rigaku_stride2_32x40", 32, 40, 600, 0.02, 12, stride=2)
+    rigaku_case("rigaku_avg3_flat_32x40", 32, 40, 600, 0.02, 13, avg=3, flat=True)
+    rigaku_case("rigaku_stride2_avg2_32x40", 32, 40, 800, 0.02, 14, stride=2, avg=2)
+    hdf5_case("hdf5_stack_u32_24x32", 24, 32, 200, 0.03, 15, begin=2, dtype=np.uint32)
 
 
 if __name__ == "__main__":

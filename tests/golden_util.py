@@ -33,6 +33,7 @@ class Case:
         self.flat = self.inp.get("flat")
         self.fmt = str(self.inp["fmt"]) if "fmt" in self.inp else "imm"   # imm | ufxc | rigaku
         self.late_window = self.fmt == "rigaku"                           # XPCS_COMPAT_LATE_WINDOW
+        self.method = str(self.inp["method"]) if "method" in self.inp else "symmetric"   # two-time smoothing
 
 
 def rel_err(a, b):

@@ -45,8 +45,10 @@ def _run_corr(pkg, c, tmp_path, extra=()):
     else:
         pkg.synth.write_imm_sparse(imm, h, w, c.inp["off"], c.inp["idx"], c.inp["val"])
     if c.kind == "twotime":
-        kw.update(twotime=dict(qbins=[int(q) for q in c.inp["qbins"]], wsize=int(c.inp["wsize"]), method="symmetric",
-                               filter=str(c.inp["filt"])))
+        kw.update(twotime=dict(qbins=[int(q) for q in c.inp["qbins"]], wsize=int(c.inp["wsize"]),
+                               method={"staticmap": "StaticMap"}.get(c.method, c.method), filter=str(c.inp["filt"])))
+        if "framethreading" in c.name:
+            extra = list(extra) + ["--frame_threading"]
     cfg = str(tmp_path / "config.hdf5")
     f = pkg.h5lite.File()
     for path, value in refdrv.config_items(c.dq, c.sq, c.F_raw, imm, **kw)[0]:

@@ -73,6 +73,15 @@ def delay_schedule(frames, dpl):
     return lv[:n], tv[:n]
 
 
+def comm_unique_id():
+    """ncclGetUniqueId through the library: 128 bytes for Correlator.comm_init on every rank."""
+    buf = C.create_string_buffer(128)
+    rc = cabi.load().xpcs_comm_unique_id(buf)
+    if rc != 0:
+        raise XpcsError(rc, (cabi.load().xpcs_last_error(None) or b"").decode())
+    return buf.raw
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -166,6 +175,31 @@ class Correlator:
         """Device pointers (integers); buffers stay valid until finish_ingest returns."""
         self._check(self._lib.xpcs_push_sparse_device(self._h, d_idx, d_val, d_off, n_events, nframes))
 
+    # -- multi-GPU (one Correlator per GPU; comm.cu) --
+    def comm_init(self, nranks, rank, unique_id):
+        """Collective over all ranks: joins the NCCL communicator made from `unique_id` (128 bytes from
+        comm_unique_id() on rank 0)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.xpcs_comm_init(self._h, nranks, rank, buf))
+
+    def push_sparse_slab(self, first_raw_frame, idx, val, frame_off, clock=None, ticks=None):
+        """Raw frames [first_raw_frame, +len(frame_off)-1) of the WHOLE detector; finish_ingest redistributes."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        val = np.ascontiguousarray(val, np.int16)
+        off = np.ascontiguousarray(frame_off, np.int64)
+        ck = None if clock is None else np.ascontiguousarray(clock, np.float64)
+        tk = None if ticks is None else np.ascontiguousarray(ticks, np.float64)
+        self._keep += [idx, val, off]
+        self._check(self._lib.xpcs_push_sparse_slab(self._h, first_raw_frame, idx.ctypes.data, val.ctypes.data,
+                                                    off.ctypes.data, _ptr(ck), _ptr(tk), off.size - 1))
+
+    def push_sparse_slab_raw(self, first_raw_frame, idx_ptr, val_ptr, off_ptr, nframes):
+        """Host pointers as integers (pinned torch tensors); caller keeps them alive until finish_ingest."""
+        self._check(self._lib.xpcs_push_sparse_slab(self._h, first_raw_frame, idx_ptr, val_ptr, off_ptr, None, None, nframes))
+
+    def push_sparse_slab_device(self, first_raw_frame, d_idx, d_val, d_off, n_events, nframes):
+        self._check(self._lib.xpcs_push_sparse_slab_device(self._h, first_raw_frame, d_idx, d_val, d_off, n_events, nframes))
+
     def push_dense(self, frames, clock=None, ticks=None):
         f = np.ascontiguousarray(frames, np.int16).reshape(-1, self.P)
         ck = None if clock is None else np.ascontiguousarray(clock, np.float64)
@@ -219,6 +253,14 @@ class Correlator:
         self._check(self._lib.xpcs_multitau(self._h, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
         return tuple(out)
 
+    def correlators(self, pixels):
+        """G2, IP, IF of the listed detector pixels, each (T, n) -- the columns of multitau()'s arrays."""
+        pix = np.ascontiguousarray(pixels, np.int32)
+        out = [np.zeros((self.T, pix.size), np.float32) for _ in range(3)]
+        self._check(self._lib.xpcs_get_correlators(self._h, pix.ctypes.data, pix.size, out[0].ctypes.data,
+                                                   out[1].ctypes.data, out[2].ctypes.data))
+        return tuple(out)
+
     def normalize(self):
         """Corr::normalizeG2s -> (g2, stderr) each (T, Q)."""
         g2 = np.zeros((self.T, max(self.Q, 1)), np.float32)
@@ -240,16 +282,22 @@ class Correlator:
         return g2[:, : self.Q], se[:, : self.Q]
 
     def twotime(self, qbin, wsize, method="symmetric", average=False, want_c=True):
+        """Corr::twotime for one dynamic bin.  method: "none" | "symmetric" | "staticmap".
+        sg comes back as (rows, F or 1): one row for symmetric, one per static partition for staticmap."""
         F = self.F
         partials = max((F - wsize) // wsize, 0)
         Cm = np.zeros((F, F), np.float32) if want_c else None
         gf = np.zeros(F, np.float32)
         gp = np.zeros(max(wsize * partials, 1), np.float32)
-        sg = np.zeros(1 if average else F, np.float32)
-        m = {"none": 0, "symmetric": 1}[method.lower()]
-        self._check(self._lib.xpcs_twotime(self._h, qbin, wsize, m, int(bool(average)), _ptr(Cm),
-                                           gf.ctypes.data, gp.ctypes.data, sg.ctypes.data))
-        return dict(C=Cm, g2full=gf, g2partials=gp[: wsize * partials].reshape(wsize, partials), sg=sg)
+        m = {"none": 0, "symmetric": 1, "staticmap": 2}[method.lower()]
+        cols = 1 if average else F
+        sg = np.zeros((max(self.S, 1) if m == 2 else 1) * cols, np.float32)
+        rows = C.c_int(0)
+        self._check(self._lib.xpcs_twotime_sg(self._h, qbin, wsize, m, int(bool(average)), _ptr(Cm),
+                                              gf.ctypes.data, gp.ctypes.data, sg.ctypes.data, C.byref(rows)))
+        sg = sg[: rows.value * cols].reshape(rows.value, cols)
+        return dict(C=Cm, g2full=gf, g2partials=gp[: wsize * partials].reshape(wsize, partials),
+                    sg=sg if m == 2 else sg.ravel())
 
     # -- measurement --
     def kernel_timing(self, on=True):

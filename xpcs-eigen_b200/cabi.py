@@ -79,10 +79,17 @@ SYMBOLS = {
     "xpcs_get_timestamps": (_i, [_vp, _vp, _vp]),
     "xpcs_get_frames": (_i, [_vp, C.c_int, _vp]),
     "xpcs_multitau": (_i, [_vp, _vp, _vp, _vp]),
+    "xpcs_get_correlators": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "xpcs_normalize": (_i, [_vp, _vp, _vp]),
     "xpcs_normalize_partials": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "xpcs_normalize_finish": (_i, [_vp, _vp, _vp]),
+    "xpcs_comm_unique_id": (_i, [_vp]),
+    "xpcs_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "xpcs_comm_nccl_version": (_i, []),
+    "xpcs_push_sparse_slab": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "xpcs_push_sparse_slab_device": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i]),
     "xpcs_twotime": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "xpcs_twotime_sg": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(C.c_int)]),
     "xpcs_kernel_timing": (_i, [_vp, _i]),
     "xpcs_launch_count": (_i64, [_vp]),
     "xpcs_multitau_fallback_slices": (_i64, [_vp]),

@@ -1,0 +1,423 @@
+// comm.cu -- the cross-GPU part of the path: one process (or thread) per GPU, one handle per GPU, one NCCL
+// communicator rank per handle.
+//
+// The reference is a single-node OpenMP program; its pixel loop (corr.cpp:329-332) is what shards.  What has to
+// cross GPUs:
+//   1. the events.  Every GPU receives a contiguous SLAB OF FRAMES of the whole detector (its share of the file,
+//      so the host->device traffic of a job is the file once, spread over all PCIe links) and owns a contiguous
+//      range of pixel rows.  comm_exchange_slab() partitions the slab by owner on the device (k_demux_count /
+//      k_demux_scan / k_demux_scatter: stable, frame order kept) and moves every partition to its owner with one
+//      grouped ncclSend/ncclRecv over NVLink; the owner concatenates the streams of all sources in rank order =
+//      frame order and ends up with an ordinary frame-major event list of its own pixels for ALL frames -- the
+//      input the single-GPU ingest takes.
+//   2. the per-frame sums (sparse_filter.cpp:175,190: frameSum covers all pixels), the per-static-bin sums and
+//      pixelSum: element-wise SUM all-reduce after the ingest (every static bin lives on one GPU, so the sums
+//      are the single-GPU values; exact for integer counts).
+//   3. the normalisation partials (normalize.cu): element-wise SUM all-reduce, bit-identical to one GPU.
+// NCCL is bound at run time (dlopen "libnccl.so.2"): inside a process that already carries an NCCL (PyTorch's)
+// the same copy is used; the standalone host program gets the system library.  No NCCL, no multi-GPU -- the
+// single-GPU path does not need it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+
+#include "internal.h"
+
+namespace xpcs {
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    std::string error;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("XPCS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) {
+            api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+            return;
+        }
+        bool ok = true;
+        auto sym = [&](const char *name) {
+            void *p = dlsym(api.lib, name);
+            if (!p) {
+                ok = false;
+                api.error = std::string("libnccl lacks ") + name;
+            }
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+        if (!ok) {
+            dlclose(api.lib);
+            api.lib = nullptr;
+        }
+    });
+    return api.lib ? &api : nullptr;
+}
+
+int nccl_check(xpcs_handle_s *h, ncclResult_t r, const char *what)
+{
+    if (r == ncclSuccess) return XPCS_OK;
+    NcclApi *n = nccl_api();
+    return fail(h, XPCS_E_CUDA, "%s: NCCL error %d (%s)", what, (int)r, n ? n->GetErrorString(r) : "?");
+}
+
+constexpr int kMaxRanks = 32;
+constexpr int kDmWarps = 8;
+
+// Pass 1 of the partition: one warp per frame of the slab counts the frame's events per owner.
+// cnt[d * (nfr + 1) + j] = events of slab frame j that belong to shard d (masked pixels belong to nobody).
+__global__ void __launch_bounds__(kDmWarps * 32) k_demux_count(const int32_t *__restrict__ idx, const int64_t *__restrict__ off,
+                                                               int nfr, const unsigned char *__restrict__ owner, int P, int N,
+                                                               int64_t *__restrict__ cnt)
+{
+    __shared__ int sc[kDmWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kDmWarps + warp;
+    if (j >= nfr) return;  // warp-uniform; no block barrier below
+    sc[warp][lane] = 0;
+    __syncwarp();
+    const int64_t a = off[j], b = off[j + 1];
+    for (int64_t e0 = a; e0 < b; e0 += 32) {
+        const int64_t e = e0 + lane;
+        int o = 255;
+        if (e < b) {
+            const int pix = idx[e];
+            if ((unsigned)pix < (unsigned)P) o = owner[pix];
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, o);
+        if (o < N && lane == __ffs(peers) - 1) sc[warp][o] += __popc(peers);
+        __syncwarp();
+    }
+    if (lane < N) cnt[(int64_t)lane * (nfr + 1) + j] = (int64_t)sc[warp][lane];
+}
+
+// Exclusive scan over the slab's frames, one CTA per destination, in place; entry nfr = the total.
+// meta = [first frame of the slab, frames of the slab, events for shard 0, 1, ...]: what every rank tells the others.
+__global__ void __launch_bounds__(1024) k_demux_scan(int64_t *__restrict__ cnt, int nfr, int first, int64_t *__restrict__ meta)
+{
+    __shared__ long long part[1024];
+    const int d = blockIdx.x, tid = threadIdx.x;
+    int64_t *c = cnt + (int64_t)d * (nfr + 1);
+    const int per = (nfr + 1023) / 1024;
+    const int a = min(nfr, tid * per), b = min(nfr, a + per);
+    long long s = 0;
+    for (int i = a; i < b; i++) s += c[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long x = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += x;
+        __syncthreads();
+    }
+    long long run = part[tid] - s;
+    for (int i = a; i < b; i++) {
+        const long long v = c[i];
+        c[i] = run;
+        run += v;
+    }
+    if (tid == 1023) {
+        c[nfr] = part[1023];
+        meta[2 + d] = part[1023];
+        if (d == 0) {
+            meta[0] = first;
+            meta[1] = nfr;
+        }
+    }
+}
+
+struct DemuxDst {
+    int32_t *idx[kMaxRanks];  // where the stream for shard d starts (send buffer, or the final list for the own shard)
+    int16_t *val[kMaxRanks];
+};
+
+// Pass 2: the same walk, every event goes to position (frame offset of its owner's stream + rank inside the
+// frame); stable, so a stream is the slab restricted to the owner's pixels, frame by frame, pixel order kept.
+__global__ void __launch_bounds__(kDmWarps * 32) k_demux_scatter(const int32_t *__restrict__ idx, const int16_t *__restrict__ val,
+                                                                 const int64_t *__restrict__ off, int nfr,
+                                                                 const unsigned char *__restrict__ owner, int P, int N,
+                                                                 const int64_t *__restrict__ dm_off, DemuxDst dst)
+{
+    __shared__ long long cur[kDmWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kDmWarps + warp;
+    if (j >= nfr) return;
+    cur[warp][lane] = lane < N ? dm_off[(int64_t)lane * (nfr + 1) + j] : 0;
+    __syncwarp();
+    const int64_t a = off[j], b = off[j + 1];
+    for (int64_t e0 = a; e0 < b; e0 += 32) {
+        const int64_t e = e0 + lane;
+        int o = 255, pix = 0;
+        int16_t v = 0;
+        if (e < b) {
+            pix = idx[e];
+            v = val[e];
+            if ((unsigned)pix < (unsigned)P) o = owner[pix];
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, o);
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        if (o < N) {
+            const long long pos = cur[warp][o] + before;
+            dst.idx[o][pos] = pix;
+            dst.val[o][pos] = v;
+        }
+        __syncwarp();
+        if (o < N && before == 0) cur[warp][o] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+struct MergeRanges {
+    int first[kMaxRanks], nfr[kMaxRanks];
+    long long base[kMaxRanks];
+};
+
+// received per-source offsets -> one frame-offset array over all raw frames of the job
+__global__ void k_merge_offsets(const int64_t *__restrict__ recv_off, int64_t *__restrict__ frame_off, MergeRanges r, int N,
+                                int raw_total, long long total)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > raw_total) return;
+    if (f == raw_total) {
+        frame_off[f] = total;
+        return;
+    }
+    int s = 0;
+    while (s + 1 < N && f >= r.first[s] + r.nfr[s]) s++;
+    frame_off[f] = r.base[s] + recv_off[(int64_t)r.first[s] + s + (f - r.first[s])];
+}
+
+}  // namespace
+
+bool comm_active(const xpcs_handle_s *h) { return h->comm != nullptr && h->comm_nranks > 1; }
+
+int comm_allreduce_f64(xpcs_handle_s *h, double *d_buf, size_t n)
+{
+    if (!comm_active(h) || n == 0) return XPCS_OK;
+    NcclApi *api = nccl_api();
+    LaunchScope ls(h, "nccl_allreduce", false);
+    return nccl_check(h, api->AllReduce(d_buf, d_buf, n, ncclFloat64, ncclSum, (ncclComm_t)h->comm, h->stream), "ncclAllReduce");
+}
+
+int comm_allreduce_f32(xpcs_handle_s *h, float *d_buf, size_t n)
+{
+    if (!comm_active(h) || n == 0) return XPCS_OK;
+    NcclApi *api = nccl_api();
+    LaunchScope ls(h, "nccl_allreduce", false);
+    return nccl_check(h, api->AllReduce(d_buf, d_buf, n, ncclFloat32, ncclSum, (ncclComm_t)h->comm, h->stream), "ncclAllReduce");
+}
+
+void comm_destroy(xpcs_handle_s *h)
+{
+    if (h->comm) {
+        NcclApi *api = nccl_api();
+        if (api) api->CommDestroy((ncclComm_t)h->comm);
+        h->comm = nullptr;
+    }
+    release(h->d_owner_of_pixel);
+    release(h->d_slab_idx); release(h->d_slab_val); release(h->d_slab_off);
+    release(h->d_dm_off); release(h->d_dm_meta); release(h->d_dm_all);
+    release(h->d_send_idx); release(h->d_send_val); release(h->d_recv_off);
+}
+
+// Frame slabs -> pixel shards.  On return the handle holds a frame-major event list of its own pixels over all
+// raw frames of the job (ev_idx / ev_val / ev_off), exactly what xpcs_push_sparse_device would have set up.
+int comm_exchange_slab(xpcs_handle_s *h)
+{
+    const int N = h->comm_nranks, me = h->comm_rank, nfr = h->slab_frames;
+    NcclApi *api = nccl_api();
+    int rc;
+    if ((rc = ensure(h, h->d_dm_off, (size_t)N * (nfr + 1), "slab partition offsets"))) return rc;
+    if ((rc = ensure(h, h->d_dm_meta, (size_t)N + 2, "slab partition totals"))) return rc;
+    if ((rc = ensure(h, h->d_dm_all, (size_t)N * (N + 2), "slab partition table"))) return rc;
+    cudaMemsetAsync(h->d_dm_off.p, 0, sizeof(int64_t) * (size_t)N * (nfr + 1), h->stream);
+    if (nfr > 0) {
+        LaunchScope ls(h, "k_demux_count");
+        k_demux_count<<<(nfr + kDmWarps - 1) / kDmWarps, kDmWarps * 32, 0, h->stream>>>(
+            h->slab_idx, h->slab_off, nfr, h->d_owner_of_pixel.p, h->P, N, h->d_dm_off.p);
+    }
+    {
+        LaunchScope ls(h, "k_demux_scan");
+        k_demux_scan<<<N, 1024, 0, h->stream>>>(h->d_dm_off.p, nfr, h->slab_first, h->d_dm_meta.p);
+    }
+    {
+        LaunchScope ls(h, "nccl_allgather", false);
+        if ((rc = nccl_check(h, api->AllGather(h->d_dm_meta.p, h->d_dm_all.p, (size_t)N + 2, ncclInt64, (ncclComm_t)h->comm, h->stream),
+                             "ncclAllGather")))
+            return rc;
+    }
+    std::vector<int64_t> all((size_t)N * (N + 2));
+    if ((rc = check_cuda(h, cudaMemcpyAsync(all.data(), h->d_dm_all.p, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, h->stream),
+                         "slab table D2H")))
+        return rc;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "slab partition"))) return rc;
+    auto at = [&](int s, int k) { return all[(size_t)s * (N + 2) + k]; };
+    // the slabs must tile the raw frames of the job in rank order
+    MergeRanges mr{};
+    int64_t raw_total = 0, E_me = 0;
+    h->slab_first_of_rank.assign(N, 0);
+    h->slab_frames_of_rank.assign(N, 0);
+    for (int s = 0; s < N; s++) {
+        if (at(s, 0) != raw_total)
+            return fail(h, XPCS_E_ARG, "frame slabs do not tile the job: rank %d starts at frame %lld, expected %lld", s,
+                        (long long)at(s, 0), (long long)raw_total);
+        mr.first[s] = (int)at(s, 0);
+        mr.nfr[s] = (int)at(s, 1);
+        mr.base[s] = E_me;
+        h->slab_first_of_rank[s] = mr.first[s];
+        h->slab_frames_of_rank[s] = mr.nfr[s];
+        raw_total += at(s, 1);
+        E_me += at(s, 2 + me);
+    }
+    if (raw_total > 0x7fffffffLL) return fail(h, XPCS_E_ARG, "too many raw frames");
+    int64_t send_total = 0;
+    std::vector<int64_t> sbase(N, 0);
+    for (int d = 0; d < N; d++) {
+        sbase[d] = send_total;
+        if (d != me) send_total += at(me, 2 + d);
+    }
+    size_t need = (size_t)E_me;
+    if (h->prm.reserve_events > (int64_t)need) need = (size_t)h->prm.reserve_events;
+    if ((rc = ensure(h, h->d_idx, need + 8, "event indices"))) return rc;
+    if ((rc = ensure(h, h->d_val, need + 8, "event values"))) return rc;
+    if ((rc = ensure(h, h->d_send_idx, (size_t)send_total + 8, "send indices"))) return rc;
+    if ((rc = ensure(h, h->d_send_val, (size_t)send_total + 8, "send values"))) return rc;
+    if ((rc = ensure(h, h->d_recv_off, (size_t)raw_total + N + 1, "received offsets"))) return rc;
+    if ((rc = ensure(h, h->d_frame_off, (size_t)raw_total + 1, "frame offsets"))) return rc;
+    DemuxDst dst{};
+    for (int d = 0; d < N; d++) {
+        if (d == me) {
+            dst.idx[d] = h->d_idx.p + mr.base[me];
+            dst.val[d] = h->d_val.p + mr.base[me];
+        } else {
+            dst.idx[d] = h->d_send_idx.p + sbase[d];
+            dst.val[d] = h->d_send_val.p + sbase[d];
+        }
+    }
+    if (nfr > 0) {
+        LaunchScope ls(h, "k_demux_scatter");
+        k_demux_scatter<<<(nfr + kDmWarps - 1) / kDmWarps, kDmWarps * 32, 0, h->stream>>>(
+            h->slab_idx, h->slab_val, h->slab_off, nfr, h->d_owner_of_pixel.p, h->P, N, h->d_dm_off.p, dst);
+    }
+    cudaMemcpyAsync(h->d_recv_off.p + mr.first[me] + me, h->d_dm_off.p + (size_t)me * (nfr + 1), sizeof(int64_t) * ((size_t)nfr + 1),
+                    cudaMemcpyDeviceToDevice, h->stream);
+    {
+        LaunchScope ls(h, "nccl_exchange", false);
+        ncclComm_t comm = (ncclComm_t)h->comm;
+        ncclResult_t r = api->GroupStart();
+        for (int s = 0; s < N && r == ncclSuccess; s++) {
+            if (s == me) continue;
+            const int64_t ns = at(me, 2 + s), nr = at(s, 2 + me);
+            if (ns > 0) {
+                r = api->Send(dst.idx[s], (size_t)ns, ncclInt32, s, comm, h->stream);
+                if (r == ncclSuccess) r = api->Send(dst.val[s], (size_t)ns * 2, ncclInt8, s, comm, h->stream);
+            }
+            if (r == ncclSuccess)
+                r = api->Send(h->d_dm_off.p + (size_t)s * (nfr + 1), (size_t)nfr + 1, ncclInt64, s, comm, h->stream);
+            if (nr > 0 && r == ncclSuccess) {
+                r = api->Recv(h->d_idx.p + mr.base[s], (size_t)nr, ncclInt32, s, comm, h->stream);
+                if (r == ncclSuccess) r = api->Recv(h->d_val.p + mr.base[s], (size_t)nr * 2, ncclInt8, s, comm, h->stream);
+            }
+            if (r == ncclSuccess)
+                r = api->Recv(h->d_recv_off.p + mr.first[s] + s, (size_t)mr.nfr[s] + 1, ncclInt64, s, comm, h->stream);
+        }
+        const ncclResult_t r2 = api->GroupEnd();
+        if ((rc = nccl_check(h, r != ncclSuccess ? r : r2, "event exchange (ncclSend/ncclRecv)"))) return rc;
+    }
+    {
+        LaunchScope ls(h, "k_merge_offsets");
+        k_merge_offsets<<<(int)((raw_total + 1 + 255) / 256), 256, 0, h->stream>>>(h->d_recv_off.p, h->d_frame_off.p, mr, N,
+                                                                                 (int)raw_total, (long long)E_me);
+    }
+    h->ev_idx = h->d_idx.p;
+    h->ev_val = h->d_val.p;
+    h->ev_off = h->d_frame_off.p;
+    h->E = E_me;
+    h->raw_frames = (int)raw_total;
+    h->external_events = true;
+    h->ts_clock.resize((size_t)raw_total, 0.0);
+    h->ts_ticks.resize((size_t)raw_total, 0.0);
+    return check_cuda(h, cudaGetLastError(), "slab exchange kernels");
+}
+
+}  // namespace xpcs
+
+using namespace xpcs;
+
+extern "C" int xpcs_comm_unique_id(void *id128)
+{
+    if (!id128) return XPCS_E_ARG;
+    NcclApi *api = nccl_api();
+    if (!api) return fail(nullptr, XPCS_E_CUDA, "NCCL unavailable");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, XPCS_E_CUDA, "ncclGetUniqueId: %s", api->GetErrorString(r));
+    memcpy(id128, &id, sizeof(id));
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_comm_init(xpcs_handle h, int nranks, int rank, const void *id128)
+{
+    if (!h || !id128) return h ? fail(h, XPCS_E_ARG, "comm_init: bad arguments") : XPCS_E_ARG;
+    if (nranks != h->prm.shard_count || rank != h->prm.shard_index)
+        return fail(h, XPCS_E_ARG, "comm_init: rank %d of %d does not match the handle's shard %d of %d", rank, nranks,
+                    h->prm.shard_index, h->prm.shard_count);
+    if (nranks > kMaxRanks) return fail(h, XPCS_E_ARG, "comm_init: at most %d ranks", kMaxRanks);
+    if (h->comm) return fail(h, XPCS_E_STATE, "comm_init called twice");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(h, XPCS_E_CUDA, "NCCL unavailable (libnccl.so.2 not loadable)");
+    cudaSetDevice(h->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    int rc = nccl_check(h, api->CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
+    if (rc) return rc;
+    h->comm = comm;
+    h->comm_nranks = nranks;
+    h->comm_rank = rank;
+    if ((rc = ensure(h, h->d_owner_of_pixel, (size_t)h->P, "pixel owners"))) return rc;
+    return check_cuda(h, cudaMemcpy(h->d_owner_of_pixel.p, h->owner_of_pixel.data(), (size_t)h->P, cudaMemcpyHostToDevice),
+                      "pixel owners H2D");
+}
+
+extern "C" int xpcs_comm_nccl_version(void)
+{
+    NcclApi *api = nccl_api();
+    int v = 0;
+    if (!api || api->GetVersion(&v) != ncclSuccess) return 0;
+    return v;
+}

@@ -70,7 +70,7 @@ struct IngestArgs {
 };
 
 // summary slots
-enum { kSumBadCount = 0, kSumMaxLen = 1, kSumEvents = 2, kSumOverflow = 3, kSumWords = 4, kSumSlots = 8 };
+enum { kSumBadCount = 0, kSumMaxLen = 1, kSumEvents = 2, kSumOverflow = 3, kSumWords = 4, kSumMaxCount = 5, kSumSlots = 8 };
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     // sums in frame order (pixels_sum_ += v is sequential fp32 in the reference)
     const int sb = a.sbin_of_row[r];
     double total;
+    int cmax = 0;
     {
         float fsum = 0.0f;
         long long isum = 0;
@@ -614,6 +615,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
                 t = (int)(w >> kCountBits);
                 int c = (int)(w & ((1u << kCountBits) - 1));
                 isum += c;
+                cmax = max(cmax, c);
                 v = (double)c;
             } else {
                 unsigned long long w = (unsigned long long)col[(int64_t)i * kSlice];
@@ -640,6 +642,7 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     else a.row_sum[r] = total;
     if (sb >= 0 && m > 0) atomicAdd(a.part_total + sb, total);
     a.row_len[r] = m;
+    if (KIND == kPacked && cmax > 2048) atomicMax(a.summary + kSumMaxCount, (long long)cmax);  // rare: fp16 two-time operand
     if (in_smem) {
         __syncwarp();
         for (int j = 0; j < len; j++)
@@ -743,6 +746,7 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
                     outw = (W)((key << kCountBits) | (c & ((1u << kCountBits) - 1u)));
                     itot += c;
                     v = (double)c;
+                    if (c > 2048u) atomicMax(a.summary + kSumMaxCount, (long long)c);  // rare: fp16 two-time operand
                 } else {
                     float x = __uint_as_float((uint32_t)w);
                     for (int k = i + 1; k < n && (uint32_t)(A[k] >> kShift) == key; k++)
@@ -1369,6 +1373,10 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     if (KIND == kFloat && h->prm.normalize_by_framesum) {
         rc = ensure(h, h->d_frame_scale, (size_t)F, "frame scale");
         if (rc) return rc;
+        if (comm_active(h) && !h->frame_acc_reduced) {  // the scale needs the frame sums over ALL pixels (main.cpp:313-337)
+            if ((rc = comm_allreduce_f64(h, h->d_frame_acc.p, (size_t)F))) return rc;
+            h->frame_acc_reduced = true;
+        }
         LaunchScope ls(h, "k_frame_scale");
         k_frame_scale<<<1, 256, 0, h->stream>>>(h->d_frame_acc.p, h->d_frame_scale.p, F, h->P);
         fa.frame_scale = h->d_frame_scale.p;
@@ -1416,6 +1424,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     if (rc) return rc;
     if (KIND == kPacked && sum[kSumOverflow]) return 1;
     h->events_stored = sum[kSumEvents];
+    h->max_count = std::max(h->max_count, KIND == kPacked ? std::max(1, (int)sum[kSumMaxCount]) : 0);
     return XPCS_OK;
 }
 

@@ -150,6 +150,7 @@ struct xpcs_handle_s {
     int64_t store_words = 0;
     int64_t events_stored = 0;
     int max_row = 0;
+    int max_count = 0;                    // largest merged photon count of the packed store (two-time: fp16 is exact up to 2048)
     xpcs::DevBuf<long long> d_summary;    // small device scratch for host-visible scalars
     xpcs::DevBuf<double> d_frame_acc;     // [F] per-output-frame sums (exact for counts)
     xpcs::DevBuf<double> d_row_sum;       // [R_pad]
@@ -185,6 +186,31 @@ struct xpcs_handle_s {
     xpcs::DevBuf<unsigned int> d_tt_sgint;
     xpcs::DevBuf<double> d_tt_diag;
 
+    // ---- multi-GPU (comm.cu) ----
+    void *comm = nullptr;                 // ncclComm_t
+    int comm_nranks = 1, comm_rank = 0;
+    std::vector<unsigned char> owner_of_pixel;     // [P] shard that owns the pixel, 255 = masked (plan_maps)
+    xpcs::DevBuf<unsigned char> d_owner_of_pixel;  // uploaded at xpcs_comm_init
+    // frame-slab ingest: this handle was given raw frames [slab_first, slab_first + slab_frames) of the WHOLE
+    // detector; xpcs_finish_ingest redistributes the events to the pixel owners
+    bool slab_mode = false;
+    int slab_first = 0, slab_frames = 0;
+    int64_t slab_events = 0;
+    const int32_t *slab_idx = nullptr;    // device views (the caller's buffers or the d_slab_* copies)
+    const int16_t *slab_val = nullptr;
+    const int64_t *slab_off = nullptr;
+    xpcs::DevBuf<int32_t> d_slab_idx;
+    xpcs::DevBuf<int16_t> d_slab_val;
+    xpcs::DevBuf<int64_t> d_slab_off;
+    xpcs::DevBuf<int64_t> d_dm_off;       // [nranks][slab_frames + 1] per-destination event offsets of the slab's frames
+    xpcs::DevBuf<int64_t> d_dm_meta;      // [nranks + 2] first frame, frames, events per destination
+    xpcs::DevBuf<int64_t> d_dm_all;       // [nranks][nranks + 2] the same of every rank
+    xpcs::DevBuf<int32_t> d_send_idx;
+    xpcs::DevBuf<int16_t> d_send_val;
+    xpcs::DevBuf<int64_t> d_recv_off;     // [raw frames + nranks] offsets as received, one stream per source rank
+    bool frame_acc_reduced = false;       // the per-frame sums already cover every shard
+    std::vector<int> slab_first_of_rank, slab_frames_of_rank;  // filled by the exchange
+
     // ---- measurement ----
     bool timing = false;
     int64_t launches = 0;
@@ -199,7 +225,8 @@ struct LaunchScope {
     xpcs_handle_s *h;
     const char *name;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    LaunchScope(xpcs_handle_s *h_, const char *name_);
+    // own = false: a library kernel (NCCL) -- timed under its name, not counted as one of ours
+    LaunchScope(xpcs_handle_s *h_, const char *name_, bool own = true);
     ~LaunchScope();
 };
 
@@ -228,6 +255,13 @@ void release(DevBuf<T> &b)
     b.n = 0;
 }
 
+// ---- cross-GPU exchange (comm.cu): NCCL bound at run time, one communicator per handle ----
+bool comm_active(const xpcs_handle_s *h);                            // communicator with more than one rank
+int comm_allreduce_f64(xpcs_handle_s *h, double *d_buf, size_t n);   // in place, SUM, on the handle's stream
+int comm_allreduce_f32(xpcs_handle_s *h, float *d_buf, size_t n);
+int comm_exchange_slab(xpcs_handle_s *h);                            // frame slabs -> pixel shards (xpcs_push_sparse_slab*)
+void comm_destroy(xpcs_handle_s *h);
+
 // ---- launchers (ingest.cu) ----
 int launch_ingest(xpcs_handle_s *h);             // histogram -> slices -> scatter -> finalize
 int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1);  // same for raw frames [f0, f1) into the next chunk store; 1 = not representable
@@ -248,6 +282,6 @@ int launch_normalize_partials(xpcs_handle_s *h);
 int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);
 // ---- launchers (twotime.cu) ----
 int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int average, float *C,
-                   float *g2full, float *g2partials, float *sg);
+                   float *g2full, float *g2partials, float *sg, int *sg_rows_out);
 
 }  // namespace xpcs

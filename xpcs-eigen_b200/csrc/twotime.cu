@@ -20,9 +20,17 @@
 // four warps read TMEM with tcgen05.ld.32x32b, scale and store.
 // Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
 // Float-valued rows (flat-field, averaging) are split x = hi + lo in fp16 and contracted in
-// three passes (hi*hi + hi*lo + lo*hi) into the same accumulator (~2e-7 relative).
+// three passes (hi*hi + hi*lo + lo*hi) into the same accumulator (~2e-7 relative); so are integer
+// counts above 2048, which fp16 no longer holds exactly.
+// "StaticMap" smoothing (SmoothingStaticMap / ComputeSGStaticMap, corr.cpp:433-494, :1228-1305) divides
+// every event by the sg of its STATIC partition, which does not factor out of the contraction: the
+// operand is built from z = x / sg_s[t] (one fp32 division per event, as the reference does) and takes
+// the three-pass path; the epilogue then only divides by N.
 #include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
 
 #include "internal.h"
 
@@ -112,6 +120,7 @@ struct TtGemmArgs {
     const float *sg;    // [F] (or [1] when sg_scalar)
     int F, kblocks, npass, sg_scalar, use_sg;
     float npix;
+    float unscale;      // 1 / op_scale^2 (a power of two): the operand was scaled to stay inside fp16
 };
 
 __global__ void __launch_bounds__(kTtThreads, 1)
@@ -204,7 +213,7 @@ k_twotime_gemm(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                                 const float s_col = a.sg_scalar ? s_row : a.sg[col];
                                 x = __fdiv_rn(x, __fmul_rn(s_row, s_col));
                             }
-                            x = __fdiv_rn(x, a.npix);
+                            x = __fdiv_rn(__fmul_rn(x, a.unscale), a.npix);
                         }
                         dst[j] = x;
                     }
@@ -225,10 +234,18 @@ struct TtBuildArgs {
     const void *store;
     const int64_t *slice_base;
     const int *row_len;
-    __half *xt_hi, *xt_lo;        // [F][npad]
-    unsigned int *sg_int;         // [F] integer column sums (packed rows)
-    float *sg_f;                  // [F] float column sums
+    __half *xt_hi, *xt_lo;        // [F][npad]; xt_lo nullptr = single pass (exact small integers)
+    unsigned int *sg_int;         // [sg_rows][F] integer column sums (packed rows)
+    float *sg_f;                  // [sg_rows][F] float column sums
     int row0, row1, npad, F, n_slices;
+    // static-map smoothing: rows belong to sg row (segment index - seg0); symmetric: everything is sg row 0
+    const int *lseg_row_start;    // [local segments + 1]
+    int seg0, nseg, per_segment;
+    int do_sum, do_write;         // accumulate the column sums / write the operand
+    const float *sg_div;          // static map, operand pass: divide by sg_div[row * (scalar ? 1 : F) + t]
+    int sg_scalar;
+    unsigned int *max_bits;       // sum pass: bit pattern of the largest value seen (values are >= 0)
+    float op_scale;               // power of two
 };
 
 template <int KIND>
@@ -241,47 +258,66 @@ __global__ void k_twotime_build(TtBuildArgs a)
     if (r < a.row0 || r >= a.row1) return;
     const int n = a.row_len[r];
     const int p = r - a.row0;
-    if (KIND == kPacked) {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane;
-        for (int j = 0; j < n; j++) {
-            const uint32_t w = g[(int64_t)j * kSlice];
-            const int t = (int)(w >> kCountBits);
-            const unsigned c = w & ((1u << kCountBits) - 1u);
-            if (t < a.F) {
-                a.xt_hi[(size_t)t * a.npad + p] = __float2half_rn((float)c);
-                atomicAdd(a.sg_int + t, c);
-            }
+    int sgrow = 0;
+    if (a.per_segment) {  // last segment of [seg0, seg0 + nseg) that starts at or before r
+        int lo = a.seg0, hi = a.seg0 + a.nseg;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.lseg_row_start[mid] <= r) lo = mid;
+            else hi = mid;
         }
-    } else {
-        const unsigned long long *g = reinterpret_cast<const unsigned long long *>(a.store) + a.slice_base[s] + lane;
-        for (int j = 0; j < n; j++) {
-            const unsigned long long w = g[(int64_t)j * kSlice];
-            const int t = (int)(w >> 32);
-            const float x = __uint_as_float((uint32_t)w);
-            if (t < a.F) {
-                const __half hi = __float2half_rn(x);
-                a.xt_hi[(size_t)t * a.npad + p] = hi;
-                a.xt_lo[(size_t)t * a.npad + p] = __float2half_rn(__fsub_rn(x, __half2float(hi)));
-                atomicAdd(a.sg_f + t, x);
-            }
+        sgrow = lo - a.seg0;
+    }
+    const size_t sgbase = (size_t)sgrow * a.F;
+    unsigned int mb = 0u;
+    for (int j = 0; j < n; j++) {
+        int t;
+        float x;
+        unsigned c = 0;
+        if (KIND == kPacked) {
+            const uint32_t w = (reinterpret_cast<const uint32_t *>(a.store) + a.slice_base[s] + lane)[(int64_t)j * kSlice];
+            t = (int)(w >> kCountBits);
+            c = w & ((1u << kCountBits) - 1u);
+            x = (float)c;
+        } else {
+            const unsigned long long w = (reinterpret_cast<const unsigned long long *>(a.store) + a.slice_base[s] + lane)[(int64_t)j * kSlice];
+            t = (int)(w >> 32);
+            x = __uint_as_float((uint32_t)w);
+        }
+        if (t >= a.F) continue;
+        if (a.do_sum) {
+            if (KIND == kPacked) atomicAdd(a.sg_int + sgbase + t, c);
+            else atomicAdd(a.sg_f + sgbase + t, x);
+            mb = max(mb, __float_as_uint(fmaxf(x, 0.0f)));
+        }
+        if (a.do_write) {
+            if (a.sg_div) x = __fdiv_rn(x, a.sg_div[a.sg_scalar ? (size_t)sgrow : sgbase + t]);  // corr.cpp:470-478
+            x = __fmul_rn(x, a.op_scale);
+            const __half hi = __float2half_rn(x);
+            a.xt_hi[(size_t)t * a.npad + p] = hi;
+            if (a.xt_lo) a.xt_lo[(size_t)t * a.npad + p] = __float2half_rn(__fsub_rn(x, __half2float(hi)));
         }
     }
+    if (a.do_sum && mb) atomicMax(a.max_bits, mb);
 }
 
 // sg[t] = column sum / N (corr.cpp:1207-1215); "Average": one value, the fp32 mean over t in
 // frame order (corr.cpp:1217-1224)
-__global__ void k_twotime_sg(const unsigned int *sg_int, const float *sg_f, float *sg, float *sg_avg, int F,
-                             float npix, int packed)
+// blockIdx.y = sg row (one for symmetric smoothing, one per static partition for StaticMap)
+__global__ void k_twotime_sg(const unsigned int *sg_int, const float *sg_f, float *sg, const float *npix_of_row, int F,
+                             int packed)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < F) sg[t] = __fdiv_rn(packed ? (float)sg_int[t] : sg_f[t], npix);
+    const size_t o = (size_t)blockIdx.y * F + t;
+    if (t < F) sg[o] = __fdiv_rn(packed ? (float)sg_int[o] : sg_f[o], npix_of_row[blockIdx.y]);
 }
 __global__ void k_twotime_sg_average(const float *sg, float *sg_avg, int F)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+        const float *row = sg + (size_t)blockIdx.x * F;
         float acc = 0.0f;
-        for (int t = 0; t < F; t++) acc = __fadd_rn(acc, sg[t]);
-        sg_avg[0] = __fdiv_rn(acc, (float)F);
+        for (int t = 0; t < F; t++) acc = __fadd_rn(acc, row[t]);
+        sg_avg[blockIdx.x] = __fdiv_rn(acc, (float)F);
     }
 }
 
@@ -347,84 +383,133 @@ static int make_operand_map(xpcs_handle_s *h, CUtensorMap *map, const __half *pt
 }
 
 int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int average, float *C, float *g2full,
-                   float *g2partials, float *sg)
+                   float *g2partials, float *sg, int *sg_rows_out)
 {
     const int F = h->prm.frames;
-    if (method != 0 && method != 1) return fail(h, XPCS_E_ARG, "two-time: smoothing method %d not built (0 = none, 1 = symmetric)", method);
+    if (method < 0 || method > 2) return fail(h, XPCS_E_ARG, "two-time: smoothing method %d unknown (0 = none, 1 = symmetric, 2 = static map)", method);
     if (wsize <= 0) return fail(h, XPCS_E_ARG, "two-time: twotime2onetime_window_size must be > 0 (corr.cpp:796 divides by it)");
     if (h->prm.shard_count != 1) return fail(h, XPCS_E_ARG, "two-time runs one dynamic partition per GPU: create the handle with shard_count = 1");
     // rows of the dynamic partition: contiguous, because rows are sorted by (dq, sq, pixel)
-    int row0 = -1, row1 = -1;
+    int row0 = -1, row1 = -1, seg0 = -1, nseg = 0;
     for (int s = h->seg_first; s < h->seg_last; s++)
         if (h->seg_dq[s] == qbin) {
-            if (row0 < 0) row0 = h->lseg_row_start[s - h->seg_first];
+            if (row0 < 0) {
+                row0 = h->lseg_row_start[s - h->seg_first];
+                seg0 = s - h->seg_first;
+            }
             row1 = h->lseg_row_start[s - h->seg_first + 1];
+            nseg++;
         }
     if (row0 < 0) return fail(h, XPCS_E_ARG, "two-time: dynamic partition %d has no pixels", qbin);
     const int N = row1 - row0;
     const int npad = (N + kTtBK - 1) / kTtBK * kTtBK;
     const int partials = (F - wsize) / wsize > 0 ? (F - wsize) / wsize : 0;
     const bool packed = h->kind == kPacked;
+    const bool static_map = method == 2;
+    const int sg_rows = static_map ? nseg : 1;
+    if (sg_rows_out) *sg_rows_out = sg_rows;
+    // the fp16 operand is exact for integer counts up to 2048 only; anything else takes hi + lo and three passes
+    const bool split = !packed || static_map || h->max_count > 2048;
+    float op_scale = 1.0f;  // static map: set once sg is known (below)
     int rc;
     const size_t xt_elems = (size_t)F * npad;
+    const size_t sg_elems = (size_t)sg_rows * F;
     if ((rc = ensure(h, h->d_tt_hi, xt_elems, "two-time operand"))) return rc;
-    if (!packed && (rc = ensure(h, h->d_tt_lo, xt_elems, "two-time operand (low part)"))) return rc;
+    if (split && (rc = ensure(h, h->d_tt_lo, xt_elems, "two-time operand (low part)"))) return rc;
     if ((rc = ensure(h, h->d_tt_C, (size_t)F * F, "two-time matrix"))) return rc;
-    if ((rc = ensure(h, h->d_tt_sg, (size_t)2 * F + 8, "two-time sg"))) return rc;
-    if ((rc = ensure(h, h->d_tt_sgint, (size_t)F, "two-time sg sums"))) return rc;
+    if ((rc = ensure(h, h->d_tt_sg, 2 * sg_elems + 2 * (size_t)sg_rows + 8, "two-time sg"))) return rc;
+    if ((rc = ensure(h, h->d_tt_sgint, sg_elems + 1, "two-time sg sums"))) return rc;
     if ((rc = ensure(h, h->d_tt_diag, (size_t)F + (size_t)wsize * (partials > 0 ? partials : 1), "two-time diagonals"))) return rc;
     if ((rc = ensure(h, h->d_tt_out, (size_t)F + (size_t)wsize * (partials > 0 ? partials : 1), "two-time diagonal means"))) return rc;
     cudaStream_t st = h->stream;
     cudaMemsetAsync(h->d_tt_hi.p, 0, xt_elems * sizeof(__half), st);
-    if (!packed) cudaMemsetAsync(h->d_tt_lo.p, 0, xt_elems * sizeof(__half), st);
+    if (split) cudaMemsetAsync(h->d_tt_lo.p, 0, xt_elems * sizeof(__half), st);
     cudaMemsetAsync(h->d_tt_C.p, 0, (size_t)F * F * sizeof(float), st);
-    cudaMemsetAsync(h->d_tt_sg.p, 0, ((size_t)2 * F + 8) * sizeof(float), st);
-    cudaMemsetAsync(h->d_tt_sgint.p, 0, (size_t)F * sizeof(unsigned int), st);
+    cudaMemsetAsync(h->d_tt_sg.p, 0, (2 * sg_elems + 2 * (size_t)sg_rows + 8) * sizeof(float), st);
+    cudaMemsetAsync(h->d_tt_sgint.p, 0, (sg_elems + 1) * sizeof(unsigned int), st);
     cudaMemsetAsync(h->d_tt_diag.p, 0, ((size_t)F + (size_t)wsize * (partials > 0 ? partials : 1)) * sizeof(double), st);
 
-    float *d_sg = h->d_tt_sg.p;           // [F] per-frame sg
-    float *d_sg_f = h->d_tt_sg.p + F;     // [F] float column sums
-    float *d_sg_avg = h->d_tt_sg.p + 2 * F;
-    {
-        TtBuildArgs b{};
-        b.store = h->d_store.p;
-        b.slice_base = h->d_slice_base.p;
-        b.row_len = h->d_row_len.p;
-        b.xt_hi = (__half *)h->d_tt_hi.p;
-        b.xt_lo = packed ? nullptr : (__half *)h->d_tt_lo.p;
-        b.sg_int = h->d_tt_sgint.p;
-        b.sg_f = d_sg_f;
-        b.row0 = row0;
-        b.row1 = row1;
-        b.npad = npad;
-        b.F = F;
-        b.n_slices = h->n_slices;
+    float *d_sg = h->d_tt_sg.p;                          // [sg_rows][F] per-frame sg
+    float *d_sg_f = h->d_tt_sg.p + sg_elems;             // [sg_rows][F] float column sums
+    float *d_sg_avg = h->d_tt_sg.p + 2 * sg_elems;       // [sg_rows]
+    float *d_npix = d_sg_avg + sg_rows;                  // [sg_rows] pixels behind every sg row
+    std::vector<float> npix((size_t)sg_rows, (float)N);  // (stays alive until the synchronisation below)
+    if (static_map)
+        for (int k = 0; k < nseg; k++) npix[(size_t)k] = (float)(h->lseg_row_start[seg0 + k + 1] - h->lseg_row_start[seg0 + k]);
+    if ((rc = check_cuda(h, cudaMemcpyAsync(d_npix, npix.data(), sizeof(float) * (size_t)sg_rows, cudaMemcpyHostToDevice, st), "sg pixel counts")))
+        return rc;
+    TtBuildArgs b{};
+    b.store = h->d_store.p;
+    b.slice_base = h->d_slice_base.p;
+    b.row_len = h->d_row_len.p;
+    b.xt_hi = (__half *)h->d_tt_hi.p;
+    b.xt_lo = split ? (__half *)h->d_tt_lo.p : nullptr;
+    b.sg_int = h->d_tt_sgint.p;
+    b.sg_f = d_sg_f;
+    b.row0 = row0;
+    b.row1 = row1;
+    b.npad = npad;
+    b.F = F;
+    b.n_slices = h->n_slices;
+    b.lseg_row_start = h->d_lseg_row_start.p;
+    b.seg0 = seg0;
+    b.nseg = nseg;
+    b.per_segment = static_map ? 1 : 0;
+    b.op_scale = 1.0f;
+    b.max_bits = h->d_tt_sgint.p + sg_elems;
+    const int wpb = 8;
+    auto run_build = [&](int do_sum, int do_write, const float *div) {
+        b.do_sum = do_sum;
+        b.do_write = do_write;
+        b.sg_div = div;
+        b.sg_scalar = average ? 1 : 0;
         LaunchScope ls(h, "k_twotime_build");
-        const int wpb = 8;
         if (packed) k_twotime_build<kPacked><<<(h->n_slices + wpb - 1) / wpb, wpb * 32, 0, st>>>(b);
         else k_twotime_build<kFloat><<<(h->n_slices + wpb - 1) / wpb, wpb * 32, 0, st>>>(b);
-    }
+    };
+    run_build(1, static_map ? 0 : 1, nullptr);  // column sums (and, when sg factors out, the operand itself)
     {
         LaunchScope ls(h, "k_twotime_sg");
-        k_twotime_sg<<<(F + 255) / 256, 256, 0, st>>>(h->d_tt_sgint.p, d_sg_f, d_sg, d_sg_avg, F, (float)N, packed ? 1 : 0);
+        k_twotime_sg<<<dim3((F + 255) / 256, sg_rows), 256, 0, st>>>(h->d_tt_sgint.p, d_sg_f, d_sg, d_npix, F, packed ? 1 : 0);
     }
     if (average) {
         LaunchScope ls(h, "k_twotime_sg_average");
-        k_twotime_sg_average<<<1, 32, 0, st>>>(d_sg, d_sg_avg, F);
+        k_twotime_sg_average<<<sg_rows, 32, 0, st>>>(d_sg, d_sg_avg, F);
+    }
+    if (static_map) {
+        // z = x / sg_s can leave the fp16 range: per frame z <= N_s (x over the mean of a sum that contains it),
+        // with the "Average" filter z <= max x / min sg.  The operand is scaled by a power of two, undone in the epilogue.
+        unsigned int mb = 0;
+        std::vector<float> avg((size_t)sg_rows, 1.0f);
+        cudaMemcpyAsync(&mb, h->d_tt_sgint.p + sg_elems, sizeof(mb), cudaMemcpyDeviceToHost, st);
+        if (average) cudaMemcpyAsync(avg.data(), d_sg_avg, sizeof(float) * (size_t)sg_rows, cudaMemcpyDeviceToHost, st);
+        if ((rc = check_cuda(h, cudaStreamSynchronize(st), "two-time sg"))) return rc;
+        float maxval;
+        memcpy(&maxval, &mb, sizeof(float));
+        double bound = 1.0;
+        for (int k = 0; k < sg_rows; k++) {
+            if (average) {
+                if (avg[(size_t)k] > 0.0f) bound = std::max(bound, (double)maxval / (double)avg[(size_t)k]);
+            } else bound = std::max(bound, (double)npix[(size_t)k]);
+        }
+        while (bound * op_scale > 16384.0 && op_scale > 1e-12f) op_scale *= 0.5f;
+        b.op_scale = op_scale;
+        run_build(0, 1, average ? d_sg_avg : d_sg);  // operand z = x / sg of the pixel's static partition
     }
     CUtensorMap map_hi, map_lo;
     if ((rc = make_operand_map(h, &map_hi, (const __half *)h->d_tt_hi.p, F, npad))) return rc;
-    if ((rc = make_operand_map(h, &map_lo, (const __half *)(packed ? h->d_tt_hi.p : h->d_tt_lo.p), F, npad))) return rc;
+    if ((rc = make_operand_map(h, &map_lo, (const __half *)(split ? h->d_tt_lo.p : h->d_tt_hi.p), F, npad))) return rc;
     {
         TtGemmArgs g{};
         g.C = h->d_tt_C.p;
         g.sg = average ? d_sg_avg : d_sg;
         g.F = F;
         g.kblocks = npad / kTtBK;
-        g.npass = packed ? 1 : 3;
+        g.npass = split ? 3 : 1;
         g.sg_scalar = average ? 1 : 0;
         g.use_sg = method == 1 ? 1 : 0;
         g.npix = (float)N;
+        g.unscale = 1.0f / (op_scale * op_scale);
         rc = check_cuda(h, cudaFuncSetAttribute(k_twotime_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTtSmemBytes),
                         "two-time smem attr");
         if (rc) return rc;
@@ -453,8 +538,9 @@ int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int averag
     if (g2partials && partials > 0)
         cudaMemcpyAsync(g2partials, d_g2part, (size_t)wsize * partials * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (sg) {
-        if (method == 1) cudaMemcpyAsync(sg, average ? d_sg_avg : d_sg, (average ? 1 : (size_t)F) * sizeof(float), cudaMemcpyDeviceToHost, st);
-        else for (int i = 0; i < (average ? 1 : F); i++) sg[i] = 1.0f;
+        const size_t n = (size_t)sg_rows * (average ? 1 : (size_t)F);
+        if (method != 0) cudaMemcpyAsync(sg, average ? d_sg_avg : d_sg, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+        else for (size_t i = 0; i < n; i++) sg[i] = 1.0f;
     }
     return check_cuda(h, cudaStreamSynchronize(st), "two-time");
 }

@@ -36,9 +36,9 @@ int check_cuda(xpcs_handle_s *h, cudaError_t e, const char *what)
     return fail(h, XPCS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
-LaunchScope::LaunchScope(xpcs_handle_s *h_, const char *name_) : h(h_), name(name_)
+LaunchScope::LaunchScope(xpcs_handle_s *h_, const char *name_, bool own) : h(h_), name(name_)
 {
-    h->launches++;
+    if (own) h->launches++;
     if (h->timing) {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
@@ -205,6 +205,16 @@ static int plan_maps(xpcs_handle_s *h)
     }
     h->seg_first = cut[k];
     h->seg_last = cut[k + 1];
+    // which shard owns which pixel (the frame-slab exchange of comm.cu partitions by it); 255 = masked
+    h->owner_of_pixel.assign((size_t)P, 255);
+    if (K <= 254) {
+        for (int sh = 0; sh < K; sh++)
+            for (int s = cut[sh]; s < cut[sh + 1]; s++)
+                for (int i = 0; i < kept[s]->n; i++) h->owner_of_pixel[valid[kept[s]->start + i]] = (unsigned char)sh;
+        for (const Cell &c : cells)  // pixels lost by the duplicate removal: trailing rows of the last shard
+            if (!c.kept)
+                for (int i = 0; i < c.n; i++) h->owner_of_pixel[valid[c.start + i]] = (unsigned char)(K - 1);
+    }
 
     h->pixel_of_row.clear();
     h->lseg_row_start.assign(1, 0);
@@ -307,10 +317,19 @@ static void reset_ingest(xpcs_handle_s *h)
     h->events_stored = 0;
     h->store_words = 0;
     h->max_row = 0;
+    h->max_count = 0;
     h->pipe_on = false;
     h->pipe_broken = false;
     h->pipe_chunks = 0;
     h->frame_off_uploaded = 0;
+    h->slab_mode = false;
+    h->slab_first = 0;
+    h->slab_frames = 0;
+    h->slab_events = 0;
+    h->slab_idx = nullptr;
+    h->slab_val = nullptr;
+    h->slab_off = nullptr;
+    h->frame_acc_reduced = false;
 }
 
 static int check_params(const XpcsParams *prm)
@@ -323,8 +342,7 @@ static int check_params(const XpcsParams *prm)
         !prm->sqmap || prm->shard_count <= 0 || prm->shard_index < 0 || prm->shard_index >= prm->shard_count)
         return fail(nullptr, XPCS_E_ARG, "invalid XpcsParams (dimensions, frames, dpl, stride/avg, window, maps or shard)");
     if ((int64_t)prm->width * prm->height > 0x7fffffffLL) return fail(nullptr, XPCS_E_ARG, "detector too large");
-    if (prm->normalize_by_framesum && prm->shard_count > 1)
-        return fail(nullptr, XPCS_E_ARG, "normalize_by_framesum needs the frame sums of all shards; not supported with shard_count > 1");
+    if (prm->shard_count > 254) return fail(nullptr, XPCS_E_ARG, "at most 254 shards");
     return XPCS_OK;
 }
 
@@ -414,6 +432,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
         }
+    comm_destroy(h);
     release(h->d_row_of_pixel); release(h->d_pixel_of_row); release(h->d_sbin_of_row); release(h->d_flat);
     release(h->d_lseg_row_start); release(h->d_seg_dq_all); release(h->d_seg_npix_all);
     release(h->d_dark_avg); release(h->d_dark_std); release(h->d_dense_bound); release(h->d_dense_every); release(h->d_dense_args);
@@ -690,6 +709,85 @@ extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, cons
     return XPCS_OK;
 }
 
+// ---- frame-slab pushes (multi-GPU: every GPU gets its share of the FRAMES of the whole detector) ----
+static int slab_begin(xpcs_handle_s *h, int first_raw_frame, int nframes, int64_t n_events)
+{
+    if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->raw_frames > 0 || h->slab_mode || h->external_events || h->dense_source)
+        return fail(h, XPCS_E_STATE, "a frame slab must be the only push of an ingest");
+    if (first_raw_frame < 0 || nframes < 0 || n_events < 0) return fail(h, XPCS_E_ARG, "push_sparse_slab: bad arguments");
+    if (h->prm.shard_count > 1 && !comm_active(h))
+        return fail(h, XPCS_E_STATE, "push_sparse_slab needs the communicator (xpcs_comm_init) when shard_count > 1");
+    if (h->prm.shard_count == 1 && first_raw_frame != 0) return fail(h, XPCS_E_ARG, "a single shard's slab starts at frame 0");
+    return XPCS_OK;
+}
+
+// one shard: a slab is a plain push (unless a one-rank communicator exists and the tests force the exchange)
+static bool slab_is_plain_push(const xpcs_handle_s *h)
+{
+    return h->prm.shard_count == 1 && !(h->comm && getenv("XPCS_SLAB_FORCE_EXCHANGE"));
+}
+
+extern "C" int xpcs_push_sparse_slab_device(xpcs_handle h, int first_raw_frame, const int32_t *d_idx, const int16_t *d_val,
+                                            const int64_t *d_frame_offsets, int64_t n_events, int nframes)
+{
+    if (!h || !d_frame_offsets) return h ? fail(h, XPCS_E_ARG, "push_sparse_slab_device: bad arguments") : XPCS_E_ARG;
+    int rc = slab_begin(h, first_raw_frame, nframes, n_events);
+    if (rc) return rc;
+    if (slab_is_plain_push(h)) return xpcs_push_sparse_device(h, d_idx, d_val, d_frame_offsets, n_events, nframes);
+    h->slab_mode = true;
+    h->slab_first = first_raw_frame;
+    h->slab_frames = nframes;
+    h->slab_events = n_events;
+    h->slab_idx = d_idx;
+    h->slab_val = d_val;
+    h->slab_off = d_frame_offsets;
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_push_sparse_slab(xpcs_handle h, int first_raw_frame, const int32_t *idx, const int16_t *val,
+                                     const int64_t *frame_offsets, const double *clock, const double *ticks, int nframes)
+{
+    if (!h || !frame_offsets) return h ? fail(h, XPCS_E_ARG, "push_sparse_slab: bad arguments") : XPCS_E_ARG;
+    const int64_t n = nframes >= 0 ? frame_offsets[nframes] - frame_offsets[0] : -1;
+    int rc = slab_begin(h, first_raw_frame, nframes, n);
+    if (rc) return rc;
+    if (slab_is_plain_push(h)) return xpcs_push_sparse(h, idx, val, frame_offsets, clock, ticks, nframes);
+    if (n > 0 && (!idx || !val)) return fail(h, XPCS_E_ARG, "push_sparse_slab: NULL payload");
+    for (int i = 0; i < nframes; i++)
+        if (frame_offsets[i + 1] < frame_offsets[i]) return fail(h, XPCS_E_ARG, "push_sparse_slab: frame offsets not monotone");
+    cudaSetDevice(h->device);
+    if ((rc = ensure(h, h->d_slab_idx, (size_t)n + 8, "slab indices"))) return rc;
+    if ((rc = ensure(h, h->d_slab_val, (size_t)n + 8, "slab values"))) return rc;
+    if ((rc = ensure(h, h->d_slab_off, (size_t)nframes + 1, "slab offsets"))) return rc;
+    // (with pinned host memory the three copies are asynchronous; the partition kernels of the exchange queue behind them)
+    rc = check_cuda(h, cudaMemcpyAsync(h->d_slab_off.p, frame_offsets, sizeof(int64_t) * ((size_t)nframes + 1),
+                                       cudaMemcpyHostToDevice, h->stream), "slab offsets H2D");
+    if (!rc && n > 0) {
+        rc = check_cuda(h, cudaMemcpyAsync(h->d_slab_idx.p, idx + frame_offsets[0], sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice,
+                                           h->stream), "slab idx H2D");
+        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_slab_val.p, val + frame_offsets[0], sizeof(int16_t) * (size_t)n,
+                                                    cudaMemcpyHostToDevice, h->stream), "slab val H2D");
+    }
+    if (rc) return rc;
+    if (frame_offsets[0] != 0) {
+        LaunchScope ls(h, "k_rebase_offsets");
+        k_rebase_offsets<<<(nframes + 256) / 256, 256, 0, h->stream>>>(h->d_slab_off.p, nframes + 1, -frame_offsets[0]);
+    }
+    h->slab_mode = true;
+    h->slab_first = first_raw_frame;
+    h->slab_frames = nframes;
+    h->slab_events = n;
+    h->slab_idx = h->d_slab_idx.p;
+    h->slab_val = h->d_slab_val.p;
+    h->slab_off = h->d_slab_off.p;
+    // timestamps of the slab's frames; the other frames' stay with their ranks (xpcs_get_timestamps)
+    h->ts_clock.assign((size_t)first_raw_frame, 0.0);
+    h->ts_ticks.assign((size_t)first_raw_frame, 0.0);
+    push_timestamps(h, clock, ticks, nframes);
+    return XPCS_OK;
+}
+
 static int dense_prepare(xpcs_handle_s *h)
 {
     if (h->dense_source) return XPCS_OK;
@@ -803,6 +901,18 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     cudaSetDevice(h->device);
     const int F = h->prm.frames;
     int rc;
+    if (h->prm.normalize_by_framesum && h->prm.shard_count > 1 && !comm_active(h))
+        return fail(h, XPCS_E_STATE, "normalize_by_framesum with shard_count > 1 needs the frame sums of all shards: call xpcs_comm_init");
+    if (h->slab_mode) {
+        std::vector<double> ck, tk;  // the slab's own timestamps survive the exchange
+        ck.swap(h->ts_clock);
+        tk.swap(h->ts_ticks);
+        if ((rc = comm_exchange_slab(h))) return rc;
+        for (size_t i = 0; i < ck.size() && i < h->ts_clock.size(); i++) {
+            h->ts_clock[i] = ck[i];
+            h->ts_ticks[i] = tk[i];
+        }
+    }
     const bool piped = h->pipe_on && !h->pipe_broken && h->pipe_chunks > 0;
     if (!h->dense_source && !h->external_events && !piped) {
         if ((rc = ensure(h, h->d_frame_off, h->frame_off_host.size(), "frame offsets"))) return rc;
@@ -821,6 +931,15 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     else rc = launch_ingest(h);
     if (rc) return rc;
     h->ingest_done = true;
+    const int windows_all0 = (F + h->prm.static_window - 1) / h->prm.static_window;
+    if (comm_active(h)) {
+        // every static bin lives on one shard and frameSum covers all pixels (sparse_filter.cpp:175,190): the
+        // element-wise sums over the shards are the single-GPU values (exact for integer counts)
+        if (!h->frame_acc_reduced && (rc = comm_allreduce_f64(h, h->d_frame_acc.p, (size_t)F))) return rc;
+        h->frame_acc_reduced = true;
+        if ((rc = comm_allreduce_f64(h, h->d_part_total.p, (size_t)h->S))) return rc;
+        if ((rc = comm_allreduce_f64(h, h->d_part_partial.p, (size_t)windows_all0 * h->S))) return rc;
+    }
 
     // ---- Filter getters, post-scaled as in main.cpp:339-343 and :360-378 ----
     // pixelSum and frameSum are formed on the device (same fp32 operations) and land in the caller's
@@ -843,6 +962,7 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
                 LaunchScope ls(h, "k_get_pixel_sum");
                 k_get_pixel_sum<<<(h->R + 255) / 256, 256, 0, h->stream>>>(h->d_row_sum.p, h->d_pixel_of_row.p, d_ps, h->R, F);
             }
+            if ((rc = comm_allreduce_f32(h, d_ps, (size_t)h->P))) return rc;  // every pixel has one owner: zeros elsewhere
             cudaMemcpyAsync(pixel_sum, d_ps, sizeof(float) * (size_t)h->P, cudaMemcpyDeviceToHost, h->stream);
         }
         if (frame_sum) cudaMemcpyAsync(frame_sum, d_fs, sizeof(float) * 2 * (size_t)F, cudaMemcpyDeviceToHost, h->stream);
@@ -959,6 +1079,45 @@ extern "C" int xpcs_multitau(xpcs_handle h, float *G2, float *IP, float *IF)
     return XPCS_OK;
 }
 
+// G2 / IP / IF of selected detector pixels, [T][n] each: the tau-major layout of xpcs_multitau restricted to the
+// listed columns (pixels this shard does not own, or masked ones, come back as zeros)
+__global__ void k_gather_correlators(const float *__restrict__ G2, const float *__restrict__ IP, const float *__restrict__ IF,
+                                     const int *__restrict__ row_of_pixel, const int *__restrict__ pixels, int n, int T,
+                                     int R_pad, int P, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (i >= n) return;
+    const int pix = pixels[i];
+    const int r = (unsigned)pix < (unsigned)P ? row_of_pixel[pix] : -1;
+    const size_t plane = (size_t)T * n, o = (size_t)t * n + i;
+    out[o] = r >= 0 ? G2[(size_t)t * R_pad + r] : 0.0f;
+    out[plane + o] = r >= 0 ? IP[(size_t)t * R_pad + r] : 0.0f;
+    out[2 * plane + o] = r >= 0 ? IF[(size_t)t * R_pad + r] : 0.0f;
+}
+
+extern "C" int xpcs_get_correlators(xpcs_handle h, const int32_t *pixels, int n, float *G2, float *IP, float *IF)
+{
+    if (!h || !pixels || n <= 0) return h ? fail(h, XPCS_E_ARG, "get_correlators: bad arguments") : XPCS_E_ARG;
+    if (!h->multitau_done) return fail(h, XPCS_E_STATE, "get_correlators before multitau");
+    cudaSetDevice(h->device);
+    const size_t plane = (size_t)h->T * n;
+    int rc = ensure(h, h->d_scratch, 3 * plane + (size_t)n + 4, "correlator gather");
+    if (rc) return rc;
+    int *d_pix = reinterpret_cast<int *>(h->d_scratch.p + 3 * plane);
+    rc = check_cuda(h, cudaMemcpyAsync(d_pix, pixels, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream), "pixel list H2D");
+    if (rc) return rc;
+    {
+        LaunchScope ls(h, "k_gather_correlators");
+        k_gather_correlators<<<dim3((n + 255) / 256, h->T), 256, 0, h->stream>>>(h->d_G2.p, h->d_IP.p, h->d_IF.p, h->d_row_of_pixel.p,
+                                                                                d_pix, n, h->T, h->R_pad, h->P, h->d_scratch.p);
+    }
+    if (G2) cudaMemcpyAsync(G2, h->d_scratch.p, sizeof(float) * plane, cudaMemcpyDeviceToHost, h->stream);
+    if (IP) cudaMemcpyAsync(IP, h->d_scratch.p + plane, sizeof(float) * plane, cudaMemcpyDeviceToHost, h->stream);
+    if (IF) cudaMemcpyAsync(IF, h->d_scratch.p + 2 * plane, sizeof(float) * plane, cudaMemcpyDeviceToHost, h->stream);
+    return check_cuda(h, cudaStreamSynchronize(h->stream), "correlator gather");
+}
+
 extern "C" int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t *count)
 {
     if (!h) return XPCS_E_ARG;
@@ -966,6 +1125,8 @@ extern "C" int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t
     cudaSetDevice(h->device);
     int rc = launch_normalize_partials(h);
     if (rc) return rc;
+    // with a communicator the exchange happens here (every segment is owned by one shard, the others hold zeros)
+    if ((rc = comm_allreduce_f64(h, h->d_partials.p, (size_t)h->partials_count))) return rc;
     h->partials_done = true;
     if (d_partials) *d_partials = h->d_partials.p;
     if (count) *count = h->partials_count;
@@ -994,14 +1155,20 @@ extern "C" int xpcs_normalize(xpcs_handle h, float *g2, float *se)
     return xpcs_normalize_finish(h, g2, se);
 }
 
-extern "C" int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int method, int average, float *C,
-                            float *g2full, float *g2partials, float *sg)
+extern "C" int xpcs_twotime_sg(xpcs_handle h, int qbin, int wsize, int method, int average, float *C,
+                               float *g2full, float *g2partials, float *sg, int *sg_rows)
 {
     if (!h) return XPCS_E_ARG;
     if (!h->ingest_done) return fail(h, XPCS_E_STATE, "twotime before finish_ingest");
     if (h->rows_consumed) return fail(h, XPCS_E_STATE, "the event rows were consumed by multitau; re-ingest");
     cudaSetDevice(h->device);
-    return launch_twotime(h, qbin, wsize, method, average, C, g2full, g2partials, sg);
+    return launch_twotime(h, qbin, wsize, method, average, C, g2full, g2partials, sg, sg_rows);
+}
+
+extern "C" int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int method, int average, float *C,
+                            float *g2full, float *g2partials, float *sg)
+{
+    return xpcs_twotime_sg(h, qbin, wsize, method, average, C, g2full, g2partials, sg, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -19,7 +19,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <algorithm>
 #include <string>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "../../include/xpcs_b200.h"
@@ -62,6 +65,7 @@ struct Flags {
     bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false, hdf5 = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     int device = 0;
+    int gpus = 1;  // --gpus N: pixel-shard a sparse multi-tau job over GPUs device .. device+N-1 (NCCL inside the library)
     int frameout = 0;
 };
 
@@ -96,9 +100,15 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "exchange") f.exchange = need();
             else if (name == "entry") f.entry = need();
             else if (name == "device") f.device = atoi(need().c_str());
+            else if (name == "gpus") f.gpus = std::max(1, atoi(need().c_str()));
             else if (name == "no_compat") f.no_compat = true;
             else if (name == "frame_threading" || name == "noframe_threading") {
-            }  // the two-time contraction has one (tensor-core) path
+                // Corr::twotime(data, frameThreading) picks between two summation orders of the same C
+                // (corr.cpp:562-572); here the contraction has one (tensor-core) path, equal to both within 1e-5
+                if (name == "frame_threading" && (!has_val || val == "true" || val == "1"))
+                    fprintf(stderr, "corr: --frame_threading selects a CPU threading strategy of the reference; the two-time "
+                                    "contraction runs on the tensor cores either way\n");
+            }
             else if (name == "frameout") f.frameout = atoi(need().c_str());
             else if (name == "ufxc") f.ufxc = !has_val || val == "true" || val == "1";
             else if (name == "rigaku") f.rigaku = !has_val || val == "true" || val == "1";
@@ -229,6 +239,346 @@ static std::string lower(std::string s)
         }                                                                              \
     } while (0)
 
+// One whole sparse input held on the host: what xpcs_push_sparse takes.
+struct SparseInput {
+    std::vector<int32_t> idx;
+    std::vector<int16_t> val;
+    std::vector<int64_t> offs;  // raw frames + 1
+    std::vector<double> clock, ticks;
+    int raw_frames() const { return (int)offs.size() - 1; }
+};
+
+static int raw_block(const Config &conf)
+{
+    int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;  // main.cpp:258-261
+    if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
+    return block;
+}
+
+// --ufxc (main.cpp:206-207; io/ufxc.cpp:59-153): a stream of 32-bit event words -- frame counter in bits 31..21
+// (11 bits, unwrapped by +-2048 when it jumps by more than 2000; the first word is frame 0), count in bits 16..15,
+// column-major pixel in bits 14..0.  Frames come out in file order, a missing frame is an empty frame, the
+// reader's SkipFrames does nothing (the frame range always starts at the first frame), clock = ticks = frame number.
+static void load_ufxc(const Config &conf, int frames, SparseInput &in)
+{
+    FILE *fp = fopen(conf.imm_path.c_str(), "rb");
+    if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
+    std::vector<uint32_t> words;
+    {
+        uint32_t buf[4096];
+        size_t got;
+        while ((got = fread(buf, sizeof(uint32_t), 4096, fp)) > 0) words.insert(words.end(), buf, buf + got);
+        fclose(fp);
+    }
+    const int64_t raw_todo = (int64_t)frames * raw_block(conf);
+    std::vector<int64_t> &count = in.offs;
+    count.assign((size_t)raw_todo + 1, 0);
+    std::vector<int64_t> frame_of(words.size(), -1);
+    if (!words.empty()) {
+        const long first = (long)(words[0] >> 21);
+        long prev = first, wrap = 0;
+        for (size_t i = 0; i < words.size(); i++) {
+            const long c = (long)(words[i] >> 21);
+            if (i > 0) {
+                const long diff = c - prev;
+                if (diff < -2000) wrap += 2048;
+                else if (diff > 2000) wrap -= 2048;
+            }
+            const long ff = c + wrap - first;
+            prev = c;
+            if (ff >= 0 && ff < raw_todo) {
+                frame_of[i] = ff;
+                count[(size_t)ff + 1]++;
+            }
+        }
+    }
+    for (int64_t f = 0; f < raw_todo; f++) count[(size_t)f + 1] += count[(size_t)f];
+    in.idx.assign((size_t)count[(size_t)raw_todo] + 1, 0);
+    in.val.assign((size_t)count[(size_t)raw_todo] + 1, 0);
+    {
+        std::vector<int64_t> cur(count.begin(), count.end() - 1);
+        const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
+        for (size_t i = 0; i < words.size(); i++) {
+            if (frame_of[i] < 0) continue;
+            const uint32_t pix = words[i] & 0x7fffu;
+            const int64_t at = cur[(size_t)frame_of[i]]++;  // file order inside a frame
+            in.idx[(size_t)at] = (int32_t)((pix % H) * W + pix / H);
+            in.val[(size_t)at] = (int16_t)((words[i] >> 15) & 0x3u);
+        }
+    }
+    in.clock.resize((size_t)raw_todo);
+    for (int64_t f = 0; f < raw_todo; f++) in.clock[(size_t)f] = (double)f;
+    in.ticks = in.clock;
+}
+
+// --hdf5 (main.cpp:211-216; io/hdf5.cpp:62-228): /entry/data/data, uint16 or uint32 [frames][.][.] (contiguous or
+// chunked with the deflate / shuffle filters -- h5lite inflates them); every non-zero sample of a frame is an event
+// at its linear index, the frames before data_begin_todo are skipped, clock = ticks = frame number in the stack.
+static void load_hdf5_stack(const Config &conf, int frames, int pixels, SparseInput &in)
+{
+    const h5lite::File stack = h5lite::File::load(conf.imm_path);
+    const h5lite::Dataset &d = stack.dataset("/entry/data/data");
+    if (d.dims.size() != 3 || (d.type != Type::U16 && d.type != Type::U32))
+        throw std::runtime_error("/entry/data/data must be a 3-d uint16 or uint32 dataset");
+    const uint64_t nfr = d.dims[0], per = d.dims[1] * d.dims[2];
+    if (per != (uint64_t)pixels) throw std::runtime_error("/entry/data/data: frame size differs from the detector");
+    const int64_t raw_todo = (int64_t)frames * raw_block(conf);
+    const int64_t first = conf.frame_start_todo > 1 ? conf.frame_start_todo - 1 : 0;  // main.cpp:241-245
+    if ((uint64_t)(first + raw_todo) > nfr) throw std::runtime_error("/entry/data/data holds too few frames");
+    in.offs.assign(1, 0);
+    const uint16_t *p16 = reinterpret_cast<const uint16_t *>(d.data.data());
+    const uint32_t *p32 = reinterpret_cast<const uint32_t *>(d.data.data());
+    for (int64_t f = first; f < first + raw_todo; f++) {
+        for (uint64_t i = 0; i < per; i++) {
+            const uint32_t v = d.type == Type::U16 ? p16[(uint64_t)f * per + i] : p32[(uint64_t)f * per + i];
+            if (v == 0) continue;
+            if (v > 32767u) throw std::runtime_error("/entry/data/data: a sample above 32767 does not fit the int16 event payload");
+            in.idx.push_back((int32_t)i);
+            in.val.push_back((int16_t)v);
+        }
+        in.offs.push_back((int64_t)in.idx.size());
+        in.clock.push_back((double)f);
+    }
+    in.ticks = in.clock;
+    in.idx.push_back(0);
+    in.val.push_back(0);
+}
+
+// --rigaku (main.cpp:208-210; io/rigaku.cpp:139-267): 64-bit event words, frame number in bits 63..40, column-major
+// pixel in bits 35..16, count in bits 10..0.  Words of frames up to data_begin_todo - 1 are skipped; with
+// stride_frames > 1 so are the words of frames that are not a multiple of the stride (:161-162).  An output frame is
+// closed when the frame number of a word differs from the previous one (avg_frames == 1) or passes the next boundary
+// data_begin_todo - 1 + k * block (avg_frames > 1) (:166-168) -- so frames without events vanish, and a run that
+// does not start where the reader expects opens with an empty output frame; reading stops when `frames` output
+// frames are closed; masked pixels are dropped after the frame bookkeeping; what is still open at the end of the
+// file counts only if it holds more than one pixel (:232); clock = ticks = output frame number.
+// The reader sums the words of an output frame per pixel and divides by avg_frames -- the arithmetic of the Filter
+// stage over a block of stride * avg raw frames (sparse_filter.cpp:143-172) -- so every output frame is handed to
+// the library as such a block, with the words in its first raw frame.
+static void load_rigaku(const Config &conf, int frames, int pixels, SparseInput &in)
+{
+    FILE *fp = fopen(conf.imm_path.c_str(), "rb");
+    if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
+    const int block = raw_block(conf);
+    const uint64_t stride = (uint64_t)conf.stride, avg = (uint64_t)conf.avg;
+    const uint64_t start = (uint64_t)(conf.frame_start_todo > 0 ? conf.frame_start_todo - 1 : 0);
+    const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
+    std::vector<int32_t> &idx = in.idx;
+    std::vector<int16_t> &val = in.val;
+    std::vector<int64_t> &offs = in.offs;
+    offs.assign(1, 0);
+    uint64_t previous = start + 1, next_expected = start + (uint64_t)block;
+    int64_t closed = 0;
+    size_t open_at = 0;  // first event of the output frame still open
+    bool stop = false;
+    auto close_frame = [&]() {
+        for (int k = 0; k < block; k++) offs.push_back((int64_t)idx.size());
+        open_at = idx.size();
+        closed++;
+    };
+    std::vector<uint64_t> buf(1 << 15);
+    size_t got;
+    while (!stop && (got = fread(buf.data(), sizeof(uint64_t), buf.size(), fp)) > 0) {
+        for (size_t i = 0; i < got; i++) {
+            const uint64_t wd = buf[i];
+            const uint64_t fr = (wd >> 40) & 0xffffffffull;
+            if (fr <= start) continue;
+            if (closed >= frames) {
+                stop = true;
+                break;
+            }
+            if (stride > 1 && fr != 0 && fr % stride != 0) continue;
+            if ((avg > 1 && fr > next_expected) || (avg == 1 && fr != previous)) {
+                close_frame();
+                previous = fr;
+                next_expected += (uint64_t)block;
+            }
+            uint32_t pix = (uint32_t)((wd >> 16) & 0xfffffu);
+            pix = (pix % H) * W + pix / H;
+            if (pix >= (uint32_t)pixels || conf.dqmap[pix] < 1 || conf.sqmap[pix] < 1) continue;
+            idx.push_back((int32_t)pix);
+            val.push_back((int16_t)(wd & 0x7ffu));
+        }
+    }
+    fclose(fp);
+    if (closed < frames) {  // the open frame: kept if it has more than one distinct pixel
+        bool two = false;
+        for (size_t k = open_at + 1; k < idx.size() && !two; k++) two = idx[k] != idx[open_at];
+        if (two) close_frame();
+        else {
+            idx.resize(open_at);
+            val.resize(open_at);
+        }
+    } else {  // all frames closed: whatever was collected for the next one is dropped
+        idx.resize((size_t)offs.back());
+        val.resize((size_t)offs.back());
+    }
+    const int64_t raw_total = (int64_t)frames * block;
+    while ((int64_t)offs.size() - 1 < raw_total) offs.push_back((int64_t)idx.size());
+    in.clock.resize((size_t)raw_total);
+    for (int64_t f = 0; f < raw_total; f++) in.clock[(size_t)f] = (double)f;
+    in.ticks = in.clock;
+    idx.push_back(0);
+    val.push_back(0);
+}
+
+// the whole frame range of a sparse IMM file (multi-GPU path; the single-GPU path streams it in batches)
+static void load_imm_sparse(xpcs_host::ImmReader &reader, const Config &conf, int frames, int pixels, SparseInput &in)
+{
+    const int frame_from = conf.frame_start_todo - 1;
+    if (frame_from > 0) reader.skip(frame_from);  // main.cpp:241-245
+    const int64_t raw_todo = (int64_t)frames * raw_block(conf);
+    xpcs_host::ImmBatch b;
+    in.offs.assign(1, 0);
+    for (int64_t done = 0; done < raw_todo;) {
+        const int n = (int)std::min<int64_t>(4096, raw_todo - done);
+        reader.next(n, b, pixels);
+        const int64_t base = (int64_t)in.idx.size();
+        in.idx.insert(in.idx.end(), b.idx.begin(), b.idx.end());
+        in.val.insert(in.val.end(), b.val.begin(), b.val.end());
+        for (int i = 1; i <= n; i++) in.offs.push_back(base + b.offsets[(size_t)i]);
+        in.clock.insert(in.clock.end(), b.clock.begin(), b.clock.end());
+        in.ticks.insert(in.ticks.end(), b.ticks.begin(), b.ticks.end());
+        done += n;
+    }
+    in.idx.push_back(0);
+    in.val.push_back(0);
+}
+
+struct FilterSums {
+    std::vector<float> pixel_sum, frame_sum, pm_total, pm_partial;
+    std::vector<double> clock, ticks;  // [2][raw frames seen]
+    int raw_seen = 0;
+};
+
+// Multi-GPU multi-tau job (--gpus N): one thread and one handle per GPU, the input cut into N slabs of frames
+// balanced by event count; the library redistributes the events to the pixel owners over NVLink and reduces the
+// sums (comm.cu), so that every rank ends with the whole-detector results.  Returns 0 or an exit code.
+static int run_sharded(const Flags &fl, XpcsParams prm, const SparseInput &in, int n_gpus, FilterSums &sums, int T, int Q,
+                       int pixels, std::vector<float> *G2, std::vector<float> *IP, std::vector<float> *IF, std::vector<float> &g2,
+                       std::vector<float> &se)
+{
+    const int raw = in.raw_frames();
+    const int64_t E = in.offs[(size_t)raw];
+    std::vector<int> cut(n_gpus + 1, raw);
+    cut[0] = 0;
+    for (int r = 1; r < n_gpus; r++) {
+        const int64_t target = E * r / n_gpus;
+        int f = (int)(std::lower_bound(in.offs.begin(), in.offs.end(), target) - in.offs.begin());
+        cut[r] = std::min(std::max(f, cut[r - 1]), raw);
+    }
+    unsigned char id[128];
+    if (int rc = xpcs_comm_unique_id(id)) {
+        fprintf(stderr, "corr: xpcs_comm_unique_id failed (%d): %s\n", rc, xpcs_last_error(nullptr));
+        return 3;
+    }
+    std::vector<xpcs_handle> hs(n_gpus, nullptr);
+    std::vector<int> status(n_gpus, 0);
+    std::vector<std::string> errors(n_gpus);
+    std::vector<std::vector<float>> pG2(n_gpus), pIP(n_gpus), pIF(n_gpus);
+    const int F = prm.frames, S_windows = F / prm.static_window;
+    XpcsInfo info0;
+    memset(&info0, 0, sizeof(info0));
+    std::vector<double> stage_ms(3, 0.0);
+    auto worker = [&](int r) {
+        XpcsParams p = prm;
+        p.shard_index = r;
+        p.shard_count = n_gpus;
+        xpcs_handle h = nullptr;
+        auto bad = [&](const char *what, int rc) {
+            status[r] = rc;
+            errors[r] = std::string(what) + ": " + (h ? xpcs_last_error(h) : xpcs_last_error(nullptr));
+        };
+        int rc = xpcs_create(&p, fl.device + r, &h);
+        if (rc) return bad("xpcs_create", rc);
+        hs[r] = h;
+        if ((rc = xpcs_comm_init(h, n_gpus, r, id))) return bad("xpcs_comm_init", rc);
+        XpcsInfo info;
+        xpcs_get_info(h, &info);
+        const int S = info.n_static;
+        auto t0 = std::chrono::steady_clock::now();
+        const int f0 = cut[r], f1 = cut[r + 1];
+        rc = xpcs_push_sparse_slab(h, f0, in.idx.data(), in.val.data(), in.offs.data() + f0, in.clock.data() + f0,
+                                   in.ticks.data() + f0, f1 - f0);
+        if (rc) return bad("xpcs_push_sparse_slab", rc);
+        std::vector<float> ps, fs, pt, pp;
+        if (r == 0) {
+            sums.pixel_sum.assign((size_t)pixels, 0.f);
+            sums.frame_sum.assign(2 * (size_t)F, 0.f);
+            sums.pm_total.assign((size_t)std::max(S, 1), 0.f);
+            sums.pm_partial.assign((size_t)std::max(S_windows, 1) * std::max(S, 1), 0.f);
+            rc = xpcs_finish_ingest(h, sums.pixel_sum.data(), sums.frame_sum.data(), sums.pm_total.data(), sums.pm_partial.data());
+        } else {  // the same collectives, results dropped
+            ps.assign((size_t)pixels, 0.f);
+            fs.assign(2 * (size_t)F, 0.f);
+            pt.assign((size_t)std::max(S, 1), 0.f);
+            pp.assign((size_t)std::max(S_windows, 1) * std::max(S, 1), 0.f);
+            rc = xpcs_finish_ingest(h, ps.data(), fs.data(), pt.data(), pp.data());
+        }
+        if (rc) return bad("xpcs_finish_ingest", rc);
+        auto t1 = std::chrono::steady_clock::now();
+        if (G2) {
+            pG2[r].resize((size_t)T * pixels);
+            pIP[r].resize((size_t)T * pixels);
+            pIF[r].resize((size_t)T * pixels);
+            rc = xpcs_multitau(h, pG2[r].data(), pIP[r].data(), pIF[r].data());
+        } else rc = xpcs_multitau(h, nullptr, nullptr, nullptr);
+        if (rc) return bad("xpcs_multitau", rc);
+        auto t2 = std::chrono::steady_clock::now();
+        std::vector<float> g2r((size_t)T * Q), ser((size_t)T * Q);
+        rc = xpcs_normalize(h, r == 0 ? g2.data() : g2r.data(), r == 0 ? se.data() : ser.data());
+        if (rc) return bad("xpcs_normalize", rc);
+        auto t3 = std::chrono::steady_clock::now();
+        if (r == 0) {
+            xpcs_get_info(h, &info0);
+            stage_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+            stage_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+            stage_ms[2] = std::chrono::duration<double, std::milli>(t3 - t2).count();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_gpus; r++) th.emplace_back(worker, r);
+    for (auto &t : th) t.join();
+    int bad_rc = 0;
+    for (int r = 0; r < n_gpus; r++)
+        if (status[r]) {
+            fprintf(stderr, "corr: rank %d: %s (%d)\n", r, errors[r].c_str(), status[r]);
+            bad_rc = 3;
+        }
+    if (!bad_rc) {
+        log_info("Loading data took %.0f ms", stage_ms[0]);
+        log_info("Computing G2 MultiTau took %.0f ms", stage_ms[1]);
+        log_info("Normalizing Data took %.0f ms", stage_ms[2]);
+        // timestamps: the input's own (every rank only saw its slab's)
+        sums.raw_seen = raw;
+        sums.clock.assign(2 * (size_t)raw, 0.0);
+        sums.ticks.assign(2 * (size_t)raw, 0.0);
+        for (int i = 0; i < raw; i++) {
+            sums.clock[i] = sums.ticks[i] = i + 1;
+            sums.clock[raw + i] = in.clock[(size_t)i];
+            sums.ticks[raw + i] = in.ticks[(size_t)i];
+        }
+        if (G2) {  // every pixel has one owner; the other ranks hold zeros there
+            *G2 = std::move(pG2[0]);
+            *IP = std::move(pIP[0]);
+            *IF = std::move(pIF[0]);
+            for (int r = 1; r < n_gpus; r++) {
+                const size_t n = (size_t)T * pixels;
+                for (size_t i = 0; i < n; i++) {
+                    (*G2)[i] += pG2[r][i];
+                    (*IP)[i] += pIP[r][i];
+                    (*IF)[i] += pIF[r][i];
+                }
+                std::vector<float>().swap(pG2[r]);
+                std::vector<float>().swap(pIP[r]);
+                std::vector<float>().swap(pIF[r]);
+            }
+        }
+    }
+    for (xpcs_handle h : hs) xpcs_destroy(h);
+    return bad_rc;
+}
+
 int main(int argc, char **argv)
 {
     Flags fl;
@@ -268,10 +618,8 @@ int main(int argc, char **argv)
     if (conf.twotime) {
         const std::string m = lower(conf.smoothing_method);
         if (m == "symmetric") method = 1;
-        else if (m == "staticmap") {
-            fprintf(stderr, "corr: smoothing_method StaticMap is not built yet (symmetric is)\n");
-            return 1;
-        } else {
+        else if (m == "staticmap") method = 2;
+        else {
             fprintf(stderr, "Smoothing method is not valid\n");  // main.cpp:160-163
             return 1;
         }
@@ -293,15 +641,7 @@ int main(int argc, char **argv)
     prm.static_window = conf.static_window > 0 ? conf.static_window : 1;
     prm.normalize_by_framesum = conf.normalize_by_framesum;
     prm.compat_flags = fl.no_compat ? 0u : XPCS_COMPAT_STALE_TAIL;
-    if (fl.rigaku) {
-        // the Rigaku reader plays the Filter stage itself and counts the static windows its own way
-        // (io/rigaku.cpp:190-193); its stride / average modes are not covered here
-        if (conf.stride > 1 || conf.avg > 1) {
-            fprintf(stderr, "corr: --rigaku with stride_frames / avg_frames > 1 is outside the scope of this build\n");
-            return 2;
-        }
-        prm.compat_flags |= XPCS_COMPAT_LATE_WINDOW;
-    }
+    if (fl.rigaku) prm.compat_flags |= XPCS_COMPAT_LATE_WINDOW;  // the reader counts the static windows its own way (io/rigaku.cpp:190-193)
     prm.lld = conf.lld;
     prm.sigma = conf.sigma;
     prm.dqmap = conf.dqmap.data();
@@ -309,6 +649,88 @@ int main(int argc, char **argv)
     prm.flatfield = conf.flatfield_enabled ? conf.flatfield.data() : nullptr;
     prm.shard_index = 0;
     prm.shard_count = 1;
+    const std::string out = conf.output_path;
+    const uint64_t uy = (uint64_t)conf.ydim, ux = (uint64_t)conf.xdim;
+
+    // ---- the sharded multi-tau job: sparse inputs only (a dense stack would cross PCIe once per GPU; two-time
+    // partitions are independent and run on one GPU each)
+    bool sharded = fl.gpus > 1 && !conf.twotime && fl.frameout <= 0;
+    std::unique_ptr<xpcs_host::ImmReader> imm_reader;
+    if (!fl.ufxc && !fl.hdf5 && !fl.rigaku) {
+        try {
+            imm_reader.reset(new xpcs_host::ImmReader(conf.imm_path));
+        } catch (const std::exception &e) {
+            fprintf(stderr, "corr: %s\n", e.what());
+            return 1;
+        }
+        if (!imm_reader->sparse()) sharded = false;
+    }
+    if (fl.gpus > 1 && !sharded) log_info("--gpus %d: this job (two-time, dense frames or --frameout) runs on one GPU", fl.gpus);
+    if (sharded) {
+        try {
+            int T = xpcs_delay_schedule(frames, conf.dpl, nullptr, nullptr, 0);
+            XpcsShardPlan plan;
+            if (int rc = xpcs_plan_shard(&prm, &plan, nullptr, 0)) {
+                fprintf(stderr, "corr: xpcs_plan_shard failed (%d): %s\n", rc, xpcs_last_error(nullptr));
+                return 3;
+            }
+            const int S = plan.n_static, Q = plan.n_dynamic;
+            SparseInput in;
+            {
+                Scope sc("Reading input");
+                if (fl.ufxc) load_ufxc(conf, frames, in);
+                else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
+                else if (fl.rigaku) load_rigaku(conf, frames, pixels, in);
+                else load_imm_sparse(*imm_reader, conf, frames, pixels, in);
+            }
+            FilterSums sums;
+            std::vector<float> G2, IP, IF, g2((size_t)T * Q), se((size_t)T * Q);
+            log_info("Sharding over %d GPUs (frame slabs in, pixel rows out)", fl.gpus);
+            if (int rc = run_sharded(fl, prm, in, fl.gpus, sums, T, Q, pixels, fl.g2out ? &G2 : nullptr, fl.g2out ? &IP : nullptr,
+                                     fl.g2out ? &IF : nullptr, g2, se))
+                return rc;
+            const int windows = frames / prm.static_window;
+            file.put(out + "/pixelSum", Type::F32, {uy, ux}, sums.pixel_sum.data());
+            file.put(out + "/frameSum", Type::F32, {2, (uint64_t)frames}, sums.frame_sum.data());
+            file.put(out + "/partition-mean-total", Type::F32, {1, (uint64_t)S}, sums.pm_total.data());
+            file.put(out + "/partition-mean-partial", Type::F32, {(uint64_t)windows, (uint64_t)S}, sums.pm_partial.data());
+            file.put(out + "/partition_norm_factor", Type::F32, {1, 1}, &conf.norm_factor);
+            std::vector<double> ck(2 * (size_t)real_frames, 0.0), tk(2 * (size_t)real_frames, 0.0);
+            for (int i = 0; i < real_frames && i < sums.raw_seen; i++) {
+                ck[i] = sums.clock[i];
+                ck[real_frames + i] = sums.clock[sums.raw_seen + i];
+                tk[i] = sums.ticks[i];
+                tk[real_frames + i] = sums.ticks[sums.raw_seen + i];
+            }
+            if (fl.rigaku)
+                for (int i = 0; i < real_frames; i++) {
+                    ck[i] = tk[i] = (double)i;
+                    ck[real_frames + i] = tk[real_frames + i] = 0.0;
+                }
+            file.put(out + "/timestamp_clock", Type::F64, {2, (uint64_t)real_frames}, ck.data());
+            file.put(out + "/timestamp_tick", Type::F64, {2, (uint64_t)real_frames}, tk.data());
+            std::vector<int32_t> lv(T), tv(T);
+            xpcs_delay_schedule(frames, conf.dpl, lv.data(), tv.data(), T);
+            std::vector<float> tau(T);
+            for (int i = 0; i < T; i++) tau[i] = (float)tv[i];
+            file.put(out + "/tau", Type::F32, {1, (uint64_t)T}, tau.data());
+            file.put(out + "/norm-0-g2", Type::F32, {(uint64_t)T, (uint64_t)Q}, g2.data());
+            file.put(out + "/norm-0-stderr", Type::F32, {(uint64_t)T, (uint64_t)Q}, se.data());
+            if (fl.g2out) {
+                Scope sc("Writing G2s, IPs and IFs");
+                file.put(out + "/G2", Type::F32, {(uint64_t)T, (uint64_t)pixels}, G2.data());
+                file.put(out + "/IP", Type::F32, {(uint64_t)T, (uint64_t)pixels}, IP.data());
+                file.put(out + "/IF", Type::F32, {(uint64_t)T, (uint64_t)pixels}, IF.data());
+            }
+            Scope sc("Writing results");
+            file.save(fl.config);
+        } catch (const std::exception &e) {
+            fprintf(stderr, "corr: %s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
+
     xpcs_handle h = nullptr;
     if (int rc = xpcs_create(&prm, fl.device, &h)) {
         fprintf(stderr, "corr: xpcs_create failed (%d): %s\n", rc, xpcs_last_error(nullptr));
@@ -317,165 +739,20 @@ int main(int argc, char **argv)
     XpcsInfo info;
     CHECK(xpcs_get_info(h, &info));
     const int T = info.n_delays, S = info.n_static, Q = info.n_dynamic;
-    const std::string out = conf.output_path;
-    const uint64_t uy = (uint64_t)conf.ydim, ux = (uint64_t)conf.xdim;
 
     try {
         bool had_dark = false;
         {
             Scope sc("Loading data");
-            if (fl.ufxc) {
-                // --ufxc (main.cpp:206-207; io/ufxc.cpp:59-153): a stream of 32-bit event words -- frame counter
-                // in bits 31..21 (11 bits, unwrapped by +-2048 when it jumps by more than 2000; the first word
-                // is frame 0), count in bits 16..15, column-major pixel in bits 14..0.  Frames come out in
-                // file order, a missing frame is an empty frame, the reader's SkipFrames does nothing (the
-                // frame range always starts at the first frame), clock = ticks = frame number.
-                FILE *fp = fopen(conf.imm_path.c_str(), "rb");
-                if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
-                std::vector<uint32_t> words;
-                {
-                    uint32_t buf[4096];
-                    size_t got;
-                    while ((got = fread(buf, sizeof(uint32_t), 4096, fp)) > 0) words.insert(words.end(), buf, buf + got);
-                    fclose(fp);
-                }
-                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
-                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
-                const int64_t raw_todo = (int64_t)frames * block;
-                std::vector<int64_t> count((size_t)raw_todo + 1, 0);
-                std::vector<int64_t> frame_of(words.size(), -1);
-                if (!words.empty()) {
-                    const long first = (long)(words[0] >> 21);
-                    long prev = first, wrap = 0;
-                    for (size_t i = 0; i < words.size(); i++) {
-                        const long c = (long)(words[i] >> 21);
-                        if (i > 0) {
-                            const long diff = c - prev;
-                            if (diff < -2000) wrap += 2048;
-                            else if (diff > 2000) wrap -= 2048;
-                        }
-                        const long ff = c + wrap - first;
-                        prev = c;
-                        if (ff >= 0 && ff < raw_todo) {
-                            frame_of[i] = ff;
-                            count[(size_t)ff + 1]++;
-                        }
-                    }
-                }
-                for (int64_t f = 0; f < raw_todo; f++) count[(size_t)f + 1] += count[(size_t)f];
-                std::vector<int32_t> idx((size_t)count[(size_t)raw_todo] + 1);
-                std::vector<int16_t> val((size_t)count[(size_t)raw_todo] + 1);
-                {
-                    std::vector<int64_t> cur(count.begin(), count.end() - 1);
-                    const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
-                    for (size_t i = 0; i < words.size(); i++) {
-                        if (frame_of[i] < 0) continue;
-                        const uint32_t pix = words[i] & 0x7fffu;
-                        const int64_t at = cur[(size_t)frame_of[i]]++;  // file order inside a frame
-                        idx[(size_t)at] = (int32_t)((pix % H) * W + pix / H);
-                        val[(size_t)at] = (int16_t)((words[i] >> 15) & 0x3u);
-                    }
-                }
-                std::vector<double> stamp((size_t)raw_todo);
-                for (int64_t f = 0; f < raw_todo; f++) stamp[(size_t)f] = (double)f;
-                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), count.data(), stamp.data(), stamp.data(), (int)raw_todo));
-            } else if (fl.hdf5) {
-                // --hdf5 (main.cpp:211-216; io/hdf5.cpp:62-228): /entry/data/data, uint16 or uint32 [frames][.][.];
-                // every non-zero sample of a frame is an event at its linear index, the frames before
-                // data_begin_todo are skipped, clock = ticks = frame number in the stack.
-                const h5lite::File stack = h5lite::File::load(conf.imm_path);
-                const h5lite::Dataset &d = stack.dataset("/entry/data/data");
-                if (d.dims.size() != 3 || (d.type != Type::U16 && d.type != Type::U32))
-                    throw std::runtime_error("/entry/data/data must be a 3-d uint16 or uint32 dataset");
-                const uint64_t nfr = d.dims[0], per = d.dims[1] * d.dims[2];
-                if (per != (uint64_t)pixels) throw std::runtime_error("/entry/data/data: frame size differs from the detector");
-                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
-                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
-                const int64_t raw_todo = (int64_t)frames * block;
-                const int64_t first = conf.frame_start_todo > 1 ? conf.frame_start_todo - 1 : 0;  // main.cpp:241-245
-                if ((uint64_t)(first + raw_todo) > nfr) throw std::runtime_error("/entry/data/data holds too few frames");
-                std::vector<int32_t> idx;
-                std::vector<int16_t> val;
-                std::vector<int64_t> offs(1, 0);
-                std::vector<double> stamp;
-                const uint16_t *p16 = reinterpret_cast<const uint16_t *>(d.data.data());
-                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(d.data.data());
-                for (int64_t f = first; f < first + raw_todo; f++) {
-                    for (uint64_t i = 0; i < per; i++) {
-                        const uint32_t v = d.type == Type::U16 ? p16[(uint64_t)f * per + i] : p32[(uint64_t)f * per + i];
-                        if (v == 0) continue;
-                        if (v > 32767u) throw std::runtime_error("/entry/data/data: a sample above 32767 does not fit the int16 event payload");
-                        idx.push_back((int32_t)i);
-                        val.push_back((int16_t)v);
-                    }
-                    offs.push_back((int64_t)idx.size());
-                    stamp.push_back((double)f);
-                }
-                idx.push_back(0);
-                val.push_back(0);
-                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), offs.data(), stamp.data(), stamp.data(), (int)raw_todo));
-            } else if (fl.rigaku) {
-                // --rigaku (main.cpp:208-210; io/rigaku.cpp:139-267, stride = average = 1): 64-bit event words,
-                // frame number in bits 63..40, column-major pixel in bits 35..16, count in bits 10..0.  Words of
-                // frames up to data_begin_todo - 1 are skipped; an output frame is closed when the frame number
-                // changes, so frames without events vanish (a run that does not start at data_begin_todo opens
-                // with an empty output frame); reading stops when `frames` output frames are closed; masked
-                // pixels are dropped after the frame bookkeeping; the frame still open at the end of the file
-                // counts only if it holds more than one pixel; clock = ticks = output frame number.
-                FILE *fp = fopen(conf.imm_path.c_str(), "rb");
-                if (!fp) throw std::runtime_error("cannot open " + conf.imm_path);
-                const uint64_t start = (uint64_t)(conf.frame_start_todo > 0 ? conf.frame_start_todo - 1 : 0);
-                const uint32_t H = (uint32_t)conf.ydim, W = (uint32_t)conf.xdim;
-                std::vector<int32_t> idx;
-                std::vector<int16_t> val;
-                std::vector<int64_t> offs(1, 0);
-                uint64_t open_frame = start + 1;
-                size_t open_at = 0;  // first event of the frame still open
-                bool stop = false;
-                std::vector<uint64_t> buf(1 << 15);
-                size_t got;
-                while (!stop && (got = fread(buf.data(), sizeof(uint64_t), buf.size(), fp)) > 0) {
-                    for (size_t i = 0; i < got; i++) {
-                        const uint64_t wd = buf[i];
-                        const uint64_t fr = (wd >> 40) & 0xffffffffull;
-                        if (fr <= start) continue;
-                        if ((int64_t)offs.size() - 1 >= frames) {
-                            stop = true;
-                            break;
-                        }
-                        if (fr != open_frame) {
-                            offs.push_back((int64_t)idx.size());
-                            open_frame = fr;
-                            open_at = idx.size();
-                        }
-                        uint32_t pix = (uint32_t)((wd >> 16) & 0xfffffu);
-                        pix = (pix % H) * W + pix / H;
-                        if (pix >= (uint32_t)pixels || conf.dqmap[pix] < 1 || conf.sqmap[pix] < 1) continue;
-                        idx.push_back((int32_t)pix);
-                        val.push_back((int16_t)(wd & 0x7ffu));
-                    }
-                }
-                fclose(fp);
-                if ((int64_t)offs.size() - 1 < frames) {  // the open frame: kept if it has more than one distinct pixel
-                    bool two = false;
-                    for (size_t k = open_at + 1; k < idx.size() && !two; k++) two = idx[k] != idx[open_at];
-                    if (two) offs.push_back((int64_t)idx.size());
-                    else {
-                        idx.resize(open_at);
-                        val.resize(open_at);
-                    }
-                } else {  // `frames` closed: whatever was collected for the next one is dropped
-                    idx.resize((size_t)offs.back());
-                    val.resize((size_t)offs.back());
-                }
-                while ((int64_t)offs.size() - 1 < frames) offs.push_back((int64_t)idx.size());
-                std::vector<double> stamp((size_t)frames);
-                for (int f = 0; f < frames; f++) stamp[(size_t)f] = (double)f;
-                idx.push_back(0);
-                val.push_back(0);
-                CHECK(xpcs_push_sparse(h, idx.data(), val.data(), offs.data(), stamp.data(), stamp.data(), frames));
+            if (fl.ufxc || fl.hdf5 || fl.rigaku) {
+                SparseInput in;
+                if (fl.ufxc) load_ufxc(conf, frames, in);
+                else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
+                else load_rigaku(conf, frames, pixels, in);
+                CHECK(xpcs_push_sparse(h, in.idx.data(), in.val.data(), in.offs.data(), in.clock.data(), in.ticks.data(),
+                                       in.raw_frames()));
             } else {
-                xpcs_host::ImmReader reader(conf.imm_path);
+                xpcs_host::ImmReader &reader = *imm_reader;
                 xpcs_host::ImmBatch b;
                 int r = 0;
                 if (!reader.sparse() && conf.darks > 0) {  // main.cpp:227-239: darks come from the file start
@@ -486,9 +763,7 @@ int main(int argc, char **argv)
                 }
                 const int frame_from = conf.frame_start_todo - 1;
                 if (frame_from > 0 && r < frame_from) reader.skip(frame_from - r);  // main.cpp:241-245
-                int block = conf.stride > 1 ? (int)conf.stride : (int)conf.avg;      // main.cpp:258-261
-                if (conf.stride > 1 && conf.avg > 1) block = (int)(conf.stride * conf.avg);
-                const int64_t raw_todo = (int64_t)frames * block;
+                const int64_t raw_todo = (int64_t)frames * raw_block(conf);
                 const int chunk = reader.sparse() ? 4096 : std::max(1, (int)((256ll << 20) / ((int64_t)pixels * 2)));
                 for (int64_t done = 0; done < raw_todo;) {
                     const int n = (int)std::min<int64_t>(chunk, raw_todo - done);
@@ -557,11 +832,15 @@ int main(int argc, char **argv)
             const bool average = conf.smoothing_filter == "Average";
             const int F = frames, w = conf.wsize, partials = std::max((F - w) / w, 0);
             const size_t B = bins.size();
-            std::vector<float> C((size_t)F * F), gf(F), gp((size_t)std::max(w * partials, 1)), sg(average ? 1 : F);
-            std::vector<float> g2full((size_t)F * B), g2part((size_t)w * partials * B), sgall((average ? 1 : (size_t)F) * B);
+            const size_t sg_cols = average ? 1 : (size_t)F;
+            std::vector<float> C((size_t)F * F), gf(F), gp((size_t)std::max(w * partials, 1));
+            std::vector<float> g2full((size_t)F * B), g2part((size_t)w * partials * B);
+            std::vector<float> sgall;   // rows: one per dynamic bin (symmetric) or per static bin of the bins (StaticMap)
+            std::vector<float> sg((size_t)std::max(S, 1) * sg_cols);
             size_t b = 0;
             for (int q : bins) {
-                int rc = xpcs_twotime(h, q, w, method, average ? 1 : 0, C.data(), gf.data(), gp.data(), sg.data());
+                int sg_rows = 0;
+                int rc = xpcs_twotime_sg(h, q, w, method, average ? 1 : 0, C.data(), gf.data(), gp.data(), sg.data(), &sg_rows);
                 if (rc == XPCS_E_ARG) continue;  // partition without pixels: the reference skips it too
                 if (rc) {
                     fprintf(stderr, "corr: xpcs_twotime failed (%d): %s\n", rc, xpcs_last_error(h));
@@ -573,10 +852,10 @@ int main(int argc, char **argv)
                 for (int f = 0; f < F; f++) g2full[(size_t)f * B + b] = gf[f];
                 for (int d = 0; d < w; d++)
                     for (int p = 0; p < partials; p++) g2part[((size_t)d * partials + p) * B + b] = gp[(size_t)d * partials + p];
-                for (size_t i = 0; i < sg.size(); i++) sgall[b * sg.size() + i] = sg[i];
+                sgall.insert(sgall.end(), sg.begin(), sg.begin() + (size_t)sg_rows * sg_cols);
                 b++;
             }
-            file.put(out + "/sg", Type::F32, {(uint64_t)B, (uint64_t)sg.size()}, sgall.data());
+            file.put(out + "/sg", Type::F32, {(uint64_t)(sgall.size() / sg_cols), (uint64_t)sg_cols}, sgall.data());
             file.put(out + "/g2full", Type::F32, {(uint64_t)F, (uint64_t)B}, g2full.data());
             file.put(out + "/g2partials", Type::F32, {(uint64_t)w, (uint64_t)partials, (uint64_t)B}, g2part.data());
         } else {
