@@ -3,7 +3,7 @@
 TAG=${1:-r2a}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -2
-timeout 1700 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+timeout 1700 python -m pytest tests -m gpu -q 2>&1 | tail -40
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 summ() {
 python - "$1" <<'PY'

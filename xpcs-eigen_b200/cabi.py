@@ -102,6 +102,24 @@ SYMBOLS = {
 _lib = None
 
 
+def _pick_nccl():
+    """The library binds NCCL at run time (csrc/comm.cu: an NCCL already in the process, else $XPCS_NCCL_LIB, else
+    the system libnccl.so.2).  In a Python process PyTorch may be imported LATER and would then be handed whatever
+    libnccl.so.2 is already loaded, so point the library at the copy PyTorch itself ships (no torch import here)."""
+    if os.environ.get("XPCS_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["XPCS_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load libxpcs_b200.so; raises (never falls back) when it is missing."""
     global _lib
@@ -111,6 +129,7 @@ def load():
         raise ImportError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C xpcs-eigen_b200 lib`). There is no CPU fallback." % LIB_PATH)
+    _pick_nccl()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError = header/library drift

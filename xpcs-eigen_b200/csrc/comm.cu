@@ -49,11 +49,13 @@ NcclApi *nccl_api()
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // an NCCL the process already carries (PyTorch's) first; then the caller's choice; then the system library
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
         const char *names[] = {getenv("XPCS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
+            if (api.lib) break;
             if (!n || !*n) continue;
             api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
-            if (api.lib) break;
         }
         if (!api.lib) {
             api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");

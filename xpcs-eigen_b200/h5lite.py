@@ -33,6 +33,11 @@ def _load():
         L.h5l_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_ulonglong]
         L.h5l_put.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_void_p,
                               C.c_ulonglong]
+        L.h5l_extra_count.argtypes = [C.c_void_p, C.c_char_p]
+        L.h5l_extra_get.restype = C.c_long
+        L.h5l_extra_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_long]
+        L.h5l_report.restype = C.c_long
+        L.h5l_report.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_long]
         _lib = L
     return _lib
 
@@ -108,6 +113,27 @@ class File:
             rc = L.h5l_put(self._h, path.encode(), code, a.ndim, dims, a.ctypes.data, 0)
         if rc != 0:
             raise H5Error(L.h5l_error().decode())
+
+    def extra(self, path):
+        """[(message type, raw bytes)] of the attribute (0x0C) / comment (0x0D) messages carried by `path`."""
+        L = _load()
+        out = []
+        for i in range(max(L.h5l_extra_count(self._h, path.encode()), 0)):
+            t = C.c_int()
+            n = L.h5l_extra_get(self._h, path.encode(), i, C.byref(t), None, 0)
+            buf = C.create_string_buffer(max(n, 1))
+            L.h5l_extra_get(self._h, path.encode(), i, C.byref(t), buf, n)
+            out.append((t.value, buf.raw[:n]))
+        return out
+
+    def report(self, which="lossy"):
+        """lines of File::lossy (content a save cannot reproduce) or File::notes (re-encoded content)."""
+        L = _load()
+        w = 0 if which == "lossy" else 1
+        n = L.h5l_report(self._h, w, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        L.h5l_report(self._h, w, buf, n + 1)
+        return [x for x in buf.value.decode().split("\n") if x]
 
     def walk(self, group="/"):
         """{relative path: value} of every dataset below `group`."""

@@ -64,6 +64,7 @@ struct Scope {
 struct Flags {
     bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false, hdf5 = false;
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
+    std::string outfile;  // --outfile=PATH: write configuration + results there and leave the input file untouched
     int device = 0;
     int gpus = 1;  // --gpus N: pixel-shard a sparse multi-tau job over GPUs device .. device+N-1 (NCCL inside the library)
     int frameout = 0;
@@ -99,6 +100,7 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "outpath") f.outpath = need();
             else if (name == "exchange") f.exchange = need();
             else if (name == "entry") f.entry = need();
+            else if (name == "outfile") f.outfile = need();
             else if (name == "device") f.device = atoi(need().c_str());
             else if (name == "gpus") f.gpus = std::max(1, atoi(need().c_str()));
             else if (name == "no_compat") f.no_compat = true;
@@ -595,6 +597,32 @@ int main(int argc, char **argv)
         fprintf(stderr, "corr: %s\n", e.what());
         return 1;
     }
+    // The results go back into the configuration file (h5_result.cpp:67-103).  h5lite rewrites the file whole:
+    // attributes and comments are carried over verbatim, everything else it read is written back with the same
+    // values; content it cannot reproduce is reported, and the input is then kept as <file>.orig.
+    const std::string result_file = fl.outfile.empty() ? fl.config : fl.outfile;
+    for (const std::string &n : file.notes) log_info("note: %s", n.c_str());
+    if (!file.lossy.empty()) {
+        for (const std::string &n : file.lossy) fprintf(stderr, "corr: warning: %s\n", n.c_str());
+        if (fl.outfile.empty()) {
+            const std::string bak = fl.config + ".orig";
+            struct stat sb;
+            if (stat(bak.c_str(), &sb) != 0) {
+                FILE *src = fopen(fl.config.c_str(), "rb"), *dst = fopen(bak.c_str(), "wb");
+                bool ok = src && dst;
+                char buf[1 << 16];
+                size_t got;
+                while (ok && (got = fread(buf, 1, sizeof(buf), src)) > 0) ok = fwrite(buf, 1, got, dst) == got;
+                if (src) fclose(src);
+                if (dst) fclose(dst);
+                if (!ok) {
+                    fprintf(stderr, "corr: cannot keep a backup of %s; use --outfile to write the results elsewhere\n", fl.config.c_str());
+                    return 1;
+                }
+            }
+            fprintf(stderr, "corr: warning: the input file holds content that cannot be carried over; original kept as %s\n", bak.c_str());
+        }
+    }
     if (!fl.imm.empty()) conf.imm_path = fl.imm;
     if (!fl.inpath.empty() && !fl.outpath.empty()) {  // main.cpp:127-140
         size_t pos = conf.imm_path.find(fl.inpath);
@@ -723,7 +751,7 @@ int main(int argc, char **argv)
                 file.put(out + "/IF", Type::F32, {(uint64_t)T, (uint64_t)pixels}, IF.data());
             }
             Scope sc("Writing results");
-            file.save(fl.config);
+            file.save(result_file);
         } catch (const std::exception &e) {
             fprintf(stderr, "corr: %s\n", e.what());
             return 1;
@@ -890,7 +918,7 @@ int main(int argc, char **argv)
         }
         {
             Scope sc("Writing results");
-            file.save(fl.config);
+            file.save(result_file);
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "corr: %s\n", e.what());

@@ -176,6 +176,8 @@ struct Rd {
     uint64_t base = 0;
     int so = 8, sl = 8;
     int depth = 0;
+    std::vector<std::string> *lossy = nullptr, *notes = nullptr;
+    std::string path;  // of the node being read
 
     const uint8_t *at(uint64_t off, uint64_t n) const
     {
@@ -203,6 +205,7 @@ struct Msg {
     int type;
     uint64_t pos;  // absolute file offset of the message data
     int size;
+    int flags;
 };
 
 std::vector<Msg> read_object_header(const Rd &r, uint64_t addr)
@@ -221,6 +224,7 @@ std::vector<Msg> read_object_header(const Rd &r, uint64_t addr)
             Msg m;
             m.type = r.u16(p);
             m.size = r.u16(p + 2);
+            m.flags = r.u8(p + 4);
             m.pos = p + 8;
             r.at(m.pos, m.size);
             if (m.type == 0x0010) blocks.emplace_back(r.abs(r.off_(m.pos)), r.len_(m.pos + r.so));
@@ -379,6 +383,51 @@ std::string read_vlen_string(const Rd &r, const uint8_t *elem)
 
 void read_node(Rd &r, uint64_t ohdr_addr, Node &node);
 
+// Can an attribute message be copied byte for byte into another file?  Not if the message is shared, or if its
+// datatype / dataspace are shared, or if its values live in the global heap (variable-length, reference).
+bool attribute_is_self_contained(const Rd &r, const Msg &m, std::string &name)
+{
+    if (m.size < 8) return false;
+    const int ver = r.u8(m.pos);
+    const int name_sz = r.u16(m.pos + 2);
+    uint64_t p = m.pos + (ver == 3 ? 9 : 8);
+    if (ver < 1 || ver > 3 || p + name_sz > m.pos + m.size) return false;
+    const char *nm = (const char *)r.at(p, name_sz);
+    name.assign(nm, strnlen(nm, name_sz));
+    if (m.flags & 0x02) return false;                      // shared message
+    if (ver >= 2 && (r.u8(m.pos + 1) & 0x03)) return false;  // shared datatype / dataspace
+    p += ver == 1 ? ((uint64_t)name_sz + 7) & ~7ull : (uint64_t)name_sz;
+    if (p + 4 > m.pos + m.size) return false;
+    const int cls = r.u8(p) & 0x0f;
+    return cls == 0 || cls == 1 || cls == 3 || cls == 4 || cls == 5 || cls == 8;
+}
+
+void collect_extra(Rd &r, const std::vector<Msg> &msgs, Node &node)
+{
+    for (const Msg &m : msgs) {
+        if (m.type == 0x000C) {
+            std::string name;
+            if (attribute_is_self_contained(r, m, name)) {
+                RawMessage x;
+                x.type = (uint16_t)m.type;
+                x.flags = (uint8_t)(m.flags & ~0x02);
+                x.body.assign(r.at(m.pos, m.size), r.at(m.pos, m.size) + m.size);
+                x.body.resize((x.body.size() + 7) & ~7ull, 0);
+                node.extra.push_back(std::move(x));
+            } else if (r.lossy)
+                r.lossy->push_back("attribute '" + name + "' of " + (r.path.empty() ? "/" : r.path) +
+                                   " (variable-length, reference or shared: cannot be carried over)");
+        } else if (m.type == 0x000D && !(m.flags & 0x02)) {
+            RawMessage x;
+            x.type = (uint16_t)m.type;
+            x.flags = (uint8_t)m.flags;
+            x.body.assign(r.at(m.pos, m.size), r.at(m.pos, m.size) + m.size);
+            x.body.resize((x.body.size() + 7) & ~7ull, 0);
+            node.extra.push_back(std::move(x));
+        } else if (m.type == 0x0007 && r.lossy) r.lossy->push_back("external storage of " + r.path);
+    }
+}
+
 void read_group_entries(Rd &r, uint64_t btree, uint64_t heap, Node &node)
 {
     const uint64_t h = r.abs(heap);
@@ -407,7 +456,10 @@ void read_group_entries(Rd &r, uint64_t btree, uint64_t heap, Node &node)
             const char *nm = (const char *)r.at(hdata + noff, 1);
             std::string name(nm, strnlen(nm, r.buf.size() - (hdata + noff)));
             std::unique_ptr<Node> c(new Node());
+            const std::string outer = r.path;
+            r.path = outer + "/" + name;
             read_node(r, oaddr, *c);
+            r.path = outer;
             node.children[name] = std::move(c);
         }
     }
@@ -426,6 +478,7 @@ void read_node(Rd &r, uint64_t ohdr_addr, Node &node)
         else if (m.type == 0x000B) pipeline = &m;
         else if (m.type == 0x0002) throw Error("new-style (link info) groups are not supported");
     }
+    collect_extra(r, msgs, node);
     if (stab) {
         node.is_group = true;
         read_group_entries(r, r.off_(stab->pos), r.off_(stab->pos + r.so), node);
@@ -484,6 +537,7 @@ void read_node(Rd &r, uint64_t ohdr_addr, Node &node)
                 }
             }
             read_chunk_tree(r, bt, rank, d.dims, cd, disk_es, filters, raw);
+            if (r.notes) r.notes->push_back(r.path + ": chunked" + (filters.empty() ? "" : " + filtered") + " -> contiguous");
         } else throw Error("unsupported layout class");
     } else if (lver == 1 || lver == 2) {
         const int dim = r.u8(layout->pos + 1);
@@ -505,6 +559,7 @@ void read_node(Rd &r, uint64_t ohdr_addr, Node &node)
         } else throw Error("unsupported layout class");
     } else throw Error("unsupported layout message version");
     if (ti.vlen_string) {
+        if (r.notes) r.notes->push_back(r.path + ": variable-length string -> fixed-length string");
         std::string s = n ? read_vlen_string(r, raw.data()) : std::string();
         d.elem_size = s.size() + 1;
         d.dims = {1};
@@ -550,6 +605,8 @@ File File::load(const std::string &path)
     // root symbol table entry
     const uint64_t root_ohdr = r.off_(p + r.so);
     File out;
+    r.lossy = &out.lossy;
+    r.notes = &out.notes;
     read_node(r, root_ohdr, out.root);
     if (!out.root.is_group) throw Error("root object is not a group");
     return out;
@@ -615,8 +672,27 @@ size_t datatype_body(const Dataset &d, uint8_t *out)
     }
 }
 
-uint64_t write_dataset(Wr &w, const Dataset &d)
+size_t extra_bytes(const Node &n)
 {
+    size_t b = 0;
+    for (const RawMessage &x : n.extra) b += 8 + x.body.size();
+    return b;
+}
+
+void write_extra(Wr &w, uint64_t &p, const Node &n)
+{
+    for (const RawMessage &x : n.extra) {
+        w.w16(p, x.type);
+        w.w16(p + 2, (uint32_t)x.body.size());
+        w.w8(p + 4, x.flags);
+        w.bytes(p + 8, x.body.data(), x.body.size());
+        p += 8 + x.body.size();
+    }
+}
+
+uint64_t write_dataset(Wr &w, const Node &node)
+{
+    const Dataset &d = node.ds;
     const uint64_t nbytes = d.data.size();
     const uint64_t daddr = nbytes ? w.alloc(nbytes) : UNDEF;
     if (nbytes) w.bytes(daddr, d.data.data(), nbytes);
@@ -626,10 +702,10 @@ uint64_t write_dataset(Wr &w, const Dataset &d)
     const size_t space_sz = 8 + 8ull * rank;
     const size_t type_sz = (tlen + 7) & ~7ull;
     const size_t fill_sz = 8, layout_sz = 24;
-    const size_t hsize = 4 * 8 + space_sz + type_sz + fill_sz + layout_sz;
+    const size_t hsize = 4 * 8 + space_sz + type_sz + fill_sz + layout_sz + extra_bytes(node);
     const uint64_t o = w.alloc(16 + hsize);
     w.w8(o, 1);
-    w.w16(o + 2, 4);
+    w.w16(o + 2, 4 + (uint32_t)node.extra.size());
     w.w32(o + 4, 1);
     w.w32(o + 8, (uint32_t)hsize);
     uint64_t p = o + 16;
@@ -654,6 +730,7 @@ uint64_t write_dataset(Wr &w, const Dataset &d)
     w.w8(q + 1, 1);
     w.w64(q + 2, daddr);
     w.w64(q + 10, nbytes);
+    write_extra(w, p, node);
     return o;
 }
 
@@ -664,7 +741,7 @@ GroupAddr write_group(Wr &w, const Node &g)
     // children first
     std::vector<std::pair<std::string, uint64_t>> entries;  // std::map order == strcmp order for ASCII
     for (auto &kv : g.children) {
-        uint64_t addr = kv.second->is_group ? write_group(w, *kv.second).ohdr : write_dataset(w, kv.second->ds);
+        uint64_t addr = kv.second->is_group ? write_group(w, *kv.second).ohdr : write_dataset(w, *kv.second);
         entries.emplace_back(kv.first, addr);
     }
     if ((int)entries.size() > 2 * kLeafK * 2 * kIntK) throw Error("too many entries in one group");
@@ -719,17 +796,19 @@ GroupAddr write_group(Wr &w, const Node &g)
         p += 16;
     }
     // object header: symbol-table message + a NIL message
-    const uint64_t o = w.alloc(16 + 32);
+    const uint64_t o = w.alloc(16 + 32 + extra_bytes(g));
     w.w8(o, 1);
-    w.w16(o + 2, 2);
+    w.w16(o + 2, 2 + (uint32_t)g.extra.size());
     w.w32(o + 4, 1);
-    w.w32(o + 8, 32);
+    w.w32(o + 8, 32 + (uint32_t)extra_bytes(g));
     w.w16(o + 16, 0x0011);
     w.w16(o + 18, 16);
     w.w64(o + 24, bt);
     w.w64(o + 32, heap);
     w.w16(o + 40, 0x0000);
     w.w16(o + 42, 0);
+    uint64_t xp = o + 48;
+    write_extra(w, xp, g);
     return GroupAddr{o, bt, heap};
 }
 

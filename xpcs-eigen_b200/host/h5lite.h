@@ -14,6 +14,12 @@
 //        library reads.  A file is held as an in-memory tree; save() rewrites it whole, which
 //        gives the reference's "open RDWR, add or overwrite datasets" behaviour
 //        (h5_result.cpp:67-103) without in-place B-tree surgery.
+// Attribute and object-comment messages of groups and datasets are carried over VERBATIM (the reference opens
+// the user's file read-write and only adds datasets, h5_result.cpp:67-103, so a rewrite must not strip
+// metadata); an attribute whose bytes point elsewhere in the file (variable-length or reference data, shared
+// datatypes) cannot be moved that way: it is listed in File::lossy and the host program then keeps a backup of
+// the input.  Datasets found chunked / compressed / with variable-length strings are rewritten contiguous /
+// fixed-length (same values; listed in File::notes).
 // Not supported (reported as errors, never silently skipped): superblock v2/v3, v2 object
 // headers ("OHDR"), compound / array / reference datatypes, external storage.
 #pragma once
@@ -45,8 +51,15 @@ struct Dataset {
     double scalar() const;
 };
 
+struct RawMessage {   // an object-header message kept as found (attribute 0x000C, comment 0x000D)
+    uint16_t type = 0;
+    uint8_t flags = 0;
+    std::vector<uint8_t> body;   // length is a multiple of 8 (version-1 object headers)
+};
+
 struct Node {
     bool is_group = true;
+    std::vector<RawMessage> extra;                           // carried over by save()
     std::map<std::string, std::unique_ptr<Node>> children;  // groups (sorted by name, as SNODs are)
     Dataset ds;                                              // datasets
 };
@@ -71,6 +84,8 @@ public:
     Dataset &put_string(const std::string &path, const std::string &value);
     std::vector<std::string> list(const std::string &group) const;
     Node root;
+    std::vector<std::string> lossy;   // content of the loaded file a save() cannot reproduce
+    std::vector<std::string> notes;   // content a save() reproduces in another encoding (same values)
 };
 
 }  // namespace h5lite

@@ -87,4 +87,33 @@ int h5l_put(void *h, const char *path, int type, int rank, const unsigned long l
     }
 }
 
+// attribute / comment messages carried by the object at `path`: count, and raw body i (returns its length)
+int h5l_extra_count(void *h, const char *path)
+{
+    const Node *n = ((File *)h)->find(path);
+    return n ? (int)n->extra.size() : -1;
+}
+
+long h5l_extra_get(void *h, const char *path, int i, int *type, void *out, long cap)
+{
+    const Node *n = ((File *)h)->find(path);
+    if (!n || i < 0 || i >= (int)n->extra.size()) return -1;
+    const RawMessage &x = n->extra[(size_t)i];
+    if (type) *type = x.type;
+    if (out && cap >= (long)x.body.size() && !x.body.empty()) memcpy(out, x.body.data(), x.body.size());
+    return (long)x.body.size();
+}
+
+// newline-separated: which = 0 lossy, 1 notes
+long h5l_report(void *h, int which, char *buf, long cap)
+{
+    std::string s;
+    for (const std::string &n : (which == 0 ? ((File *)h)->lossy : ((File *)h)->notes)) s += n + "\n";
+    if (buf && cap > 0) {
+        strncpy(buf, s.c_str(), (size_t)cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (long)s.size() + 1;
+}
+
 }  // extern "C"
