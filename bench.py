@@ -477,11 +477,14 @@ def bench_twotime(args, wl):
     rep = c.kernel_report(reset=True)
     gemm_ms = rep["k_twotime_gemm"][0] / max(rep["k_twotime_gemm"][1], 1)
     flops = float(P) * F * (F + 1)            # upper triangle incl. diagonal, 2 flop per MAC
-    tn = (F + 127) // 128
-    flops_issued = 2.0 * (tn * (tn + 1) / 2) * 128 * 128 * (-(-P // 64) * 64)
-    peak_tf = 1402.4
+    tm, tn = (F + 127) // 128, (F + 255) // 256     # 128 x 256 tiles that touch the upper triangle (csrc/twotime.cu)
+    n_tiles = sum(1 for mt in range(tm) for nt in range(tn) if nt * 256 + 255 >= mt * 128)
+    flops_issued = 2.0 * n_tiles * 128 * 256 * (-(-P // 64) * 64)
+    peak_tf, peak_sus = 1402.4, None
     try:
-        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_tf = float(pk["bf16_tflops"])
+        peak_sus = float(pk.get("bf16_tflops_sustained", 0)) or None
     except Exception:
         pass
     line = {
@@ -495,6 +498,7 @@ def bench_twotime(args, wl):
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak_tf,
                      "traffic": None, "flops_algorithmic": flops, "flops_issued": flops_issued,
                      "achieved_issued": flops_issued / (gemm_ms * 1e-3) / 1e12, "ms_per_launch": gemm_ms,
+                     "peak_sustained": peak_sus, "frac_of_sustained": (flops / (gemm_ms * 1e-3) / 1e12 / peak_sus) if peak_sus else None,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same rate)"},
         "kernels": {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in rep.items() if v[1]},
         "g2full_head": [float(x) for x in r["g2full"][:4]],
@@ -534,10 +538,15 @@ def parity_block(torch, pkg, O, c, dq, sq, F, dev_events, own_pixels, g2_dev, n_
     def events_of(pixels):
         lut = torch.zeros(P, dtype=torch.bool, device=dev)
         lut[torch.from_numpy(np.asarray(pixels, np.int64)).to(dev)] = True
-        m = lut[d_idx.long()]
-        e = torch.nonzero(m).squeeze(1)
-        fr = torch.searchsorted(d_off, e, right=True) - 1
-        return d_idx[e].cpu().numpy(), fr.cpu().numpy(), d_val[e].cpu().numpy()
+        ep, ef, ev = [], [], []
+        step = 1 << 28   # bounded temporaries: the event list of a C5 point does not fit twice
+        for a in range(0, int(d_idx.numel()), step):
+            sl = slice(a, min(a + step, int(d_idx.numel())))
+            e = torch.nonzero(lut[d_idx[sl].long()]).squeeze(1) + a
+            ep.append(d_idx[e].cpu().numpy())
+            ef.append((torch.searchsorted(d_off, e, right=True) - 1).cpu().numpy())
+            ev.append(d_val[e].cpu().numpy())
+        return np.concatenate(ep), np.concatenate(ef), np.concatenate(ev)
 
     T = c.T
     out = {"rows": int(samp.size), "row_entries": int(3 * T * samp.size)}
@@ -646,9 +655,10 @@ def bench_sparse(args, wl):
         d_idx, d_val, d_off = gen_slabs(my)
         first, nfr = slab_first[my[0]], sum(slab_frames[k] for k in my)
     E = int(d_idx.numel())
-    h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
-    h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
-    h_off = torch.empty(nfr + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
+    if not args.no_e2e:
+        h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
+        h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
+        h_off = torch.empty(nfr + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
     torch.cuda.synchronize()
 
     def step_device():
@@ -712,28 +722,30 @@ def bench_sparse(args, wl):
     Es = int(c.info().events_stored)
 
     # ---- end-to-end timing through the public API with host buffers ----
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        sums, g2e, see = step_e2e()
-    e1.record(stream)
-    barrier()
-    wall = (time.perf_counter() - t0) / args.steps
-    ms_e2e = reduce_over_ranks(max(e0.elapsed_time(e1) / args.steps, 1e3 * wall), dist.ReduceOp.MAX if world > 1 else None)
+    ms_e2e, e2e_identical = None, None
+    if not args.no_e2e:
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            sums, g2e, see = step_e2e()
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) / args.steps
+        ms_e2e = reduce_over_ranks(max(e0.elapsed_time(e1) / args.steps, 1e3 * wall), dist.ReduceOp.MAX if world > 1 else None)
+        e2e_identical = bool(np.array_equal(g2e, g2_timed, equal_nan=True))
     clocks = sampler.stop() if rank == 0 else None
     h2d = 4 * E + 2 * E + 8 * (nfr + 1)
     d2h = 4 * (P + 2 * F + S + (F // c.static_window) * S) + 2 * 4 * T * Q
     E_total = reduce_over_ranks(E, dist.ReduceOp.SUM if world > 1 else None)
     R_total = reduce_over_ranks(R, dist.ReduceOp.SUM if world > 1 else None)
     h2d_total = reduce_over_ranks(h2d, dist.ReduceOp.SUM if world > 1 else None)
-    e2e_identical = bool(np.array_equal(g2e, g2_timed, equal_nan=True))
 
     jobs = world if weak else 1
     value = jobs * F / (ms_dev * 1e-3)
-    e2e_value = jobs * F / (ms_e2e * 1e-3)
+    e2e_value = jobs * F / (ms_e2e * 1e-3) if ms_e2e else None
 
     # ---- roofline of the dominant kernel (rank 0's launches; library (NCCL) kernels listed but not ranked) ----
     peak, peak_src = peaks()
@@ -786,7 +798,7 @@ def bench_sparse(args, wl):
                    "compat_stale_tail": not args.no_compat},
         "pixel_frames_per_s": float(R_total) * F / (ms_dev * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "h2d_bytes_per_step_per_gpu": h2d,
+        "e2e": None if ms_e2e is None else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "h2d_bytes_per_step_per_gpu": h2d,
                 "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "g2_identical_to_device_resident_run": e2e_identical,
                 "api": "Correlator.push_sparse_slab/finish_ingest/multitau/normalize (C-ABI xpcs_*), pinned host buffers"},
         "gpu_launches": launches,

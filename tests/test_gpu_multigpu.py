@@ -131,7 +131,7 @@ def test_sharded_equals_single_gpu(pkg, n):
             assert G.n_diff(sums[k], ref[0][k]) == 0, (r, k)
         assert np.array_equal(g2, ref[2], equal_nan=True), r
         assert np.array_equal(se, ref[3], equal_nan=True), r
-        assert rep.get("nccl_exchange", (0, 0))[1] == 1 and rep.get("nccl_allreduce", (0, 0))[1] >= 4
+        assert rep.get("nccl_exchange", (0, 0))[1] == 1 and rep.get("nccl_allreduce", (0, 0))[1] >= 2
         for k in range(3):
             Gsum[k] += Gs[k]   # every pixel has one owner, the others hold zeros
     for k in range(3):

@@ -242,6 +242,19 @@ int comm_allreduce_f32(xpcs_handle_s *h, float *d_buf, size_t n)
     return nccl_check(h, api->AllReduce(d_buf, d_buf, n, ncclFloat32, ncclSum, (ncclComm_t)h->comm, h->stream), "ncclAllReduce");
 }
 
+// several in-place SUM all-reduces of doubles as ONE grouped NCCL launch (small buffers: launch latency dominates)
+int comm_allreduce_f64_group(xpcs_handle_s *h, double *const *bufs, const size_t *counts, int n)
+{
+    if (!comm_active(h)) return XPCS_OK;
+    NcclApi *api = nccl_api();
+    LaunchScope ls(h, "nccl_allreduce", false);
+    ncclResult_t r = api->GroupStart();
+    for (int i = 0; i < n && r == ncclSuccess; i++)
+        if (counts[i] > 0) r = api->AllReduce(bufs[i], bufs[i], counts[i], ncclFloat64, ncclSum, (ncclComm_t)h->comm, h->stream);
+    const ncclResult_t r2 = api->GroupEnd();
+    return nccl_check(h, r != ncclSuccess ? r : r2, "grouped ncclAllReduce");
+}
+
 void comm_destroy(xpcs_handle_s *h)
 {
     if (h->comm) {

@@ -185,6 +185,7 @@ struct xpcs_handle_s {
     xpcs::DevBuf<float> d_tt_sg, d_tt_out;
     xpcs::DevBuf<unsigned int> d_tt_sgint;
     xpcs::DevBuf<double> d_tt_diag;
+    xpcs::DevBuf<int> d_tt_tiles;                   // (row tile, column tile) pairs of the GEMM grid
 
     // ---- multi-GPU (comm.cu) ----
     void *comm = nullptr;                 // ncclComm_t
@@ -209,6 +210,7 @@ struct xpcs_handle_s {
     xpcs::DevBuf<int16_t> d_send_val;
     xpcs::DevBuf<int64_t> d_recv_off;     // [raw frames + nranks] offsets as received, one stream per source rank
     bool frame_acc_reduced = false;       // the per-frame sums already cover every shard
+    bool part_sums_reduced = false;       // so do the per-static-bin sums
     std::vector<int> slab_first_of_rank, slab_frames_of_rank;  // filled by the exchange
 
     // ---- measurement ----
@@ -259,6 +261,7 @@ void release(DevBuf<T> &b)
 bool comm_active(const xpcs_handle_s *h);                            // communicator with more than one rank
 int comm_allreduce_f64(xpcs_handle_s *h, double *d_buf, size_t n);   // in place, SUM, on the handle's stream
 int comm_allreduce_f32(xpcs_handle_s *h, float *d_buf, size_t n);
+int comm_allreduce_f64_group(xpcs_handle_s *h, double *const *bufs, const size_t *counts, int n);
 int comm_exchange_slab(xpcs_handle_s *h);                            // frame slabs -> pixel shards (xpcs_push_sparse_slab*)
 void comm_destroy(xpcs_handle_s *h);
 

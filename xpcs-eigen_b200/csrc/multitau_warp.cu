@@ -31,6 +31,7 @@
 // search wrong) is bounded from below on the sparse levels and tracked exactly on the dense
 // ones; only when it drops below L_l is the boundary walk of multitau.cu replayed, with
 // rank/select over the events instead of a materialised array.
+#include <algorithm>
 #include <cstdlib>
 
 #include "internal.h"
@@ -584,6 +585,11 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     const size_t budget2 = (size_t)(smem_cap + 1024) / 2 - 1024 - 512;  // two resident CTAs (1 KB reserved each)
     const size_t budget3 = (size_t)(smem_cap + 1024) / 3 - 1024 - 512;  // three
     int len_cap = h->max_row > 0 ? h->max_row : 1;
+    {   // a few outlier rows (hot pixels) must not dictate the shared-memory budget of every CTA: slices more than
+        // four times longer than the mean slice go to the lane-per-row kernel
+        const int64_t mean_len = h->n_slices > 0 ? h->store_words / kSlice / h->n_slices : 0;
+        len_cap = (int)std::min<int64_t>(len_cap, std::max<int64_t>(256, 4 * mean_len));
+    }
     int warps = kMwWarps;
     m.parts = 1;
     if (bytes_for(len_cap, 16, 2) <= budget3) m.parts = 2;
@@ -591,8 +597,28 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
         if (bytes_for(len_cap, 12) <= budget2) warps = 12;
         else if (bytes_for(len_cap, 8) <= budget2) warps = 8;
         else {
+            // long rows (C5 at >= 0.1 %: ~10^3 events): fewer rows per CTA.  Pick the (CTAs per slice, warps) pair that
+            // keeps most warps resident on an SM; rows beyond every choice go to the lane-per-row kernel.
             const size_t budget1 = (size_t)smem_cap - 512;
-            while (len_cap > 1 && bytes_for(len_cap, 16) > budget1) len_cap = len_cap * 3 / 4;
+            int best_rw = 0, best_parts = 1, best_warps = 16;
+            for (int parts = 1; parts <= 16; parts *= 2)
+                for (int w : {16, 12, 8, 4, 2}) {
+                    if (w > 32 / parts) continue;
+                    const size_t b = bytes_for(len_cap, w, parts);
+                    if (b > budget1) continue;
+                    int ctas = (int)std::min<size_t>(32, ((size_t)smem_cap + 1024) / (b + 1024));
+                    ctas = std::min(ctas, 48 / w > 0 ? 48 / w : 1);  // 42-register build: 1536 threads per SM
+                    if (ctas * w > best_rw) {
+                        best_rw = ctas * w;
+                        best_parts = parts;
+                        best_warps = w;
+                    }
+                }
+            if (best_rw > 0) {
+                m.parts = best_parts;
+                warps = best_warps;
+            } else
+                while (len_cap > 1 && bytes_for(len_cap, 16) > budget1) len_cap = len_cap * 3 / 4;
         }
     }
     if (const char *e = getenv("XPCS_MW_WARPS")) {  // diagnostics: warps per CTA (4..16)
@@ -601,7 +627,7 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     }
     if (const char *e = getenv("XPCS_MW_PARTS")) {  // diagnostics: CTAs per slice (1, 2, 4)
         const int q = atoi(e);
-        if (q == 1 || q == 2 || q == 4) m.parts = q;
+        if (q == 1 || q == 2 || q == 4 || q == 8 || q == 16) m.parts = q;
     }
     if (bytes_for(len_cap, warps, m.parts) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);

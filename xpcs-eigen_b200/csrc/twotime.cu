@@ -12,12 +12,17 @@
 // tensor cores see the raw photon counts -- exact in fp16, exact fp32 accumulation -- and the
 // only rounding happens in the epilogue.
 //
-// k_twotime_gemm: one CTA per 128x128 tile of the upper triangle.  Operands are 128x64 fp16
-// tiles of the frame-major matrix Xt[F][Npad] (K-major for both A and B), fetched by TMA
+// k_twotime_gemm: one CTA per 128x256 tile of the upper triangle.  Operands are 128x64 (A) and 256x64 (B)
+// fp16 tiles of the frame-major matrix Xt[F][Npad] (K-major for both), fetched by TMA
 // (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a 4-stage mbarrier ring; one thread issues
-// tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with the fp32 accumulator in TMEM
-// (128 columns); tcgen05.commit releases smem stages and finally signals the epilogue, whose
-// four warps read TMEM with tcgen05.ld.32x32b, scale and store.
+// tcgen05.mma (cta_group::1, kind::f16, M=128, N=256, K=16) with the fp32 accumulator in TMEM
+// (256 columns); tcgen05.commit releases smem stages and finally signals the epilogue, whose
+// four warps read TMEM with tcgen05.ld.32x32b, scale and store.  The wide tile moves 48 KB of operands
+// per 4.2 MFLOP (87 flop/B against 64 for 128x128): the shared-memory fill out of L2, not the tensor
+// pipe, is what bounds this contraction (K = the pixel count of the partition is long, 1024 k-blocks at
+// 64k pixels).  The CTAs walk the tiles in super-blocks of 16 x 8 tiles (a host-built tile list), so that the
+// ~148 CTAs in flight share 24 row panels of the operand in L2 instead of ~80 (round 1: 33 GB of DRAM
+// reads for a 1.3 GB operand).
 // Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
 // Float-valued rows (flat-field, averaging) are split x = hi + lo in fp16 and contracted in
 // three passes (hi*hi + hi*lo + lo*hi) into the same accumulator (~2e-7 relative); so are integer
@@ -36,11 +41,13 @@
 
 namespace xpcs {
 
-constexpr int kTtBM = 128, kTtBN = 128, kTtBK = 64, kTtStages = 4;
-constexpr int kTtTileBytes = kTtBM * kTtBK * 2;  // 16 KiB per operand tile
+constexpr int kTtBM = 128, kTtBN = 256, kTtBK = 64, kTtStages = 4;
+constexpr int kTtTileA = kTtBM * kTtBK * 2;      // 16 KiB
+constexpr int kTtTileB = kTtBN * kTtBK * 2;      // 32 KiB
+constexpr int kTtStageBytes = kTtTileA + kTtTileB;
 constexpr int kTtThreads = 192;
-constexpr int kTtTmemCols = 128;
-constexpr size_t kTtSmemBytes = (size_t)kTtStages * 2 * kTtTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kTtTmemCols = 256;
+constexpr size_t kTtSmemBytes = (size_t)kTtStages * kTtStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers --------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +123,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 struct TtGemmArgs {
+    const int2 *tiles;  // (row tile of 128, column tile of 256) of every CTA, in L2-friendly order
     float *C;           // [F][F] row-major, pre-zeroed
     const float *sg;    // [F] (or [1] when sg_scalar)
     int F, kblocks, npass, sg_scalar, use_sg;
@@ -124,14 +132,16 @@ struct TtGemmArgs {
 };
 
 __global__ void __launch_bounds__(kTtThreads, 1)
-k_twotime_gemm(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TtGemmArgs a)
+k_twotime_gemm(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, TtGemmArgs a)
 {
-    const int mt = blockIdx.y, nt = blockIdx.x;
-    if (nt < mt) return;  // lower triangle stays zero (corr.cpp:826: k starts at j)
+    // only tiles that touch the upper triangle are listed (the lower one stays zero, corr.cpp:826: k starts at j)
+    const int2 tile = a.tiles[blockIdx.x];
+    const int mt = tile.x, nt = tile.y;
     extern __shared__ unsigned char tt_smem_raw[];
     const uint32_t base = (smem_u32(tt_smem_raw) + 1023u) & ~1023u;
-    const uint32_t tiles = base;                                    // [stage][A|B] 16 KiB each
-    const uint32_t bars = base + kTtStages * 2 * kTtTileBytes;      // full[4], empty[4], tmem_full, tmem_slot
+    const uint32_t tiles = base;                                    // [stage]: A 16 KiB, B 32 KiB
+    const uint32_t bars = base + kTtStages * kTtStageBytes;         // full[4], empty[4], tmem_full, tmem_slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kTtStages + s); };
     const uint32_t tmem_full_bar = bars + 8u * (2 * kTtStages);
@@ -164,11 +174,11 @@ k_twotime_gemm(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                 const uint32_t ph = (uint32_t)(kb / kTtStages) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const int pass = kb / a.kblocks, kk = kb - pass * a.kblocks;
-                const CUtensorMap *ma = pass == 2 ? &map_lo : &map_hi;
-                const CUtensorMap *mb = pass == 1 ? &map_lo : &map_hi;
-                mbar_expect_tx(full_bar(s), 2 * kTtTileBytes);
-                tma_load_2d(tiles + (uint32_t)(s * 2) * kTtTileBytes, ma, kk * kTtBK, mt * kTtBM, full_bar(s));
-                tma_load_2d(tiles + (uint32_t)(s * 2 + 1) * kTtTileBytes, mb, kk * kTtBK, nt * kTtBN, full_bar(s));
+                const CUtensorMap *ma = pass == 2 ? &mapA_lo : &mapA_hi;
+                const CUtensorMap *mb = pass == 1 ? &mapB_lo : &mapB_hi;
+                mbar_expect_tx(full_bar(s), kTtStageBytes);
+                tma_load_2d(tiles + (uint32_t)s * kTtStageBytes, ma, kk * kTtBK, mt * kTtBM, full_bar(s));
+                tma_load_2d(tiles + (uint32_t)s * kTtStageBytes + kTtTileA, mb, kk * kTtBK, nt * kTtBN, full_bar(s));
             }
         }
     } else if (warp == 1) {
@@ -178,8 +188,8 @@ k_twotime_gemm(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                 const uint32_t ph = (uint32_t)(kb / kTtStages) & 1u;
                 mbar_wait(full_bar(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = tiles + (uint32_t)(s * 2) * kTtTileBytes;
-                const uint32_t sb = sa + kTtTileBytes;
+                const uint32_t sa = tiles + (uint32_t)s * kTtStageBytes;
+                const uint32_t sb = sa + kTtTileA;
 #pragma unroll
                 for (int k = 0; k < kTtBK / 16; k++) {
                     // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom
@@ -361,7 +371,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_operand_map(xpcs_handle_s *h, CUtensorMap *map, const __half *ptr, int F, int npad)
+static int make_operand_map(xpcs_handle_s *h, CUtensorMap *map, const __half *ptr, int F, int npad, int box_rows)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -373,7 +383,7 @@ static int make_operand_map(xpcs_handle_s *h, CUtensorMap *map, const __half *pt
     }
     const cuuint64_t dims[2] = {(cuuint64_t)npad, (cuuint64_t)F};
     const cuuint64_t strides[1] = {(cuuint64_t)npad * sizeof(__half)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTtBK, (cuuint32_t)kTtBM};
+    const cuuint32_t box[2] = {(cuuint32_t)kTtBK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -496,11 +506,30 @@ int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int averag
         b.op_scale = op_scale;
         run_build(0, 1, average ? d_sg_avg : d_sg);  // operand z = x / sg of the pixel's static partition
     }
-    CUtensorMap map_hi, map_lo;
-    if ((rc = make_operand_map(h, &map_hi, (const __half *)h->d_tt_hi.p, F, npad))) return rc;
-    if ((rc = make_operand_map(h, &map_lo, (const __half *)(split ? h->d_tt_lo.p : h->d_tt_hi.p), F, npad))) return rc;
+    CUtensorMap mapA_hi, mapA_lo, mapB_hi, mapB_lo;
+    const __half *p_hi = (const __half *)h->d_tt_hi.p, *p_lo = (const __half *)(split ? h->d_tt_lo.p : h->d_tt_hi.p);
+    if ((rc = make_operand_map(h, &mapA_hi, p_hi, F, npad, kTtBM))) return rc;
+    if ((rc = make_operand_map(h, &mapA_lo, p_lo, F, npad, kTtBM))) return rc;
+    if ((rc = make_operand_map(h, &mapB_hi, p_hi, F, npad, kTtBN))) return rc;
+    if ((rc = make_operand_map(h, &mapB_lo, p_lo, F, npad, kTtBN))) return rc;
+    // tile list: super-blocks of 16 x 8 tiles (2048 x 2048 frames) row by row, tiles row-major inside; a tile is
+    // listed when its last column reaches its first row
+    std::vector<int2> tl;
+    {
+        const int tm = (F + kTtBM - 1) / kTtBM, tnn = (F + kTtBN - 1) / kTtBN;
+        const int SM_ = 16, SN_ = 8;
+        for (int bm = 0; bm < tm; bm += SM_)
+            for (int bn = 0; bn < tnn; bn += SN_)
+                for (int mt = bm; mt < std::min(tm, bm + SM_); mt++)
+                    for (int nt = bn; nt < std::min(tnn, bn + SN_); nt++)
+                        if (nt * kTtBN + kTtBN - 1 >= mt * kTtBM) tl.push_back(make_int2(mt, nt));
+    }
+    if ((rc = ensure(h, h->d_tt_tiles, tl.size() * 2 + 2, "two-time tile list"))) return rc;
+    if ((rc = check_cuda(h, cudaMemcpyAsync(h->d_tt_tiles.p, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, st), "tile list")))
+        return rc;
     {
         TtGemmArgs g{};
+        g.tiles = reinterpret_cast<const int2 *>(h->d_tt_tiles.p);
         g.C = h->d_tt_C.p;
         g.sg = average ? d_sg_avg : d_sg;
         g.F = F;
@@ -513,9 +542,8 @@ int launch_twotime(xpcs_handle_s *h, int qbin, int wsize, int method, int averag
         rc = check_cuda(h, cudaFuncSetAttribute(k_twotime_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTtSmemBytes),
                         "two-time smem attr");
         if (rc) return rc;
-        const int tn = (F + kTtBM - 1) / kTtBM;
         LaunchScope ls(h, "k_twotime_gemm");
-        k_twotime_gemm<<<dim3(tn, tn), kTtThreads, kTtSmemBytes, st>>>(map_hi, map_lo, g);
+        k_twotime_gemm<<<(unsigned)tl.size(), kTtThreads, kTtSmemBytes, st>>>(mapA_hi, mapA_lo, mapB_hi, mapB_lo, g);
     }
     if ((rc = check_cuda(h, cudaGetLastError(), "k_twotime_gemm"))) return rc;
     double *d_full = h->d_tt_diag.p;

@@ -330,6 +330,7 @@ static void reset_ingest(xpcs_handle_s *h)
     h->slab_val = nullptr;
     h->slab_off = nullptr;
     h->frame_acc_reduced = false;
+    h->part_sums_reduced = false;
 }
 
 static int check_params(const XpcsParams *prm)
@@ -448,7 +449,7 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_row_sum); release(h->d_part_total); release(h->d_part_partial); release(h->d_frame_scale);
     release(h->d_G2); release(h->d_IP); release(h->d_IF); release(h->d_partials); release(h->d_scratch); release(h->d_mt_fallback);
     release(h->d_tt_hi); release(h->d_tt_lo); release(h->d_tt_C); release(h->d_tt_sg); release(h->d_tt_out);
-    release(h->d_tt_sgint); release(h->d_tt_diag);
+    release(h->d_tt_sgint); release(h->d_tt_diag); release(h->d_tt_tiles);
     if (h->stage) cudaFreeHost(h->stage);
     release(h->d_dense_stage[0]); release(h->d_dense_stage[1]);
     for (int b = 0; b < 2; b++) {
@@ -931,16 +932,6 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     else rc = launch_ingest(h);
     if (rc) return rc;
     h->ingest_done = true;
-    const int windows_all0 = (F + h->prm.static_window - 1) / h->prm.static_window;
-    if (comm_active(h)) {
-        // every static bin lives on one shard and frameSum covers all pixels (sparse_filter.cpp:175,190): the
-        // element-wise sums over the shards are the single-GPU values (exact for integer counts)
-        if (!h->frame_acc_reduced && (rc = comm_allreduce_f64(h, h->d_frame_acc.p, (size_t)F))) return rc;
-        h->frame_acc_reduced = true;
-        if ((rc = comm_allreduce_f64(h, h->d_part_total.p, (size_t)h->S))) return rc;
-        if ((rc = comm_allreduce_f64(h, h->d_part_partial.p, (size_t)windows_all0 * h->S))) return rc;
-    }
-
     // ---- Filter getters, post-scaled as in main.cpp:339-343 and :360-378 ----
     // pixelSum and frameSum are formed on the device (same fp32 operations) and land in the caller's
     // arrays directly; the small partition sums are finished on the host
@@ -948,6 +939,27 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     const int windows_all = (F + h->prm.static_window - 1) / h->prm.static_window;
     const int windows = F / h->prm.static_window;
     if (!pixel_sum && !frame_sum && !part_total && !part_partial) return XPCS_OK;  // nothing to read back
+    if (comm_active(h)) {
+        // every static bin lives on one shard and frameSum covers all pixels (sparse_filter.cpp:175,190): the
+        // element-wise sums over the shards are the single-GPU values (exact for integer counts).  One grouped
+        // launch, and only when a caller asks for the sums (every rank must ask for the same ones).
+        double *bufs[3];
+        size_t counts[3];
+        int nb = 0;
+        if (frame_sum && !h->frame_acc_reduced) {
+            bufs[nb] = h->d_frame_acc.p;
+            counts[nb++] = (size_t)F;
+            h->frame_acc_reduced = true;
+        }
+        if ((part_total || part_partial) && !h->part_sums_reduced) {
+            bufs[nb] = h->d_part_total.p;
+            counts[nb++] = (size_t)S;
+            bufs[nb] = h->d_part_partial.p;
+            counts[nb++] = (size_t)windows_all * S;
+            h->part_sums_reduced = true;
+        }
+        if (nb > 0 && (rc = comm_allreduce_f64_group(h, bufs, counts, nb))) return rc;
+    }
     std::vector<double> ptot(S), ppart((size_t)windows_all * S);
     if (pixel_sum || frame_sum) {
         if ((rc = ensure(h, h->d_scratch, (size_t)h->P + 2 * (size_t)F, "filter getters"))) return rc;
