@@ -521,15 +521,15 @@ def rows_of_pixels(O, pix_sorted, ev_pix, ev_frame, ev_val):
     return O.Rows(np.cumsum(row_ptr), t, v)
 
 
-def parity_block(torch, pkg, O, c, dq, sq, F, dev_events, own_pixels, g2_dev, n_rows=2000, compat=True, seed=5):
+def parity_block(torch, pkg, O, c, dq, sq, F, ev_source, own_pixels, g2_dev, n_rows=2000, compat=True, seed=5):
     """Bit-for-bit check of the timed configuration itself (not of a small stand-in):
     (1) G2 / IP / IF of ~n_rows sampled pixel rows against oracle.multitau (corr.cpp:315-431) on those rows' events;
     (2) norm-0-g2 of a few dynamic bins recomputed by oracle.normalize (corr.cpp:927-1091) from the device's
         G2 / IP / IF of the bins' pixels.
-    dev_events = (idx, val, off) device tensors of ALL frames of the job (whole detector)."""
-    d_idx, d_val, d_off = dev_events
+    ev_source() yields (idx, val, off, first_frame) device tensors that together cover ALL frames of the job (whole
+    detector), one slab of frames at a time (a C5 point does not fit a GPU twice)."""
     P = dq.size
-    dev = d_idx.device
+    dev = torch.device("cuda", torch.cuda.current_device())
     rng = np.random.default_rng(seed)
     valid = np.flatnonzero((dq.ravel() > 0) & (sq.ravel() > 0))
     own = np.asarray(own_pixels, np.int64)
@@ -539,13 +539,15 @@ def parity_block(torch, pkg, O, c, dq, sq, F, dev_events, own_pixels, g2_dev, n_
         lut = torch.zeros(P, dtype=torch.bool, device=dev)
         lut[torch.from_numpy(np.asarray(pixels, np.int64)).to(dev)] = True
         ep, ef, ev = [], [], []
-        step = 1 << 28   # bounded temporaries: the event list of a C5 point does not fit twice
-        for a in range(0, int(d_idx.numel()), step):
-            sl = slice(a, min(a + step, int(d_idx.numel())))
-            e = torch.nonzero(lut[d_idx[sl].long()]).squeeze(1) + a
-            ep.append(d_idx[e].cpu().numpy())
-            ef.append((torch.searchsorted(d_off, e, right=True) - 1).cpu().numpy())
-            ev.append(d_val[e].cpu().numpy())
+        step = 1 << 28   # bounded temporaries
+        for d_idx, d_val, d_off, f0 in ev_source():
+            for a in range(0, int(d_idx.numel()), step):
+                sl = slice(a, min(a + step, int(d_idx.numel())))
+                e = torch.nonzero(lut[d_idx[sl].long()]).squeeze(1) + a
+                ep.append(d_idx[e].cpu().numpy())
+                ef.append((torch.searchsorted(d_off, e, right=True) - 1 + f0).cpu().numpy())
+                ev.append(d_val[e].cpu().numpy())
+            del d_idx, d_val, d_off
         return np.concatenate(ep), np.concatenate(ef), np.concatenate(ev)
 
     T = c.T
@@ -655,6 +657,7 @@ def bench_sparse(args, wl):
         d_idx, d_val, d_off = gen_slabs(my)
         first, nfr = slab_first[my[0]], sum(slab_frames[k] for k in my)
     E = int(d_idx.numel())
+    torch.cuda.empty_cache()   # the generator's temporaries go back to the driver: the library allocates with cudaMalloc
     if not args.no_e2e:
         h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
         h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
@@ -819,10 +822,22 @@ def bench_sparse(args, wl):
         par = {}
         if rank == 0:
             O = entry.load_oracle()
-            all_ev = (d_idx, d_val, d_off) if world == 1 else gen_slabs(range(n_slabs))
-            par = parity_block(torch, pkg, O, c, dq, sq, F, all_ev, c.row_pixels(), g2p, n_rows=args.parity_rows,
+
+            def ev_source():
+                if world == 1:
+                    yield d_idx, d_val, d_off, 0
+                else:
+                    for k in range(n_slabs):
+                        torch.cuda.empty_cache()
+                        yield gen_slabs([k]) + (slab_first[k],)
+
+            par = parity_block(torch, pkg, O, c, dq, sq, F, ev_source, c.row_pixels(), g2p, n_rows=args.parity_rows,
                                compat=not args.no_compat)
-            if world > 1:
+            if world > 1 and 6.0 * E_total > 40e9:
+                par["single_gpu_g2_identical"] = None   # the whole event list does not fit one GPU next to this rank's share
+            elif world > 1:
+                torch.cuda.empty_cache()
+                all_ev = gen_slabs(range(n_slabs))
                 # the same job on ONE GPU (this one), same data: g2 / stderr must be bit-identical
                 c1 = pkg.Correlator(dq, sq, F, dpl=8, compat=not args.no_compat, device=local, reserve_events=int(all_ev[0].numel()))
                 c1.push_sparse_device(all_ev[0].data_ptr(), all_ev[1].data_ptr(), all_ev[2].data_ptr(), int(all_ev[0].numel()), F)

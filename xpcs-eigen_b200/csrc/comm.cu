@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "internal.h"
@@ -328,8 +329,12 @@ int comm_exchange_slab(xpcs_handle_s *h)
     if (h->prm.reserve_events > (int64_t)need) need = (size_t)h->prm.reserve_events;
     if ((rc = ensure(h, h->d_idx, need + 8, "event indices"))) return rc;
     if ((rc = ensure(h, h->d_val, need + 8, "event values"))) return rc;
-    if ((rc = ensure(h, h->d_send_idx, (size_t)send_total + 8, "send indices"))) return rc;
-    if ((rc = ensure(h, h->d_send_val, (size_t)send_total + 8, "send values"))) return rc;
+    // the send streams live in the record buffer of the store build, which is only written after the exchange
+    // (6 bytes per event to send against 8 bytes per event to keep)
+    const size_t send_words = ((size_t)send_total * 6 + 64) / 8 + 8;
+    if ((rc = ensure(h, h->d_rec, std::max(send_words, (size_t)E_me + 1), "event records / send streams"))) return rc;
+    int32_t *send_idx = reinterpret_cast<int32_t *>(h->d_rec.p);
+    int16_t *send_val = reinterpret_cast<int16_t *>(send_idx + (((size_t)send_total + 7) & ~(size_t)7));
     if ((rc = ensure(h, h->d_recv_off, (size_t)raw_total + N + 1, "received offsets"))) return rc;
     if ((rc = ensure(h, h->d_frame_off, (size_t)raw_total + 1, "frame offsets"))) return rc;
     DemuxDst dst{};
@@ -338,8 +343,8 @@ int comm_exchange_slab(xpcs_handle_s *h)
             dst.idx[d] = h->d_idx.p + mr.base[me];
             dst.val[d] = h->d_val.p + mr.base[me];
         } else {
-            dst.idx[d] = h->d_send_idx.p + sbase[d];
-            dst.val[d] = h->d_send_val.p + sbase[d];
+            dst.idx[d] = send_idx + sbase[d];
+            dst.val[d] = send_val + sbase[d];
         }
     }
     if (nfr > 0) {

@@ -363,21 +363,29 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
                 else raw[j] = a.val[e0 + j];
             }
         }
+        // three rounds over the thread's four events, so that the four row look-ups and then the four returning
+        // atomics are in flight together (the kernel is bound by the latency of the atomics, not by their count)
+        int rr[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            rr[j] = -1;
             if (j >= nv || e0 + j < a.ev_begin) continue;
-            int tj;
-            if (DENSE_SRC) tj = t[j];
-            else {
+            if (!DENSE_SRC) {
                 const int64_t e = e0 + j;
                 while (f + 1 < a.nraw && e >= __ldg(a.off + f + 1)) f++;
-                tj = out_frame(f + a.frame_base, a.rawblock, a.stride, a.F);
+                t[j] = out_frame(f + a.frame_base, a.rawblock, a.stride, a.F);
             }
-            if (tj < 0 || (unsigned)pix[j] >= (unsigned)a.P) continue;
-            const int r = __ldg(a.row_of_pixel + pix[j]);
-            if (r < 0) continue;
-            const int sl = r >> 5;
-            const unsigned long long pos = atomicAdd(a.slice_end + sl, ~0ull) - 1ull;  // -1: the stream fills from its end
+            if (t[j] < 0 || (unsigned)pix[j] >= (unsigned)a.P) continue;
+            rr[j] = __ldg(a.row_of_pixel + pix[j]);
+        }
+        unsigned long long pos[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (rr[j] >= 0) pos[j] = atomicAdd(a.slice_end + (rr[j] >> 5), ~0ull) - 1ull;  // -1: the stream fills from its end
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (rr[j] < 0) continue;
+            const int r = rr[j], tj = t[j];
             unsigned long long rec;
             if (KIND == kPacked) {
                 rec = ((unsigned long long)(r & 31) << 32) |
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
                 rec = ((unsigned long long)(r & 31) << kRecLaneShiftF) | ((unsigned long long)(uint32_t)tj << 32) |
                       (unsigned long long)__float_as_uint(v);
             }
-            a.rec[pos] = rec;
+            a.rec[pos[j]] = rec;
         }
     }
 }
@@ -1324,7 +1332,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     // then works in global memory.
     const int smem_cap = max_dyn_smem(h->device) - 1024;
     const size_t lane_bytes_all = (size_t)h->max_row * kSlice * sizeof(W);
-    const bool use_warp = lane_bytes_all > 24 * 1024 && !getenv("XPCS_FIN_LANE");
+    const bool use_warp = (lane_bytes_all > 24 * 1024 || getenv("XPCS_FIN_WARP")) && !getenv("XPCS_FIN_LANE");
     const bool fused_place = !direct && !use_warp && (long long)lane_bytes_all <= smem_cap && !getenv("XPCS_PLACE_KERNEL");
     if (nblocks > 0 && direct) {
         LaunchScope ls(h, dense ? "k_scatter_dense" : "k_scatter");

@@ -601,8 +601,8 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
             // keeps most warps resident on an SM; rows beyond every choice go to the lane-per-row kernel.
             const size_t budget1 = (size_t)smem_cap - 512;
             int best_rw = 0, best_parts = 1, best_warps = 16;
-            for (int parts = 1; parts <= 16; parts *= 2)
-                for (int w : {16, 12, 8, 4, 2}) {
+            for (int parts = 1; parts <= 32; parts *= 2)
+                for (int w : {16, 12, 8, 4, 2, 1}) {
                     if (w > 32 / parts) continue;
                     const size_t b = bytes_for(len_cap, w, parts);
                     if (b > budget1) continue;
@@ -627,7 +627,7 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     }
     if (const char *e = getenv("XPCS_MW_PARTS")) {  // diagnostics: CTAs per slice (1, 2, 4)
         const int q = atoi(e);
-        if (q == 1 || q == 2 || q == 4 || q == 8 || q == 16) m.parts = q;
+        if (q == 1 || q == 2 || q == 4 || q == 8 || q == 16 || q == 32) m.parts = q;
     }
     if (bytes_for(len_cap, warps, m.parts) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
