@@ -589,7 +589,8 @@ class G:  # tiny helper namespace (NaN-aware inequality count)
         return int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
 
 
-N_SLABS = 8  # the synthetic job is generated as 8 slabs of frames seeded by slab number: the same data for every GPU count
+N_SLABS = 64  # the synthetic job is generated as 64 slabs of frames seeded by slab number: the same data for every GPU
+              # count, and generator temporaries that stay bounded at 4e10 events
 
 
 def bench_sparse(args, wl):
@@ -888,6 +889,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = ONE detector sharded over the GPUs (default); weak = N modules, one per GPU")
     ap.add_argument("--frames", type=int, default=0, help="override the frame count (debug)")
+    ap.add_argument("--hw", type=int, nargs=2, default=None, help="override the detector height and width (debug: one GPU's share of a sharded job)")
     ap.add_argument("--occupancy", type=float, default=0.0, help="override the occupancy of a sparse workload (c5 sweep)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -899,6 +901,9 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
         wl["F"] = args.frames
+    if args.hw:
+        wl["h"], wl["w"] = args.hw
+        wl["name"] += " [detector %dx%d]" % tuple(args.hw)
     if args.occupancy and wl["kind"] == "sparse":
         wl["occ"] = args.occupancy
         wl["name"] += " [occupancy %g]" % args.occupancy
