@@ -248,6 +248,13 @@ int xpcs_twotime_sg(xpcs_handle h, int qbin, int wsize, int smoothing_method, in
 int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int smoothing_method, int smoothing_average,
                  float *C, float *g2full, float *g2partials, float *sg);
 
+/* ---- pinned host memory ----
+ * Page-locked host buffers (cudaHostAlloc) for callers that do not link the CUDA runtime themselves: pushes from
+ * and result copies into such buffers are asynchronous and run at the full PCIe rate (pageable memory is staged
+ * by the driver at a fraction of it).  Returns NULL on failure. */
+void *xpcs_host_alloc(size_t bytes);
+void xpcs_host_free(void *p);
+
 /* ---- measurement hooks (bench.py, profiles/) ---- */
 /* record a CUDA event pair around every kernel launch of this handle */
 int xpcs_kernel_timing(xpcs_handle h, int enable);

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-def _run_corr(pkg, c, tmp_path, extra=()):
+def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None):
     corr = os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
     imm = str(tmp_path / "data.imm")
     h, w = c.dq.shape
@@ -32,6 +32,8 @@ def _run_corr(pkg, c, tmp_path, extra=()):
     elif c.fmt == "hdf5":  # a frame stack /entry/data/data (io/hdf5.cpp), read through --hdf5
         st = pkg.h5lite.File()
         st.put("/entry/data/data", c.inp["stack"])
+        if stack_storage:
+            st.set_storage("/entry/data/data", **stack_storage)
         st.save(imm)
         st.close()
         kw.update(begin=int(c.inp["begin"]))
@@ -119,3 +121,26 @@ def test_corr_frameout(pkg, tmp_path):
         np.add.at(want[f], idx[sl], val[sl].astype(np.float32))
     want *= valid[None, :]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["hdf5_stack_24x32", "hdf5_stack_u32_24x32"])
+def test_corr_hdf5_chunked_deflate_shuffle_stack(pkg, tmp_path, name):
+    """--hdf5 on a frame stack stored the way detector files are: one chunk per frame, byte shuffle + deflate
+    (io/hdf5.cpp:62-221 reads through H5Dread, which decodes them; h5lite's chunk reader does here).  Same results
+    as the reference produced from the contiguous stack of the fixture."""
+    c = G.Case(name)
+    h, w = c.dq.shape
+    res, _ = _run_corr(pkg, c, tmp_path, stack_storage=dict(chunk=(1, h, w), deflate=6, shuffle=True))
+    for k in ("G2", "IP", "IF", "norm-0-g2", "pixelSum", "frameSum"):
+        assert G.n_diff(res[k], c.ref[k]) == 0, k
+
+
+def test_corr_twotime_matrix_is_stored_as_one_deflate_chunk(pkg, tmp_path):
+    """C2T_all/g2_* leave `corr` the way the reference stores them (write2DData(..., compression = true)): chunked +
+    deflate; h5lite reads them back (values checked against the fixture by the parametrised test above)."""
+    c = G.Case("twotime_symmetric_none")
+    res, _ = _run_corr(pkg, c, tmp_path)
+    g = pkg.h5lite.File(str(tmp_path / "config.hdf5"))
+    notes = g.report("notes")
+    g.close()
+    assert any("C2T_all/g2_00001" in n and "chunked + filtered" in n for n in notes), notes

@@ -317,3 +317,23 @@ def test_late_window_partition_sums(pkg, oracle, flat, F, sw):
         assert_exact(out[True][key], out[False][key], key)
     if sw > 1:
         assert np.any(out[True]["part_partial"] != out[False]["part_partial"])
+
+
+def test_pinned_result_buffers_give_the_same_arrays(pkg):
+    """Correlator.pinned_results(): results land in page-locked buffers owned by the library (xpcs_host_alloc) and are
+    reused from call to call; the values are those of the default (fresh numpy arrays) path."""
+    dq, sq, off, idx, val = make_case(pkg, 40, 32, 600, 0.03, 77)
+    out = []
+    for pinned in (False, True):
+        c = pkg.Correlator(dq, sq, 600)
+        c.pinned_results(pinned)
+        for _ in range(2):  # the second round reuses the buffers
+            c.reset()
+            c.push_sparse(idx, val, off)
+            sums = c.finish_ingest()
+            c.multitau(want=False)
+            g2, se = c.normalize()
+        out.append({k: np.array(v, copy=True) for k, v in sums.items()} | {"g2": np.array(g2, copy=True), "se": np.array(se, copy=True)})
+        c.close()
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k], equal_nan=True), k

@@ -126,3 +126,57 @@ def test_corr_fails_loudly_without_gpu(pkg, tmp_path):
     p = subprocess.run([corr, cfg], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 3 and "no CPU path" in p.stderr
     assert subprocess.run([corr], stdout=subprocess.PIPE, stderr=subprocess.PIPE).returncode == 1
+
+
+@pytest.mark.parametrize("deflate,shuffle", [(0, False), (6, False), (6, True)])
+def test_chunked_filtered_datasets_roundtrip(pkg, tmp_path, deflate, shuffle):
+    """Chunked storage with the deflate / shuffle filters (H5Pset_chunk / H5Pset_deflate / H5Pset_shuffle): edge chunks,
+    a 3-d frame stack chunked per frame with more than 64 chunks (B-tree with an internal level), a single-chunk
+    matrix (how the reference stores C2T_all/g2_*).  Written and read back by h5lite; the reader's chunk path is the
+    one that decodes libhdf5-written files."""
+    H = pkg.h5lite
+    rng = np.random.default_rng(3)
+    stack = (rng.random((70, 24, 32)) < 0.03).astype(np.uint16) * rng.integers(1, 5, (70, 24, 32)).astype(np.uint16)
+    mat = rng.standard_normal((37, 53)).astype(np.float32)
+    vol = rng.integers(-1000, 1000, (5, 7, 9)).astype(np.int32)
+    f = H.File()
+    f.put("/entry/data/data", stack)
+    f.set_storage("/entry/data/data", chunk=(1, 24, 32), deflate=deflate, shuffle=shuffle)
+    f.put("/exchange/C2T_all/g2_00001", mat)
+    f.set_storage("/exchange/C2T_all/g2_00001", chunk=mat.shape, deflate=deflate, shuffle=shuffle)
+    f.put("/odd/vol", vol)
+    f.set_storage("/odd/vol", chunk=(2, 4, 4), deflate=deflate, shuffle=shuffle)   # edge chunks on every axis
+    f.put("/plain", np.arange(10, dtype=np.float64))
+    p = str(tmp_path / "c.h5")
+    f.save(p)
+    f.close()
+    g = H.File(p)
+    assert np.array_equal(g.get("/entry/data/data"), stack)
+    assert np.array_equal(g.get("/exchange/C2T_all/g2_00001"), mat)
+    assert np.array_equal(g.get("/odd/vol"), vol)
+    assert np.array_equal(g.get("/plain"), np.arange(10, dtype=np.float64))
+    notes = g.report("notes")
+    assert any("/entry/data/data" in n and "chunked" in n for n in notes)
+    g.close()
+    if deflate:
+        assert os.path.getsize(p) < stack.nbytes   # the sparse stack compresses
+
+
+def test_attributes_of_a_genuine_file_survive_a_rewrite(pkg, tmp_path):
+    """The reference adds datasets to the user's file in place; h5lite rewrites the file, so the attribute messages of
+    every object must be carried over byte for byte (MATLAB_class on the dataset of the genuine sample file)."""
+    H = pkg.h5lite
+    f = H.File(SAMPLE)
+    names = f.list("/")
+    before = {n: f.extra("/" + n) for n in names}
+    assert any(len(v) > 0 and any(b"MATLAB_class" in body for _, body in v) for v in before.values())
+    assert f.report("lossy") == []
+    f.put("/exchange/new", np.arange(4, dtype=np.float32))
+    p = str(tmp_path / "rw.h5")
+    f.save(p)
+    f.close()
+    g = H.File(p)
+    for n in names:
+        assert g.extra("/" + n) == before[n], n
+    assert np.array_equal(g.get("/exchange/new"), np.arange(4, dtype=np.float32))
+    g.close()

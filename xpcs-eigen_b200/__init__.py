@@ -110,6 +110,7 @@ class Correlator:
             raise XpcsError(rc, (self._lib.xpcs_last_error(None) or b"").decode())
         self._h = h
         self._keep = []  # host buffers that must outlive asynchronous copies
+        self._pinned = {}  # name -> (pointer, numpy view): persistent page-locked result buffers (pinned_results())
         i = self.info()
         self.T, self.S, self.Q = i.n_delays, i.n_static, i.n_dynamic
 
@@ -118,7 +119,29 @@ class Correlator:
         if rc != 0:
             raise XpcsError(rc, (self._lib.xpcs_last_error(self._h) or b"").decode())
 
+    def pinned_results(self, on=True):
+        """Keep the result arrays of finish_ingest() / normalize() in page-locked buffers owned by this object
+        (allocated once, reused by every call: the arrays returned are views, valid until the next call)."""
+        self._use_pinned = bool(on)
+
+    def _out(self, name, n, dtype=np.float32):
+        if not getattr(self, "_use_pinned", False):
+            return np.empty(n, dtype)
+        have = self._pinned.get(name)
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        if have is None or have[2] < nbytes:
+            if have is not None:
+                self._lib.xpcs_host_free(have[0])
+            p = self._lib.xpcs_host_alloc(max(nbytes, 1))
+            if not p:
+                raise XpcsError(-4, "xpcs_host_alloc(%d) failed" % nbytes)
+            self._pinned[name] = have = (p, (C.c_char * max(nbytes, 1)).from_address(p), nbytes)
+        return np.frombuffer(have[1], dtype=dtype, count=int(n))
+
     def close(self):
+        for p, _, _ in getattr(self, "_pinned", {}).values():
+            self._lib.xpcs_host_free(p)
+        self._pinned = {}
         if getattr(self, "_h", None):
             self._lib.xpcs_destroy(self._h)
             self._h = None
@@ -220,10 +243,12 @@ class Correlator:
             self._keep = []
             return None
         F, S = self.F, self.S
-        ps = np.empty(self.P, np.float32)   # fully written by the library
-        fs = np.empty(2 * F, np.float32)
-        pt = np.zeros(max(S, 1), np.float32)
-        pp = np.zeros(max((F // self.static_window) * S, 1), np.float32)
+        ps = self._out("pixel_sum", self.P)   # fully written by the library
+        fs = self._out("frame_sum", 2 * F)
+        pt = self._out("part_total", max(S, 1))
+        pp = self._out("part_partial", max((F // self.static_window) * S, 1))
+        pt[:] = 0
+        pp[:] = 0
         self._check(self._lib.xpcs_finish_ingest(self._h, ps.ctypes.data, fs.ctypes.data, pt.ctypes.data,
                                                  pp.ctypes.data))
         self._keep = []
@@ -263,8 +288,10 @@ class Correlator:
 
     def normalize(self):
         """Corr::normalizeG2s -> (g2, stderr) each (T, Q)."""
-        g2 = np.zeros((self.T, max(self.Q, 1)), np.float32)
-        se = np.zeros((self.T, max(self.Q, 1)), np.float32)
+        g2 = self._out("g2", self.T * max(self.Q, 1)).reshape(self.T, max(self.Q, 1))
+        se = self._out("se", self.T * max(self.Q, 1)).reshape(self.T, max(self.Q, 1))
+        g2[:] = 0
+        se[:] = 0
         self._check(self._lib.xpcs_normalize(self._h, g2.ctypes.data, se.ctypes.data))
         return g2[:, : self.Q], se[:, : self.Q]
 

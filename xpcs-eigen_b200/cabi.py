@@ -90,6 +90,8 @@ SYMBOLS = {
     "xpcs_push_sparse_slab_device": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i]),
     "xpcs_twotime": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "xpcs_twotime_sg": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(C.c_int)]),
+    "xpcs_host_alloc": (_vp, [C.c_size_t]),
+    "xpcs_host_free": (None, [_vp]),
     "xpcs_kernel_timing": (_i, [_vp, _i]),
     "xpcs_launch_count": (_i64, [_vp]),
     "xpcs_multitau_fallback_slices": (_i64, [_vp]),

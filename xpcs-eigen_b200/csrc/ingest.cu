@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kFwWarps * 32) k_finalize_warp(FinalizeArgs a)
                 bool ok = true;
                 for (int i = lane; i < n; i += 32) ok = ok && B[i] != kMaxW && (i + 1 >= n || !(B[i] > B[i + 1]));
                 if (__all_sync(0xffffffffu, ok) || D >= n) break;
-                D = n;
+                D = 4 * D < n ? 4 * D : n;  // (the displacement grows with the GPU count: fewer rows share the same scatter CTAs)
                 __syncwarp();
             }
             W *t = A;

@@ -1184,6 +1184,25 @@ extern "C" int xpcs_twotime(xpcs_handle h, int qbin, int wsize, int method, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// pinned host memory for callers without a CUDA runtime of their own (the host program, the ctypes mirror):
+// copies to and from such buffers are asynchronous and run at full PCIe rate
+// ---------------------------------------------------------------------------------------
+extern "C" void *xpcs_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void xpcs_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------
 // measurement hooks
 // ---------------------------------------------------------------------------------------
 extern "C" int xpcs_kernel_timing(xpcs_handle h, int enable)

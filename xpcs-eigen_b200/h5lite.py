@@ -33,6 +33,7 @@ def _load():
         L.h5l_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_ulonglong]
         L.h5l_put.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_void_p,
                               C.c_ulonglong]
+        L.h5l_set_storage.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
         L.h5l_extra_count.argtypes = [C.c_void_p, C.c_char_p]
         L.h5l_extra_get.restype = C.c_long
         L.h5l_extra_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_long]
@@ -113,6 +114,13 @@ class File:
             rc = L.h5l_put(self._h, path.encode(), code, a.ndim, dims, a.ctypes.data, 0)
         if rc != 0:
             raise H5Error(L.h5l_error().decode())
+
+    def set_storage(self, path, chunk=None, deflate=0, shuffle=False):
+        """How save() lays the dataset out: chunk = extents per dimension (None = contiguous), deflate level, shuffle."""
+        ch = list(chunk or [])
+        arr = (C.c_ulonglong * max(len(ch), 1))(*ch)
+        if _load().h5l_set_storage(self._h, path.encode(), len(ch), arr, int(deflate), int(bool(shuffle))) != 0:
+            raise KeyError(path)
 
     def extra(self, path):
         """[(message type, raw bytes)] of the attribute (0x0C) / comment (0x0D) messages carried by `path`."""

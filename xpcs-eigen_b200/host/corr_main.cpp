@@ -63,6 +63,7 @@ struct Scope {
 
 struct Flags {
     bool g2out = false, darkout = false, no_compat = false, ufxc = false, rigaku = false, hdf5 = false;
+    bool nocompress = false;  // --nocompress: C2T_all/g2_* contiguous instead of one deflate-6 chunk
     std::string imm, inpath, outpath, exchange, entry = "/xpcs", config;
     std::string outfile;  // --outfile=PATH: write configuration + results there and leave the input file untouched
     int device = 0;
@@ -104,6 +105,7 @@ static int parse_flags(int argc, char **argv, Flags &f)
             else if (name == "device") f.device = atoi(need().c_str());
             else if (name == "gpus") f.gpus = std::max(1, atoi(need().c_str()));
             else if (name == "no_compat") f.no_compat = true;
+            else if (name == "nocompress") f.nocompress = true;
             else if (name == "frame_threading" || name == "noframe_threading") {
                 // Corr::twotime(data, frameThreading) picks between two summation orders of the same C
                 // (corr.cpp:562-572); here the contraction has one (tensor-core) path, equal to both within 1e-5
@@ -876,7 +878,13 @@ int main(int argc, char **argv)
                 }
                 char name[64];
                 snprintf(name, sizeof(name), "/C2T_all/g2_%05d", q);
-                file.put(out + name, Type::F32, {(uint64_t)F, (uint64_t)F}, C.data());
+                // one chunk covering the matrix, deflate level 6: the reference's storage of these datasets
+                // (write2DData(..., compression = true), h5_result.cpp:140-152; corr.cpp:883-890)
+                h5lite::Dataset &c2t = file.put(out + name, Type::F32, {(uint64_t)F, (uint64_t)F}, C.data());
+                if (!fl.nocompress && (uint64_t)F * F * 4 < (1ull << 32)) {
+                    c2t.chunk = {(uint64_t)F, (uint64_t)F};
+                    c2t.deflate_level = 6;
+                }
                 for (int f = 0; f < F; f++) g2full[(size_t)f * B + b] = gf[f];
                 for (int d = 0; d < w; d++)
                     for (int p = 0; p < partials; p++) g2part[((size_t)d * partials + p) * B + b] = gp[(size_t)d * partials + p];

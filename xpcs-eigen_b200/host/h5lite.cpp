@@ -690,22 +690,152 @@ void write_extra(Wr &w, uint64_t &p, const Node &n)
     }
 }
 
+std::vector<uint8_t> shuffle_bytes(const std::vector<uint8_t> &in, size_t es)
+{
+    if (es <= 1) return in;
+    const size_t n = in.size() / es;
+    std::vector<uint8_t> out(in.size());
+    for (size_t i = 0; i < n; i++)
+        for (size_t b = 0; b < es; b++) out[b * n + i] = in[i * es + b];
+    for (size_t i = n * es; i < in.size(); i++) out[i] = in[i];
+    return out;
+}
+
+// Chunked storage: every chunk (edge chunks padded with zeros) filtered and written, then a version-1 B-tree of
+// node type 1 over them -- one leaf level of up to 2K entries, one internal level above it when needed (K = 32,
+// libhdf5's default "indexed storage" rank, which the version-0 superblock implies).  Returns the B-tree address.
+uint64_t write_chunks(Wr &w, const Dataset &d, size_t es)
+{
+    const int rank = (int)d.dims.size();
+    const int K = 32;
+    const uint64_t keysz = 8 + 8ull * (rank + 1);
+    const uint64_t node_bytes = 24 + (2 * K + 1) * keysz + 2 * K * 8ull;
+    std::vector<uint64_t> nchunks(rank), cidx(rank, 0);
+    uint64_t total = 1, celems = 1;
+    for (int i = 0; i < rank; i++) {
+        nchunks[i] = (d.dims[i] + d.chunk[i] - 1) / d.chunk[i];
+        total *= nchunks[i];
+        celems *= d.chunk[i];
+    }
+    struct Entry { uint64_t addr; uint32_t size; std::vector<uint64_t> off; };
+    std::vector<Entry> entries;
+    std::vector<uint8_t> buf(celems * es);
+    for (uint64_t c = 0; c < total; c++) {
+        // gather the chunk (row-major inside the chunk), zero padding beyond the dataset's edge
+        std::fill(buf.begin(), buf.end(), 0);
+        const uint64_t inner = d.chunk[rank - 1];
+        const uint64_t rows = celems / inner;
+        for (uint64_t row = 0; row < rows; row++) {
+            uint64_t rem = row, src = 0, stride = 1;
+            bool inside = true;
+            std::vector<uint64_t> g(rank, 0);
+            for (int k = rank - 2; k >= 0; k--) {
+                g[k] = cidx[k] * d.chunk[k] + rem % d.chunk[k];
+                rem /= d.chunk[k];
+                if (g[k] >= d.dims[k]) inside = false;
+            }
+            if (!inside) continue;
+            g[rank - 1] = cidx[rank - 1] * d.chunk[rank - 1];
+            for (int k = rank - 1; k >= 0; k--) {
+                src += g[k] * stride;
+                stride *= d.dims[k];
+            }
+            uint64_t ncopy = inner;
+            if (g[rank - 1] + ncopy > d.dims[rank - 1]) ncopy = d.dims[rank - 1] - g[rank - 1];
+            memcpy(buf.data() + row * inner * es, d.data.data() + src * es, ncopy * es);
+        }
+        std::vector<uint8_t> out = d.shuffle ? shuffle_bytes(buf, es) : buf;
+        if (d.deflate_level > 0) {
+            uLongf bound = compressBound((uLong)out.size());
+            std::vector<uint8_t> z(bound);
+            if (compress2(z.data(), &bound, out.data(), (uLong)out.size(), d.deflate_level) != Z_OK) throw Error("deflate failed");
+            z.resize(bound);
+            out.swap(z);
+        }
+        Entry e;
+        e.size = (uint32_t)out.size();
+        e.addr = w.alloc(out.size());
+        w.bytes(e.addr, out.data(), out.size());
+        for (int k = 0; k < rank; k++) e.off.push_back(cidx[k] * d.chunk[k]);
+        e.off.push_back(0);
+        entries.push_back(std::move(e));
+        for (int k = rank - 1; k >= 0; k--) {  // next chunk, last dimension fastest
+            if (++cidx[k] < nchunks[k]) break;
+            cidx[k] = 0;
+        }
+    }
+    std::vector<uint64_t> end_off;  // the key after the last chunk
+    for (int k = 0; k < rank; k++) end_off.push_back(k == 0 ? nchunks[0] * d.chunk[0] : 0);
+    end_off.push_back(0);
+    auto write_node = [&](int level, const std::vector<Entry> &es_, const std::vector<uint64_t> &last_key) {
+        const uint64_t a = w.alloc(node_bytes);
+        w.bytes(a, "TREE", 4);
+        w.w8(a + 4, 1);
+        w.w8(a + 5, level);
+        w.w16(a + 6, (uint32_t)es_.size());
+        w.w64(a + 8, UNDEF);
+        w.w64(a + 16, UNDEF);
+        uint64_t p = a + 24;
+        for (const Entry &e : es_) {
+            w.w32(p, e.size);
+            w.w32(p + 4, 0);
+            for (int k = 0; k <= rank; k++) w.w64(p + 8 + 8ull * k, e.off[k]);
+            w.w64(p + keysz, e.addr);
+            p += keysz + 8;
+        }
+        w.w32(p, 0);
+        w.w32(p + 4, 0);
+        for (int k = 0; k <= rank; k++) w.w64(p + 8 + 8ull * k, last_key[k]);
+        return a;
+    };
+    if (entries.empty()) return UNDEF;
+    if ((int)entries.size() <= 2 * K) return write_node(0, entries, end_off);
+    if (entries.size() > (size_t)(2 * K) * (2 * K)) throw Error("too many chunks (at most 4096 per dataset)");
+    std::vector<Entry> upper;
+    for (size_t i = 0; i < entries.size(); i += 2 * K) {
+        const size_t n = std::min<size_t>(2 * K, entries.size() - i);
+        std::vector<Entry> leaf(entries.begin() + i, entries.begin() + i + n);
+        const std::vector<uint64_t> &lk = i + n < entries.size() ? entries[i + n].off : end_off;
+        Entry u;
+        u.addr = write_node(0, leaf, lk);
+        u.size = leaf[0].size;
+        u.off = leaf[0].off;
+        upper.push_back(std::move(u));
+    }
+    return write_node(1, upper, end_off);
+}
+
 uint64_t write_dataset(Wr &w, const Node &node)
 {
     const Dataset &d = node.ds;
-    const uint64_t nbytes = d.data.size();
-    const uint64_t daddr = nbytes ? w.alloc(nbytes) : UNDEF;
-    if (nbytes) w.bytes(daddr, d.data.data(), nbytes);
     const int rank = (int)d.dims.size();
+    const bool chunked = !d.chunk.empty() && rank > 0 && d.count() > 0;
+    if (chunked && (int)d.chunk.size() != rank) throw Error("chunk rank differs from the dataset rank");
+    if (chunked)
+        for (uint64_t c : d.chunk)
+            if (c == 0) throw Error("chunk extent 0");
+    const size_t es = d.type == Type::STR ? d.elem_size : type_size(d.type);
+    const uint64_t nbytes = d.data.size();
+    uint64_t daddr = UNDEF;
+    if (chunked) daddr = write_chunks(w, d, es);
+    else if (nbytes) {
+        daddr = w.alloc(nbytes);
+        w.bytes(daddr, d.data.data(), nbytes);
+    }
     uint8_t tbody[24];
     const size_t tlen = datatype_body(d, tbody);
     const size_t space_sz = 8 + 8ull * rank;
     const size_t type_sz = (tlen + 7) & ~7ull;
-    const size_t fill_sz = 8, layout_sz = 24;
-    const size_t hsize = 4 * 8 + space_sz + type_sz + fill_sz + layout_sz + extra_bytes(node);
+    const int nfilters = chunked ? (d.shuffle ? 1 : 0) + (d.deflate_level > 0 ? 1 : 0) : 0;
+    // pipeline v1: 8 bytes, then per filter id(2) name length(2) flags(2) n client values(2) + values (padded to 8)
+    const size_t pipe_sz = nfilters ? 8 + (size_t)nfilters * 16 : 0;
+    const size_t fill_sz = 8;
+    const size_t layout_sz = chunked ? ((2 + 1 + 8 + 4ull * (rank + 1) + 7) & ~7ull) : 24;
+    const int nmsg = 4 + (nfilters ? 1 : 0) + (int)node.extra.size();
+    const size_t hsize = (size_t)(4 + (nfilters ? 1 : 0)) * 8 + space_sz + type_sz + fill_sz + layout_sz + pipe_sz + extra_bytes(node);
     const uint64_t o = w.alloc(16 + hsize);
     w.w8(o, 1);
-    w.w16(o + 2, 4 + (uint32_t)node.extra.size());
+    w.w16(o + 2, (uint32_t)nmsg);
     w.w32(o + 4, 1);
     w.w32(o + 8, (uint32_t)hsize);
     uint64_t p = o + 16;
@@ -724,12 +854,36 @@ uint64_t write_dataset(Wr &w, const Node &node)
     q = msg(0x0003, type_sz, 1);            // datatype v1
     w.bytes(q, tbody, tlen);
     q = msg(0x0005, fill_sz, 1);            // fill value v1: late allocation, write if set, defined, size 0
-    w.w8(q, 1); w.w8(q + 1, 2); w.w8(q + 2, 2); w.w8(q + 3, 1);
-    q = msg(0x0008, layout_sz, 0);          // layout v3, contiguous
+    w.w8(q, 1); w.w8(q + 1, chunked ? 3 : 2); w.w8(q + 2, 2); w.w8(q + 3, 1);
+    if (nfilters) {
+        q = msg(0x000B, pipe_sz, 0);        // filter pipeline v1
+        w.w8(q, 1);
+        w.w8(q + 1, nfilters);
+        uint64_t f = q + 8;
+        if (d.shuffle) {
+            w.w16(f, 2); w.w16(f + 2, 0); w.w16(f + 4, 1); w.w16(f + 6, 1);   // shuffle: optional, one value = element size
+            w.w32(f + 8, (uint32_t)es);
+            f += 16;
+        }
+        if (d.deflate_level > 0) {
+            w.w16(f, 1); w.w16(f + 2, 0); w.w16(f + 4, 1); w.w16(f + 6, 1);   // deflate: optional, one value = level
+            w.w32(f + 8, (uint32_t)d.deflate_level);
+            f += 16;
+        }
+    }
+    q = msg(0x0008, layout_sz, 0);          // layout v3
     w.w8(q, 3);
-    w.w8(q + 1, 1);
-    w.w64(q + 2, daddr);
-    w.w64(q + 10, nbytes);
+    if (chunked) {
+        w.w8(q + 1, 2);
+        w.w8(q + 2, rank + 1);
+        w.w64(q + 3, daddr);
+        for (int i = 0; i < rank; i++) w.w32(q + 11 + 4ull * i, (uint32_t)d.chunk[i]);
+        w.w32(q + 11 + 4ull * rank, (uint32_t)es);
+    } else {
+        w.w8(q + 1, 1);
+        w.w64(q + 2, daddr);
+        w.w64(q + 10, nbytes);
+    }
     write_extra(w, p, node);
     return o;
 }

@@ -41,6 +41,12 @@ struct Dataset {
     size_t elem_size = 4;            // for STR: the fixed string length
     std::vector<uint64_t> dims;      // empty = scalar
     std::vector<uint8_t> data;       // little-endian, row-major
+    // storage chosen by save(): empty chunk = contiguous; else chunked (one chunk extent per dimension, edge chunks
+    // padded), each chunk optionally byte-shuffled and deflated -- what H5Pset_chunk / H5Pset_shuffle /
+    // H5Pset_deflate produce (the reference stores C2T_all/g2_* as one deflate-6 chunk, corr.cpp:883-923)
+    std::vector<uint64_t> chunk;
+    int deflate_level = 0;           // 0 = not compressed
+    bool shuffle = false;
     uint64_t count() const;
     // conversions (numeric types convert like H5Dread with a native memory type)
     std::vector<int32_t> as_i32() const;

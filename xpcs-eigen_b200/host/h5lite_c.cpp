@@ -87,6 +87,17 @@ int h5l_put(void *h, const char *path, int type, int rank, const unsigned long l
     }
 }
 
+// storage of a dataset at the next save(): rank chunk extents (rank 0 = contiguous), deflate level, byte shuffle
+int h5l_set_storage(void *h, const char *path, int rank, const unsigned long long *chunk, int deflate_level, int shuffle)
+{
+    Node *n = ((File *)h)->find(path);
+    if (!n || n->is_group) return -1;
+    n->ds.chunk.assign(chunk, chunk + rank);
+    n->ds.deflate_level = deflate_level;
+    n->ds.shuffle = shuffle != 0;
+    return 0;
+}
+
 // attribute / comment messages carried by the object at `path`: count, and raw body i (returns its length)
 int h5l_extra_count(void *h, const char *path)
 {
