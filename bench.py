@@ -222,6 +222,14 @@ def cpu_sample_job(pkg, O, wl, F_s, seed=1234):
     return run, kind, threads, int(idx.size)
 
 
+def full_config(wl_key):
+    """The one full-size run of the reference binary per round (profiles/ref_full_config.py), if recorded."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ref_full_config.json"))).get(wl_key)
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, wl, wl_key):
     """--impl reference: the reference's CPU implementation of the path on this box's host
     cores (oracle/_ref when it was compiled, else the oracle port), rank 0 only."""
@@ -253,7 +261,7 @@ def run_reference_arm(args, wl, wl_key):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "workload_key": wl_key, "sample": sample, "same_config": F_s == wl["F"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-                         "stages_s": stages},
+                         "same_config": F_s == wl["F"], "stages_s": stages, "full_config": full_config(wl_key)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -149,7 +149,8 @@ int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val,
                      const int64_t *frame_offsets, const double *clock, const double *ticks,
                      int nframes);
 /* same, but idx/val/frame_offsets are DEVICE pointers that stay valid (and unmodified)
- * until xpcs_finish_ingest returns; no copy is made.  One call per ingest. */
+ * until xpcs_finish_ingest returns; no copy is made.  One call per ingest.  d_idx must be 16-byte aligned,
+ * d_val and d_frame_offsets 8-byte aligned (XPCS_E_ARG otherwise): the kernels read four events per load. */
 int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
                             const int64_t *d_frame_offsets, int64_t n_events, int nframes);
 /* replaces: Imm::NextFrames for uncompressed files + DenseFilter::Apply

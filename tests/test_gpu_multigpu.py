@@ -186,3 +186,52 @@ def test_corr_gpus_flag_equals_single_gpu_file(pkg, tmp_path):
     for k in one:
         assert one[k].shape == many[k].shape and one[k].dtype == many[k].dtype, k
         assert G.n_diff(one[k], many[k]) == 0, k
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_sharded_ragged_slabs(pkg):
+    """Edge cases of the exchange: a rank whose slab has no frames at all, a rank whose frames hold no events, frames
+    without events in the middle, and a job with fewer frames than would fill every rank."""
+    n = 2
+    dq, sq, off, idx, val = make_case(pkg, 32, 32, 40, 0.02, 39, n_dynamic=3, static_per_dynamic=2)
+    F = 40
+    # frames 10..19 empty
+    keep = np.ones(idx.size, bool)
+    keep[int(off[10]):int(off[20])] = False
+    cnt = np.diff(off)
+    cnt[10:20] = 0
+    idx, val = idx[keep], val[keep]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    ref = _single(pkg, dq, sq, F, off, idx, val)
+    uid = pkg.comm_unique_id()
+    out, err = [None] * n, [None] * n
+    cuts = {"empty_rank": [0, 0, F], "empty_frames_rank": [0, 10, F]}
+    for name, cut in cuts.items():
+        uid = pkg.comm_unique_id()
+
+        def worker(r):
+            try:
+                c = pkg.Correlator(dq, sq, F, device=r, shard_index=r, shard_count=n)
+                c.comm_init(n, r, uid)
+                a, b = cut[r], cut[r + 1]
+                c.push_sparse_slab(a, idx, val, off[a: b + 1])
+                sums = c.finish_ingest()
+                c.multitau(want=False)
+                out[r] = (sums, c.normalize())
+                c.close()
+            except Exception as e:  # noqa: BLE001
+                err[r] = e
+
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+        assert not any(t.is_alive() for t in th), name
+        for e in err:
+            if e is not None:
+                raise e
+        for r in range(n):
+            for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
+                assert G.n_diff(out[r][0][k], ref[0][k]) == 0, (name, r, k)
+            assert np.array_equal(out[r][1][0], ref[2], equal_nan=True), (name, r)

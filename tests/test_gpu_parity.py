@@ -337,3 +337,13 @@ def test_pinned_result_buffers_give_the_same_arrays(pkg):
         c.close()
     for k in out[0]:
         assert np.array_equal(out[0][k], out[1][k], equal_nan=True), k
+
+
+def test_push_sparse_device_rejects_misaligned_pointers(pkg):
+    """A sliced device view (d_idx not 16-byte aligned) must come back as XPCS_E_ARG, not as a misaligned-address fault."""
+    dq, sq, off, idx, val = make_case(pkg, 16, 16, 50, 0.05, 78)
+    c = pkg.Correlator(dq, sq, 50)
+    with pytest.raises(pkg.XpcsError) as e:
+        c.push_sparse_device(0x7f0000000004, 0x7f0000100000, 0x7f0000200000, 10, 50)
+    assert e.value.code == -1 and "aligned" in str(e.value)
+    c.close()

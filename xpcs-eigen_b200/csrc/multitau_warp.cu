@@ -52,6 +52,7 @@ struct MwArgs {
     int T;
     int lastl, cnt_last;       // last level >= 1 with delays (0 = none) and its delay count
     int parts;                 // CTAs per slice (1, 2 or 4): a CTA stages 32 / parts rows
+    int ld_factor;             // dense levels start where L_l <= ld_factor * n (4: measured best of 1..4 on C3 and C1 -- 5.64 / 4.37 / 4.18 / 4.08 ms; at most 4, the bin buffer)
 };
 
 __device__ __forceinline__ float mw_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
@@ -236,10 +237,11 @@ __global__ void __launch_bounds__(kMwWarps * 32, MINB) k_multitau_warp(MtArgs a,
         }
         __syncwarp();
 
-        // first dense level: L_l <= 4 n
+        // first dense level: L_l <= ld_factor * n (levels below it cost one pair per partner, levels from it on one
+        // bin per 2^l frames: the crossover lies where about every second bin is occupied)
         int ld;
         {
-            const unsigned mk = __ballot_sync(kFull, lane >= 1 && lane < nl && (F >> lane) <= 4 * max(n, 1));
+            const unsigned mk = __ballot_sync(kFull, lane >= 1 && lane < nl && (F >> lane) <= m.ld_factor * max(n, 1));
             ld = mk ? (__ffs(mk) - 1) : nl;
         }
 
@@ -632,6 +634,11 @@ int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a)
     if (bytes_for(len_cap, warps, m.parts) > (size_t)smem_cap) {  // T too large for the stage: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
         return XPCS_OK;
+    }
+    m.ld_factor = 4;
+    if (const char *e = getenv("XPCS_MW_LD")) {  // diagnostics: 1..4
+        const int q = atoi(e);
+        if (q >= 1 && q <= 4) m.ld_factor = q;
     }
     m.len_cap = len_cap;
     m.pitch_e = len_cap | 1;

@@ -699,6 +699,10 @@ extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, cons
     if (!h || !d_frame_offsets || nframes < 0 || n_events < 0) return h ? fail(h, XPCS_E_ARG, "push_sparse_device: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
     if (h->raw_frames > 0) return fail(h, XPCS_E_STATE, "push_sparse_device must be the only push of an ingest");
+    // the ingest kernels read four events per thread with 16- and 8-byte loads
+    if ((reinterpret_cast<uintptr_t>(d_idx) & 15u) || (reinterpret_cast<uintptr_t>(d_val) & 7u) ||
+        (reinterpret_cast<uintptr_t>(d_frame_offsets) & 7u))
+        return fail(h, XPCS_E_ARG, "push_sparse_device: d_idx must be 16-byte aligned, d_val and d_frame_offsets 8-byte aligned");
     h->external_events = true;
     h->ev_idx = d_idx;
     h->ev_val = d_val;
