@@ -808,6 +808,8 @@ def bench_sparse(args, wl):
                    if not weak else "1-Mpixel-module frames/s = n_gpus*F/t",
                    "l2": "inputs (%.0f MB/step per GPU) exceed the 126 MB L2; no flush needed" % (6 * E / 1e6)
                    if 6 * E > 126e6 else "inputs %.0f MB/step per GPU; results %.0f MB/step written in between evict them" % (6 * E / 1e6, 12.0 * T * R / 1e6),
+                   "event_transport": {1: "direct NVLink stores from the partition kernel into the owners' lists (CUDA IPC mappings)",
+                                       0: "staged: per-owner streams + grouped ncclSend/ncclRecv", -1: None}[c.comm_transport()],
                    "compat_stale_tail": not args.no_compat},
         "pixel_frames_per_s": float(R_total) * F / (ms_dev * 1e-3),
         "clocks": clocks,

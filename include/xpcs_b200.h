@@ -220,6 +220,12 @@ int xpcs_normalize_finish(xpcs_handle h, float *g2, float *stderr_out);
 int xpcs_comm_unique_id(void *id128);                                    /* ncclGetUniqueId: 128 bytes out   */
 int xpcs_comm_init(xpcs_handle h, int nranks, int rank, const void *id128); /* collective: ncclCommInitRank  */
 int xpcs_comm_nccl_version(void);                                        /* 0 = NCCL not loadable            */
+/* how the slab exchange of this handle moves the events: 1 = DIRECT, the partition kernel stores every event
+ * straight into its owner's list over NVLink (peer access inside a process, CUDA IPC mappings between
+ * processes; the transfer is the partition, an all-reduced word is the barrier); 0 = STAGED, per-owner streams
+ * and one grouped ncclSend/ncclRecv (ranks on several hosts, no peer access, or XPCS_NO_P2P); -1 = no communicator.
+ * Agreed by all ranks at xpcs_comm_init; a rank that cannot map a peer's buffers moves everybody to STAGED. */
+int xpcs_comm_transport(xpcs_handle h);
 /* Frame-slab ingest: this rank holds raw frames [first_raw_frame, first_raw_frame + nframes) of the WHOLE
  * detector (all pixels) -- e.g. its 1/n of the IMM file, so a job's host->device traffic is the file once,
  * spread over every GPU's PCIe link.  The slabs of ranks 0..n-1 must tile the job's raw frames in rank order.

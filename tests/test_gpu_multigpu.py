@@ -55,8 +55,9 @@ def _cuts(off, n):
     return cut
 
 
-def _sharded(pkg, n, dq, sq, F, off, idx, val, want_g=True, **kw):
-    """n threads = n ranks; returns rank results list of (sums, (G2, IP, IF) or None, g2, se, kernel report)"""
+def _sharded(pkg, n, dq, sq, F, off, idx, val, want_g=True, rounds=1, **kw):
+    """n threads = n ranks; returns rank results list of (sums, (G2, IP, IF) or None, g2, se, kernel report, rows,
+    transport).  rounds > 1 repeats the job on the same handles (buffers and peer mappings are reused)."""
     uid = pkg.comm_unique_id()
     cut = _cuts(off, n)
     out = [None] * n
@@ -67,11 +68,13 @@ def _sharded(pkg, n, dq, sq, F, off, idx, val, want_g=True, **kw):
             c = pkg.Correlator(dq, sq, F, device=r, shard_index=r, shard_count=n, **kw)
             c.comm_init(n, r, uid)
             a, b = cut[r], cut[r + 1]
-            c.push_sparse_slab(a, idx, val, off[a: b + 1])
-            sums = c.finish_ingest()
-            Gs = c.multitau() if want_g else c.multitau(want=False)
-            g2, se = c.normalize()
-            out[r] = (sums, Gs, g2, se, c.kernel_report(), c.info().n_rows)
+            for _ in range(rounds):
+                c.reset()
+                c.push_sparse_slab(a, idx, val, off[a: b + 1])
+                sums = c.finish_ingest()
+                Gs = c.multitau() if want_g else c.multitau(want=False)
+                g2, se = c.normalize()
+            out[r] = (sums, Gs, g2, se, c.kernel_report(), c.info().n_rows, c.comm_transport())
             c.close()
         except Exception as e:  # noqa: BLE001
             err[r] = e
@@ -125,13 +128,18 @@ def test_sharded_equals_single_gpu(pkg, n):
     assert sum(r[5] for r in res) == int(((dq > 0) & (sq > 0)).sum())
     Gsum = [np.zeros_like(ref[1][0]) for _ in range(3)]
     for r in range(n):
-        sums, Gs, g2, se, rep, _ = res[r]
+        sums, Gs, g2, se, rep, _, transport = res[r]
         # whole-detector sums and g2 on EVERY rank, bit-identical to one GPU
         for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
             assert G.n_diff(sums[k], ref[0][k]) == 0, (r, k)
         assert np.array_equal(g2, ref[2], equal_nan=True), r
         assert np.array_equal(se, ref[3], equal_nan=True), r
-        assert rep.get("nccl_exchange", (0, 0))[1] == 1 and rep.get("nccl_allreduce", (0, 0))[1] >= 2
+        if transport == 1:   # direct NVLink stores: no staged exchange, one barrier
+            assert rep.get("k_demux_scatter_p2p", (0, 0))[1] == 1 and rep.get("nccl_barrier", (0, 0))[1] == 1
+            assert "nccl_exchange" not in rep
+        else:
+            assert rep.get("nccl_exchange", (0, 0))[1] == 1
+        assert rep.get("nccl_allreduce", (0, 0))[1] >= 2
         for k in range(3):
             Gsum[k] += Gs[k]   # every pixel has one owner, the others hold zeros
     for k in range(3):
@@ -150,7 +158,7 @@ def test_sharded_framesum_normalisation_and_flatfield(pkg, oracle):
     ref = _single(pkg, dq, sq, F, off, idx, val, **kw)
     res = _sharded(pkg, n, dq, sq, F, off, idx, val, **kw)
     for r in range(n):
-        sums, Gs, g2, se, rep, _ = res[r]
+        sums, Gs, g2, se, rep, _, _ = res[r]
         for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
             err, nanmis = G.rel_err(sums[k], ref[0][k])
             assert nanmis == 0 and err <= 1e-5, (r, k, err)
@@ -235,3 +243,60 @@ def test_sharded_ragged_slabs(pkg):
             for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
                 assert G.n_diff(out[r][0][k], ref[0][k]) == 0, (name, r, k)
             assert np.array_equal(out[r][1][0], ref[2], equal_nan=True), (name, r)
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("staged", [False, True])
+def test_both_transports_and_buffer_reuse(pkg, monkeypatch, staged):
+    """The slab exchange over direct NVLink stores (default inside one process: peer access) and over the staged
+    ncclSend/ncclRecv path (XPCS_NO_P2P), three jobs in a row on the same handles, the second one larger than the
+    first (the receive buffers grow and the peers' mappings must follow): always the single-GPU result."""
+    if staged:
+        monkeypatch.setenv("XPCS_NO_P2P", "1")
+    n = 2
+    dq, sq, off, idx, val = make_case(pkg, 64, 64, 2500, 0.012, 41, n_dynamic=4, static_per_dynamic=3)
+    F = 2500
+    ref = _single(pkg, dq, sq, F, off, idx, val)
+    # a smaller job first (half the events dropped), then the full one twice
+    keep = np.arange(idx.size) % 2 == 0
+    cnt = np.add.reduceat(keep.astype(np.int64), off[:-1].clip(max=idx.size - 1)) * (np.diff(off) > 0)
+    off_small = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    uid = pkg.comm_unique_id()
+    out, err = [None] * n, [None] * n
+    cut = _cuts(off, n)
+
+    def worker(r):
+        try:
+            c = pkg.Correlator(dq, sq, F, device=r, shard_index=r, shard_count=n)
+            c.comm_init(n, r, uid)
+            a, b = cut[r], cut[r + 1]
+            c.push_sparse_slab(a, idx[keep], val[keep], off_small[a: b + 1])
+            c.finish_ingest(want=False)
+            c.multitau(want=False)
+            c.normalize()
+            for _ in range(2):
+                c.reset()
+                c.push_sparse_slab(a, idx, val, off[a: b + 1])
+                sums = c.finish_ingest()
+                c.multitau(want=False)
+                g2, se = c.normalize()
+            out[r] = (sums, g2, se, c.comm_transport(), c.kernel_report())
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in th)
+    for e in err:
+        if e is not None:
+            raise e
+    for r in range(n):
+        sums, g2, se, transport, rep = out[r]
+        assert transport == (0 if staged else 1), "transport %d" % transport
+        for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
+            assert G.n_diff(sums[k], ref[0][k]) == 0, (r, k)
+        assert np.array_equal(g2, ref[2], equal_nan=True) and np.array_equal(se, ref[3], equal_nan=True)

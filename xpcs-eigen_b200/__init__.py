@@ -205,6 +205,10 @@ class Correlator:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._check(self._lib.xpcs_comm_init(self._h, nranks, rank, buf))
 
+    def comm_transport(self):
+        """1 = direct NVLink stores into the owners' buffers, 0 = staged ncclSend/ncclRecv, -1 = no communicator."""
+        return int(self._lib.xpcs_comm_transport(self._h))
+
     def push_sparse_slab(self, first_raw_frame, idx, val, frame_off, clock=None, ticks=None):
         """Raw frames [first_raw_frame, +len(frame_off)-1) of the WHOLE detector; finish_ingest redistributes."""
         idx = np.ascontiguousarray(idx, np.int32)

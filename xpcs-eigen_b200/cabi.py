@@ -86,6 +86,7 @@ SYMBOLS = {
     "xpcs_comm_unique_id": (_i, [_vp]),
     "xpcs_comm_init": (_i, [_vp, _i, _i, _vp]),
     "xpcs_comm_nccl_version": (_i, []),
+    "xpcs_comm_transport": (_i, [_vp]),
     "xpcs_push_sparse_slab": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "xpcs_push_sparse_slab_device": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i]),
     "xpcs_twotime": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -19,6 +19,7 @@
 // single-GPU path does not need it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <mutex>
@@ -203,6 +204,25 @@ __global__ void __launch_bounds__(kDmWarps * 32) k_demux_scatter(const int32_t *
     }
 }
 
+struct OffDst {
+    int64_t *p[kMaxRanks];
+};
+
+// direct path: the per-destination frame offsets of this slab go straight into the owners' offset tables
+__global__ void k_push_offsets(const int64_t *__restrict__ dm_off, int nfr, OffDst dst)
+{
+    const int64_t *src = dm_off + (int64_t)blockIdx.x * (nfr + 1);
+    int64_t *d = dst.p[blockIdx.x];
+    for (int i = threadIdx.x; i <= nfr; i += blockDim.x) d[i] = src[i];
+}
+
+// what a rank tells the others about its receive buffers (28 x int64)
+struct PeerRec {
+    unsigned long long idx, val, off, pid;
+    cudaIpcMemHandle_t hidx, hval, hoff;
+};
+static_assert(sizeof(PeerRec) == 224, "PeerRec is 28 int64");
+
 struct MergeRanges {
     int first[kMaxRanks], nfr[kMaxRanks];
     long long base[kMaxRanks];
@@ -263,22 +283,108 @@ void comm_destroy(xpcs_handle_s *h)
         if (api) api->CommDestroy((ncclComm_t)h->comm);
         h->comm = nullptr;
     }
+    for (void *p : h->peer_opened) cudaIpcCloseMemHandle(p);
+    h->peer_opened.clear();
+    release(h->d_p2p_xchg);
     release(h->d_owner_of_pixel);
     release(h->d_slab_idx); release(h->d_slab_val); release(h->d_slab_off);
     release(h->d_dm_off); release(h->d_dm_meta); release(h->d_dm_all);
     release(h->d_send_idx); release(h->d_send_val); release(h->d_recv_off);
 }
 
+// Make the receive buffers of every rank addressable from this device: same process -> the pointers themselves
+// (peer access enabled at xpcs_comm_init), other processes -> CUDA IPC mappings.  Collective.  On any failure
+// anywhere, every rank drops to the staged ncclSend/ncclRecv path for good (the decision is all-reduced).
+static int p2p_exchange_mappings(xpcs_handle_s *h)
+{
+    const int N = h->comm_nranks, me = h->comm_rank;
+    NcclApi *api = nccl_api();
+    int rc;
+    constexpr size_t kRecWords = sizeof(PeerRec) / 8;
+    if ((rc = ensure(h, h->d_p2p_xchg, (size_t)(N + 1) * kRecWords + 8, "peer mapping records"))) return rc;
+    PeerRec mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.idx = (unsigned long long)(uintptr_t)h->d_idx.p;
+    mine.val = (unsigned long long)(uintptr_t)h->d_val.p;
+    mine.off = (unsigned long long)(uintptr_t)h->d_recv_off.p;
+    mine.pid = (unsigned long long)getpid();
+    bool ok = cudaIpcGetMemHandle(&mine.hidx, h->d_idx.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.hval, h->d_val.p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.hoff, h->d_recv_off.p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    int64_t *d_mine = h->d_p2p_xchg.p, *d_all = h->d_p2p_xchg.p + kRecWords;
+    if ((rc = check_cuda(h, cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream), "peer record H2D"))) return rc;
+    {
+        LaunchScope ls(h, "nccl_allgather", false);
+        if ((rc = nccl_check(h, api->AllGather(d_mine, d_all, kRecWords, ncclInt64, (ncclComm_t)h->comm, h->stream), "ncclAllGather (peer records)")))
+            return rc;
+    }
+    std::vector<PeerRec> all((size_t)N);
+    if ((rc = check_cuda(h, cudaMemcpyAsync(all.data(), d_all, sizeof(PeerRec) * (size_t)N, cudaMemcpyDeviceToHost, h->stream), "peer records D2H")))
+        return rc;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "peer records"))) return rc;
+    for (void *p : h->peer_opened) cudaIpcCloseMemHandle(p);
+    h->peer_opened.clear();
+    h->peer_idx.assign(N, nullptr);
+    h->peer_val.assign(N, nullptr);
+    h->peer_off.assign(N, nullptr);
+    for (int s = 0; s < N && ok; s++) {
+        if (s == me) {
+            h->peer_idx[s] = h->d_idx.p;
+            h->peer_val[s] = h->d_val.p;
+            h->peer_off[s] = h->d_recv_off.p;
+        } else if (all[s].pid == mine.pid) {  // another thread of this process: one address space
+            h->peer_idx[s] = reinterpret_cast<int32_t *>((uintptr_t)all[s].idx);
+            h->peer_val[s] = reinterpret_cast<int16_t *>((uintptr_t)all[s].val);
+            h->peer_off[s] = reinterpret_cast<int64_t *>((uintptr_t)all[s].off);
+        } else {
+            void *pi = nullptr, *pv = nullptr, *po = nullptr;
+            ok = cudaIpcOpenMemHandle(&pi, all[s].hidx, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) h->peer_opened.push_back(pi);
+            ok = ok && cudaIpcOpenMemHandle(&pv, all[s].hval, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) h->peer_opened.push_back(pv);
+            ok = ok && cudaIpcOpenMemHandle(&po, all[s].hoff, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) h->peer_opened.push_back(po);
+            if (!ok) cudaGetLastError();
+            h->peer_idx[s] = (int32_t *)pi;
+            h->peer_val[s] = (int16_t *)pv;
+            h->peer_off[s] = (int64_t *)po;
+        }
+    }
+    // all or nothing: MIN over the ranks of "every mapping worked here"
+    int64_t flag = ok ? 1 : 0;
+    if ((rc = check_cuda(h, cudaMemcpyAsync(d_mine, &flag, sizeof(flag), cudaMemcpyHostToDevice, h->stream), "p2p flag H2D"))) return rc;
+    {
+        LaunchScope ls(h, "nccl_allreduce", false);
+        if ((rc = nccl_check(h, api->AllReduce(d_mine, d_mine, 1, ncclInt64, ncclMin, (ncclComm_t)h->comm, h->stream), "ncclAllReduce (p2p)")))
+            return rc;
+    }
+    if ((rc = check_cuda(h, cudaMemcpyAsync(&flag, d_mine, sizeof(flag), cudaMemcpyDeviceToHost, h->stream), "p2p flag D2H"))) return rc;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "p2p agreement"))) return rc;
+    if (!flag) {
+        for (void *p : h->peer_opened) cudaIpcCloseMemHandle(p);
+        h->peer_opened.clear();
+        h->p2p_enabled = false;
+        h->p2p_mapped = false;
+        return XPCS_OK;
+    }
+    h->p2p_mapped = true;
+    return XPCS_OK;
+}
+
 // Frame slabs -> pixel shards.  On return the handle holds a frame-major event list of its own pixels over all
 // raw frames of the job (ev_idx / ev_val / ev_off), exactly what xpcs_push_sparse_device would have set up.
+// Two transports: DIRECT (default on one host with peer access) -- the partition kernel stores every event
+// straight into its owner's list over NVLink, the transfer IS the partition; STAGED -- per-owner streams in a send
+// buffer, one grouped ncclSend/ncclRecv (XPCS_NO_P2P, or whenever peer mappings cannot be had).
 int comm_exchange_slab(xpcs_handle_s *h)
 {
     const int N = h->comm_nranks, me = h->comm_rank, nfr = h->slab_frames;
+    const int W = N + 6;  // table row: first frame, frames, events per destination [N], receive capacities (events, offsets), buffer generation, wants mappings
     NcclApi *api = nccl_api();
     int rc;
     if ((rc = ensure(h, h->d_dm_off, (size_t)N * (nfr + 1), "slab partition offsets"))) return rc;
-    if ((rc = ensure(h, h->d_dm_meta, (size_t)N + 2, "slab partition totals"))) return rc;
-    if ((rc = ensure(h, h->d_dm_all, (size_t)N * (N + 2), "slab partition table"))) return rc;
+    if ((rc = ensure(h, h->d_dm_meta, (size_t)W, "slab partition totals"))) return rc;
+    if ((rc = ensure(h, h->d_dm_all, (size_t)N * W, "slab partition table"))) return rc;
     cudaMemsetAsync(h->d_dm_off.p, 0, sizeof(int64_t) * (size_t)N * (nfr + 1), h->stream);
     if (nfr > 0) {
         LaunchScope ls(h, "k_demux_count");
@@ -290,17 +396,25 @@ int comm_exchange_slab(xpcs_handle_s *h)
         k_demux_scan<<<N, 1024, 0, h->stream>>>(h->d_dm_off.p, nfr, h->slab_first, h->d_dm_meta.p);
     }
     {
+        // buffers that moved outside an exchange (a plain push grew them) invalidate the peers' mappings as well
+        if (h->p2p_mapped && (int)h->peer_idx.size() == N &&
+            (h->peer_idx[me] != h->d_idx.p || h->peer_val[me] != h->d_val.p || h->peer_off[me] != h->d_recv_off.p))
+            h->p2p_gen++;
+        const int64_t extra[4] = {h->d_idx.p && h->d_val.p ? (int64_t)std::min(h->d_idx.n, h->d_val.n) : 0,
+                                  h->d_recv_off.p ? (int64_t)h->d_recv_off.n : 0, (int64_t)h->p2p_gen, h->p2p_mapped ? 0 : 1};
+        if ((rc = check_cuda(h, cudaMemcpyAsync(h->d_dm_meta.p + N + 2, extra, sizeof(extra), cudaMemcpyHostToDevice, h->stream), "table H2D")))
+            return rc;
         LaunchScope ls(h, "nccl_allgather", false);
-        if ((rc = nccl_check(h, api->AllGather(h->d_dm_meta.p, h->d_dm_all.p, (size_t)N + 2, ncclInt64, (ncclComm_t)h->comm, h->stream),
+        if ((rc = nccl_check(h, api->AllGather(h->d_dm_meta.p, h->d_dm_all.p, (size_t)W, ncclInt64, (ncclComm_t)h->comm, h->stream),
                              "ncclAllGather")))
             return rc;
     }
-    std::vector<int64_t> all((size_t)N * (N + 2));
+    std::vector<int64_t> all((size_t)N * W);
     if ((rc = check_cuda(h, cudaMemcpyAsync(all.data(), h->d_dm_all.p, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, h->stream),
                          "slab table D2H")))
         return rc;
     if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "slab partition"))) return rc;
-    auto at = [&](int s, int k) { return all[(size_t)s * (N + 2) + k]; };
+    auto at = [&](int s, int k) { return all[(size_t)s * W + k]; };
     // the slabs must tile the raw frames of the job in rank order
     MergeRanges mr{};
     int64_t raw_total = 0, E_me = 0;
@@ -319,42 +433,103 @@ int comm_exchange_slab(xpcs_handle_s *h)
         E_me += at(s, 2 + me);
     }
     if (raw_total > 0x7fffffffLL) return fail(h, XPCS_E_ARG, "too many raw frames");
+    // The receive buffers grow only when the capacities published in the table say so -- every rank can then tell
+    // from the table alone whose buffers move in this exchange (the peers' mappings must follow).
+    if (at(me, N + 2) < E_me + 8) {
+        size_t want = (size_t)E_me + (size_t)E_me / 16;
+        if (h->prm.reserve_events > (int64_t)want) want = (size_t)h->prm.reserve_events;
+        release(h->d_idx);
+        release(h->d_val);
+        if ((rc = ensure(h, h->d_idx, want + 8, "event indices"))) return rc;
+        if ((rc = ensure(h, h->d_val, want + 8, "event values"))) return rc;
+        h->p2p_gen++;
+    }
+    if (at(me, N + 3) < raw_total + N + 1) {
+        release(h->d_recv_off);
+        if ((rc = ensure(h, h->d_recv_off, (size_t)raw_total + N + 1, "received offsets"))) return rc;
+        if (!(at(me, N + 2) < E_me + 8)) h->p2p_gen++;  // (one bump per exchange, whatever moved)
+    }
+    if ((rc = ensure(h, h->d_frame_off, (size_t)raw_total + 1, "frame offsets"))) return rc;
+
+    bool direct = h->p2p_enabled;
+    if (direct) {
+        // Every rank derives from the table whether ANY receive buffer moves in this exchange (the same answer
+        // everywhere): then, or when somebody still lacks mappings, the mapping records go round once more.
+        bool remap = false;
+        for (int s = 0; s < N; s++) {
+            int64_t E_s = 0;
+            for (int q = 0; q < N; q++) E_s += at(q, 2 + s);
+            const bool grows = at(s, N + 2) < E_s + 8 || at(s, N + 3) < raw_total + N + 1;
+            const bool unseen = (int)h->peer_gen_seen.size() != N || h->peer_gen_seen[s] != at(s, N + 4);
+            remap = remap || grows || unseen || at(s, N + 5) != 0;
+        }
+        if (remap) {
+            if ((rc = p2p_exchange_mappings(h))) return rc;
+            h->peer_gen_seen.assign(N, -1);
+            // generations after this exchange: a rank that had to grow has bumped its own by exactly one
+            for (int s = 0; s < N; s++) {
+                int64_t E_s = 0;
+                for (int q = 0; q < N; q++) E_s += at(q, 2 + s);
+                const bool grows = at(s, N + 2) < E_s + 8 || at(s, N + 3) < raw_total + N + 1;
+                h->peer_gen_seen[s] = at(s, N + 4) + (grows ? 1 : 0);
+            }
+            h->peer_gen_seen[me] = h->p2p_gen;
+        }
+        direct = h->p2p_enabled && h->p2p_mapped;
+    }
+
+    DemuxDst dst{};
     int64_t send_total = 0;
     std::vector<int64_t> sbase(N, 0);
-    for (int d = 0; d < N; d++) {
-        sbase[d] = send_total;
-        if (d != me) send_total += at(me, 2 + d);
-    }
-    size_t need = (size_t)E_me;
-    if (h->prm.reserve_events > (int64_t)need) need = (size_t)h->prm.reserve_events;
-    if ((rc = ensure(h, h->d_idx, need + 8, "event indices"))) return rc;
-    if ((rc = ensure(h, h->d_val, need + 8, "event values"))) return rc;
-    // the send streams live in the record buffer of the store build, which is only written after the exchange
-    // (6 bytes per event to send against 8 bytes per event to keep)
-    const size_t send_words = ((size_t)send_total * 6 + 64) / 8 + 8;
-    if ((rc = ensure(h, h->d_rec, std::max(send_words, (size_t)E_me + 1), "event records / send streams"))) return rc;
-    int32_t *send_idx = reinterpret_cast<int32_t *>(h->d_rec.p);
-    int16_t *send_val = reinterpret_cast<int16_t *>(send_idx + (((size_t)send_total + 7) & ~(size_t)7));
-    if ((rc = ensure(h, h->d_recv_off, (size_t)raw_total + N + 1, "received offsets"))) return rc;
-    if ((rc = ensure(h, h->d_frame_off, (size_t)raw_total + 1, "frame offsets"))) return rc;
-    DemuxDst dst{};
-    for (int d = 0; d < N; d++) {
-        if (d == me) {
-            dst.idx[d] = h->d_idx.p + mr.base[me];
-            dst.val[d] = h->d_val.p + mr.base[me];
-        } else {
-            dst.idx[d] = send_idx + sbase[d];
-            dst.val[d] = send_val + sbase[d];
+    if (direct) {
+        // position of my stream inside owner d's list: behind the streams of the ranks before me
+        for (int d = 0; d < N; d++) {
+            int64_t base = 0;
+            for (int q = 0; q < me; q++) base += at(q, 2 + d);
+            dst.idx[d] = h->peer_idx[d] + base;
+            dst.val[d] = h->peer_val[d] + base;
+        }
+    } else {
+        for (int d = 0; d < N; d++) {
+            sbase[d] = send_total;
+            if (d != me) send_total += at(me, 2 + d);
+        }
+        // the send streams live in the record buffer of the store build, which is only written after the exchange
+        // (6 bytes per event to send against 8 bytes per event to keep)
+        const size_t send_words = ((size_t)send_total * 6 + 64) / 8 + 8;
+        if ((rc = ensure(h, h->d_rec, std::max(send_words, (size_t)E_me + 1), "event records / send streams"))) return rc;
+        int32_t *send_idx = reinterpret_cast<int32_t *>(h->d_rec.p);
+        int16_t *send_val = reinterpret_cast<int16_t *>(send_idx + (((size_t)send_total + 7) & ~(size_t)7));
+        for (int d = 0; d < N; d++) {
+            if (d == me) {
+                dst.idx[d] = h->d_idx.p + mr.base[me];
+                dst.val[d] = h->d_val.p + mr.base[me];
+            } else {
+                dst.idx[d] = send_idx + sbase[d];
+                dst.val[d] = send_val + sbase[d];
+            }
         }
     }
     if (nfr > 0) {
-        LaunchScope ls(h, "k_demux_scatter");
+        LaunchScope ls(h, direct ? "k_demux_scatter_p2p" : "k_demux_scatter");
         k_demux_scatter<<<(nfr + kDmWarps - 1) / kDmWarps, kDmWarps * 32, 0, h->stream>>>(
             h->slab_idx, h->slab_val, h->slab_off, nfr, h->d_owner_of_pixel.p, h->P, N, h->d_dm_off.p, dst);
     }
-    cudaMemcpyAsync(h->d_recv_off.p + mr.first[me] + me, h->d_dm_off.p + (size_t)me * (nfr + 1), sizeof(int64_t) * ((size_t)nfr + 1),
-                    cudaMemcpyDeviceToDevice, h->stream);
-    {
+    if (direct) {
+        OffDst od{};
+        for (int d = 0; d < N; d++) od.p[d] = h->peer_off[d] + mr.first[me] + me;
+        {
+            LaunchScope ls(h, "k_push_offsets");
+            k_push_offsets<<<N, 256, 0, h->stream>>>(h->d_dm_off.p, nfr, od);
+        }
+        // nobody reads its list before every rank has finished storing into it: a one-word all-reduce as the barrier
+        LaunchScope ls(h, "nccl_barrier", false);
+        if ((rc = nccl_check(h, api->AllReduce(h->d_dm_all.p, h->d_dm_all.p, 1, ncclInt64, ncclSum, (ncclComm_t)h->comm, h->stream),
+                             "ncclAllReduce (barrier)")))
+            return rc;
+    } else {
+        cudaMemcpyAsync(h->d_recv_off.p + mr.first[me] + me, h->d_dm_off.p + (size_t)me * (nfr + 1), sizeof(int64_t) * ((size_t)nfr + 1),
+                        cudaMemcpyDeviceToDevice, h->stream);
         LaunchScope ls(h, "nccl_exchange", false);
         ncclComm_t comm = (ncclComm_t)h->comm;
         ncclResult_t r = api->GroupStart();
@@ -430,8 +605,54 @@ extern "C" int xpcs_comm_init(xpcs_handle h, int nranks, int rank, const void *i
     h->comm_nranks = nranks;
     h->comm_rank = rank;
     if ((rc = ensure(h, h->d_owner_of_pixel, (size_t)h->P, "pixel owners"))) return rc;
-    return check_cuda(h, cudaMemcpy(h->d_owner_of_pixel.p, h->owner_of_pixel.data(), (size_t)h->P, cudaMemcpyHostToDevice),
-                      "pixel owners H2D");
+    if ((rc = check_cuda(h, cudaMemcpy(h->d_owner_of_pixel.p, h->owner_of_pixel.data(), (size_t)h->P, cudaMemcpyHostToDevice),
+                         "pixel owners H2D")))
+        return rc;
+    // Direct NVLink stores need every rank on this host and peer access between the devices.  Who is where is
+    // all-gathered once; the verdict is all-reduced so that every rank takes the same transport.
+    h->p2p_enabled = false;
+    h->p2p_mapped = false;
+    if (nranks > 1) {
+        int64_t mine[3] = {(int64_t)getpid(), (int64_t)gethostid(), (int64_t)h->device};
+        if ((rc = ensure(h, h->d_p2p_xchg, (size_t)3 * (nranks + 1) + 8, "peer identities"))) return rc;
+        int64_t *d_mine = h->d_p2p_xchg.p, *d_all = h->d_p2p_xchg.p + 3;
+        std::vector<int64_t> all((size_t)3 * nranks);
+        cudaMemcpyAsync(d_mine, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream);
+        if ((rc = nccl_check(h, api->AllGather(d_mine, d_all, 3, ncclInt64, comm, h->stream), "ncclAllGather (identities)"))) return rc;
+        cudaMemcpyAsync(all.data(), d_all, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, h->stream);
+        if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "peer identities"))) return rc;
+        bool ok = !getenv("XPCS_NO_P2P");
+        h->peer_pid.assign(nranks, 0);
+        for (int s = 0; s < nranks && ok; s++) {
+            h->peer_pid[s] = all[(size_t)3 * s];
+            if (all[(size_t)3 * s + 1] != mine[1]) ok = false;  // another host: NCCL only
+            if (s != rank && all[(size_t)3 * s] == mine[0]) {   // another thread of this process
+                const int dev = (int)all[(size_t)3 * s + 2];
+                int can = 0;
+                if (dev == h->device || cudaDeviceCanAccessPeer(&can, h->device, dev) != cudaSuccess || !can) ok = false;
+                else {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                    cudaGetLastError();
+                }
+            }
+        }
+        int64_t flag = ok ? 1 : 0;
+        cudaMemcpyAsync(d_mine, &flag, sizeof(flag), cudaMemcpyHostToDevice, h->stream);
+        if ((rc = nccl_check(h, api->AllReduce(d_mine, d_mine, 1, ncclInt64, ncclMin, comm, h->stream), "ncclAllReduce (transport)"))) return rc;
+        cudaMemcpyAsync(&flag, d_mine, sizeof(flag), cudaMemcpyDeviceToHost, h->stream);
+        if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "transport agreement"))) return rc;
+        h->p2p_enabled = flag != 0;
+    }
+    return XPCS_OK;
+}
+
+/* 1 = the slab exchange of this handle stores directly into the owners' buffers over NVLink (peer mappings),
+ * 0 = it stages and uses ncclSend/ncclRecv, -1 = no communicator */
+extern "C" int xpcs_comm_transport(xpcs_handle h)
+{
+    if (!h || !h->comm) return -1;
+    return h->p2p_enabled ? 1 : 0;
 }
 
 extern "C" int xpcs_comm_nccl_version(void)

@@ -209,6 +209,16 @@ struct xpcs_handle_s {
     xpcs::DevBuf<int32_t> d_send_idx;
     xpcs::DevBuf<int16_t> d_send_val;
     xpcs::DevBuf<int64_t> d_recv_off;     // [raw frames + nranks] offsets as received, one stream per source rank
+    // direct NVLink stores (comm.cu): the partition kernel writes every event straight into its owner's list
+    bool p2p_enabled = false;             // all ranks on one host, peer access possible, not disabled by XPCS_NO_P2P
+    bool p2p_mapped = false;              // peer pointers below are current
+    long long p2p_gen = 0;                // bumped whenever this rank's receive buffers move
+    std::vector<long long> peer_pid, peer_gen_seen;
+    std::vector<int32_t *> peer_idx;      // [nranks] the ranks' d_idx / d_val / d_recv_off as seen from this device
+    std::vector<int16_t *> peer_val;
+    std::vector<int64_t *> peer_off;
+    std::vector<void *> peer_opened;      // IPC mappings to close
+    xpcs::DevBuf<int64_t> d_p2p_xchg;     // mapping records, mine + everyone's
     bool frame_acc_reduced = false;       // the per-frame sums already cover every shard
     bool part_sums_reduced = false;       // so do the per-static-bin sums
     std::vector<int> slab_first_of_rank, slab_frames_of_rank;  // filled by the exchange
