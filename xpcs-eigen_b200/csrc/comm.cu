@@ -213,7 +213,7 @@ __global__ void k_push_offsets(const int64_t *__restrict__ dm_off, int nfr, OffD
 {
     const int64_t *src = dm_off + (int64_t)blockIdx.x * (nfr + 1);
     int64_t *d = dst.p[blockIdx.x];
-    for (int i = threadIdx.x; i <= nfr; i += blockDim.x) d[i] = src[i];
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i <= nfr; i += gridDim.y * blockDim.x) d[i] = src[i];
 }
 
 // what a rank tells the others about its receive buffers (28 x int64)
@@ -520,7 +520,7 @@ int comm_exchange_slab(xpcs_handle_s *h)
         for (int d = 0; d < N; d++) od.p[d] = h->peer_off[d] + mr.first[me] + me;
         {
             LaunchScope ls(h, "k_push_offsets");
-            k_push_offsets<<<N, 256, 0, h->stream>>>(h->d_dm_off.p, nfr, od);
+            k_push_offsets<<<dim3(N, 16), 256, 0, h->stream>>>(h->d_dm_off.p, nfr, od);
         }
         // nobody reads its list before every rank has finished storing into it: a one-word all-reduce as the barrier
         LaunchScope ls(h, "nccl_barrier", false);

@@ -560,9 +560,15 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
             col[(int64_t)j * kSlice] = x;
         }
     }
-    // insertion sort by frame (the key sits in the high bits of the word)
+    // insertion sort by frame (the key sits in the high bits of the word); the largest word so far stays in a
+    // register, so that a row that is sorted already costs one load and one compare per event
+    W top = n > 0 ? col[0] : (W)0;
     for (int i = 1; i < n; i++) {
         W w = col[(int64_t)i * kSlice];
+        if (w >= top) {
+            top = w;
+            continue;
+        }
         int j = i;
         while (j > 0) {
             W p = col[(int64_t)(j - 1) * kSlice];
@@ -613,8 +619,11 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     {
         float fsum = 0.0f;
         long long isum = 0;
-        int win = -1, wend = 0;  // current static window and its first frame beyond
+        // current static window and its first frame beyond; window w holds the frames [w * swindow + late, (w + 1) *
+        // swindow + late) (frame 0 belongs to window 0 either way)
+        int win = 0, wend = a.swindow + (a.late_window ? 1 : 0);
         double wacc = 0.0;
+        bool open = false;
         for (int i = 0; i < m; i++) {
             int t;
             double v;
@@ -635,15 +644,22 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
                 if (a.frame_scale) x = __fdiv_rn(x, a.frame_scale[t]);
                 col[(int64_t)i * kSlice] = (W)(((unsigned long long)(uint32_t)t << 32) | __float_as_uint(x));
             }
-            if (t >= wend) {  // frames ascend: a division only when the static window changes
-                if (win >= 0 && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
-                win = a.late_window ? (t > 0 ? (t - 1) / a.swindow : 0) : t / a.swindow;
-                wend = (win + 1) * a.swindow + (a.late_window ? 1 : 0);
+            if (t >= wend) {
+                // frames ascend.  The lanes of the warp cross their window borders at different events, so whatever
+                // stands here runs in nearly every iteration: step to the next window, no integer division (which was
+                // 19 % of this kernel's instructions)
+                if (open && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
+                do {
+                    win++;
+                    wend += a.swindow;
+                } while (t >= wend);
                 wacc = 0.0;
+                open = false;
             }
             wacc += v;
+            open = true;
         }
-        if (win >= 0 && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
+        if (open && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
         total = (KIND == kPacked) ? (double)isum : (double)fsum;
     }
     if (a.accumulate) a.row_sum[r] += total;
