@@ -144,3 +144,28 @@ def test_corr_twotime_matrix_is_stored_as_one_deflate_chunk(pkg, tmp_path):
     notes = g.report("notes")
     g.close()
     assert any("C2T_all/g2_00001" in n and "chunked + filtered" in n for n in notes), notes
+
+
+def test_corr_outfile_leaves_the_input_untouched(pkg, tmp_path):
+    """--outfile=PATH: configuration + results go to PATH, the user's file is not rewritten."""
+    c = G.Case("sparse_int_24x24")
+    out = str(tmp_path / "results.hdf5")
+    corr = os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
+    imm = str(tmp_path / "data.imm")
+    h, w = c.dq.shape
+    pkg.synth.write_imm_sparse(imm, h, w, c.inp["off"], c.inp["idx"], c.inp["val"])
+    cfg = str(tmp_path / "config.hdf5")
+    f = pkg.h5lite.File()
+    for path, value in refdrv.config_items(c.dq, c.sq, c.F_raw, imm, dpl=c.dpl, static_window=c.swindow)[0]:
+        f.put(path, value)
+    f.save(cfg)
+    f.close()
+    before = open(cfg, "rb").read()
+    p = subprocess.run([corr, cfg, "--outfile=" + out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert open(cfg, "rb").read() == before
+    g = pkg.h5lite.File(out)
+    res = g.walk("/exchange")
+    assert g.get("/xpcs/delays_per_level")[0, 0] == c.dpl
+    g.close()
+    assert G.n_diff(res["norm-0-g2"], c.ref["norm-0-g2"]) == 0

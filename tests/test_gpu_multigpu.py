@@ -91,13 +91,17 @@ def _sharded(pkg, n, dq, sq, F, off, idx, val, want_g=True, rounds=1, **kw):
     return out
 
 
-def test_slab_partition_kernels_on_one_gpu(pkg, monkeypatch):
+@pytest.mark.parametrize("runs", ["0", "1"])
+def test_slab_partition_kernels_on_one_gpu(pkg, monkeypatch, runs):
     """A one-rank communicator with the exchange forced: the slab goes through count / scan / scatter / merge and
-    must give exactly what a plain push gives."""
+    must give exactly what a plain push gives -- with the event-by-event scatter and with the run-gathering one
+    (the kernel the direct NVLink transport uses from four ranks on; frames of up to 3 000 events here, so that a
+    frame spans several 1 024-event chunks)."""
     if pkg.cabi.load().xpcs_comm_nccl_version() == 0:
         pytest.skip("NCCL not loadable")
-    dq, sq, off, idx, val = make_case(pkg, 48, 40, 700, 0.02, 21, n_dynamic=5, static_per_dynamic=3)
-    F = 700
+    monkeypatch.setenv("XPCS_DEMUX_RUNS", runs)
+    dq, sq, off, idx, val = make_case(pkg, 96, 80, 300, 0.35, 21, n_dynamic=5, static_per_dynamic=3)
+    F = 300
     ref = _single(pkg, dq, sq, F, off, idx, val)
     monkeypatch.setenv("XPCS_SLAB_FORCE_EXCHANGE", "1")
     c = pkg.Correlator(dq, sq, F, device=0)

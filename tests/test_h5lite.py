@@ -180,3 +180,46 @@ def test_attributes_of_a_genuine_file_survive_a_rewrite(pkg, tmp_path):
         assert g.extra("/" + n) == before[n], n
     assert np.array_equal(g.get("/exchange/new"), np.arange(4, dtype=np.float32))
     g.close()
+
+
+def test_independent_parser_reads_what_h5lite_writes(pkg, tmp_path):
+    """tests/h5check.py walks the file format on its own (pure Python, no code shared with h5lite) and is first pointed
+    at the genuine libhdf5-written sample; it must then find every group, dataset, attribute and value in a file h5lite
+    wrote -- contiguous, chunked (with and without filters, edge chunks, > 64 chunks) and a rewritten genuine file."""
+    from h5check import H5Check
+    ref = H5Check(SAMPLE)                                  # the parser itself, on genuine libhdf5 output
+    assert list(ref.datasets) == ["/testdouble"] and ref.datasets["/testdouble"].dtype == np.float64
+    assert any(b"MATLAB_class" in a for a in ref.attrs["/testdouble"])
+    H = pkg.h5lite
+    g = H.File(SAMPLE)
+    assert np.array_equal(g.get("/testdouble"), ref.datasets["/testdouble"])   # both readers agree on the genuine file
+    rng = np.random.default_rng(5)
+    vals = {"/xpcs/dqmap": rng.integers(0, 37, (64, 48)).astype(np.int32),
+            "/xpcs/delays_per_level": np.array([[8]], np.int32),
+            "/measurement/instrument/detector/efficiency": np.array([[0.5]], np.float32),
+            "/exchange/norm-0-g2": rng.standard_normal((88, 36)).astype(np.float32),
+            "/exchange/timestamp_clock": rng.standard_normal((2, 500)),
+            "/exchange/frames_out": rng.standard_normal((4, 6, 3)).astype(np.float32),
+            "/exchange/C2T_all/g2_00001": np.triu(rng.standard_normal((150, 150))).astype(np.float32),
+            "/entry/data/data": (rng.random((70, 12, 16)) < 0.05).astype(np.uint16)}
+    for k, v in vals.items():
+        g.put(k, v)
+    for i in range(150):                                   # a group that needs several symbol nodes
+        g.put("/many/d%03d" % i, np.array([i], np.int64))
+    g.put("/xpcs/compression", "ENABLED")
+    g.set_storage("/exchange/C2T_all/g2_00001", chunk=(150, 150), deflate=6)
+    g.set_storage("/entry/data/data", chunk=(1, 12, 16), deflate=6, shuffle=True)
+    g.set_storage("/exchange/frames_out", chunk=(3, 4, 2))
+    p = str(tmp_path / "w.h5")
+    g.save(p)
+    g.close()
+    chk = H5Check(p)
+    for k, v in vals.items():
+        assert k in chk.datasets, k
+        assert chk.datasets[k].dtype == v.dtype and chk.datasets[k].shape == v.shape, k
+        assert np.array_equal(chk.datasets[k], v), k
+    assert np.array_equal(chk.datasets["/testdouble"], ref.datasets["/testdouble"])
+    assert chk.attrs["/testdouble"] == ref.attrs["/testdouble"]            # attribute messages byte for byte
+    assert chk.datasets["/xpcs/compression"].tobytes().rstrip(b"\0") == b"ENABLED"
+    assert all(int(chk.datasets["/many/d%03d" % i][0]) == i for i in range(150))
+    assert {"/", "/xpcs", "/exchange", "/exchange/C2T_all", "/many", "/entry/data"} <= set(chk.groups)

@@ -606,7 +606,10 @@ int comm_exchange_slab(xpcs_handle_s *h)
         // event-by-event stores carry 32 / N events per owner and warp store: wide enough for two ranks (measured 0.57
         // against 0.91 ms with the run gather, whose three passes over the slab then dominate), too narrow from four on
         // (0.68 / 0.64 against 0.53 / 0.35 ms at 4 / 8 GPUs)
-        if (direct && N >= 4)
+        // (XPCS_DEMUX_RUNS = 1 / 0 forces one kernel or the other, also on the staged path: the tests run both on one GPU)
+        bool runs = direct && N >= 4;
+        if (const char *e = getenv("XPCS_DEMUX_RUNS")) runs = atoi(e) != 0;
+        if (runs)
             k_demux_scatter_runs<<<(nfr + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, h->stream>>>(
                 h->slab_idx, h->slab_val, h->slab_off, nfr, h->d_owner_of_pixel.p, h->P, N, h->d_dm_off.p, dst);
         else
