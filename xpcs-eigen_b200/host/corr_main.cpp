@@ -249,6 +249,18 @@ struct SparseInput {
     std::vector<int16_t> val;
     std::vector<int64_t> offs;  // raw frames + 1
     std::vector<double> clock, ticks;
+    int32_t *raw_idx = nullptr;  // set by the mapped IMM reader instead of the vectors (malloc'ed)
+    int16_t *raw_val = nullptr;
+    SparseInput() = default;
+    SparseInput(const SparseInput &) = delete;
+    SparseInput &operator=(const SparseInput &) = delete;
+    ~SparseInput()
+    {
+        free(raw_idx);
+        free(raw_val);
+    }
+    const int32_t *idxp() const { return raw_idx ? raw_idx : idx.data(); }
+    const int16_t *valp() const { return raw_val ? raw_val : val.data(); }
     int raw_frames() const { return (int)offs.size() - 1; }
 };
 
@@ -426,27 +438,13 @@ static void load_rigaku(const Config &conf, int frames, int pixels, SparseInput 
     val.push_back(0);
 }
 
-// the whole frame range of a sparse IMM file (multi-GPU path; the single-GPU path streams it in batches)
-static void load_imm_sparse(xpcs_host::ImmReader &reader, const Config &conf, int frames, int pixels, SparseInput &in)
+// the whole frame range of a sparse IMM file: headers walked and payloads gathered from a read-only mapping
+static void load_imm_sparse(const Config &conf, int frames, SparseInput &in)
 {
-    const int frame_from = conf.frame_start_todo - 1;
-    if (frame_from > 0) reader.skip(frame_from);  // main.cpp:241-245
+    const int frame_from = conf.frame_start_todo - 1;  // main.cpp:241-245
     const int64_t raw_todo = (int64_t)frames * raw_block(conf);
-    xpcs_host::ImmBatch b;
-    in.offs.assign(1, 0);
-    for (int64_t done = 0; done < raw_todo;) {
-        const int n = (int)std::min<int64_t>(4096, raw_todo - done);
-        reader.next(n, b, pixels);
-        const int64_t base = (int64_t)in.idx.size();
-        in.idx.insert(in.idx.end(), b.idx.begin(), b.idx.end());
-        in.val.insert(in.val.end(), b.val.begin(), b.val.end());
-        for (int i = 1; i <= n; i++) in.offs.push_back(base + b.offsets[(size_t)i]);
-        in.clock.insert(in.clock.end(), b.clock.begin(), b.clock.end());
-        in.ticks.insert(in.ticks.end(), b.ticks.begin(), b.ticks.end());
-        done += n;
-    }
-    in.idx.push_back(0);
-    in.val.push_back(0);
+    xpcs_host::read_sparse_imm_mapped(conf.imm_path, frame_from > 0 ? frame_from : 0, raw_todo, in.raw_idx, in.raw_val, in.offs,
+                                      in.clock, in.ticks);
 }
 
 struct FilterSums {
@@ -502,7 +500,7 @@ static int run_sharded(const Flags &fl, XpcsParams prm, const SparseInput &in, i
         const int S = info.n_static;
         auto t0 = std::chrono::steady_clock::now();
         const int f0 = cut[r], f1 = cut[r + 1];
-        rc = xpcs_push_sparse_slab(h, f0, in.idx.data(), in.val.data(), in.offs.data() + f0, in.clock.data() + f0,
+        rc = xpcs_push_sparse_slab(h, f0, in.idxp(), in.valp(), in.offs.data() + f0, in.clock.data() + f0,
                                    in.ticks.data() + f0, f1 - f0);
         if (rc) return bad("xpcs_push_sparse_slab", rc);
         std::vector<float> ps, fs, pt, pp;
@@ -711,7 +709,7 @@ int main(int argc, char **argv)
                 if (fl.ufxc) load_ufxc(conf, frames, in);
                 else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
                 else if (fl.rigaku) load_rigaku(conf, frames, pixels, in);
-                else load_imm_sparse(*imm_reader, conf, frames, pixels, in);
+                else load_imm_sparse(conf, frames, in);
             }
             FilterSums sums;
             std::vector<float> G2, IP, IF, g2((size_t)T * Q), se((size_t)T * Q);
@@ -761,11 +759,35 @@ int main(int argc, char **argv)
         return 0;
     }
 
+    // The handle (CUDA context, partition maps on the device) is created on a second thread while this one reads
+    // the input: both take a few hundred milliseconds and neither needs the other.
     xpcs_handle h = nullptr;
-    if (int rc = xpcs_create(&prm, fl.device, &h)) {
-        fprintf(stderr, "corr: xpcs_create failed (%d): %s\n", rc, xpcs_last_error(nullptr));
-        return 3;
+    int create_rc = 0;
+    std::string create_err;
+    std::thread creator([&]() {
+        create_rc = xpcs_create(&prm, fl.device, &h);
+        if (create_rc) create_err = xpcs_last_error(nullptr);  // (the message is kept per thread)
+    });
+    auto join_creator = [&]() {
+        if (creator.joinable()) creator.join();
+        if (create_rc) fprintf(stderr, "corr: xpcs_create failed (%d): %s\n", create_rc, create_err.c_str());
+        return create_rc == 0;
+    };
+    const bool sparse_input = fl.ufxc || fl.hdf5 || fl.rigaku || imm_reader->sparse();
+    SparseInput in;
+    std::chrono::steady_clock::time_point t_load = std::chrono::steady_clock::now();
+    try {
+        if (fl.ufxc) load_ufxc(conf, frames, in);
+        else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
+        else if (fl.rigaku) load_rigaku(conf, frames, pixels, in);
+        else if (sparse_input) load_imm_sparse(conf, frames, in);
+    } catch (const std::exception &e) {
+        creator.join();
+        fprintf(stderr, "corr: %s\n", e.what());
+        xpcs_destroy(h);
+        return 1;
     }
+    if (!join_creator()) return 3;
     XpcsInfo info;
     CHECK(xpcs_get_info(h, &info));
     const int T = info.n_delays, S = info.n_static, Q = info.n_dynamic;
@@ -773,19 +795,25 @@ int main(int argc, char **argv)
     try {
         bool had_dark = false;
         {
-            Scope sc("Loading data");
-            if (fl.ufxc || fl.hdf5 || fl.rigaku) {
-                SparseInput in;
-                if (fl.ufxc) load_ufxc(conf, frames, in);
-                else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
-                else load_rigaku(conf, frames, pixels, in);
-                CHECK(xpcs_push_sparse(h, in.idx.data(), in.val.data(), in.offs.data(), in.clock.data(), in.ticks.data(),
-                                       in.raw_frames()));
+            // the stage line covers reading the input too, as the reference's "Loading data" does
+            struct LoadScope {
+                std::chrono::steady_clock::time_point t0;
+                ~LoadScope()
+                {
+                    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    if (ms < 1000.0) log_info("Loading data took %.0f ms", ms);
+                    else log_info("Loading data took %.3f s", ms / 1e3);
+                }
+            } sc{t_load};
+            if (sparse_input) {
+                // one push of the whole frame range: large pushes of plain photon counts are cut into chunks that are
+                // ingested while the next chunk crosses PCIe
+                CHECK(xpcs_push_sparse(h, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames()));
             } else {
                 xpcs_host::ImmReader &reader = *imm_reader;
                 xpcs_host::ImmBatch b;
                 int r = 0;
-                if (!reader.sparse() && conf.darks > 0) {  // main.cpp:227-239: darks come from the file start
+                if (conf.darks > 0) {  // main.cpp:227-239: darks come from the file start
                     reader.next(conf.darks, b, pixels);
                     CHECK(xpcs_set_dark(h, b.val.data(), conf.darks));
                     had_dark = true;
@@ -794,13 +822,11 @@ int main(int argc, char **argv)
                 const int frame_from = conf.frame_start_todo - 1;
                 if (frame_from > 0 && r < frame_from) reader.skip(frame_from - r);  // main.cpp:241-245
                 const int64_t raw_todo = (int64_t)frames * raw_block(conf);
-                const int chunk = reader.sparse() ? 4096 : std::max(1, (int)((256ll << 20) / ((int64_t)pixels * 2)));
+                const int chunk = std::max(1, (int)((256ll << 20) / ((int64_t)pixels * 2)));
                 for (int64_t done = 0; done < raw_todo;) {
                     const int n = (int)std::min<int64_t>(chunk, raw_todo - done);
                     reader.next(n, b, pixels);
-                    if (reader.sparse())
-                        CHECK(xpcs_push_sparse(h, b.idx.data(), b.val.data(), b.offsets.data(), b.clock.data(), b.ticks.data(), n));
-                    else CHECK(xpcs_push_dense(h, b.val.data(), b.clock.data(), b.ticks.data(), n));
+                    CHECK(xpcs_push_dense(h, b.val.data(), b.clock.data(), b.ticks.data(), n));
                     done += n;
                 }
             }

@@ -7,11 +7,18 @@
 // int32 / int16 arrays of consecutive frames (what xpcs_push_sparse / xpcs_push_dense take) and
 // every read is checked.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace xpcs_host {
@@ -100,5 +107,86 @@ private:
     FILE *f_ = nullptr;
     bool sparse_ = false;
 };
+
+// A whole frame range of a SPARSE IMM file in two passes over a read-only mapping: pass 1 walks the 1024-byte
+// headers (frames to skip, then `nframes` frames: payload position, dlen, elapsed, corecotick), pass 2 copies the
+// int32 index and int16 value payloads into two contiguous arrays with a few threads.  Replaces 3 fread calls and two
+// vector resizes per frame of ImmReader::next (1.0 s for the 731 MB file of the 1-Mpixel / 100 k-frame configuration)
+// by memory-speed copies; the result is exactly what next() delivers.  idx / val are malloc'ed (8 spare elements),
+// owned by the caller.
+inline void read_sparse_imm_mapped(const std::string &path, int skip_frames, int64_t nframes, int32_t *&idx, int16_t *&val,
+                                   std::vector<int64_t> &offsets, std::vector<double> &clock, std::vector<double> &ticks)
+{
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open IMM file " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 1024) {
+        close(fd);
+        throw std::runtime_error("IMM file has no frame header: " + path);
+    }
+    const size_t size = (size_t)st.st_size;
+    void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) throw std::runtime_error("cannot map IMM file " + path);
+    madvise(map, size, MADV_SEQUENTIAL);
+    const unsigned char *base = static_cast<const unsigned char *>(map);
+    struct Unmap {
+        void *p;
+        size_t n;
+        ~Unmap() { munmap(p, n); }
+    } unmap{map, size};
+    size_t pos = 0;
+    auto dlen_at = [&](size_t p) {
+        uint32_t d;
+        memcpy(&d, base + p + 152, 4);
+        return (size_t)d;
+    };
+    for (int i = 0; i < skip_frames; i++) {
+        if (pos + 1024 > size) throw std::runtime_error("IMM file ends inside the skipped range: " + path);
+        pos += 1024 + dlen_at(pos) * 6;
+    }
+    std::vector<size_t> payload((size_t)nframes);
+    offsets.assign((size_t)nframes + 1, 0);
+    clock.resize((size_t)nframes);
+    ticks.resize((size_t)nframes);
+    for (int64_t f = 0; f < nframes; f++) {
+        if (pos + 1024 > size) throw std::runtime_error("IMM file ends before the configured frame range: " + path);
+        const size_t d = dlen_at(pos);
+        double elapsed;
+        int32_t tick;
+        memcpy(&elapsed, base + pos + 128, 8);
+        memcpy(&tick, base + pos + 620, 4);
+        if (pos + 1024 + d * 6 > size) throw std::runtime_error("IMM frame payload truncated: " + path);
+        payload[(size_t)f] = pos + 1024;
+        offsets[(size_t)f + 1] = offsets[(size_t)f] + (int64_t)d;
+        clock[(size_t)f] = elapsed;
+        ticks[(size_t)f] = (double)tick;
+        pos += 1024 + d * 6;
+    }
+    const int64_t total = offsets[(size_t)nframes];
+    idx = static_cast<int32_t *>(malloc(sizeof(int32_t) * ((size_t)total + 8)));
+    val = static_cast<int16_t *>(malloc(sizeof(int16_t) * ((size_t)total + 8)));
+    if (!idx || !val) {
+        free(idx);
+        free(val);
+        idx = nullptr;
+        val = nullptr;
+        throw std::runtime_error("out of memory reading " + path);
+    }
+    memset(idx + total, 0, sizeof(int32_t) * 8);
+    memset(val + total, 0, sizeof(int16_t) * 8);
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(8, total / (4 << 20)));
+    auto copy_range = [&](int64_t f0, int64_t f1) {
+        for (int64_t f = f0; f < f1; f++) {
+            const size_t d = (size_t)(offsets[(size_t)f + 1] - offsets[(size_t)f]);
+            if (!d) continue;
+            memcpy(idx + offsets[(size_t)f], base + payload[(size_t)f], d * 4);
+            memcpy(val + offsets[(size_t)f], base + payload[(size_t)f] + d * 4, d * 2);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(copy_range, nframes * t / nthreads, nframes * (t + 1) / nthreads);
+    for (auto &t : th) t.join();
+}
 
 }  // namespace xpcs_host
