@@ -759,20 +759,18 @@ int main(int argc, char **argv)
         return 0;
     }
 
-    // The handle (CUDA context, partition maps on the device) is created on a second thread while this one reads
-    // the input: both take a few hundred milliseconds and neither needs the other.
+    // The handle first, then the input: creating the CUDA context on a second thread while this one faults in a few
+    // hundred MB of file and buffers was measured slower than doing one after the other (both sides serialise on the
+    // process's memory-map lock: 2.2 s against 1.8 s for the 731 MB file of the 1-Mpixel configuration).
     xpcs_handle h = nullptr;
-    int create_rc = 0;
-    std::string create_err;
-    std::thread creator([&]() {
-        create_rc = xpcs_create(&prm, fl.device, &h);
-        if (create_rc) create_err = xpcs_last_error(nullptr);  // (the message is kept per thread)
-    });
+    int create_rc = xpcs_create(&prm, fl.device, &h);
+    std::string create_err = create_rc ? xpcs_last_error(nullptr) : "";
+    std::thread creator;
     auto join_creator = [&]() {
-        if (creator.joinable()) creator.join();
         if (create_rc) fprintf(stderr, "corr: xpcs_create failed (%d): %s\n", create_rc, create_err.c_str());
         return create_rc == 0;
     };
+    if (!join_creator()) return 3;
     const bool sparse_input = fl.ufxc || fl.hdf5 || fl.rigaku || imm_reader->sparse();
     SparseInput in;
     std::chrono::steady_clock::time_point t_load = std::chrono::steady_clock::now();
@@ -782,12 +780,10 @@ int main(int argc, char **argv)
         else if (fl.rigaku) load_rigaku(conf, frames, pixels, in);
         else if (sparse_input) load_imm_sparse(conf, frames, in);
     } catch (const std::exception &e) {
-        creator.join();
         fprintf(stderr, "corr: %s\n", e.what());
         xpcs_destroy(h);
         return 1;
     }
-    if (!join_creator()) return 3;
     XpcsInfo info;
     CHECK(xpcs_get_info(h, &info));
     const int T = info.n_delays, S = info.n_static, Q = info.n_dynamic;
