@@ -67,14 +67,10 @@ struct IngestArgs {
     // chunked ingest: the events [ev_begin, E) of idx/val, off points at the chunk's first frame
     int64_t ev_begin;  // first event of the chunk (the blocks start at ev_begin & ~3: aligned vector loads)
     int frame_base;    // raw frame number of off[0]
-    // frame segments (short-row finalisation): output frame t belongs to segment t >> seg_shift; the histogram is
-    // kept per (segment, row) and every (slice, segment) has its own record stream
-    int seg_shift, n_seg, R_pad;
 };
 
 // summary slots
-enum { kSumBadCount = 0, kSumMaxLen = 1, kSumEvents = 2, kSumOverflow = 3, kSumWords = 4, kSumMaxCount = 5, kSumSegMaxLen = 6,
-       kSumSegMerged = 7, kSumSlots = 8 };
+enum { kSumBadCount = 0, kSumMaxLen = 1, kSumEvents = 2, kSumOverflow = 3, kSumWords = 4, kSumMaxCount = 5, kSumSlots = 8 };
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -141,7 +137,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_hist(IngestArgs a)
             int r = -1;
             if (t[j] >= 0 && (unsigned)pix[j] < (unsigned)a.P) r = __ldg(a.row_of_pixel + pix[j]);
             if (r < 0) { t[j] = -1; continue; }
-            atomicAdd(a.row_count + (size_t)(t[j] >> a.seg_shift) * a.R_pad + r, 1);
+            atomicAdd(a.row_count + r, 1);
             if (DENSE_SRC) v[j] = (double)rawf[j];
             else if (KIND == kPacked) {
                 v[j] = (double)raw[j];
@@ -176,31 +172,22 @@ __global__ void __launch_bounds__(kIngestThreads) k_hist(IngestArgs a)
     }
 }
 
-// slice length = longest row of the slice; also copies the histogram to row_len.  With frame segments the
-// histogram is per (segment, row): the row length is the sum over the segments, every (slice, segment) gets the size
-// of its record stream, and the longest segment of any row bounds the tile of the segmented finalisation.
+// slice length = longest row of the slice; also copies the histogram to row_len.
 __global__ void k_slice_len(const int *__restrict__ row_count, int *__restrict__ row_len,
                             int *__restrict__ slice_len, int *__restrict__ slice_cur, int n_slices,
-                            long long *summary, int n_seg, int R_pad)
+                            long long *summary)
 {
     int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (s >= n_slices) return;
-    int c = 0, segmax = 0;
-    for (int h = 0; h < n_seg; h++) {
-        const int ch = row_count[(size_t)h * R_pad + s * kSlice + lane];
-        const int tot_h = __reduce_add_sync(0xffffffffu, ch);
-        segmax = max(segmax, __reduce_max_sync(0xffffffffu, ch));
-        if (lane == 0) slice_cur[s * n_seg + h] = tot_h;
-        c += ch;
-    }
+    int c = row_count[s * kSlice + lane];
     row_len[s * kSlice + lane] = c;
     int m = __reduce_max_sync(0xffffffffu, c);
     int tot = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) {
         slice_len[s] = m;
+        slice_cur[s] = tot;
         atomicMax(summary + kSumMaxLen, (long long)m);
-        atomicMax(summary + kSumSegMaxLen, (long long)segmax);
         atomicAdd((unsigned long long *)summary + kSumEvents, (unsigned long long)tot);
     }
 }
@@ -212,13 +199,13 @@ __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ sli
                                                      const int *__restrict__ slice_tot,
                                                      int64_t *__restrict__ slice_rec,
                                                      unsigned long long *__restrict__ slice_end,
-                                                     int n_slices, long long *summary, int n_streams)
+                                                     int n_slices, long long *summary)
 {
     __shared__ long long part[1024];
     const int tid = threadIdx.x;
-    if (blockIdx.x == 1) {  // record streams: one per (slice, frame segment)
-        const int per = (n_streams + 1023) / 1024;
-        const int a = min(n_streams, tid * per), b = min(n_streams, a + per);
+    const int per = (n_slices + 1023) / 1024;
+    const int a = tid * per, b = min(n_slices, a + per);
+    if (blockIdx.x == 1) {
         long long s = 0;
         for (int i = a; i < b; i++) s += (long long)slice_tot[i];
         part[tid] = s;
@@ -235,11 +222,9 @@ __global__ void __launch_bounds__(1024) k_slice_scan(const int *__restrict__ sli
             run += (long long)slice_tot[i];
             slice_end[i] = (unsigned long long)run;
         }
-        if (tid == 1023) slice_rec[n_streams] = part[1023];
+        if (tid == 1023) slice_rec[n_slices] = part[1023];
         return;
     }
-    const int per = (n_slices + 1023) / 1024;
-    const int a = min(n_slices, tid * per), b = min(n_slices, a + per);
     long long s = 0;
     for (int i = a; i < b; i++) s += (long long)slice_len[i] * kSlice;
     part[tid] = s;
@@ -396,8 +381,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_scatter_rec(IngestArgs a)
         unsigned long long pos[4];
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (rr[j] >= 0)  // -1: the stream of the (slice, frame segment) fills from its end
-                pos[j] = atomicAdd(a.slice_end + (size_t)(rr[j] >> 5) * a.n_seg + (t[j] >> a.seg_shift), ~0ull) - 1ull;
+            if (rr[j] >= 0) pos[j] = atomicAdd(a.slice_end + (rr[j] >> 5), ~0ull) - 1ull;  // -1: the stream fills from its end
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (rr[j] < 0) continue;
@@ -502,12 +486,6 @@ struct FinalizeArgs {
     const int64_t *slice_rec;
     int accumulate;          // chunked ingest: row_sum += instead of =
     int late_window;         // XPCS_COMPAT_LATE_WINDOW: frame t > 0 belongs to static window (t - 1) / swindow
-    // lane-per-row kernel, frame segments: CTA (s, h) finalises the events of slice s whose frame lies in segment h
-    // -- a quarter of the tile, four times the CTAs per SM (the kernel is bound by the latency of dependent
-    // shared-memory accesses, so what it needs is more resident warps).  Segments are frame ranges in order, so the
-    // finished piece goes behind the pieces of the earlier segments of the row; row_sum is pre-zeroed and added to.
-    int n_seg, R_pad;
-    const int *row_count;    // [n_seg][R_pad]
 };
 
 template <int KIND>
@@ -516,25 +494,17 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
     typedef typename WordT<KIND>::type W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int curS[kSlice];
-    const int s = blockIdx.x / a.n_seg, seg = blockIdx.x % a.n_seg;
+    const int s = blockIdx.x;
     const int lane = threadIdx.x;
     const int r = s * kSlice + lane;
     if (a.flagged && !a.flagged[s]) return;  // done by k_finalize_warp
-    int len, n, row_off = 0;
-    if (a.n_seg == 1) {
-        len = a.slice_len[s];
-        n = a.row_len[r];
-        if (len == 0) {
-            if (!a.accumulate) a.row_sum[r] = 0.0;
-            return;
-        }
-    } else {
-        n = a.row_count[(size_t)seg * a.R_pad + r];
-        for (int hh = 0; hh < seg; hh++) row_off += a.row_count[(size_t)hh * a.R_pad + r];
-        len = __reduce_max_sync(0xffffffffu, n);
-        if (len == 0) return;
+    const int len = a.slice_len[s];
+    if (len == 0) {
+        if (!a.accumulate) a.row_sum[r] = 0.0;
+        return;
     }
-    W *g = reinterpret_cast<W *>(a.store) + a.slice_base[s] + lane + (int64_t)row_off * kSlice;
+    W *g = reinterpret_cast<W *>(a.store) + a.slice_base[s] + lane;
+    const int n = a.row_len[r];
     const bool in_smem = len <= a.smem_len;
     W *col;
     if (in_smem && a.rec) {
@@ -542,8 +512,8 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
         // record of rank k goes to position n - 1 - k of its row and the column is close to ascending
         W *tile = reinterpret_cast<W *>(smem_raw);
         col = tile + lane;
-        const int64_t r0 = a.slice_rec[blockIdx.x];   // stream of this (slice, segment)
-        const int nrec = (int)(a.slice_rec[blockIdx.x + 1] - r0);
+        const int64_t r0 = a.slice_rec[s];
+        const int nrec = (int)(a.slice_rec[s + 1] - r0);
         curS[lane] = 0;  // records of every row placed so far
         __syncwarp();
         unsigned long long x1 = lane < nrec ? a.rec[r0 + lane] : 0ull;
@@ -692,15 +662,10 @@ __global__ void __launch_bounds__(32) k_finalize(FinalizeArgs a)
         if (open && sb >= 0) atomicAdd(a.part_partial + (int64_t)win * a.S + sb, wacc);
         total = (KIND == kPacked) ? (double)isum : (double)fsum;
     }
-    if (a.n_seg > 1) {
-        if (m != n) a.summary[kSumSegMerged] = 1;  // a merged duplicate leaves a hole before the next segment: redo unsegmented
-        if (m > 0) atomicAdd(a.row_sum + r, total);
-    } else {
-        if (a.accumulate) a.row_sum[r] += total;
-        else a.row_sum[r] = total;
-        a.row_len[r] = m;
-    }
+    if (a.accumulate) a.row_sum[r] += total;
+    else a.row_sum[r] = total;
     if (sb >= 0 && m > 0) atomicAdd(a.part_total + sb, total);
+    a.row_len[r] = m;
     if (KIND == kPacked && cmax > 2048) atomicMax(a.summary + kSumMaxCount, (long long)cmax);  // rare: fp16 two-time operand
     if (in_smem) {
         __syncwarp();
@@ -1354,14 +1319,12 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         LaunchScope ls(h, "k_slice_len");
         int threads = 256, warps = h->n_slices;
         k_slice_len<<<(warps * 32 + threads - 1) / threads, threads, 0, h->stream>>>(
-            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p, h->fin_segs,
-            h->R_pad);
+            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p);
     }
     {
         LaunchScope ls(h, "k_slice_scan");
         k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
-                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p,
-                                                h->n_slices * h->fin_segs);
+                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p);
     }
     long long sum[kSumSlots];
     int rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream),
@@ -1387,8 +1350,6 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     const size_t lane_bytes_all = (size_t)h->max_row * kSlice * sizeof(W);
     const bool use_warp = (lane_bytes_all > 24 * 1024 || getenv("XPCS_FIN_WARP")) && !getenv("XPCS_FIN_LANE");
     const bool fused_place = !direct && !use_warp && (long long)lane_bytes_all <= smem_cap && !getenv("XPCS_PLACE_KERNEL");
-    // frame segments exist only for the fused short-row path (the finalisation takes the records itself)
-    if (h->fin_segs > 1 && !(fused_place && nblocks > 0)) return 2;  // caller redoes the histogram unsegmented
     if (nblocks > 0 && direct) {
         LaunchScope ls(h, dense ? "k_scatter_dense" : "k_scatter");
         if (dense) k_scatter<KIND, true><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
@@ -1447,10 +1408,6 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     fa.rec = (fused_place && nblocks > 0) ? h->d_rec.p : nullptr;
     fa.slice_rec = h->d_slice_rec.p;
     fa.flagged = nullptr;
-    fa.n_seg = h->fin_segs;
-    fa.R_pad = h->R_pad;
-    fa.row_count = h->d_row_count.p;
-    if (h->fin_segs > 1) cudaMemsetAsync(h->d_row_sum.p, 0, sizeof(double) * (size_t)h->R_pad, h->stream);
     if (use_warp && h->n_slices > 0) {
         rc = ensure(h, h->d_mt_fallback, (size_t)h->n_slices, "finalize flags");
         if (rc) return rc;
@@ -1467,7 +1424,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
         LaunchScope ls(h, "k_finalize_warp");
         k_finalize_warp<KIND><<<h->n_slices, kFwWarps * 32, wbytes, h->stream>>>(fa);
     }
-    int smem_len = h->fin_segs > 1 ? (int)sum[kSumSegMaxLen] : h->max_row;  // a segment's tile is its longest row piece
+    int smem_len = h->max_row;
     size_t bytes = (size_t)smem_len * kSlice * sizeof(W);
     if (use_warp) {  // only flagged (very long) slices arrive here: global-memory path
         smem_len = 0;
@@ -1482,7 +1439,7 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     if (rc) return rc;
     if (h->n_slices > 0 && (!use_warp || h->max_row > fa.row_cap)) {
         LaunchScope ls(h, "k_finalize");
-        k_finalize<KIND><<<h->n_slices * h->fin_segs, 32, bytes, h->stream>>>(fa);
+        k_finalize<KIND><<<h->n_slices, 32, bytes, h->stream>>>(fa);
     }
     rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream),
                     "summary D2H");
@@ -1490,7 +1447,6 @@ static int run_store_build(xpcs_handle_s *h, IngestArgs &ia, int nblocks, bool d
     rc = check_cuda(h, cudaStreamSynchronize(h->stream), "ingest pass 2");
     if (rc) return rc;
     if (KIND == kPacked && sum[kSumOverflow]) return 1;
-    if (h->fin_segs > 1 && sum[kSumSegMerged]) return 2;  // duplicates inside a frame: the segmented rows have holes
     h->events_stored = sum[kSumEvents];
     h->max_count = std::max(h->max_count, KIND == kPacked ? std::max(1, (int)sum[kSumMaxCount]) : 0);
     return XPCS_OK;
@@ -1556,27 +1512,11 @@ int launch_ingest(xpcs_handle_s *h)
     // exact integer path only for plain photon counts
     bool want_packed = !dense && h->flat_is_one && h->prm.avg_frames == 1 && !h->prm.normalize_by_framesum &&
                        F <= (1 << (32 - kCountBits));
-    // Frame segments for the short-row finalisation (rows of some tens to a few hundred events, integer counts --
-    // their sums do not depend on the order): segment = frame >> shift, at most kMaxFinSegs of them.
-    int want_segs = 1;
-    if (want_packed && ia.rawblock == 1 && h->R > 0 && F >= 64 && E / h->R >= 32 && E / h->R <= 1000) want_segs = kMaxFinSegs;
-    if (const char *e = getenv("XPCS_FIN_SEGS")) want_segs = std::max(1, std::min(kMaxFinSegs, atoi(e)));
-    ia.R_pad = h->R_pad;
-    for (int attempt = 0; attempt < 3; attempt++) {
+    for (int attempt = 0; attempt < 2; attempt++) {
         const int kind = want_packed ? kPacked : kFloat;
         h->kind = kind;
-        h->fin_segs = 1;
-        h->fin_shift = 31;
-        if (kind == kPacked && want_segs > 1) {
-            int sh = 0;
-            while (((F - 1) >> sh) >= want_segs) sh++;
-            h->fin_shift = sh;
-            h->fin_segs = ((F - 1) >> sh) + 1;
-        }
-        ia.seg_shift = h->fin_shift;
-        ia.n_seg = h->fin_segs;
         cudaMemsetAsync(h->d_summary.p, 0, sizeof(long long) * kSumSlots, h->stream);
-        cudaMemsetAsync(h->d_row_count.p, 0, sizeof(int) * (size_t)h->R_pad * h->fin_segs, h->stream);
+        cudaMemsetAsync(h->d_row_count.p, 0, sizeof(int) * (size_t)h->R_pad, h->stream);
         if (!dense) cudaMemsetAsync(h->d_frame_acc.p, 0, sizeof(double) * (size_t)F, h->stream);
         if (nblocks > 0) {
             LaunchScope ls(h, dense ? "k_hist_dense" : "k_hist");
@@ -1586,10 +1526,6 @@ int launch_ingest(xpcs_handle_s *h)
         }
         rc = (kind == kPacked) ? run_store_build<kPacked>(h, ia, nblocks, dense)
                                : run_store_build<kFloat>(h, ia, nblocks, dense);
-        if (rc == 2) {  // the segmented finalisation does not apply (long rows, duplicates inside a frame)
-            want_segs = 1;
-            continue;
-        }
         if (rc == 1 && kind == kPacked) {  // counts do not fit the packed word: redo as floats
             want_packed = false;
             continue;
@@ -1633,11 +1569,6 @@ int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1)
     ia.stride = 1;
     ia.rawblock = 1;
     ia.P = h->P;
-    ia.seg_shift = 31;  // a chunk is a frame segment already
-    ia.n_seg = 1;
-    ia.R_pad = h->R_pad;
-    h->fin_segs = 1;
-    h->fin_shift = 31;
     const int nblocks = (int)((e1 - (e0 & ~3LL) + kEvPerBlock - 1) / kEvPerBlock);
     if ((rc = ensure(h, h->d_block_first, (size_t)nblocks + 1, "block frames"))) return rc;
     ia.block_first = h->d_block_first.p;
@@ -1745,12 +1676,12 @@ int launch_ingest_concat(xpcs_handle_s *h)
         LaunchScope ls(h, "k_slice_len");
         int threads = 256, warps = h->n_slices;
         k_slice_len<<<(warps * 32 + threads - 1) / threads, threads, 0, h->stream>>>(
-            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p, 1, h->R_pad);
+            h->d_row_count.p, h->d_row_len.p, h->d_slice_len.p, h->d_slice_cur.p, h->n_slices, h->d_summary.p);
     }
     {
         LaunchScope ls(h, "k_slice_scan");
         k_slice_scan<<<2, 1024, 0, h->stream>>>(h->d_slice_len.p, h->d_slice_base.p, h->d_slice_cur.p,
-                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p, h->n_slices);
+                                                h->d_slice_rec.p, h->d_slice_end.p, h->n_slices, h->d_summary.p);
     }
     long long sum[kSumSlots];
     rc = check_cuda(h, cudaMemcpyAsync(sum, h->d_summary.p, sizeof(sum), cudaMemcpyDeviceToHost, h->stream), "summary D2H");

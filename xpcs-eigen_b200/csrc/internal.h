@@ -17,7 +17,6 @@ constexpr int kCountBits = 12;      // packed word at level l: key << (12+l) | c
 constexpr int kMaxLevels = 24;
 constexpr int kEvPerBlock = 4096;   // events per CTA in the frame-major passes
 constexpr int kIngestThreads = 256;
-constexpr int kMaxFinSegs = 4;      // frame segments the short-row finalisation may cut a slice into
 
 enum ValueKind { kPacked = 0, kFloat = 1 };
 
@@ -151,7 +150,6 @@ struct xpcs_handle_s {
     int64_t store_words = 0;
     int64_t events_stored = 0;
     int max_row = 0;
-    int fin_segs = 1, fin_shift = 31;     // frame segments of the current store build: segment = frame >> fin_shift
     int max_count = 0;                    // largest merged photon count of the packed store (two-time: fp16 is exact up to 2048)
     xpcs::DevBuf<long long> d_summary;    // small device scratch for host-visible scalars
     xpcs::DevBuf<double> d_frame_acc;     // [F] per-output-frame sums (exact for counts)

@@ -259,13 +259,13 @@ static int build_maps(xpcs_handle_s *h)
     if ((rc = ensure(h, h->d_lseg_row_start, h->lseg_row_start.size(), "segment rows"))) return rc;
     if ((rc = ensure(h, h->d_seg_dq_all, (size_t)std::max(1, h->nseg_total), "segment dq"))) return rc;
     if ((rc = ensure(h, h->d_seg_npix_all, (size_t)std::max(1, h->nseg_total), "segment sizes"))) return rc;
-    if ((rc = ensure(h, h->d_row_count, (size_t)h->R_pad * kMaxFinSegs, "row histogram"))) return rc;
+    if ((rc = ensure(h, h->d_row_count, (size_t)h->R_pad, "row histogram"))) return rc;
     if ((rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths"))) return rc;
     if ((rc = ensure(h, h->d_slice_len, (size_t)h->n_slices, "slice lengths"))) return rc;
     if ((rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets"))) return rc;
-    if ((rc = ensure(h, h->d_slice_cur, (size_t)h->n_slices * kMaxFinSegs + 1, "slice cursors"))) return rc;
-    if ((rc = ensure(h, h->d_slice_rec, (size_t)h->n_slices * kMaxFinSegs + 1, "slice record offsets"))) return rc;
-    if ((rc = ensure(h, h->d_slice_end, (size_t)h->n_slices * kMaxFinSegs + 1, "slice stream cursors"))) return rc;
+    if ((rc = ensure(h, h->d_slice_cur, (size_t)h->n_slices + 1, "slice cursors"))) return rc;
+    if ((rc = ensure(h, h->d_slice_rec, (size_t)h->n_slices + 1, "slice record offsets"))) return rc;
+    if ((rc = ensure(h, h->d_slice_end, (size_t)h->n_slices + 1, "slice stream cursors"))) return rc;
     cudaMemcpy(h->d_row_of_pixel.p, row_of_pixel.data(), sizeof(int) * P, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_pixel_of_row.p, pix_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_sbin_of_row.p, sbin_of_row.data(), sizeof(int) * h->R_pad, cudaMemcpyHostToDevice);
@@ -276,7 +276,7 @@ static int build_maps(xpcs_handle_s *h)
         cudaMemcpy(h->d_seg_dq_all.p, h->seg_dq.data(), sizeof(int) * h->nseg_total, cudaMemcpyHostToDevice);
         cudaMemcpy(h->d_seg_npix_all.p, h->seg_pixels_n.data(), sizeof(int) * h->nseg_total, cudaMemcpyHostToDevice);
     }
-    cudaMemset(h->d_row_count.p, 0, sizeof(int) * (size_t)h->R_pad * kMaxFinSegs);
+    cudaMemset(h->d_row_count.p, 0, sizeof(int) * h->R_pad);
     cudaMemset(h->d_row_len.p, 0, sizeof(int) * h->R_pad);
     return check_cuda(h, cudaGetLastError(), "map upload");
 }
