@@ -57,6 +57,22 @@ def assert_close(a, b, what, rtol=RTOL, atol=0.0):
         what, bad.sum(), a.size, rtol, np.nanmax(err / np.maximum(np.abs(b), 1e-300)))
 
 
+def compare_exact(got, ref):
+    """(sums, (G2, IP, IF), g2, se[, info]) of the GPU against the oracle's: integer path, everything but the
+    std-error bit for bit."""
+    sums, G, g2, se = got[:4]
+    rsums, rG, rg2, rse = ref
+    for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
+        assert_exact(sums[k], rsums[k], k)
+    for k, nm in enumerate(("G2", "IP", "IF")):
+        assert_exact(G[k], rG[k], nm)
+    assert_exact(g2, rg2, "norm-0-g2")
+    ok = np.isfinite(rse)
+    assert_close(se[ok], rse[ok], "norm-0-stderr")
+    if len(got) > 4:
+        assert got[4].value_kind == 0
+
+
 CASES = [  # h, w, F, occupancy, seed, dpl
     (32, 32, 100, 0.05, 1, 8),
     (48, 40, 601, 0.02, 2, 8),     # odd frame count: last frame dropped at level 1
@@ -347,3 +363,23 @@ def test_push_sparse_device_rejects_misaligned_pointers(pkg):
         c.push_sparse_device(0x7f0000000004, 0x7f0000100000, 0x7f0000200000, 10, 50)
     assert e.value.code == -1 and "aligned" in str(e.value)
     c.close()
+
+
+def test_duplicates_inside_a_frame_are_merged(pkg, oracle):
+    """A pixel listed twice in one frame is summed by the Filter stage (sparse_filter.cpp:152-158): rows of ~75 events,
+    one of them with a duplicate, rows that live in the last tenth of the run only, rows that never fire."""
+    dq, sq, off, idx, val = make_case(pkg, 32, 32, 1500, 0.05, 82)
+    F = 1500
+    fr = np.repeat(np.arange(F), np.diff(off))
+    keep = ~(((idx >= 100) & (idx < 140) & (fr < 1350)) | ((idx >= 200) & (idx < 210)))
+    cnt = np.bincount(fr[keep], minlength=F)
+    idx, val = idx[keep], val[keep]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    a, b = int(off[700]), int(off[701])   # frame 700: its first event once more at the end of the frame
+    idx = np.concatenate([idx[:b], idx[a:a + 1], idx[b:]])
+    val = np.concatenate([val[:b], np.array([2], np.int16), val[b:]])
+    off = off.copy()
+    off[701:] += 1
+    got = run_gpu(pkg, dq, sq, F, off, idx, val)
+    ref = run_oracle(oracle, dq, sq, F, off, idx, val)
+    compare_exact(got, ref)
