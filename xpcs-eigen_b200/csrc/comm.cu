@@ -399,9 +399,15 @@ static int p2p_exchange_mappings(xpcs_handle_s *h)
     mine.val = (unsigned long long)(uintptr_t)h->d_val.p;
     mine.off = (unsigned long long)(uintptr_t)h->d_recv_off.p;
     mine.pid = (unsigned long long)getpid();
-    bool ok = cudaIpcGetMemHandle(&mine.hidx, h->d_idx.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.hval, h->d_val.p) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.hoff, h->d_recv_off.p) == cudaSuccess;
-    if (!ok) cudaGetLastError();
+    // IPC handles only when some rank lives in another process (threads of one process share the address space)
+    bool need_ipc = false;
+    for (int s = 0; s < N; s++) need_ipc = need_ipc || ((int)h->peer_pid.size() == N && h->peer_pid[s] != (long long)mine.pid);
+    bool ok = true;
+    if (need_ipc) {
+        ok = cudaIpcGetMemHandle(&mine.hidx, h->d_idx.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.hval, h->d_val.p) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.hoff, h->d_recv_off.p) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
     int64_t *d_mine = h->d_p2p_xchg.p, *d_all = h->d_p2p_xchg.p + kRecWords;
     if ((rc = check_cuda(h, cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream), "peer record H2D"))) return rc;
     {
