@@ -304,3 +304,38 @@ def test_both_transports_and_buffer_reuse(pkg, monkeypatch, staged):
         for k in ("pixel_sum", "frame_sum", "part_total", "part_partial"):
             assert G.n_diff(sums[k], ref[0][k]) == 0, (r, k)
         assert np.array_equal(g2, ref[2], equal_nan=True) and np.array_equal(se, ref[3], equal_nan=True)
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_corr_twotime_partitions_over_gpus(pkg, tmp_path):
+    """Two-time with --gpus 2: the listed dynamic partitions are independent (corr.cpp:799) and are spread over the
+    GPUs, one handle per GPU; the result file equals the one-GPU file and the reference's fixture."""
+    c = G.Case("twotime_staticmap_none")
+    corr = os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
+    imm = str(tmp_path / "data.imm")
+    h, w = c.dq.shape
+    pkg.synth.write_imm_sparse(imm, h, w, c.inp["off"], c.inp["idx"], c.inp["val"])
+    results = []
+    for gpus in (1, 2):
+        cfg = str(tmp_path / ("tt%d.hdf5" % gpus))
+        f = pkg.h5lite.File()
+        kw = dict(dpl=c.dpl, static_window=c.swindow,
+                  twotime=dict(qbins=[int(q) for q in c.inp["qbins"]], wsize=int(c.inp["wsize"]), method="StaticMap",
+                               filter=str(c.inp["filt"])))
+        for path, value in refdrv.config_items(c.dq, c.sq, c.F_raw, imm, **kw)[0]:
+            f.put(path, value)
+        f.save(cfg)
+        f.close()
+        p = subprocess.run([corr, cfg, "--gpus", str(gpus)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-3000:]
+        if gpus > 1:
+            assert "dynamic partitions over 2 GPUs" in p.stdout
+        g = pkg.h5lite.File(cfg)
+        results.append(g.walk("/exchange"))
+        g.close()
+    one, two = results
+    assert sorted(one) == sorted(two) == sorted(c.ref)
+    for k in one:
+        assert G.n_diff(one[k], two[k]) == 0, k
+        err, nanmis = G.rel_err(two[k], c.ref[k])
+        assert nanmis == 0 and err <= 1e-5, (k, err)

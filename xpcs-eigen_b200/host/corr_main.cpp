@@ -680,8 +680,8 @@ int main(int argc, char **argv)
     const std::string out = conf.output_path;
     const uint64_t uy = (uint64_t)conf.ydim, ux = (uint64_t)conf.xdim;
 
-    // ---- the sharded multi-tau job: sparse inputs only (a dense stack would cross PCIe once per GPU; two-time
-    // partitions are independent and run on one GPU each)
+    // ---- the sharded multi-tau job: sparse inputs only (a dense stack would cross PCIe once per GPU); two-time
+    // jobs spread their dynamic partitions over the GPUs further down
     bool sharded = fl.gpus > 1 && !conf.twotime && fl.frameout <= 0;
     std::unique_ptr<xpcs_host::ImmReader> imm_reader;
     if (!fl.ufxc && !fl.hdf5 && !fl.rigaku) {
@@ -693,7 +693,7 @@ int main(int argc, char **argv)
         }
         if (!imm_reader->sparse()) sharded = false;
     }
-    if (fl.gpus > 1 && !sharded) log_info("--gpus %d: this job (two-time, dense frames or --frameout) runs on one GPU", fl.gpus);
+    if (fl.gpus > 1 && !sharded && !conf.twotime) log_info("--gpus %d: this job (dense frames or --frameout) runs on one GPU", fl.gpus);
     if (sharded) {
         try {
             int T = xpcs_delay_schedule(frames, conf.dpl, nullptr, nullptr, 0);
@@ -885,32 +885,79 @@ int main(int argc, char **argv)
             const int F = frames, w = conf.wsize, partials = std::max((F - w) / w, 0);
             const size_t B = bins.size();
             const size_t sg_cols = average ? 1 : (size_t)F;
-            std::vector<float> C((size_t)F * F), gf(F), gp((size_t)std::max(w * partials, 1));
             std::vector<float> g2full((size_t)F * B), g2part((size_t)w * partials * B);
             std::vector<float> sgall;   // rows: one per dynamic bin (symmetric) or per static bin of the bins (StaticMap)
-            std::vector<float> sg((size_t)std::max(S, 1) * sg_cols);
+            // Dynamic partitions are independent (corr.cpp:799 loops over them): with --gpus N every GPU ingests the
+            // input and takes every N-th listed partition ("one dynamic bin per GPU").
+            struct BinOut {
+                int rc = 0, sg_rows = 0;
+                std::string err;
+                std::vector<float> C, gf, gp, sg;
+            };
+            std::vector<BinOut> outs(B);
+            auto process = [&](xpcs_handle hh, size_t first, size_t stride) {
+                for (size_t k = first; k < B; k += stride) {
+                    BinOut &o = outs[k];
+                    o.C.resize((size_t)F * F);
+                    o.gf.resize(F);
+                    o.gp.resize((size_t)std::max(w * partials, 1));
+                    o.sg.resize((size_t)std::max(S, 1) * sg_cols);
+                    o.rc = xpcs_twotime_sg(hh, bins[k], w, method, average ? 1 : 0, o.C.data(), o.gf.data(), o.gp.data(), o.sg.data(),
+                                           &o.sg_rows);
+                    if (o.rc) {
+                        o.err = xpcs_last_error(hh);
+                        std::vector<float>().swap(o.C);
+                    }
+                }
+            };
+            const int n_tt = (fl.gpus > 1 && sparse_input) ? (int)std::min<size_t>((size_t)fl.gpus, std::max<size_t>(B, 1)) : 1;
+            if (fl.gpus > 1 && n_tt > 1) log_info("Two-time: %zu dynamic partitions over %d GPUs", B, n_tt);
+            std::vector<std::thread> helpers;
+            std::vector<std::string> helper_err((size_t)n_tt);
+            for (int r = 1; r < n_tt; r++)
+                helpers.emplace_back([&, r]() {
+                    xpcs_handle hr = nullptr;
+                    int rc = xpcs_create(&prm, fl.device + r, &hr);
+                    if (rc) {
+                        helper_err[(size_t)r] = std::string("xpcs_create: ") + xpcs_last_error(nullptr);
+                        return;
+                    }
+                    rc = xpcs_push_sparse(hr, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames());
+                    if (!rc) rc = xpcs_finish_ingest(hr, nullptr, nullptr, nullptr, nullptr);
+                    if (rc) helper_err[(size_t)r] = std::string("ingest: ") + xpcs_last_error(hr);
+                    else process(hr, (size_t)r, (size_t)n_tt);
+                    xpcs_destroy(hr);
+                });
+            process(h, 0, (size_t)n_tt);
+            for (auto &t : helpers) t.join();
+            for (int r = 1; r < n_tt; r++)
+                if (!helper_err[(size_t)r].empty()) {
+                    fprintf(stderr, "corr: GPU %d: %s\n", fl.device + r, helper_err[(size_t)r].c_str());
+                    return 3;
+                }
             size_t b = 0;
-            for (int q : bins) {
-                int sg_rows = 0;
-                int rc = xpcs_twotime_sg(h, q, w, method, average ? 1 : 0, C.data(), gf.data(), gp.data(), sg.data(), &sg_rows);
-                if (rc == XPCS_E_ARG) continue;  // partition without pixels: the reference skips it too
-                if (rc) {
-                    fprintf(stderr, "corr: xpcs_twotime failed (%d): %s\n", rc, xpcs_last_error(h));
+            for (size_t k = 0; k < B; k++) {
+                BinOut &o = outs[k];
+                const int q = bins[k];
+                if (o.rc == XPCS_E_ARG) continue;  // partition without pixels: the reference skips it too
+                if (o.rc) {
+                    fprintf(stderr, "corr: xpcs_twotime failed (%d): %s\n", o.rc, o.err.c_str());
                     return 3;
                 }
                 char name[64];
                 snprintf(name, sizeof(name), "/C2T_all/g2_%05d", q);
                 // one chunk covering the matrix, deflate level 6: the reference's storage of these datasets
                 // (write2DData(..., compression = true), h5_result.cpp:140-152; corr.cpp:883-890)
-                h5lite::Dataset &c2t = file.put(out + name, Type::F32, {(uint64_t)F, (uint64_t)F}, C.data());
+                h5lite::Dataset &c2t = file.put(out + name, Type::F32, {(uint64_t)F, (uint64_t)F}, o.C.data());
+                std::vector<float>().swap(o.C);
                 if (!fl.nocompress && (uint64_t)F * F * 4 < (1ull << 32)) {
                     c2t.chunk = {(uint64_t)F, (uint64_t)F};
                     c2t.deflate_level = 6;
                 }
-                for (int f = 0; f < F; f++) g2full[(size_t)f * B + b] = gf[f];
+                for (int f = 0; f < F; f++) g2full[(size_t)f * B + b] = o.gf[f];
                 for (int d = 0; d < w; d++)
-                    for (int p = 0; p < partials; p++) g2part[((size_t)d * partials + p) * B + b] = gp[(size_t)d * partials + p];
-                sgall.insert(sgall.end(), sg.begin(), sg.begin() + (size_t)sg_rows * sg_cols);
+                    for (int p = 0; p < partials; p++) g2part[((size_t)d * partials + p) * B + b] = o.gp[(size_t)d * partials + p];
+                sgall.insert(sgall.end(), o.sg.begin(), o.sg.begin() + (size_t)o.sg_rows * sg_cols);
                 b++;
             }
             file.put(out + "/sg", Type::F32, {(uint64_t)(sgall.size() / sg_cols), (uint64_t)sg_cols}, sgall.data());
