@@ -278,7 +278,7 @@ KERNEL_GROUP = {  # kernel name -> stage of SURVEY.md 8(d)
     "k_block_frames": "K1", "k_hist": "K1", "k_slice_len": "K1", "k_slice_scan": "K1", "k_scatter": "K1",
     "k_finalize": "K1", "k_frame_scale": "K1", "k_hist_dense": "K1", "k_scatter_dense": "K1",
     "k_finalize_warp": "K1", "k_scatter_rec": "K1", "k_scatter_rec_dense": "K1", "k_place": "K1", "k_dense_bounds": "K2",
-    "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_multitau_warp": "K4", "k_multitau_warpf": "K4",
+    "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_multitau_warp": "K4", "k_multitau_slice": "K4", "k_multitau_warpf": "K4",
     "k_unpermute": "K4",
     "k_segment_reduce": "K6", "k_normalize_finish": "K6",
 }
@@ -297,6 +297,7 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
         "k_finalize": 12 * E,                  # read + write the pixel-major rows once
         "k_multitau": 6 * E + 12 * T * R,      # read each event once, write G2/IP/IF once
         "k_multitau_warp": 6 * E + 12 * T * R,
+        "k_multitau_slice": 6 * E + 12 * T * R,
         "k_multitau_warpf": 6 * E + 12 * T * R,  # same algorithmic bytes; the float store holds 8 B/event
         "k_finalize_warp": 12 * E,
         "k_segment_reduce": 12 * T * R,        # read G2/IP/IF once
@@ -767,7 +768,7 @@ def bench_sparse(args, wl):
         if n <= 0:
             continue
         per = ms / n
-        Ek = Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_warpf") else \
+        Ek = Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_slice", "k_multitau_warpf") else \
             (E if name.startswith("k_demux") else Es)
         b = algorithmic_bytes(name, Ek, T, R, Q, P)
         kern[name] = {"ms_per_launch": per, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,

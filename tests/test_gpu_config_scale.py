@@ -98,7 +98,7 @@ def test_c1_cabi_default_pipeline_equals_reference(pkg, c1):
     c.close()
     assert info.value_kind == 0 and info.events_stored > 2.0e7
     assert rep.get("k_concat", (0, 0))[1] >= 1, "the pipelined (chunked) ingest did not run: %s" % sorted(rep)
-    assert rep.get("k_multitau_warp", (0, 0))[1] >= 1 and fallback == 0
+    assert rep.get("k_multitau_slice", (0, 0))[1] >= 1 and fallback == 0, "the short-row kernel did not take C1: %s" % sorted(rep)
     ref = c1["ref"]
     for name, got in (("G2", G2), ("IP", IP), ("IF", IF), ("norm-0-g2", g2), ("pixelSum", sums["pixel_sum"]),
                       ("frameSum", sums["frame_sum"]), ("partition-mean-partial", sums["part_partial"]),

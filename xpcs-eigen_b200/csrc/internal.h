@@ -287,6 +287,9 @@ int launch_unpermute(xpcs_handle_s *h, const float *d_src, float *d_dst);  // [T
 // ---- launchers (multitau_warp.cu) ----
 bool multitau_warp_eligible(const xpcs_handle_s *h);
 int launch_multitau_warp(xpcs_handle_s *h, MtArgs &a);   // fills h->d_mt_fallback
+// ---- launchers (multitau_slice.cu) ----
+bool multitau_slice_eligible(const xpcs_handle_s *h);
+int launch_multitau_slice(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
 // ---- launchers (multitau_warpf.cu) ----
 bool multitau_warpf_eligible(const xpcs_handle_s *h);
 int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback

@@ -489,7 +489,13 @@ int launch_multitau(xpcs_handle_s *h)
     a.sched = h->sched;
     a.only_flagged = nullptr;
     h->mt_warp_ran = false;
-    if (multitau_warp_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+    if (multitau_slice_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+        // short rows: lane = row, warps = tasks (multitau_slice.cu); it flags the slices it leaves like the
+        // warp-per-row kernel does
+        if ((rc = launch_multitau_slice(h, a))) return rc;
+        a.only_flagged = h->d_mt_fallback.p;
+        h->mt_warp_ran = true;
+    } else if (multitau_warp_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
         // warp-per-row kernel first; it flags the slices it leaves (rows too long for its shared
         // memory, or counts too large for 32-bit numerators) and the lane-per-row kernel redoes those
         if ((rc = launch_multitau_warp(h, a))) return rc;
