@@ -14,7 +14,7 @@
 using namespace xpcs::sl;
 
 template <int DPL, bool COMPAT>
-static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int len, int ld_factor,
+static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int len, int ld_factor, int ld_cap,
                int np, int nd, int nio, int nwarps, int bins_rows, float *G2, float *IP, float *IF)
 {
     const int T = sc.T, nl = sc.nl, F = sc.F;
@@ -31,17 +31,19 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
         if (tot[r] >= 65536u) return 1;
         if (tot[r] > 255u) small = false;
     }
-    int ld = nl;
-    for (int l = 1; l < nl; l++)
+    int ld = std::min(nl, ld_cap);
+    for (int l = 1; l < ld; l++)
         if ((F >> l) <= ld_factor * std::max(len, 1)) {
             ld = l;
             break;
         }
     const bool use8 = bins_rows > 0 && ld <= sc.lastl && (F >> ld) <= bins_rows && small;
-    std::vector<uint8_t> B1((size_t)std::max(bins_rows, 1) * 32, 0), B2((size_t)((bins_rows >> 1) + 1) * 32, 0);
+    std::vector<uint8_t> B1((size_t)(bins_rows + kBinPad) * 32, 0xee), B2((size_t)((bins_rows >> 1) + kBinPad) * 32, 0xee);
+    const int hsp = std::min(T, sc.cnt0 + DPL * (ld - 1));
     for (int lane = 0; lane < 32; lane++) {
         const uint32_t *ev = evS.data() + lane;
         const int n = row_len[lane];
+        int smin0 = kInfKey;
         if (COMPAT) {
             const int chunk = (len + nwarps - 1) / nwarps;
             for (int w = 0; w < nwarps; w++) lane_mlhist(ev, w * chunk, std::min(n, w * chunk + chunk), cntml.data() + lane);
@@ -55,6 +57,7 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
                 if (l >= 1 && l <= sc.lastl && (!use8 || l <= ld)) v = lane_level_limit(ev, n, l, ld, F, nlive.data() + lane, sbx.data() + lane);
                 lim[(size_t)l * 32 + lane] = v;
             }
+            for (int j = 1; j <= std::min(ld, sc.lastl); j++) smin0 = std::min(smin0, (int)sbx[(size_t)j * 32 + lane]);
         } else {
             for (int l = 0; l < nl; l++) {
                 const int Ll = F >> l;
@@ -72,11 +75,11 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
         }
         if (ld <= sc.lastl && use8) {
             if (ld + 1 <= sc.lastl) {
-                for (int t = 0; t < (F >> (ld + 1)); t++) B2[(size_t)t * 32 + lane] = 0;
-                lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B2.data() + lane, nlive.data() + lane, sbx.data() + lane, H.data() + lane);
+                for (int t = 0; t < (F >> (ld + 1)) + kBinPad; t++) B2[(size_t)t * 32 + lane] = 0;
+                lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B2.data() + lane, nlive.data() + lane, smin0, G2 + lane, 32);
             }
-            for (int t = 0; t < (F >> ld); t++) B1[(size_t)t * 32 + lane] = 0;
-            lane_dense8_first<DPL>(ev, ld, sc, B1.data() + lane, lim.data() + lane, H.data() + lane);
+            for (int t = 0; t < (F >> ld) + kBinPad; t++) B1[(size_t)t * 32 + lane] = 0;
+            lane_dense8_first<DPL>(ev, ld, sc, B1.data() + lane, lim.data() + lane, G2 + lane, 32);
         } else if (ld <= sc.lastl) {
             constexpr int W = 2 * DPL + 1;
             int bins = 0;
@@ -98,20 +101,20 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
                 }
             }
         }
-        for (int ti = 0; ti < T; ti++) G2[(size_t)ti * 32 + lane] = g2_value<DPL>(H[(size_t)ti * 32 + lane], ti, sc);
+        for (int ti = 0; ti < (use8 ? hsp : T); ti++) G2[(size_t)ti * 32 + lane] = g2_value<DPL>(H[(size_t)ti * 32 + lane], ti, sc);
     }
     return use8 ? 2 : 0;
 }
 
 // returns 1: slice flagged for the fallback kernel, 0: done with the on-the-fly dense walk, 2: done with 8-bit bins
 extern "C" int mt_slice_host(int dpl, int compat, int F, int nl, int T, int cnt0, int lastl, int cnt_last,
-                             const int *row_len, const uint32_t *words, int len, int ld_factor, int np, int nd, int nio,
+                             const int *row_len, const uint32_t *words, int len, int ld_factor, int ld_cap, int np, int nd, int nio,
                              int nwarps, int bins_rows, float *G2, float *IP, float *IF)
 {
     SlSched sc{F, nl, T, cnt0, lastl, cnt_last};
-    if (dpl == 8) return compat ? run<8, true>(sc, row_len, words, len, ld_factor, np, nd, nio, nwarps, bins_rows, G2, IP, IF)
-                                : run<8, false>(sc, row_len, words, len, ld_factor, np, nd, nio, nwarps, bins_rows, G2, IP, IF);
-    if (dpl == 4) return compat ? run<4, true>(sc, row_len, words, len, ld_factor, np, nd, nio, nwarps, bins_rows, G2, IP, IF)
-                                : run<4, false>(sc, row_len, words, len, ld_factor, np, nd, nio, nwarps, bins_rows, G2, IP, IF);
+    if (dpl == 8) return compat ? run<8, true>(sc, row_len, words, len, ld_factor, ld_cap, np, nd, nio, nwarps, bins_rows, G2, IP, IF)
+                                : run<8, false>(sc, row_len, words, len, ld_factor, ld_cap, np, nd, nio, nwarps, bins_rows, G2, IP, IF);
+    if (dpl == 4) return compat ? run<4, true>(sc, row_len, words, len, ld_factor, ld_cap, np, nd, nio, nwarps, bins_rows, G2, IP, IF)
+                                : run<4, false>(sc, row_len, words, len, ld_factor, ld_cap, np, nd, nio, nwarps, bins_rows, G2, IP, IF);
     return -1;
 }

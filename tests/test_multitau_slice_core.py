@@ -32,7 +32,7 @@ def host(tmp_path_factory):
     return lib
 
 
-def run_slice(lib, rows_f, rows_c, F, dpl, compat, ld_factor=4, np_=8, nd=4, nio=2, nwarps=8, bins8=True):
+def run_slice(lib, rows_f, rows_c, F, dpl, compat, ld_factor=4, np_=8, nd=4, nio=2, nwarps=8, bins8=True, len_cap_factor=1):
     lev, tau = O.delay_schedule(F, dpl)
     nl, first, count, lo = mm.build_sched(np.asarray(lev), np.asarray(tau))
     T = len(lev)
@@ -48,14 +48,17 @@ def run_slice(lib, rows_f, rows_c, F, dpl, compat, ld_factor=4, np_=8, nd=4, nio
     IP = np.zeros((T, 32), np.float32)
     IF = np.zeros((T, 32), np.float32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    bins_rows = 0
-    if bins8:   # as the launcher sizes the first bin array: the bins of the first dense level of the longest slice
-        for l in range(1, nl):
-            if (F >> l) <= ld_factor * max(ln, 1):
-                bins_rows = (F >> l) if count[l] > 0 else 0
-                break
+    # as the launcher plans: first dense level of the longest slice of the job (len_cap), the cap one level beyond it,
+    # the first bin array sized for that level
+    bins_rows, ld_min = 0, nl
+    for l in range(1, nl):
+        if (F >> l) <= ld_factor * max(ln * len_cap_factor, 1):
+            ld_min = l
+            bins_rows = (F >> l) if (count[l] > 0 and bins8) else 0
+            break
+    ld_cap = min(nl, ld_min + 1)
     rc = lib.mt_slice_host(dpl, int(compat), F, nl, T, count[0], lastl, cnt_last, p(n, C.c_int), p(words, C.c_uint32),
-                           ln, ld_factor, np_, nd, nio, nwarps, bins_rows, p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
+                           ln, ld_factor, ld_cap, np_, nd, nio, nwarps, bins_rows, p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
     return rc, G2, IP, IF
 
 
@@ -163,6 +166,18 @@ def test_work_split_does_not_matter(host, ld_factor, np_, nd, nio):
         kinds = [0.3 * scale, 1.0 * scale, "cluster", 0.05 * scale, "tail", "head", 0.6 * scale, "burst"] * 4
         rows_f, rows_c = make_rows(rng, F, kinds)
         check(host, rows_f, rows_c, F, dpl, True, ld_factor=ld_factor, np_=np_, nd=nd, nio=nio, nwarps=np_ + 2 + nd)
+
+
+@pytest.mark.parametrize("len_cap_factor", [2, 5, 40])
+def test_short_slices_of_a_long_job(host, len_cap_factor):
+    """a slice much shorter than the longest one of the job starts its dense levels where the launch allows (ld_cap)"""
+    rng = np.random.default_rng(31)
+    for F, dpl in ((100000, 8), (3000, 4), (20000, 8)):
+        scale = min(1.0, 100.0 / F)
+        kinds = [0.3 * scale, 1.0 * scale, "cluster", 0.05 * scale, "tail", "head_small", 0.6 * scale, "burst_small"] * 4
+        rows_f, rows_c = make_rows(rng, F, kinds)
+        check(host, rows_f, rows_c, F, dpl, True, len_cap_factor=len_cap_factor)
+        check(host, rows_f, rows_c, F, dpl, False, len_cap_factor=len_cap_factor)
 
 
 def test_stale_tail_cases_are_hit(host):

@@ -37,18 +37,32 @@ struct SlArgs {
     unsigned char *fallback;   // [n_slices]
     int len_cap;               // longest slice handled here
     int np, nd, nio;           // pieces of the pair walk, of the on-the-fly dense walk, of the IF and of the IP walk
-    int ld_factor;             // dense levels start where L_l <= ld_factor * (longest row of the slice)
+    int ld_factor;             // dense levels start where L_l <= ld_factor * (longest row of the slice) ...
+    int ld_cap;                // ... but not beyond this level (H is sized for the sparse slots up to it)
+    int h_rows;                // rows of H: the delay slots of the levels below ld_cap
     int bins_rows;             // rows of the first 8-bit bin array (0: no bin arrays, dense levels on the fly)
+    int area_words;            // the work area behind the tables (see sl_area_words)
     SlSched s;
 };
 
-// shared-memory words of a CTA
-static inline size_t sl_smem_words(int len_cap, int T, int nl, bool compat, int bins_rows)
+constexpr int kSlHdr = 96;     // rlen[32], tot[32], smin[32]
+
+// The work area holds, one after the other in time: the compat scratch tables (merge-level histogram and first
+// stale slots, dead once the limits are known), then either the two 8-bit bin arrays or -- for slices that take
+// the on-the-fly walk -- the G2 numerators of the dense levels.
+static inline size_t sl_area_words(int T, int nl, int h_rows, bool compat, int bins_rows)
 {
-    size_t w = 64 + (size_t)(len_cap + 1) * 32 + (size_t)T * 32 + (size_t)nl * 32;
-    if (compat) w += (size_t)sl::kMlRows * 32 + 2 * (size_t)nl * 32;
-    w += (size_t)bins_rows * 8 + (size_t)((bins_rows >> 1) + 1) * 8;
+    size_t w = (size_t)std::min(T, T - h_rows + 8) * 32;  // a slice may start its dense levels one level below ld_cap
+    if (compat) w = std::max(w, (size_t)(sl::kMlRows + nl) * 32);
+    if (bins_rows > 0) w = std::max(w, (size_t)(bins_rows + sl::kBinPad) * 8 + (size_t)((bins_rows >> 1) + sl::kBinPad) * 8);
     return w;
+}
+
+// shared-memory words of a CTA
+static inline size_t sl_smem_words(int len_cap, int T, int nl, int h_rows, bool compat, int bins_rows)
+{
+    return kSlHdr + (size_t)(len_cap + 1) * 32 + (size_t)h_rows * 32 + (size_t)nl * 32 + (compat ? (size_t)nl * 32 : 0) +
+           sl_area_words(T, nl, h_rows, compat, bins_rows);
 }
 
 template <int DPL, bool COMPAT>
@@ -66,15 +80,18 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     const SlSched sc = m.s;
     const int T = sc.T, nl = sc.nl, F = sc.F;
     uint32_t *rlen = sl_smem;                         // [32]
-    uint32_t *tot = sl_smem + 32;                     // [32] sum of the counts of a row; [32 + 32]: task counter
-    uint32_t *evS = sl_smem + 64;                     // [len_cap + 1][32]
-    uint32_t *H = evS + (size_t)(m.len_cap + 1) * 32; // [T][32] G2 numerators
-    uint32_t *lim = H + (size_t)T * 32;               // [nl][32] frame limit (l < ld) / key limit (l >= ld)
-    uint32_t *cntml = lim + (size_t)nl * 32;          // compat: [33][32]
-    uint32_t *nlive = cntml + (COMPAT ? sl::kMlRows * 32 : 0);  // compat: [nl][32]
-    uint32_t *sbx = nlive + (COMPAT ? (size_t)nl * 32 : 0);     // compat: [nl][32]
-    uint32_t *B1w = sbx + (COMPAT ? (size_t)nl * 32 : 0);       // [bins_rows][32] bytes
-    uint32_t *B2w = B1w + (size_t)m.bins_rows * 8;              // [bins_rows / 2 + 1][32] bytes
+    uint32_t *tot = sl_smem + 32;                     // [32] sum of the counts of a row
+    uint32_t *sminS = sl_smem + 64;                   // [32] compat: smallest first stale slot up to the first dense level
+    uint32_t *evS = sl_smem + kSlHdr;                 // [len_cap + 1][32]
+    uint32_t *H = evS + (size_t)(m.len_cap + 1) * 32; // [h_rows][32] G2 numerators of the sparse levels
+    uint32_t *lim = H + (size_t)m.h_rows * 32;        // [nl][32] frame limit (l < ld) / key limit (l >= ld)
+    uint32_t *nlive = lim + (size_t)nl * 32;          // compat: [nl][32] live bins per level
+    uint32_t *area = nlive + (COMPAT ? (size_t)nl * 32 : 0);
+    uint32_t *cntml = area;                           // compat, until the limits are known: [33][32]
+    uint32_t *sbx = area + sl::kMlRows * 32;          //                                     [nl][32]
+    uint32_t *B1w = area;                             // 8-bit bins: [bins_rows + pad][32] bytes
+    uint32_t *B2w = area + (size_t)(m.bins_rows + sl::kBinPad) * 8;  // [bins_rows / 2 + pad][32] bytes
+    uint32_t *Hd = area;                              // on-the-fly dense walk: numerators of the slots from hsp on
     __shared__ int qctr;
 
     // ---- the tile, as it lies in the store; words past the end of a row become sentinels
@@ -83,7 +100,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         tot[tid] = 0u;
     }
     if (tid == 0) qctr = 0;
-    for (int t = tid; t < T * 32; t += nthreads) H[t] = 0u;
+    for (int t = tid; t < m.h_rows * 32; t += nthreads) H[t] = 0u;
     if (COMPAT)
         for (int t = tid; t < sl::kMlRows * 32; t += nthreads) cntml[t] = 0u;
     __syncthreads();
@@ -118,13 +135,15 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     const int n = (int)rlen[lane];
     const uint32_t *ev = evS + lane;
 
-    // first dense level: L_l <= ld_factor * (longest row).  CTA-uniform, so that the warps agree on who does what
-    int ld = nl;
-    for (int l = 1; l < nl; l++)
+    // first dense level: L_l <= ld_factor * (longest row), at most ld_cap.  CTA-uniform, so that the warps agree on
+    // who does what
+    int ld = min(nl, m.ld_cap);
+    for (int l = 1; l < ld; l++)
         if ((F >> l) <= m.ld_factor * max(len, 1)) {
             ld = l;
             break;
         }
+    const int hsp = min(T, sc.cnt0 + DPL * (ld - 1));  // delay slots of the sparse levels (<= h_rows)
     // 8-bit bin arrays for the dense levels when no row's counts sum beyond 255 (CTA-uniform), else the on-the-fly walk
     const bool use8 = m.bins_rows > 0 && ld <= sc.lastl && (F >> ld) <= m.bins_rows && __all_sync(kSlFull, total <= 255u);
 
@@ -149,6 +168,11 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             if (l >= 1 && l <= sc.lastl && (!use8 || l <= ld)) v = sl::lane_level_limit(ev, n, l, ld, F, nlive + lane, sbx + lane);
             lim[l * 32 + lane] = v;
         }
+        if (warp == nwarps - 1) {
+            int sm = sl::kInfKey;
+            for (int j = 1; j <= min(ld, sc.lastl); j++) sm = min(sm, (int)sbx[j * 32 + lane]);
+            sminS[lane] = (uint32_t)sm;
+        }
     } else {
         for (int l = warp; l < nl; l += nwarps) {
             const int Ll = F >> l;
@@ -156,6 +180,10 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         }
     }
     __syncthreads();
+    if (!use8 && hsp < T) {  // CTA-uniform: the scratch tables are dead, the area now holds the dense numerators
+        for (int t = tid; t < (T - hsp) * 32; t += nthreads) Hd[t] = 0u;
+        __syncthreads();
+    }
 
     // ---- the tasks, largest first, taken by whichever warp is free
     const int64_t r = (int64_t)s * kSlice + lane;
@@ -169,12 +197,14 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         if (t < ntd) {
             if (use8) {
                 uint8_t *B = reinterpret_cast<uint8_t *>(t == 0 ? B2w : B1w);
-                const int rows = t == 0 ? (F >> (ld + 1)) : (F >> ld);
+                const int rows = (t == 0 ? (F >> (ld + 1)) : (F >> ld)) + sl::kBinPad;
                 if (t == 0 && ld + 1 > sc.lastl) continue;
                 for (int idx = lane; idx < rows * 8; idx += 32) reinterpret_cast<uint32_t *>(B)[idx] = 0u;
                 __syncwarp();
-                if (t == 0) sl::lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B + lane, nlive + lane, sbx + lane, H + lane);
-                else sl::lane_dense8_first<DPL>(ev, ld, sc, B + lane, lim + lane, H + lane);
+                if (t == 0)
+                    sl::lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B + lane, nlive + lane, COMPAT ? (int)sminS[lane] : sl::kInfKey,
+                                                      a.G2 + r, a.R_pad);
+                else sl::lane_dense8_first<DPL>(ev, ld, sc, B + lane, lim + lane, a.G2 + r, a.R_pad);
             } else {
                 constexpr int W = 2 * DPL + 1;
                 int bins = 0;
@@ -196,7 +226,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
                         sl::lane_dense<DPL>(ev, n, l, tb, te, (int)lim[l * 32 + lane], acc);
 #pragma unroll
                         for (int d = 0; d < DPL; d++)
-                            if (d < cnt) atomicAdd(&H[(sc.cnt0 + (l - 1) * DPL + d) * 32 + lane], acc[d]);
+                            if (d < cnt) atomicAdd(&Hd[(sc.cnt0 + (l - 1) * DPL + d - hsp) * 32 + lane], acc[d]);
                     }
                 }
             }
@@ -214,8 +244,12 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     }
     __syncthreads();
 
-    // ---- G2: one division per slot
-    for (int ti = warp; ti < T; ti += nwarps) a.G2[(int64_t)ti * a.R_pad + r] = sl::g2_value<DPL>(H[ti * 32 + lane], ti, sc);
+    // ---- G2: one division per slot (the 8-bit bin tasks have written theirs)
+    const int tend = use8 ? hsp : T;
+    for (int ti = warp; ti < tend; ti += nwarps) {
+        const uint32_t num = ti < hsp ? H[ti * 32 + lane] : Hd[(ti - hsp) * 32 + lane];
+        a.G2[(int64_t)ti * a.R_pad + r] = sl::g2_value<DPL>(num, ti, sc);
+    }
 }
 
 template <int DPL, bool COMPAT>
@@ -257,9 +291,24 @@ static int sl_bins_rows(const xpcs_handle_s *h, int len_cap, int ld_factor)
     return 0;
 }
 
-static size_t sl_bytes(const xpcs_handle_s *h, int len_cap, bool compat, int bins_rows)
+// first dense level of the longest slice this launch handles, and the cap of the kernel (one level beyond it)
+static int sl_ld_min(const xpcs_handle_s *h, int len_cap, int ld_factor)
 {
-    return 4 * sl_smem_words(len_cap, h->T, h->sched.n_levels, compat, bins_rows);
+    const Sched &sc = h->sched;
+    for (int l = 1; l < sc.n_levels; l++)
+        if ((sc.frames >> l) <= ld_factor * std::max(len_cap, 1)) return l;
+    return sc.n_levels;
+}
+
+static int sl_h_rows(const xpcs_handle_s *h, int ld_cap)
+{
+    return std::min(h->T, h->sched.count[0] + h->prm.delays_per_level * (ld_cap - 1));
+}
+
+static size_t sl_bytes(const xpcs_handle_s *h, int len_cap, bool compat, int ld_factor, int bins_rows)
+{
+    const int ld_cap = std::min(h->sched.n_levels, sl_ld_min(h, len_cap, ld_factor) + 1);
+    return 4 * sl_smem_words(len_cap, h->T, h->sched.n_levels, sl_h_rows(h, ld_cap), compat, bins_rows);
 }
 
 // The slice kernel covers what the warp kernel covers (integer counts, dpl 4 or 8, frames below 2^20, the
@@ -272,7 +321,7 @@ bool multitau_slice_eligible(const xpcs_handle_s *h)
         if (e[0] == 's') return true;
     }
     const bool compat = (h->prm.compat_flags & XPCS_COMPAT_STALE_TAIL) != 0;
-    return sl_bytes(h, sl_len_cap(h), compat, 0) <= 56 * 1024;
+    return sl_bytes(h, sl_len_cap(h), compat, 4, 0) <= 56 * 1024;
 }
 
 int launch_multitau_slice(xpcs_handle_s *h, MtArgs &a)
@@ -298,20 +347,23 @@ int launch_multitau_slice(xpcs_handle_s *h, MtArgs &a)
         }
     m.ld_factor = sl_env("XPCS_SL_LD", 1, 16, 4);
     int len_cap = sl_len_cap(h);
-    while (len_cap > 1 && sl_bytes(h, len_cap, compat, 0) > (size_t)smem_cap) len_cap = len_cap * 3 / 4;
-    if (sl_bytes(h, len_cap, compat, 0) > (size_t)smem_cap) {  // T too large: everything falls back
+    while (len_cap > 1 && sl_bytes(h, len_cap, compat, m.ld_factor, 0) > (size_t)smem_cap) len_cap = len_cap * 3 / 4;
+    if (sl_bytes(h, len_cap, compat, m.ld_factor, 0) > (size_t)smem_cap) {  // T too large: everything falls back
         cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
         return XPCS_OK;
     }
     m.len_cap = len_cap;
+    m.ld_cap = std::min(sc.n_levels, sl_ld_min(h, len_cap, m.ld_factor) + 1);
+    m.h_rows = sl_h_rows(h, m.ld_cap);
     // 8-bit bin arrays for the dense levels as long as three CTAs still share an SM
     m.bins_rows = sl_bins_rows(h, len_cap, m.ld_factor);
-    if (sl_bytes(h, len_cap, compat, m.bins_rows) > (size_t)(smem_cap + 1024) / 3 - 1024) m.bins_rows = 0;
+    if (sl_bytes(h, len_cap, compat, m.ld_factor, m.bins_rows) > (size_t)(smem_cap + 1024) / 3 - 1024) m.bins_rows = 0;
+    m.area_words = (int)sl_area_words(h->T, sc.n_levels, m.h_rows, compat, m.bins_rows);
     m.np = sl_env("XPCS_SL_PAIR_PIECES", 1, 32, 8);    // diagnostics
     m.nd = sl_env("XPCS_SL_DENSE_PIECES", 1, 16, 4);
     m.nio = sl_env("XPCS_SL_IO_PIECES", 1, 8, 2);
     const int warps = sl_env("XPCS_SL_WARPS", 2, kSlMaxWarps, 8);
-    const size_t bytes = sl_bytes(h, len_cap, compat, m.bins_rows);
+    const size_t bytes = sl_bytes(h, len_cap, compat, m.ld_factor, m.bins_rows);
     const int dpl = h->prm.delays_per_level;
     if (dpl == 8) rc = compat ? run_slice<8, true>(h, a, m, bytes, warps) : run_slice<8, false>(h, a, m, bytes, warps);
     else rc = compat ? run_slice<4, true>(h, a, m, bytes, warps) : run_slice<4, false>(h, a, m, bytes, warps);

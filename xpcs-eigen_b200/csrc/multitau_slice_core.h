@@ -46,6 +46,7 @@ constexpr uint32_t kCMask = (1u << kCB) - 1u;
 constexpr uint32_t kSent = 0xffffffffu;
 constexpr int kInfKey = 0x7fffffff;
 constexpr int kMlRows = 33;            // merge-level histogram rows (bit lengths 0..32)
+constexpr int kBinPad = 2 * (2 * 8 + 1);  // zero rows behind the bins of a level (two windows of the largest dpl)
 
 // launch-uniform schedule: level 0 has the delays 1..cnt0, level l in 1..lastl the level-local delays
 // dpl+1..dpl+count (count = dpl below lastl, cnt_last at lastl)
@@ -326,24 +327,26 @@ XS_HD void lane_bins8_halve(uint8_t *B, int Lnext, int want, int &cand)
         }
         B[t * kS] = (uint8_t)(a + b);
     }
+    for (int t = Lnext; t < Lnext + kBinPad; t++) B[t * kS] = 0;  // what the finer level left behind the new end
 }
 
-// acc[d] = sum over t of B[t] * B[t + dpl+1 + d], t + dpl+1 + d < L
+// acc[d] = sum over t of B[t] * B[t + dpl+1 + d], t + dpl+1 + d < L.  The rows L .. L + kBinPad - 1 of the array
+// must hold zeros: the window runs past the end instead of asking where it is.
 template <int DPL>
 XS_HD void lane_bins8_mac(const uint8_t *B, int L, uint32_t (&acc)[DPL])
 {
     constexpr int W = 2 * DPL + 1;
     uint32_t win[W];
 #pragma unroll
-    for (int k = 0; k < W; k++) win[k] = k < L ? B[k * kS] : 0u;
-    for (int t0 = 0; t0 < L; t0 += W) {
+    for (int k = 0; k < W; k++) win[k] = B[k * kS];
+    const uint8_t *pb = B + W * kS;
+    for (int t0 = 0; t0 < L; t0 += W, pb += W * kS) {
 #pragma unroll
         for (int u = 0; u < W; u++) {
             const uint32_t src = win[u];
 #pragma unroll
             for (int d = 0; d < DPL; d++) acc[d] += src * win[(u + DPL + 1 + d) % W];
-            const int key = t0 + u + W;
-            win[u] = key < L ? B[key * kS] : 0u;
+            win[u] = pb[u * kS];
         }
     }
 }
@@ -363,9 +366,10 @@ XS_HD void lane_bins8_fix(const uint8_t *B, int L, int klim, uint32_t (&acc)[DPL
     }
 }
 
-// the first dense level (bins built from the events, key limit from the tables)
+// the first dense level (bins built from the events, key limit from the tables); results leave as floats
 template <int DPL>
-XS_HD void lane_dense8_first(const uint32_t *ev, int ld, const SlSched &s, uint8_t *B, const uint32_t *lim, uint32_t *H)
+XS_HD void lane_dense8_first(const uint32_t *ev, int ld, const SlSched &s, uint8_t *B, const uint32_t *lim,
+                             float *g2, int64_t ostride)
 {
     const int L = s.F >> ld;
     int cand;
@@ -377,24 +381,21 @@ XS_HD void lane_dense8_first(const uint32_t *ev, int ld, const SlSched &s, uint8
     const int klim = (int)lim[ld * kS];
     if (klim < L) lane_bins8_fix<DPL>(B, L, klim, acc);
     const int cnt = level_count<DPL>(s, ld);
+    const int slot0 = s.cnt0 + (ld - 1) * DPL;
+    const float s2 = pow2_neg(2 * ld);
 #pragma unroll
     for (int d = 0; d < DPL; d++)
-        if (d < cnt) H[(s.cnt0 + (ld - 1) * DPL + d) * kS] = acc[d];
+        if (d < cnt) g2[(slot0 + d) * ostride] = scaled_div((float)acc[d] * s2, L - (DPL + 1 + d));
 }
 
 // the levels ld+1 .. lastl: bins of level ld+1 from the events, then halved in place level by level; in compat
-// mode the exact first stale slot of every level comes out of the same passes, and the threshold key K* is
-// looked for only where it can matter
+// mode the exact first stale slot of every level comes out of the same passes (smin0: the smallest one up to
+// level ld, from the tables), and the threshold key K* is looked for only where it can matter
 template <int DPL, bool COMPAT>
 XS_HD void lane_dense8_deep(const uint32_t *ev, int n, int ld, const SlSched &s, uint8_t *B, const uint32_t *nlive,
-                            const uint32_t *sbx, uint32_t *H)
+                            int smin0, float *g2, int64_t ostride)
 {
-    int smin = kInfKey;
-    if (COMPAT)
-        for (int j = 1; j <= ld; j++) {
-            const int v = (int)sbx[j * kS];
-            smin = v < smin ? v : smin;
-        }
+    int smin = smin0;
     for (int l = ld + 1; l <= s.lastl; l++) {
         const int L = s.F >> l;
         int cand;
@@ -416,9 +417,11 @@ XS_HD void lane_dense8_deep(const uint32_t *ev, int n, int ld, const SlSched &s,
         lane_bins8_mac<DPL>(B, L, acc);
         if (klim < L) lane_bins8_fix<DPL>(B, L, klim, acc);
         const int cnt = level_count<DPL>(s, l);
+        const int slot0 = s.cnt0 + (l - 1) * DPL;
+        const float s2 = pow2_neg(2 * l);
 #pragma unroll
         for (int d = 0; d < DPL; d++)
-            if (d < cnt) H[(s.cnt0 + (l - 1) * DPL + d) * kS] = acc[d];
+            if (d < cnt) g2[(slot0 + d) * ostride] = scaled_div((float)acc[d] * s2, L - (DPL + 1 + d));
     }
 }
 
