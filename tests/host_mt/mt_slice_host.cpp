@@ -38,7 +38,8 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
             break;
         }
     const bool use8 = bins_rows > 0 && ld <= sc.lastl && (F >> ld) <= bins_rows && small;
-    std::vector<uint8_t> B1((size_t)(bins_rows + kBinPad) * 32, 0xee), B2((size_t)((bins_rows >> 1) + kBinPad) * 32, 0xee);
+    std::vector<uint8_t> Bb[3];
+    for (int t = 0; t < 3; t++) Bb[t].assign((size_t)((bins_rows >> t) + 1) * 32, 0xee);
     const int hsp = std::min(T, sc.cnt0 + DPL * (ld - 1));
     for (int lane = 0; lane < 32; lane++) {
         const uint32_t *ev = evS.data() + lane;
@@ -74,12 +75,12 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
             lane_ip<DPL>(ev, n, tot[lane], sc, ta, tb, IP + (size_t)ta * 32 + lane, 32);
         }
         if (ld <= sc.lastl && use8) {
-            if (ld + 1 <= sc.lastl) {
-                for (int t = 0; t < (F >> (ld + 1)) + kBinPad; t++) B2[(size_t)t * 32 + lane] = 0;
-                lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B2.data() + lane, nlive.data() + lane, smin0, G2 + lane, 32);
+            for (int t = 0; t < 3; t++) {
+                if (ld + t > sc.lastl) continue;
+                for (int k = 0; k < (F >> (ld + t)); k++) Bb[t][(size_t)k * 32 + lane] = 0;
+                lane_dense8<DPL, COMPAT>(t, ev, n, ld, sc, Bb[t].data() + lane, lim.data() + lane, nlive.data() + lane, smin0,
+                                         G2 + lane, 32);
             }
-            for (int t = 0; t < (F >> ld) + kBinPad; t++) B1[(size_t)t * 32 + lane] = 0;
-            lane_dense8_first<DPL>(ev, ld, sc, B1.data() + lane, lim.data() + lane, G2 + lane, 32);
         } else if (ld <= sc.lastl) {
             constexpr int W = 2 * DPL + 1;
             int bins = 0;

@@ -54,7 +54,7 @@ static inline size_t sl_area_words(int T, int nl, int h_rows, bool compat, int b
 {
     size_t w = (size_t)std::min(T, T - h_rows + 8) * 32;  // a slice may start its dense levels one level below ld_cap
     if (compat) w = std::max(w, (size_t)(sl::kMlRows + nl) * 32);
-    if (bins_rows > 0) w = std::max(w, (size_t)(bins_rows + sl::kBinPad) * 8 + (size_t)((bins_rows >> 1) + sl::kBinPad) * 8);
+    if (bins_rows > 0) w = std::max(w, (size_t)(bins_rows + (bins_rows >> 1) + (bins_rows >> 2)) * 8);
     return w;
 }
 
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     uint32_t *area = nlive + (COMPAT ? (size_t)nl * 32 : 0);
     uint32_t *cntml = area;                           // compat, until the limits are known: [33][32]
     uint32_t *sbx = area + sl::kMlRows * 32;          //                                     [nl][32]
-    uint32_t *B1w = area;                             // 8-bit bins: [bins_rows + pad][32] bytes
-    uint32_t *B2w = area + (size_t)(m.bins_rows + sl::kBinPad) * 8;  // [bins_rows / 2 + pad][32] bytes
+    // 8-bit bins, one array per dense task: [bins_rows][32], [bins_rows / 2][32], [bins_rows / 4][32] bytes
+    const int boff1 = m.bins_rows * 8, boff2 = (m.bins_rows + (m.bins_rows >> 1)) * 8;
     uint32_t *Hd = area;                              // on-the-fly dense walk: numerators of the slots from hsp on
     __shared__ int qctr;
 
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
 
     // ---- the tasks, largest first, taken by whichever warp is free
     const int64_t r = (int64_t)s * kSlice + lane;
-    const int ntd = ld > sc.lastl ? 0 : (use8 ? 2 : m.nd);
+    const int ntd = ld > sc.lastl ? 0 : (use8 ? 3 : m.nd);
     const int ntasks = ntd + 2 * m.nio + m.np;
     for (;;) {
         int t = 0;
@@ -196,15 +196,13 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         if (t >= ntasks) break;
         if (t < ntd) {
             if (use8) {
-                uint8_t *B = reinterpret_cast<uint8_t *>(t == 0 ? B2w : B1w);
-                const int rows = (t == 0 ? (F >> (ld + 1)) : (F >> ld)) + sl::kBinPad;
-                if (t == 0 && ld + 1 > sc.lastl) continue;
+                if (ld + t > sc.lastl) continue;
+                uint8_t *B = reinterpret_cast<uint8_t *>(area + (t == 0 ? 0 : (t == 1 ? boff1 : boff2)));
+                const int rows = F >> (ld + t);
                 for (int idx = lane; idx < rows * 8; idx += 32) reinterpret_cast<uint32_t *>(B)[idx] = 0u;
                 __syncwarp();
-                if (t == 0)
-                    sl::lane_dense8_deep<DPL, COMPAT>(ev, n, ld, sc, B + lane, nlive + lane, COMPAT ? (int)sminS[lane] : sl::kInfKey,
-                                                      a.G2 + r, a.R_pad);
-                else sl::lane_dense8_first<DPL>(ev, ld, sc, B + lane, lim + lane, a.G2 + r, a.R_pad);
+                sl::lane_dense8<DPL, COMPAT>(t, ev, n, ld, sc, B + lane, lim + lane, nlive + lane,
+                                             COMPAT ? (int)sminS[lane] : sl::kInfKey, a.G2 + r, a.R_pad);
             } else {
                 constexpr int W = 2 * DPL + 1;
                 int bins = 0;

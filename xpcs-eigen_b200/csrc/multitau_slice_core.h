@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define XS_HD __host__ __device__ __forceinline__
+#define XS_HD_CALL __host__ __device__ __noinline__   // rare or long routines: one copy, called (the tasks share one instruction cache)
 #else
 #define XS_HD inline
+#define XS_HD_CALL inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -46,7 +48,6 @@ constexpr uint32_t kCMask = (1u << kCB) - 1u;
 constexpr uint32_t kSent = 0xffffffffu;
 constexpr int kInfKey = 0x7fffffff;
 constexpr int kMlRows = 33;            // merge-level histogram rows (bit lengths 0..32)
-constexpr int kBinPad = 2 * (2 * 8 + 1);  // zero rows behind the bins of a level (two windows of the largest dpl)
 
 // launch-uniform schedule: level 0 has the delays 1..cnt0, level l in 1..lastl the level-local delays
 // dpl+1..dpl+count (count = dpl below lastl, cnt_last at lastl)
@@ -60,6 +61,18 @@ XS_HD int bitlength(uint32_t x)
     return 32 - __clz((int)x);
 #else
     return x ? 32 - __builtin_clz(x) : 0;
+#endif
+}
+
+// index of the highest set bit (x != 0)
+XS_HD int top_bit(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return 31 - __builtin_clz(x);
 #endif
 }
 
@@ -187,29 +200,36 @@ XS_HD void lane_ip(const uint32_t *ev, int n, uint32_t total, const SlSched &s, 
 // lim[l * 32]: frame limit of level l (lim_l, or K* << l in compat mode); H[slot * 32]: numerators.
 // A pair whose later event lies below every level's limit (all but the last few events of a row) skips the
 // per-level limit look-ups.
+// A pair at frame distance d >= 2 dpl sits in exactly one (level, delay) slot, or in none: with l0 such that
+// d >> l0 is in [dpl, 2 dpl), the bin distance at level l0 is q0 = (f_j >> l0) - (f_i >> l0), dpl <= q0 <= 2 dpl.
+// q0 > dpl: slot (l0, q0).  q0 == dpl: nothing at level l0, and at level l0 - 1 the bin distance 2 q0 + (bit_j - bit_i)
+// is the last delay 2 dpl iff the two frames agree in bit l0 - 1.  Every other level sees a distance outside
+// dpl+1 .. 2 dpl.  (Distances up to 2 dpl are the level-0 delays; d == 2 dpl takes part in both.)
 template <int DPL, bool FULL, bool CHECK>
-XS_HD void pair_add(uint32_t fi, uint32_t fj, uint32_t cc, int ld, const SlSched &s, const uint32_t *lim, uint32_t *H)
+XS_HD void pair_add(uint32_t fi, uint32_t fj, uint32_t cc, int ld, const SlSched &s, const uint32_t *lim, uint32_t *H,
+                    uint32_t *Hl)
 {
     // FULL: every sparse level l in 1..ld-1 has all its dpl delays (ld - 1 < lastl), no need to ask the schedule
     constexpr int LG = DPL == 8 ? 3 : 2;
-    constexpr int LO = DPL + 1;
     const uint32_t d = fj - fi;
-    if (d <= (uint32_t)s.cnt0) {  // level 0 (rare: d <= 2 dpl)
+    if (d <= 2u * DPL) {  // rare
         if (d - 1u < (uint32_t)s.cnt0 && (!CHECK || fj < lim[0])) XS_ADD(&H[(d - 1u) * kS], cc);
+        if (d < 2u * DPL) return;
     }
-    if (d >= 2u * DPL) {
-        uint32_t *Hl = H + (s.cnt0 - DPL) * kS;  // slot of (level l, bin distance LO + b) = Hl[(l * DPL + b) * 32]
-        const int l0 = bitlength(d) - (LG + 1);  // d >> l0 in [dpl, 2 dpl)
-        const uint32_t b0 = (fj >> l0) - (fi >> l0) - LO;
-        if (l0 < ld && b0 < (uint32_t)(FULL ? DPL : level_count<DPL>(s, l0)) && (!CHECK || fj < lim[l0 * kS]))
-            XS_ADD(&Hl[(l0 * DPL + (int)b0) * kS], cc);
-        if (d >= 4u * DPL) {                     // l1 = l0 - 1 >= 1
-            const int l1 = l0 - 1;
-            const uint32_t b1 = (fj >> l1) - (fi >> l1);
-            if (b1 == 2u * DPL && l1 < ld && (FULL || DPL - 1 < level_count<DPL>(s, l1)) && (!CHECK || fj < lim[l1 * kS]))
-                XS_ADD(&Hl[(l1 * DPL + DPL - 1) * kS], cc);
-        }
+    const int l0 = top_bit(d) - LG;  // d >> l0 in [dpl, 2 dpl); >= 1
+    const uint32_t q0 = (fj >> l0) - (fi >> l0);
+    int l = l0;
+    uint32_t b = q0 - (DPL + 1);
+    if (q0 == (uint32_t)DPL) {
+        if (l0 < 2 || (((fj ^ fi) >> (l0 - 1)) & 1u)) return;
+        l = l0 - 1;
+        b = DPL - 1;
     }
+    if (l >= ld) return;
+    if (!FULL && b >= (uint32_t)level_count<DPL>(s, l)) return;
+    if (CHECK && fj >= lim[l * kS]) return;
+    // slot of (level l, bin distance dpl+1 + b): Hl[(l * dpl + b) * 32]
+    XS_ADD(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(Hl) + ((uint32_t)l << (LG + 7)) + (b << 7)), cc);
 }
 
 template <int DPL, bool FULL>
@@ -227,14 +247,15 @@ XS_HD void lane_pairs(const uint32_t *ev, int n, int i0, int istep, int ld, cons
     uint32_t fend = fi + dmax;
     uint32_t keyw = (fend < 0xfffffu ? fend : 0xfffffu) << kCB;
     const uint32_t *pj = pi + kS;
+    uint32_t *Hl = H + (s.cnt0 - DPL) * kS;  // Hl[(l * dpl + b) * 32]: slot b of level l >= 1
     for (;;) {
         const uint32_t wj = *pj;
         if (wj < keyw) {
             pj += kS;
             const uint32_t fj = wj >> kCB;
             const uint32_t cc = ci * (wj & kCMask);
-            if (wj < limminw) pair_add<DPL, FULL, false>(fi, fj, cc, ld, s, lim, H);
-            else pair_add<DPL, FULL, true>(fi, fj, cc, ld, s, lim, H);
+            if (wj < limminw) pair_add<DPL, FULL, false>(fi, fj, cc, ld, s, lim, H, Hl);
+            else pair_add<DPL, FULL, true>(fi, fj, cc, ld, s, lim, H, Hl);
         } else {
             pi += istep * kS;
             if (pi >= pend) break;
@@ -283,30 +304,39 @@ XS_HD void lane_dense(const uint32_t *ev, int n, int l, int tb, int te, int klim
     }
 }
 
-XS_HD int lane_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level);
+XS_HD_CALL int lane_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level);
 
 // ---- G2, dense levels, rows whose counts sum to <= 255: 8-bit bin arrays B[t * 32] (one byte per row and bin).
 // Unlike the on-the-fly walk above, nothing here depends on where a lane's events lie: all lanes run the
 // same trip counts.
 
 // bins of level l from the events.  COMPAT: cand = key of the occupied level-(l-1) bin of rank `want` (0-based;
-// the first stale slot level l leaves behind), kInfKey if there is none
-template <bool COMPAT>
-XS_HD void lane_bins8_build(const uint32_t *ev, int l, int F, uint8_t *B, int want, int &cand)
+// the first stale slot level l leaves behind), kInfKey if there is none; TWO: the same one level up
+// (cand2: occupied level-(l-2) bin of rank want2), for the task that starts two levels beyond the first dense one
+template <bool COMPAT, bool TWO>
+XS_HD void lane_bins8_build(const uint32_t *ev, int l, int F, uint8_t *B, int want, int &cand, int want2, int &cand2)
 {
     const uint32_t limw = ((uint32_t)(F >> l) << l) << kCB;
     const int sh = kCB + l - 1;
     const uint32_t *pe = ev;
     uint32_t w = *pe;
-    int occ = -1;
-    uint32_t prev = 0xffffffffu;
+    int occ = -1, occ2 = -1;
+    uint32_t prev = 0xffffffffu, prev2 = 0xffffffffu;
     cand = kInfKey;
+    cand2 = kInfKey;
     while (w < limw) {
         const uint32_t key1 = w >> sh;  // level l - 1
         B[(key1 >> 1) * kS] += (uint8_t)(w & kCMask);
         if (COMPAT && key1 != prev) {
             prev = key1;
             if (++occ == want) cand = (int)key1;
+        }
+        if (COMPAT && TWO) {
+            const uint32_t key2 = w >> (sh - 1);  // level l - 2
+            if (key2 != prev2) {
+                prev2 = key2;
+                if (++occ2 == want2) cand2 = (int)key2;
+            }
         }
         pe += kS;
         w = *pe;
@@ -327,26 +357,35 @@ XS_HD void lane_bins8_halve(uint8_t *B, int Lnext, int want, int &cand)
         }
         B[t * kS] = (uint8_t)(a + b);
     }
-    for (int t = Lnext; t < Lnext + kBinPad; t++) B[t * kS] = 0;  // what the finer level left behind the new end
 }
 
-// acc[d] = sum over t of B[t] * B[t + dpl+1 + d], t + dpl+1 + d < L.  The rows L .. L + kBinPad - 1 of the array
-// must hold zeros: the window runs past the end instead of asking where it is.
+// acc[d] = sum over t of B[t] * B[t + dpl+1 + d], t + dpl+1 + d < L: a register window of 2dpl+1 bins slides over
+// t; only the last two windows ask whether they have run past the end of the level
 template <int DPL>
 XS_HD void lane_bins8_mac(const uint8_t *B, int L, uint32_t (&acc)[DPL])
 {
     constexpr int W = 2 * DPL + 1;
     uint32_t win[W];
 #pragma unroll
-    for (int k = 0; k < W; k++) win[k] = B[k * kS];
+    for (int k = 0; k < W; k++) win[k] = k < L ? B[k * kS] : 0u;
     const uint8_t *pb = B + W * kS;
-    for (int t0 = 0; t0 < L; t0 += W, pb += W * kS) {
+    int t0 = 0;
+    for (; t0 + 2 * W <= L; t0 += W, pb += W * kS) {
 #pragma unroll
         for (int u = 0; u < W; u++) {
             const uint32_t src = win[u];
 #pragma unroll
             for (int d = 0; d < DPL; d++) acc[d] += src * win[(u + DPL + 1 + d) % W];
             win[u] = pb[u * kS];
+        }
+    }
+    for (; t0 < L; t0 += W, pb += W * kS) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const uint32_t src = win[u];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] += src * win[(u + DPL + 1 + d) % W];
+            win[u] = t0 + u + W < L ? pb[u * kS] : 0u;
         }
     }
 }
@@ -366,62 +405,69 @@ XS_HD void lane_bins8_fix(const uint8_t *B, int L, int klim, uint32_t (&acc)[DPL
     }
 }
 
-// the first dense level (bins built from the events, key limit from the tables); results leave as floats
+// one dense level, bins in B: numerators, the compat correction, one division per delay
 template <int DPL>
-XS_HD void lane_dense8_first(const uint32_t *ev, int ld, const SlSched &s, uint8_t *B, const uint32_t *lim,
-                             float *g2, int64_t ostride)
+XS_HD_CALL void lane_dense8_level(const uint8_t *B, int l, int klim, const SlSched &s, float *g2, int64_t ostride)
 {
-    const int L = s.F >> ld;
-    int cand;
-    lane_bins8_build<false>(ev, ld, s.F, B, -2, cand);
+    const int L = s.F >> l;
     uint32_t acc[DPL];
 #pragma unroll
     for (int d = 0; d < DPL; d++) acc[d] = 0u;
     lane_bins8_mac<DPL>(B, L, acc);
-    const int klim = (int)lim[ld * kS];
     if (klim < L) lane_bins8_fix<DPL>(B, L, klim, acc);
-    const int cnt = level_count<DPL>(s, ld);
-    const int slot0 = s.cnt0 + (ld - 1) * DPL;
-    const float s2 = pow2_neg(2 * ld);
+    const int cnt = level_count<DPL>(s, l);
+    const int slot0 = s.cnt0 + (l - 1) * DPL;
+    const float s2 = pow2_neg(2 * l);
 #pragma unroll
     for (int d = 0; d < DPL; d++)
         if (d < cnt) g2[(slot0 + d) * ostride] = scaled_div((float)acc[d] * s2, L - (DPL + 1 + d));
 }
 
-// the levels ld+1 .. lastl: bins of level ld+1 from the events, then halved in place level by level; in compat
-// mode the exact first stale slot of every level comes out of the same passes (smin0: the smallest one up to
-// level ld, from the tables), and the threshold key K* is looked for only where it can matter
+// Three tasks share the dense levels, each with its own bin array (zeroed by the caller) filled from the events:
+//   which = 0   level ld                 (key limit from the tables)
+//   which = 1   level ld + 1
+//   which = 2   levels ld + 2 .. lastl   (bins halved in place from level to level)
+// In compat mode the exact first stale slot of every level beyond ld comes out of the same passes (smin0: the
+// smallest one up to level ld, from the tables), and the threshold key K* is looked for only where it can matter.
 template <int DPL, bool COMPAT>
-XS_HD void lane_dense8_deep(const uint32_t *ev, int n, int ld, const SlSched &s, uint8_t *B, const uint32_t *nlive,
-                            int smin0, float *g2, int64_t ostride)
+XS_HD void lane_dense8(int which, const uint32_t *ev, int n, int ld, const SlSched &s, uint8_t *B, const uint32_t *lim,
+                       const uint32_t *nlive, int smin0, float *g2, int64_t ostride)
 {
+    int cand, cand2;
+    if (which == 0) {
+        lane_bins8_build<false, false>(ev, ld, s.F, B, -2, cand, -2, cand2);
+        lane_dense8_level<DPL>(B, ld, (int)lim[ld * kS], s, g2, ostride);
+        return;
+    }
     int smin = smin0;
-    for (int l = ld + 1; l <= s.lastl; l++) {
+    // compat: first stale slot left by level l (from the level-(l-1) bins) joins the running minimum; K* if it can matter
+    auto key_limit = [&](int l, int cnd) -> int {
         const int L = s.F >> l;
-        int cand;
-        const int want = COMPAT ? (int)nlive[l * kS] : -2;
-        if (l == ld + 1) lane_bins8_build<COMPAT>(ev, l, s.F, B, want, cand);
-        else lane_bins8_halve<COMPAT>(B, L, want, cand);
-        int klim = L;
-        if (COMPAT) {
-            const int nv = (int)nlive[l * kS];
-            if (nv < (int)nlive[(l - 1) * kS] && nv < L) smin = cand < smin ? cand : smin;
-            if (nv < n && smin < L) {
-                const int ks = lane_stale_threshold(ev, n, nlive, l);
-                klim = ks < L ? ks : L;
-            }
+        if (!COMPAT) return L;
+        const int nv = (int)nlive[l * kS];
+        if (nv < (int)nlive[(l - 1) * kS] && nv < L) smin = cnd < smin ? cnd : smin;
+        if (nv < n && smin < L) {
+            const int ks = lane_stale_threshold(ev, n, nlive, l);
+            return ks < L ? ks : L;
         }
-        uint32_t acc[DPL];
-#pragma unroll
-        for (int d = 0; d < DPL; d++) acc[d] = 0u;
-        lane_bins8_mac<DPL>(B, L, acc);
-        if (klim < L) lane_bins8_fix<DPL>(B, L, klim, acc);
-        const int cnt = level_count<DPL>(s, l);
-        const int slot0 = s.cnt0 + (l - 1) * DPL;
-        const float s2 = pow2_neg(2 * l);
-#pragma unroll
-        for (int d = 0; d < DPL; d++)
-            if (d < cnt) g2[(slot0 + d) * ostride] = scaled_div((float)acc[d] * s2, L - (DPL + 1 + d));
+        return L;
+    };
+    if (which == 1) {
+        const int l = ld + 1;
+        lane_bins8_build<COMPAT, false>(ev, l, s.F, B, COMPAT ? (int)nlive[l * kS] : -2, cand, -2, cand2);
+        lane_dense8_level<DPL>(B, l, key_limit(l, cand), s, g2, ostride);
+        return;
+    }
+    for (int l = ld + 2; l <= s.lastl; l++) {
+        if (l == ld + 2) {
+            lane_bins8_build<COMPAT, true>(ev, l, s.F, B, COMPAT ? (int)nlive[l * kS] : -2, cand,
+                                           COMPAT ? (int)nlive[(l - 1) * kS] : -2, cand2);
+            if (COMPAT) {  // level ld + 1 belongs to another task, but its first stale slot counts here too
+                const int nv = (int)nlive[(l - 1) * kS];
+                if (nv < (int)nlive[(l - 2) * kS] && nv < (s.F >> (l - 1))) smin = cand2 < smin ? cand2 : smin;
+            }
+        } else lane_bins8_halve<COMPAT>(B, s.F >> l, COMPAT ? (int)nlive[l * kS] : -2, cand);
+        lane_dense8_level<DPL>(B, l, key_limit(l, cand), s, g2, ostride);
     }
 }
 
@@ -506,7 +552,7 @@ XS_HD int lane_key_at(const uint32_t *ev, int n, const uint32_t *nlive, int leve
 
 // threshold key K*: targets with key >= K* are never found by the reference's search (the walk of
 // multitau.cu: stale_tail_threshold, along the live/stale boundary of the implicit search tree)
-XS_HD int lane_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level)
+XS_HD_CALL int lane_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level)
 {
     const int nl = (int)nlive[level * kS];
     int first = 0, len = n;
