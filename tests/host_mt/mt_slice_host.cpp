@@ -65,9 +65,18 @@ static int run(const SlSched &sc, const int *row_len, const uint32_t *words, int
                 lim[(size_t)l * 32 + lane] = l < ld ? (uint32_t)Ll << l : (uint32_t)Ll;
             }
         }
-        for (int w = 0; w < np; w++) {
-            if (ld - 1 < sc.lastl) lane_pairs<DPL, true>(ev, n, w, np, ld, sc, lim.data() + lane, H.data() + lane);
-            else lane_pairs<DPL, false>(ev, n, w, np, ld, sc, lim.data() + lane, H.data() + lane);
+        const int nps = np / 2;  // small pieces over the last quarter of the events, as in the kernel (0: none)
+        for (int w = 0; w < np + nps; w++) {
+            const int cut = nps > 0 ? n - (n >> 2) : n;
+            int piece = w, ia = 0, ib = cut, istep = np;
+            if (piece >= np) {
+                piece -= np;
+                ia = cut;
+                ib = n;
+                istep = nps;
+            }
+            if (ld - 1 < sc.lastl) lane_pairs<DPL, true>(ev, ia, ib, piece, istep, ld, sc, lim.data() + lane, H.data() + lane);
+            else lane_pairs<DPL, false>(ev, ia, ib, piece, istep, ld, sc, lim.data() + lane, H.data() + lane);
         }
         for (int part = 0; part < nio; part++) {
             const int ta = (int)((int64_t)T * part / nio), tb = (int)((int64_t)T * (part + 1) / nio);

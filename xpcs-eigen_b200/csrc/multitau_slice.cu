@@ -24,9 +24,94 @@
 #include <cstdlib>
 
 #include "internal.h"
+
+// The per-row routines are compiled for the device only here, and the rare stale-tail walk (one row in ~70 needs it on
+// the bench workload, but then for thousands of instructions in a single lane) is given to the whole warp.
+namespace xpcs {
+namespace sl {
+__device__ int coop_stale_walk(bool fire, const uint32_t *ev, int n, const uint32_t *nlive, int level);
+}
+}
+#define XS_HD __device__ __forceinline__
+#define XS_HD_CALL __device__ __noinline__
+#define XS_WALK(fire, ev, n, nlive, level) coop_stale_walk((fire), (ev), (n), (nlive), (level))
 #include "multitau_slice_core.h"
 
 namespace xpcs {
+
+namespace sl {
+
+// ---- the stale-tail walk of one row by a whole warp: lane_select_head / lane_key_at / lane_stale_threshold of
+// multitau_slice_core.h with the lanes over the events (col = the row's column of the tile, stride 32 words)
+__device__ __forceinline__ int coop_select_head(const uint32_t *col, int n, int level, int p, int lane)
+{
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int i = c0 + lane;
+        bool head = false;
+        if (i < n) head = (i == 0) || ((((col[i * kS] ^ col[(i - 1) * kS]) >> kCB) >> level) != 0u);
+        const unsigned mk = __ballot_sync(0xffffffffu, head);
+        const int c = __popc(mk);
+        if (p < base + c) return c0 + (int)__fns(mk, 0, p - base + 1);
+        base += c;
+    }
+    return n - 1;
+}
+
+__device__ __forceinline__ int coop_key_at(const uint32_t *col, int n, const uint32_t *nlive, int level, int p, int lane)
+{
+    int lv = level;
+    if (p >= (int)nlive[level * kS]) {
+        lv = level - 1;
+        while (lv > 0 && (int)nlive[lv * kS] <= p) lv--;
+    }
+    const int i = coop_select_head(col, n, lv, p, lane);
+    return (int)((col[i * kS] >> kCB) >> lv);
+}
+
+__device__ __noinline__ int coop_stale_threshold(const uint32_t *col, int n, const uint32_t *nlive, int level, int lane)
+{
+    const int nl = (int)nlive[level * kS];
+    int first = 0, len = n;
+    int curmin = kInfKey;
+    while (len > 0) {
+        const int half = len >> 1;
+        const int mid = first + half;
+        if (mid >= nl) {
+            curmin = min(curmin, coop_key_at(col, n, nlive, level, mid, lane));
+            len = half;
+        } else {
+            if (curmin != kInfKey && coop_key_at(col, n, nlive, level, mid, lane) > curmin) {
+                const int k1 = coop_key_at(col, n, nlive, level, first, lane);
+                const int j = lane_lower_bound(col, n, ((uint32_t)(curmin + 1) << level) << kCB);
+                const int k2 = j < n ? (int)((col[j * kS] >> kCB) >> level) : kInfKey;
+                return max(k1, k2);
+            }
+            first = mid + 1;
+            len = len - half - 1;
+        }
+    }
+    return kInfKey;
+}
+
+// K* of every lane that asks for it (fire), one row after the other with all 32 lanes on it
+__device__ int coop_stale_walk(bool fire, const uint32_t *ev, int n, const uint32_t *nlive, int level)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    unsigned mk = __ballot_sync(0xffffffffu, fire);
+    int ks = kInfKey;
+    while (mk) {
+        const int r = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const int nr = __shfl_sync(0xffffffffu, n, r);
+        const int k = coop_stale_threshold(ev - lane + r, nr, nlive - lane + r, level, lane);
+        if (lane == r) ks = k;
+    }
+    return ks;
+}
+
+}  // namespace sl
 
 using sl::SlSched;
 
@@ -36,7 +121,7 @@ constexpr uint32_t kSlFull = 0xffffffffu;
 struct SlArgs {
     unsigned char *fallback;   // [n_slices]
     int len_cap;               // longest slice handled here
-    int np, nd, nio;           // pieces of the pair walk, of the on-the-fly dense walk, of the IF and of the IP walk
+    int np, nps, nd, nio;      // pieces of the pair walk (large, small), of the on-the-fly dense walk, of the IF and of the IP walk
     int ld_factor;             // dense levels start where L_l <= ld_factor * (longest row of the slice) ...
     int ld_cap;                // ... but not beyond this level (H is sized for the sparse slots up to it)
     int h_rows;                // rows of H: the delay slots of the levels below ld_cap
@@ -188,7 +273,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     // ---- the tasks, largest first, taken by whichever warp is free
     const int64_t r = (int64_t)s * kSlice + lane;
     const int ntd = ld > sc.lastl ? 0 : (use8 ? 3 : m.nd);
-    const int ntasks = ntd + 2 * m.nio + m.np;
+    const int ntasks = ntd + 2 * m.nio + m.np + m.nps;
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&qctr, 1);
@@ -235,9 +320,19 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             if (q & 1) sl::lane_ip<DPL>(ev, n, total, sc, ta, tb, a.IP + (int64_t)ta * a.R_pad + r, a.R_pad);
             else sl::lane_if<DPL>(ev, n, total, sc, ta, tb, a.IF + (int64_t)ta * a.R_pad + r, a.R_pad);
         } else {
-            const int piece = t - ntd - 2 * m.nio;
-            if (ld - 1 < sc.lastl) sl::lane_pairs<DPL, true>(ev, n, piece, m.np, ld, sc, lim + lane, H + lane);
-            else sl::lane_pairs<DPL, false>(ev, n, piece, m.np, ld, sc, lim + lane, H + lane);
+            // np pieces deal out the first three quarters of a row's events, nps small ones the rest: the last tasks
+            // of the queue are short, so the warps finish close to each other
+            int piece = t - ntd - 2 * m.nio;
+            const int cut = m.nps > 0 ? n - (n >> 2) : n;
+            int ia = 0, ib = cut, istep = m.np;
+            if (piece >= m.np) {
+                piece -= m.np;
+                ia = cut;
+                ib = n;
+                istep = m.nps;
+            }
+            if (ld - 1 < sc.lastl) sl::lane_pairs<DPL, true>(ev, ia, ib, piece, istep, ld, sc, lim + lane, H + lane);
+            else sl::lane_pairs<DPL, false>(ev, ia, ib, piece, istep, ld, sc, lim + lane, H + lane);
         }
     }
     __syncthreads();
@@ -358,6 +453,7 @@ int launch_multitau_slice(xpcs_handle_s *h, MtArgs &a)
     if (sl_bytes(h, len_cap, compat, m.ld_factor, m.bins_rows) > (size_t)(smem_cap + 1024) / 3 - 1024) m.bins_rows = 0;
     m.area_words = (int)sl_area_words(h->T, sc.n_levels, m.h_rows, compat, m.bins_rows);
     m.np = sl_env("XPCS_SL_PAIR_PIECES", 1, 32, 8);    // diagnostics
+    m.nps = sl_env("XPCS_SL_PAIR_TAIL", 0, 32, 8);
     m.nd = sl_env("XPCS_SL_DENSE_PIECES", 1, 16, 4);
     m.nio = sl_env("XPCS_SL_IO_PIECES", 1, 8, 2);
     const int warps = sl_env("XPCS_SL_WARPS", 2, kSlMaxWarps, 8);

@@ -25,12 +25,14 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+#if defined(XS_HD)
+// (multitau_slice.cu: device only, with its own XS_WALK)
+#elif defined(__CUDACC__)
 #define XS_HD __host__ __device__ __forceinline__
-#define XS_HD_CALL __host__ __device__ __noinline__   // rare or long routines: one copy, called (the tasks share one instruction cache)
+#define XS_HD_CALL __host__ __device__ __noinline__
 #else
 #define XS_HD inline
-#define XS_HD_CALL inline
+#define XS_HD_CALL inline   // on the device: rare or long routines, one copy, called (the tasks share one instruction cache)
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -194,7 +196,7 @@ XS_HD void lane_ip(const uint32_t *ev, int n, uint32_t total, const SlSched &s, 
     }
 }
 
-// ---- G2, sparse levels: the pairs (i, j), i = i0, i0 + istep, ..., j > i, f_j - f_i < dmax.  ONE loop whose
+// ---- G2, sparse levels: the pairs (i, j), i = ia + i0, ia + i0 + istep, ... < ib, j > i, f_j - f_i < dmax.  ONE loop whose
 // body either takes the next partner or moves on to the next i, so that a lane's trip count is its own
 // (events + pairs) and the warp's the maximum of those -- not the sum of per-event maxima.
 // lim[l * 32]: frame limit of level l (lim_l, or K* << l in compat mode); H[slot * 32]: numerators.
@@ -233,15 +235,17 @@ XS_HD void pair_add(uint32_t fi, uint32_t fj, uint32_t cc, int ld, const SlSched
 }
 
 template <int DPL, bool FULL>
-XS_HD void lane_pairs(const uint32_t *ev, int n, int i0, int istep, int ld, const SlSched &s,
+XS_HD void lane_pairs(const uint32_t *ev, int ia, int ib, int i0, int istep, int ld, const SlSched &s,
                       const uint32_t *lim, uint32_t *H)
 {
-    if (i0 >= n) return;
+    // the events i = ia + i0, ia + i0 + istep, ... below ib (ib <= n) against all their later partners
+    i0 += ia;
+    if (i0 >= ib) return;
     const uint32_t dmax = (uint32_t)(2 * DPL + 1) << (ld - 1);
     uint32_t limmin = lim[0];
     for (int l = 1; l < ld; l++) limmin = lim[l * kS] < limmin ? lim[l * kS] : limmin;
     const uint32_t limminw = limmin << kCB;
-    const uint32_t *pi = ev + i0 * kS, *pend = ev + n * kS;
+    const uint32_t *pi = ev + i0 * kS, *pend = ev + ib * kS;
     uint32_t wi = *pi;
     uint32_t fi = wi >> kCB, ci = wi & kCMask;
     uint32_t fend = fi + dmax;
@@ -305,6 +309,11 @@ XS_HD void lane_dense(const uint32_t *ev, int n, int l, int tb, int te, int klim
 }
 
 XS_HD_CALL int lane_stale_threshold(const uint32_t *ev, int n, const uint32_t *nlive, int level);
+// K* of this lane's row if `fire`, else kInfKey.  `level` is the same for all lanes of a warp and the call sites are
+// reached by all of them together, so the device build can give the rare walk to the whole warp (multitau_slice.cu).
+#ifndef XS_WALK
+#define XS_WALK(fire, ev, n, nlive, level) ((fire) ? lane_stale_threshold((ev), (n), (nlive), (level)) : kInfKey)
+#endif
 
 // ---- G2, dense levels, rows whose counts sum to <= 255: 8-bit bin arrays B[t * 32] (one byte per row and bin).
 // Unlike the on-the-fly walk above, nothing here depends on where a lane's events lie: all lanes run the
@@ -446,11 +455,8 @@ XS_HD void lane_dense8(int which, const uint32_t *ev, int n, int ld, const SlSch
         if (!COMPAT) return L;
         const int nv = (int)nlive[l * kS];
         if (nv < (int)nlive[(l - 1) * kS] && nv < L) smin = cnd < smin ? cnd : smin;
-        if (nv < n && smin < L) {
-            const int ks = lane_stale_threshold(ev, n, nlive, l);
-            return ks < L ? ks : L;
-        }
-        return L;
+        const int ks = XS_WALK(nv < n && smin < L, ev, n, nlive, l);
+        return ks < L ? ks : L;
     };
     if (which == 1) {
         const int l = ld + 1;
@@ -589,12 +595,10 @@ XS_HD uint32_t lane_level_limit(const uint32_t *ev, int n, int l, int ld, int F,
         const int v = (int)sbx[j * kS];
         smin = v < smin ? v : smin;
     }
-    if ((int)nlive[l * kS] < n && smin < Ll) {
-        const int ks = lane_stale_threshold(ev, n, nlive, l);
-        if (ks != kInfKey) {
-            const uint32_t lim = l < ld ? (uint32_t)ks << l : (uint32_t)ks;
-            out = lim < out ? lim : out;
-        }
+    const int ks = XS_WALK((int)nlive[l * kS] < n && smin < Ll, ev, n, nlive, l);
+    if (ks != kInfKey) {
+        const uint32_t lim = l < ld ? (uint32_t)ks << l : (uint32_t)ks;
+        out = lim < out ? lim : out;
     }
     return out;
 }
