@@ -115,6 +115,13 @@ __device__ int coop_stale_walk(bool fire, const uint32_t *ev, int n, const uint3
 
 using sl::SlSched;
 
+// -DXPCS_SL_TRACE: a few CTAs print where their warps spend their cycles (diagnostics; profiles/trace_slice.py)
+#ifdef XPCS_SL_TRACE
+#define SL_TRACE(what, id) do { if (lane == 0 && trn[warp] < 15) { trc[warp][trn[warp]] = ((long long)(what) << 56) | ((long long)((id) & 0xff) << 48) | (clock64() - t_start); trn[warp]++; } } while (0)
+#else
+#define SL_TRACE(what, id) do { } while (0)
+#endif
+
 constexpr int kSlMaxWarps = 16;
 constexpr uint32_t kSlFull = 0xffffffffu;
 
@@ -164,6 +171,13 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
     }
     const SlSched sc = m.s;
     const int T = sc.T, nl = sc.nl, F = sc.F;
+#ifdef XPCS_SL_TRACE
+    __shared__ long long trc[kSlMaxWarps][16];
+    __shared__ int trn[kSlMaxWarps];
+    const long long t_start = clock64();
+    if (lane == 0) trn[warp] = 0;
+    __syncwarp();
+#endif
     uint32_t *rlen = sl_smem;                         // [32]
     uint32_t *tot = sl_smem + 32;                     // [32] sum of the counts of a row
     uint32_t *sminS = sl_smem + 64;                   // [32] compat: smallest first stale slot up to the first dense level
@@ -212,6 +226,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         atomicAdd(&tot[q4 + 3], c3);
     }
     __syncthreads();
+    SL_TRACE(1, 0);
     const uint32_t total = tot[lane];
     if (__any_sync(kSlFull, total >= 65536u)) {  // 32-bit numerators could overflow: the lane-per-row kernel redoes the slice
         if (tid == 0) m.fallback[s] = 1;         // (every warp sees the same 32 totals: the exit is CTA-uniform)
@@ -239,6 +254,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             const int i0 = warp * chunk;
             sl::lane_mlhist(ev, i0, min(n, i0 + chunk), cntml + lane);
         }
+        SL_TRACE(2, 0);
         __syncthreads();
         for (int l = 1 + warp; l <= sc.lastl; l += nwarps)
             sl::lane_level_base(ev, n, l, ld, F, cntml + lane, nlive + lane, sbx + lane, !use8);
@@ -246,6 +262,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             nlive[lane] = (uint32_t)n;
             sbx[lane] = (uint32_t)sl::kInfKey;
         }
+        SL_TRACE(3, 0);
         __syncthreads();
         for (int l = warp; l < nl; l += nwarps) {
             const int Ll = F >> l;
@@ -264,7 +281,9 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             lim[l * 32 + lane] = l < ld ? (uint32_t)Ll << l : (uint32_t)Ll;
         }
     }
+    SL_TRACE(4, 0);
     __syncthreads();
+    SL_TRACE(5, use8);
     if (!use8 && hsp < T) {  // CTA-uniform: the scratch tables are dead, the area now holds the dense numerators
         for (int t = tid; t < (T - hsp) * 32; t += nthreads) Hd[t] = 0u;
         __syncthreads();
@@ -279,6 +298,7 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         if (lane == 0) t = atomicAdd(&qctr, 1);
         t = __shfl_sync(kSlFull, t, 0);
         if (t >= ntasks) break;
+        SL_TRACE(6, t);
         if (t < ntd) {
             if (use8) {
                 if (ld + t > sc.lastl) continue;
@@ -335,7 +355,9 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
             else sl::lane_pairs<DPL, false>(ev, ia, ib, piece, istep, ld, sc, lim + lane, H + lane);
         }
     }
+    SL_TRACE(7, 0);
     __syncthreads();
+    SL_TRACE(8, 0);
 
     // ---- G2: one division per slot (the 8-bit bin tasks have written theirs)
     const int tend = use8 ? hsp : T;
@@ -343,6 +365,13 @@ __global__ void __launch_bounds__(kSlMaxWarps * 32, 2) k_multitau_slice(MtArgs a
         const uint32_t num = ti < hsp ? H[ti * 32 + lane] : Hd[(ti - hsp) * 32 + lane];
         a.G2[(int64_t)ti * a.R_pad + r] = sl::g2_value<DPL>(num, ti, sc);
     }
+    SL_TRACE(9, 0);
+#ifdef XPCS_SL_TRACE
+    if ((s % 1031) == 7 && lane == 0)
+        for (int k = 0; k < trn[warp]; k++)
+            printf("SLT %d %d %d %d %lld\n", s, warp, (int)(trc[warp][k] >> 56), (int)((trc[warp][k] >> 48) & 0xff),
+                   trc[warp][k] & 0xffffffffffffLL);
+#endif
 }
 
 template <int DPL, bool COMPAT>
