@@ -278,7 +278,7 @@ KERNEL_GROUP = {  # kernel name -> stage of SURVEY.md 8(d)
     "k_block_frames": "K1", "k_hist": "K1", "k_slice_len": "K1", "k_slice_scan": "K1", "k_scatter": "K1",
     "k_finalize": "K1", "k_frame_scale": "K1", "k_hist_dense": "K1", "k_scatter_dense": "K1",
     "k_finalize_warp": "K1", "k_scatter_rec": "K1", "k_scatter_rec_dense": "K1", "k_place": "K1", "k_dense_bounds": "K2",
-    "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_multitau_warp": "K4", "k_multitau_slice": "K4", "k_multitau_warpf": "K4",
+    "k_dense_filter": "K2", "k_dark": "K3", "k_multitau": "K4", "k_multitau_warp": "K4", "k_multitau_slice": "K4", "k_multitau_slicef": "K4", "k_multitau_warpf": "K4",
     "k_unpermute": "K4",
     "k_segment_reduce": "K6", "k_normalize_finish": "K6",
 }
@@ -299,6 +299,7 @@ def algorithmic_bytes(name, E, T, R, Q, P, F_dense=0):
         "k_multitau_warp": 6 * E + 12 * T * R,
         "k_multitau_slice": 6 * E + 12 * T * R,
         "k_multitau_warpf": 6 * E + 12 * T * R,  # same algorithmic bytes; the float store holds 8 B/event
+        "k_multitau_slicef": 6 * E + 12 * T * R,
         "k_finalize_warp": 12 * E,
         "k_segment_reduce": 12 * T * R,        # read G2/IP/IF once
         "k_normalize_finish": 8 * T * Q,
@@ -431,6 +432,19 @@ def bench_dense(args, wl):
                      "algo_bytes_per_step": k["algo_bytes"], "kernel_share_of_step": k["ms_per_step"] / ms_dev},
         "kernels": kern, "results_finite": bool(np.isfinite(g2).all()),
     }
+    if not args.no_parity:
+        # parity of the timed configuration (untimed; the oracle is the checker): the full time series of sampled
+        # pixels through the oracle's dark image, dense filter and multiTau2 against the device's G2 / IP / IF
+        # (1e-5 relative, north_star; the survivors of the filter must be the same samples)
+        try:
+            from oracle import oracle as O
+            line["parity"] = parity_block_dense(torch, O, c, dq, sq, flat, frames, darks, F, lld, sigma,
+                                                n_rows=min(args.parity_rows, 512), compat=not args.no_compat)
+        except Exception as ex:
+            line["parity"] = {"ok": False, "error": repr(ex)}
+        if not line["parity"].get("ok"):
+            print(json.dumps(line))
+            raise SystemExit("bench.py: parity block failed: %r" % (line["parity"],))
     if not args.no_cpu:
         try:
             from oracle import refdrv
@@ -588,6 +602,37 @@ def parity_block(torch, pkg, O, c, dq, sq, F, ev_source, own_pixels, g2_dev, n_r
     out["norm_mismatches"] = nm
     out["ok"] = mism == 0 and nm == 0
     return out
+
+
+def parity_block_dense(torch, O, c, dq, sq, flat, frames, darks, F, lld, sigma, n_rows=512, compat=True, seed=5, rtol=1e-5):
+    """Dense leg: ~n_rows sampled pixels as a small detector of their own -- oracle.dark_image
+    (dark_image.cpp:81-106), oracle.dense_filter (dense_filter.cpp:121-210) and oracle.multitau (corr.cpp:315-431)
+    on their full time series -- against the device's G2 / IP / IF columns of those pixels.  Floating point:
+    within rtol; the pattern of exact zeros must be identical."""
+    rng = np.random.default_rng(seed)
+    dqf, sqf = dq.ravel(), sq.ravel()
+    valid = np.flatnonzero((dqf > 0) & (sqf > 0))
+    pix = np.sort(rng.choice(valid, size=min(n_rows, valid.size), replace=False)).astype(np.int32)
+    sub = frames[:, torch.from_numpy(pix.astype(np.int64)).to(frames.device)].cpu().numpy()   # (darks + F, n)
+    qm = O.QMap(np.ones((1, pix.size), np.int32), np.ones((1, pix.size), np.int32))   # (the bins do not enter G2 / IP / IF)
+    fl = np.ascontiguousarray(np.asarray(flat, np.float64).ravel()[pix])
+    dark = O.dark_image(np.ascontiguousarray(sub[:darks]), fl)
+    fo = O.dense_filter(qm, F, np.ascontiguousarray(sub[darks:]), flat=fl, dark=dark, lld=lld, sigma=sigma,
+                        swindow=max(1, F // 10))
+    rG = O.multitau(qm.P, F, 8, fo.rows, compat=compat)
+    dG = c.correlators(pix)
+    worst, bad, zeros = 0.0, 0, 0
+    for a, b in zip(dG, rG):
+        a64, b64 = a.astype(np.float64), b.astype(np.float64)
+        err = np.abs(a64 - b64)
+        bad += int((~((np.isnan(a64) & np.isnan(b64)) | (err <= rtol * np.abs(b64)))).sum())
+        zeros += int(((a == 0.0) != (b == 0.0)).sum())
+        nz = b64 != 0
+        if nz.any():
+            worst = max(worst, float(np.nanmax(err[nz] / np.abs(b64[nz]))))
+    return {"rows": int(pix.size), "row_entries": int(3 * dG[0].size), "row_events": int(fo.n), "rtol": rtol,
+            "mismatches": bad, "zero_pattern_mismatches": zeros, "worst_rel_err": worst,
+            "nonzero_g2_entries": int((rG[0] != 0).sum()), "ok": bad == 0 and zeros == 0}
 
 
 class G:  # tiny helper namespace (NaN-aware inequality count)
@@ -768,7 +813,7 @@ def bench_sparse(args, wl):
         if n <= 0:
             continue
         per = ms / n
-        Ek = Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_slice", "k_multitau_warpf") else \
+        Ek = Es if name in ("k_finalize", "k_finalize_warp", "k_multitau", "k_multitau_warp", "k_multitau_slice", "k_multitau_slicef", "k_multitau_warpf") else \
             (E if name.startswith("k_demux") else Es)
         b = algorithmic_bytes(name, Ek, T, R, Q, P)
         kern[name] = {"ms_per_launch": per, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,

@@ -1,6 +1,6 @@
 """Dense (non-sparse IMM) path through the C-ABI against the CPU oracle on seeded frames:
 dark image, dense filter (dark subtraction, clamp, lld + sigma*std threshold, flat-field),
-store build, float-row multi-tau (warp-per-row kernel and lane-per-row kernel) and
+store build, float-row multi-tau (slice kernel, warp-per-row kernel and lane-per-row kernel) and
 normalisation.  Float results within the 1e-5 relative tolerance of BASELINE.json's
 north_star; the set of surviving samples and DarkAvg/DarkStd must match exactly.
 Reference: filter/dense_filter.cpp:121-210, data_structure/dark_image.cpp:81-106,
@@ -33,7 +33,7 @@ def oracle_dense(O, dq, sq, F, data, flat=None, darks=None, lld=0.0, sigma=0.0, 
                 G=(G2, IP, IF), g2=g2, se=se, dark=dark)
 
 
-def gpu_dense(pkg, dq, sq, F, data, darks=None, chunks=None, **kw):
+def gpu_dense(pkg, dq, sq, F, data, darks=None, chunks=None, report=False, **kw):
     c = pkg.Correlator(dq, sq, F, **kw)
     if darks is not None:
         c.set_dark(darks)
@@ -50,8 +50,9 @@ def gpu_dense(pkg, dq, sq, F, data, darks=None, chunks=None, **kw):
     g2, se = c.normalize()
     info = c.info()
     fb = c.multitau_fallback_slices()
+    rep = c.kernel_report() if report else None
     c.close()
-    return dict(sums=sums, G=G, g2=g2, se=se, info=info, fallback=fb)
+    return dict(sums=sums, G=G, g2=g2, se=se, info=info, fallback=fb, report=rep)
 
 
 def compare(got, ref, what="", check_n=True):
@@ -116,16 +117,48 @@ def test_vector_and_scalar_filters_agree_exactly(pkg):
     assert_exact(a["g2"], b["g2"], "norm-0-g2")
 
 
-def test_warp_and_lane_multitau_agree_on_float_rows(pkg, oracle):
+def test_slice_warp_and_lane_multitau_agree_on_float_rows(pkg, oracle, monkeypatch):
+    """the three float-row kernels on the same store: lane = row / warps = tasks (k_multitau_slicef, the default),
+    warp per row (k_multitau_warpf, XPCS_MTF_KERNEL=warp) and lane per row (k_multitau)"""
     dq, sq, dk, data, flat = make_dense(pkg, 32, 32, 2000, 40, 8, flat_sigma=0.005)  # no hot pixels
-    a = gpu_dense(pkg, dq, sq, 2000, data, darks=dk, flatfield=flat, lld=5.0, sigma=3.0)
-    b = gpu_dense(pkg, dq, sq, 2000, data, darks=dk, flatfield=flat, lld=5.0, sigma=3.0, lane_multitau=True)
-    assert a["fallback"] == 0, "the float warp-per-row kernel did not take every slice"
+    kw = dict(darks=dk, flatfield=flat, lld=5.0, sigma=3.0)
+    a = gpu_dense(pkg, dq, sq, 2000, data, report=True, **kw)
+    monkeypatch.setenv("XPCS_MTF_KERNEL", "warp")
+    w = gpu_dense(pkg, dq, sq, 2000, data, report=True, **kw)
+    monkeypatch.delenv("XPCS_MTF_KERNEL")
+    b = gpu_dense(pkg, dq, sq, 2000, data, lane_multitau=True, **kw)
+    assert a["report"].get("k_multitau_slicef", (0, 0))[1] == 1, sorted(a["report"])
+    assert "k_multitau_slicef" not in w["report"] and w["report"].get("k_multitau_warpf", (0, 0))[1] == 1
+    assert a["fallback"] == 0, "the float slice kernel (and the warp-per-row kernel behind it) did not take every slice"
+    assert w["fallback"] == 0, "the float warp-per-row kernel did not take every slice"
     assert b["fallback"] == -1
-    for k, nm in enumerate(("G2", "IP", "IF")):
-        assert_close(a["G"][k], b["G"][k], nm + " warp vs lane kernel")
-    # the pattern of exact zeros (pairs the reference's stale-tail search loses) must be identical
-    assert_exact(a["G"][0] == 0.0, b["G"][0] == 0.0, "G2 zero pattern")
+    for x, what in ((a, "slice"), (w, "warp")):
+        for k, nm in enumerate(("G2", "IP", "IF")):
+            assert_close(x["G"][k], b["G"][k], nm + " %s vs lane kernel" % what)
+        # the pattern of exact zeros (pairs the reference's stale-tail search loses) must be identical
+        assert_exact(x["G"][0] == 0.0, b["G"][0] == 0.0, "G2 zero pattern (%s)" % what)
+
+
+def test_float_slice_kernel_is_deterministic_and_leaves_hot_rows_to_the_others(pkg, oracle):
+    """Two pixels whose flat-field factor puts them above their threshold in every frame (the reference subtracts
+    dark_avg = mean(raw * flat) from the un-flat-fielded raw value): rows of 2000 events next to rows of
+    ~100.  The slice kernel flags their slices, the kernels behind it take them; two runs give the same bits
+    (piece-private sums, added up in a fixed order)."""
+    F = 2000
+    dq, sq, dk, data, flat = make_dense(pkg, 32, 32, F, 20, 9, flat_sigma=0.005)
+    valid = np.flatnonzero((dq.ravel() > 0) & (sq.ravel() > 0))
+    flat = flat.copy()
+    flat.ravel()[valid[[7, valid.size // 2]]] = 0.8
+    kw = dict(darks=dk, flatfield=flat, lld=5.0, sigma=3.0)
+    ref = oracle_dense(oracle, dq, sq, F, data, flat=flat, darks=dk, lld=5.0, sigma=3.0)
+    a = gpu_dense(pkg, dq, sq, F, data, report=True, **kw)
+    b = gpu_dense(pkg, dq, sq, F, data, **kw)
+    assert a["report"].get("k_multitau_slicef", (0, 0))[1] == 1, sorted(a["report"])
+    assert a["report"].get("k_multitau_warpf", (0, 0))[1] == 1, "the warp-per-row kernel runs behind the slice kernel"
+    assert 1 <= a["fallback"] <= 2, "the two hot rows (beyond 1024 events) belong to the lane-per-row kernel: %d" % a["fallback"]
+    for k in range(3):
+        assert_exact(a["G"][k], b["G"][k], "two runs of the float slice kernel")
+    compare(a, ref)
 
 
 def test_no_darks_threshold_zero(pkg, oracle):

@@ -292,7 +292,10 @@ bool multitau_slice_eligible(const xpcs_handle_s *h);
 int launch_multitau_slice(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
 // ---- launchers (multitau_warpf.cu) ----
 bool multitau_warpf_eligible(const xpcs_handle_s *h);
-int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
+int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a, bool flagged_only = false);  // fills / updates h->d_mt_fallback
+// lane = row kernel for float rows whose slices fit a shared-memory tile (multitau_slicef.cu)
+bool multitau_slicef_eligible(const xpcs_handle_s *h);
+int launch_multitau_slicef(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
 // ---- launchers (normalize.cu) ----
 int launch_normalize_partials(xpcs_handle_s *h);
 int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);

@@ -502,7 +502,14 @@ int launch_multitau(xpcs_handle_s *h)
         a.only_flagged = h->d_mt_fallback.p;
         h->mt_warp_ran = true;
     }
-    if (multitau_warpf_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+    if (multitau_slicef_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
+        // float rows whose slices fit a shared-memory tile: lane = row, warps = tasks (multitau_slicef.cu); the slices it
+        // flags (hot pixels) go to the warp-per-row kernel, and what that one leaves to the lane-per-row kernel
+        if ((rc = launch_multitau_slicef(h, a))) return rc;
+        if ((rc = launch_multitau_warpf(h, a, true))) return rc;
+        a.only_flagged = h->d_mt_fallback.p;
+        h->mt_warp_ran = true;
+    } else if (multitau_warpf_eligible(h) && !(h->prm.compat_flags & XPCS_FLAG_LANE_MULTITAU)) {
         // float rows: same split between the warp-per-row kernel and the lane-per-row one
         if ((rc = launch_multitau_warpf(h, a))) return rc;
         a.only_flagged = h->d_mt_fallback.p;

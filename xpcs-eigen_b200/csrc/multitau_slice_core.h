@@ -41,11 +41,21 @@
 #define XS_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
+// The float-row kernel (multitau_slicef.cu) compiles this file a second time, in its own namespace and with
+// XS_CB = 0: its frame plane is a packed word without a count field, so every routine that looks at frames only
+// (bin heads, live counts, first stale slots, the threshold key K*) serves both kernels from one source.
+#ifndef XS_NS
+#define XS_NS sl
+#endif
+#ifndef XS_CB
+#define XS_CB 12
+#endif
+
 namespace xpcs {
-namespace sl {
+namespace XS_NS {
 
 constexpr int kS = 32;                 // rows per slice = stride of a row's column
-constexpr int kCB = 12;                // count bits of the packed word (== kCountBits)
+constexpr int kCB = XS_CB;             // count bits of the packed word (== kCountBits; 0: frames only)
 constexpr uint32_t kCMask = (1u << kCB) - 1u;
 constexpr uint32_t kSent = 0xffffffffu;
 constexpr int kInfKey = 0x7fffffff;
@@ -603,5 +613,5 @@ XS_HD uint32_t lane_level_limit(const uint32_t *ev, int n, int l, int ld, int F,
     return out;
 }
 
-}  // namespace sl
+}  // namespace XS_NS
 }  // namespace xpcs

@@ -42,6 +42,7 @@ struct MfArgs {
     int warp_words;            // per-warp shared words
     int T;
     int bin_cap;               // bins a warp can hold (dense levels start at L_l <= min(4 n, bin_cap))
+    int inplace;               // the flags are those of k_multitau_slicef: take the flagged slices only, clear what is done
 };
 
 __device__ __forceinline__ float mf_pow2_neg(int e) { return __int_as_float((127 - e) << 23); }
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
+    if (m.inplace && !m.fallback[s]) return;  // done by k_multitau_slicef
     const int len = a.slice_len[s];
     if (len > m.len_cap) {  // CTA-uniform
         if (tid == 0) m.fallback[s] = 1;
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(kMfMaxWarps * 32) k_multitau_warpf(MtArgs a, M
             for (int t = warp; t < T; t += nwarps) d[(int64_t)t * a.R_pad] = __uint_as_float(src[t]);
         }
     }
+    if (m.inplace && tid == 0) m.fallback[s] = 0;  // (every thread read the flag before the barrier above)
 }
 
 // Same schedule shape as the integer warp kernel; the rows must be the float store.
@@ -490,16 +493,18 @@ static int run_warpf(xpcs_handle_s *h, MtArgs &a, MfArgs &m, size_t bytes, int w
     return XPCS_OK;
 }
 
-int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a)
+// flagged_only: h->d_mt_fallback holds the slices k_multitau_slicef left; they are taken here and their flags cleared
+int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a, bool flagged_only)
 {
     int rc = ensure(h, h->d_mt_fallback, (size_t)(h->n_slices > 0 ? h->n_slices : 1), "multitau fallback flags");
     if (rc) return rc;
-    cudaMemsetAsync(h->d_mt_fallback.p, 0, (size_t)(h->n_slices > 0 ? h->n_slices : 1), h->stream);
+    if (!flagged_only) cudaMemsetAsync(h->d_mt_fallback.p, 0, (size_t)(h->n_slices > 0 ? h->n_slices : 1), h->stream);
     if (h->n_slices == 0) return XPCS_OK;
     int smem_cap = 0;
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     MfArgs m{};
     m.fallback = h->d_mt_fallback.p;
+    m.inplace = flagged_only ? 1 : 0;
     m.T = h->T;
     m.pitch_t = h->T | 1;
     // shared words: stage [3][32][pitch_t] (even), then per warp Hacc (2T) + tot (64) + tables (160)
@@ -528,7 +533,7 @@ int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a)
     } else {
         while (len_cap > 1 && out_words + 4 * warp_words(len_cap, 4 * len_cap) > budget1) len_cap = len_cap * 3 / 4;
         if (out_words + 4 * warp_words(len_cap, 4 * len_cap) > budget1) {  // T too large for the stage: everything falls back
-            cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
+            if (!flagged_only) cudaMemsetAsync(h->d_mt_fallback.p, 1, (size_t)h->n_slices, h->stream);
             return XPCS_OK;
         }
         bin_cap = 4 * len_cap;
