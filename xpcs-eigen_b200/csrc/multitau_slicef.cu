@@ -33,10 +33,17 @@ namespace xpcs {
 
 using slf::SlSched;
 
+// -DXPCS_SL_TRACE: a few CTAs print where their warps spend their cycles (diagnostics; profiles/trace_slice.py)
+#ifdef XPCS_SL_TRACE
+#define SF_TRACE(what, id) do { if (lane == 0 && trn[warp] < 31) { trc[warp][trn[warp]] = ((long long)(what) << 56) | ((long long)((id) & 0xff) << 48) | (clock64() - t_start); trn[warp]++; } } while (0)
+#else
+#define SF_TRACE(what, id) do { } while (0)
+#endif
+
 constexpr int kSfMaxWarps = 24;
 constexpr int kSfMaxPairPieces = 16;
 constexpr uint32_t kSfFull = 0xffffffffu;
-constexpr int kSfHdr = 96;  // rlen[32], tot[32] (double)
+constexpr int kSfHdr = 128;  // rlen[32], tot[32] (double), pcs[32]
 
 struct SfArgs {
     unsigned char *fallback;   // [n_slices]
@@ -78,6 +85,7 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
     const int npieces = m.np + m.nps;
     uint32_t *rlen = sf_smem;                                         // [32]
     double *tot = reinterpret_cast<double *>(sf_smem + 32);           // [32] sum of the values of a row
+    int *pcs = reinterpret_cast<int *>(sf_smem + 96);                 // [32] dense pieces of level l (0 outside ld .. lastl)
     uint32_t *frS = sf_smem + kSfHdr;                                 // [len_cap + 1][32] frames
     float *vlS = reinterpret_cast<float *>(frS + (size_t)(m.len_cap + 1) * 32);  // [len_cap + 1][32] values
     float *Hp = vlS + (size_t)(m.len_cap + 1) * 32;                   // [npieces][h_rows][32] pair sums of the sparse levels
@@ -88,6 +96,13 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
     uint32_t *sbx = area + slf::kMlRows * 32;                         //                                     [nl][32]
     float *Dp = reinterpret_cast<float *>(area);                      // afterwards: [dp_rows][DPL][32] sums of the dense pieces
     __shared__ int qctr;
+#ifdef XPCS_SL_TRACE
+    __shared__ long long trc[kSfMaxWarps][32];
+    __shared__ int trn[kSfMaxWarps];
+    const long long t_start = clock64();
+    if (lane == 0) trn[warp] = 0;
+    __syncwarp();
+#endif
 
     // ---- the tile: a word of the store is value | frame << 32, so a 16-byte load carries rows 2q and 2q+1 of one step
     if (tid < 32) rlen[tid] = (uint32_t)a.row_len[s * kSlice + tid];
@@ -111,6 +126,7 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
         }
     }
     __syncthreads();
+    SF_TRACE(1, 0);
     const int n = (int)rlen[lane];
     const uint32_t *fr = frS + lane;
     const float *vl = vlS + lane;
@@ -123,6 +139,8 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             break;
         }
     const int hsp = min(T, sc.cnt0 + DPL * (ld - 1));  // delay slots of the sparse levels (<= h_rows)
+    const int target = ld <= sc.lastl ? slf::dense_target<DPL>(sc, ld, m.nd) : 0;
+    if (tid < 32) pcs[tid] = (tid >= ld && tid <= sc.lastl) ? slf::dense_pieces(sc, tid, target) : 0;
 
     // ---- row sums (last warp) and per-level limits
     if (warp == nwarps - 1) tot[lane] = slf::lanef_total(vl, n);
@@ -132,6 +150,7 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             const int i0 = warp * chunk;
             slf::lane_mlhist(fr, i0, min(n, i0 + chunk), cntml + lane);
         }
+        SF_TRACE(2, 0);
         __syncthreads();
         for (int l = 1 + warp; l <= sc.lastl; l += nwarps)
             slf::lane_level_base(fr, n, l, ld, F, cntml + lane, nlive + lane, sbx + lane, true);
@@ -139,6 +158,7 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             nlive[lane] = (uint32_t)n;
             sbx[lane] = (uint32_t)slf::kInfKey;
         }
+        SF_TRACE(3, 0);
         __syncthreads();
         for (int l = warp; l < nl; l += nwarps) {
             const int Ll = F >> l;
@@ -152,40 +172,26 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             lim[l * 32 + lane] = l < ld ? (uint32_t)Ll << l : (uint32_t)Ll;
         }
     }
+    SF_TRACE(4, 0);
     __syncthreads();  // (the scratch tables are dead from here on: the area holds the sums of the dense pieces)
+    SF_TRACE(5, 0);
     const double total = tot[lane];
 
-    // ---- the tasks, largest first, taken by whichever warp is free: dense pieces, pair pieces, IF / IP parts
+    // ---- the tasks, taken by whichever warp is free: pair pieces, dense pieces, IF / IP parts
     const int64_t r = (int64_t)s * kSlice + lane;
-    const int target = ld <= sc.lastl ? slf::dense_target<DPL>(sc, ld, m.nd) : 0;
     int ndp = 0;
-    for (int l = ld; l <= sc.lastl; l++) ndp += slf::dense_pieces(sc, l, target);
+    for (int l = ld; l <= sc.lastl; l++) ndp += pcs[l];
     const int ntasks = ndp + npieces + 2 * m.nio;
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&qctr, 1);
         t = __shfl_sync(kSfFull, t, 0);
         if (t >= ntasks) break;
-        if (t < ndp) {
-            int l = ld, k = t;
-            for (;; l++) {
-                const int np_l = slf::dense_pieces(sc, l, target);
-                if (k < np_l) break;
-                k -= np_l;
-            }
-            const int Ll = F >> l;
-            const int tb = k * target;
-            const int te = k == slf::dense_pieces(sc, l, target) - 1 ? Ll : tb + target;
-            double acc[DPL];
-#pragma unroll
-            for (int d = 0; d < DPL; d++) acc[d] = 0.0;
-            slf::lanef_dense<DPL>(fr, vl, n, l, tb, te, (int)lim[l * 32 + lane], acc);
-#pragma unroll
-            for (int d = 0; d < DPL; d++) Dp[(t * DPL + d) * 32 + lane] = (float)acc[d];
-        } else if (t < ndp + npieces) {
-            // np pieces deal out the first three quarters of a row's events, nps small ones the rest: the last tasks
-            // of the queue are short, so the warps finish close to each other
-            const int w = t - ndp;
+        SF_TRACE(6, t);
+        if (t < npieces) {
+            // np pieces deal out the first three quarters of a row's events, nps small ones the rest.  The pair pieces are
+            // the longest tasks (their number is bounded by the accumulator arrays), so they start first
+            const int w = t;
             int piece = w;
             const int cut = m.nps > 0 ? n - (n >> 2) : n;
             int ia = 0, ib = cut, istep = m.np;
@@ -198,6 +204,19 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             float *H = Hp + (size_t)w * m.h_rows * 32 + lane;
             if (ld - 1 < sc.lastl) slf::lanef_pairs<DPL, true>(fr, vl, ia, ib, piece, istep, ld, sc, lim + lane, H);
             else slf::lanef_pairs<DPL, false>(fr, vl, ia, ib, piece, istep, ld, sc, lim + lane, H);
+        } else if (t < npieces + ndp) {
+            const int p = t - npieces;
+            int l = ld, k = p;
+            for (; k >= pcs[l]; l++) k -= pcs[l];
+            const int Ll = F >> l;
+            const int tb = k * target;
+            const int te = k == pcs[l] - 1 ? Ll : tb + target;
+            double acc[DPL];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] = 0.0;
+            slf::lanef_dense<DPL>(fr, vl, n, l, tb, te, (int)lim[l * 32 + lane], acc);
+#pragma unroll
+            for (int d = 0; d < DPL; d++) Dp[(p * DPL + d) * 32 + lane] = (float)acc[d];
         } else {
             const int q = t - ndp - npieces;
             const int part = q >> 1;
@@ -206,7 +225,9 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             else slf::lanef_if<DPL>(fr, vl, n, total, sc, ta, tb, a.IF + (int64_t)ta * a.R_pad + r, a.R_pad);
         }
     }
+    SF_TRACE(7, 0);
     __syncthreads();
+    SF_TRACE(8, 0);
 
     // ---- G2: the pieces added up in a fixed order (fp64), one rounding to fp32 and one division per slot
     for (int ti = warp; ti < T; ti += nwarps) {
@@ -216,12 +237,19 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
         } else {
             const int q = ti - sc.cnt0, l = 1 + q / DPL, d = q % DPL;
             int base = 0;
-            for (int j = ld; j < l; j++) base += slf::dense_pieces(sc, j, target);
-            const int np_l = slf::dense_pieces(sc, l, target);
+            for (int j = ld; j < l; j++) base += pcs[j];
+            const int np_l = pcs[l];
             for (int k = 0; k < np_l; k++) num += (double)Dp[((base + k) * DPL + d) * 32 + lane];
         }
         a.G2[(int64_t)ti * a.R_pad + r] = slf::g2f_value<DPL>(num, ti, sc);
     }
+    SF_TRACE(9, 0);
+#ifdef XPCS_SL_TRACE
+    if ((s % 1031) == 7 && lane == 0)
+        for (int k = 0; k < trn[warp]; k++)
+            printf("SLT %d %d %d %d %lld\n", s, warp, (int)(trc[warp][k] >> 56), (int)((trc[warp][k] >> 48) & 0xff),
+                   trc[warp][k] & 0xffffffffffffLL);
+#endif
 }
 
 template <int DPL, bool COMPAT>
@@ -263,13 +291,16 @@ static bool sf_plan(const xpcs_handle_s *h, SfArgs &m, size_t &bytes, int &warps
             m.s.lastl = l;
             m.s.cnt_last = sc.count[l];
         }
-    m.ld_factor = sf_env("XPCS_SF_LD", 1, 16, 4);
-    m.nd = sf_env("XPCS_SF_DENSE_PIECES", 1, 16, 6);
+    // measured on C2 (profiles/r03_sweep_slicef.txt): the pair pieces are the longest tasks and their number is
+    // bounded by the accumulator arrays, so the dense levels start one level earlier than in k_multitau_slice
+    // (L_l <= 8 len: half the pairs), in a dozen pieces
+    m.ld_factor = sf_env("XPCS_SF_LD", 1, 16, 8);
+    m.nd = sf_env("XPCS_SF_DENSE_PIECES", 1, 64, 12);
     m.nio = sf_env("XPCS_SF_IO_PIECES", 1, 8, 2);
     m.np = sf_env("XPCS_SF_PAIR_PIECES", 1, kSfMaxPairPieces, 6);
     m.nps = sf_env("XPCS_SF_PAIR_TAIL", 0, kSfMaxPairPieces - m.np, 2);
     m.dp_rows = m.nd + sc.n_levels;
-    warps = sf_env("XPCS_SF_WARPS", 2, kSfMaxWarps, 16);
+    warps = sf_env("XPCS_SF_WARPS", 2, kSfMaxWarps, 24);
     // The rows beyond ~1000 events stay with the lane-per-row kernel, which keeps the reference's sequential fp32
     // order (multitau_warpf.cu: kMfExactLen); a few outlier rows (hot pixels) must not dictate the tile of every
     // CTA: slices more than four times longer than the mean slice are left to the kernels behind this one

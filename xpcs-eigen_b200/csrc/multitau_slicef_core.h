@@ -183,35 +183,44 @@ XS_HD void lanef_pairs(const uint32_t *fr, const float *vl, int ia, int ib, int 
 
 // ---- G2, dense level l: sources t in [tb, te), targets t + dpl+1 .. t + 2dpl, bins from klim on read as zero
 // (klim = L_l, or K* in compat mode: the lost targets are a suffix).  te - tb must be a multiple of 2dpl+1 unless
-// te >= L_l.  The bins are formed on the fly (fp64 sums of the events of a bin) while a register window of 2dpl+1
-// bins slides over t; acc[] is added to.
+// te >= L_l.  The bins are formed on the fly (fp32 sum of the few events of a bin, as the reference's own bins are)
+// while a register window of 2dpl+1 bins slides over t; the windowed products are added up in fp64 (acc[] is added
+// to).  Only the last windows before klim ask whether a bin lies beyond it.
 template <int DPL>
 XS_HD void lanef_dense(const uint32_t *fr, const float *vl, int n, int l, int tb, int te, int klim, double (&acc)[DPL])
 {
     constexpr int W = 2 * DPL + 1;
     int pe = (tb > 0 ? lane_lower_bound(fr, n, (uint32_t)tb << l) : 0) * kS;
-    uint32_t w = fr[pe];
+    uint32_t wk = fr[pe] >> l;  // key of the next event (the sentinel's is beyond every bin)
     auto fetch = [&](int key) -> double {
-        double v = 0.0;
-        if (key < klim) {
-            while ((w >> l) == (uint32_t)key) {
-                v += (double)vl[pe];
-                pe += kS;
-                w = fr[pe];
-            }
+        float v = 0.0f;
+        while (wk == (uint32_t)key) {
+            v += vl[pe];
+            pe += kS;
+            wk = fr[pe] >> l;
         }
-        return v;
+        return (double)v;
     };
     double win[W];
 #pragma unroll
-    for (int k = 0; k < W; k++) win[k] = fetch(tb + k);
-    for (int t0 = tb; t0 < te; t0 += W) {
+    for (int k = 0; k < W; k++) win[k] = tb + k < klim ? fetch(tb + k) : 0.0;
+    int t0 = tb;
+    for (; t0 < te && t0 + 2 * W <= klim; t0 += W) {
 #pragma unroll
         for (int u = 0; u < W; u++) {
             const double src = win[u];
 #pragma unroll
             for (int d = 0; d < DPL; d++) acc[d] = fma_d(src, win[(u + DPL + 1 + d) % W], acc[d]);
             win[u] = fetch(t0 + u + W);
+        }
+    }
+    for (; t0 < te; t0 += W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const double src = win[u];
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] = fma_d(src, win[(u + DPL + 1 + d) % W], acc[d]);
+            win[u] = t0 + u + W < klim ? fetch(t0 + u + W) : 0.0;
         }
     }
 }
