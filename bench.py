@@ -432,6 +432,14 @@ def bench_dense(args, wl):
                      "algo_bytes_per_step": k["algo_bytes"], "kernel_share_of_step": k["ms_per_step"] / ms_dev},
         "kernels": kern, "results_finite": bool(np.isfinite(g2).all()),
     }
+    tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the ncu --set full capture
+    if os.path.exists(tr):
+        try:
+            tj = json.load(open(tr))
+            line["roofline"]["traffic"] = tj.get("c2", {}).get(dom)
+            line["roofline"]["traffic_source"] = tj.get("_source_c2", "profiles/traffic.json")
+        except Exception:
+            pass
     if not args.no_parity:
         # parity of the timed configuration (untimed; the oracle is the checker): the full time series of sampled
         # pixels through the oracle's dark image, dense filter and multiTau2 against the device's G2 / IP / IF

@@ -52,6 +52,7 @@ struct SfArgs {
     int ld_factor, ld_cap;     // dense levels start where L_l <= ld_factor * (longest row of the slice), at most at ld_cap
     int h_rows;                // rows of a pair piece's accumulator array: the delay slots of the levels below ld_cap
     int dp_rows;               // dense piece slots available
+    int io_first;              // queue order: pair pieces, IF / IP parts, dense pieces (else the IF / IP parts last)
     SlSched s;
 };
 
@@ -188,10 +189,24 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
         t = __shfl_sync(kSfFull, t, 0);
         if (t >= ntasks) break;
         SF_TRACE(6, t);
+        // queue order: the pair pieces (the longest tasks: their number is bounded by the accumulator arrays), the IF / IP
+        // parts (the ones of the deep levels walk the whole row), then the dense pieces, whose last ones -- the deep levels
+        // -- are the shortest tasks, so that the warps finish close to each other
+        const int nio2 = 2 * m.nio;
+        int kind, idx;  // 0 pair piece, 1 dense piece, 2 IF / IP part
         if (t < npieces) {
-            // np pieces deal out the first three quarters of a row's events, nps small ones the rest.  The pair pieces are
-            // the longest tasks (their number is bounded by the accumulator arrays), so they start first
-            const int w = t;
+            kind = 0;
+            idx = t;
+        } else if (m.io_first) {
+            kind = t < npieces + nio2 ? 2 : 1;
+            idx = t - npieces - (kind == 1 ? nio2 : 0);
+        } else {
+            kind = t < npieces + ndp ? 1 : 2;
+            idx = t - npieces - (kind == 2 ? ndp : 0);
+        }
+        if (kind == 0) {
+            // np pieces deal out the first three quarters of a row's events, nps small ones the rest
+            const int w = idx;
             int piece = w;
             const int cut = m.nps > 0 ? n - (n >> 2) : n;
             int ia = 0, ib = cut, istep = m.np;
@@ -204,8 +219,8 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
             float *H = Hp + (size_t)w * m.h_rows * 32 + lane;
             if (ld - 1 < sc.lastl) slf::lanef_pairs<DPL, true>(fr, vl, ia, ib, piece, istep, ld, sc, lim + lane, H);
             else slf::lanef_pairs<DPL, false>(fr, vl, ia, ib, piece, istep, ld, sc, lim + lane, H);
-        } else if (t < npieces + ndp) {
-            const int p = t - npieces;
+        } else if (kind == 1) {
+            const int p = idx;
             int l = ld, k = p;
             for (; k >= pcs[l]; l++) k -= pcs[l];
             const int Ll = F >> l;
@@ -218,7 +233,8 @@ __global__ void __launch_bounds__(kSfMaxWarps * 32, 1) k_multitau_slicef(MtArgs 
 #pragma unroll
             for (int d = 0; d < DPL; d++) Dp[(p * DPL + d) * 32 + lane] = (float)acc[d];
         } else {
-            const int q = t - ndp - npieces;
+            // the parts of the deep levels first: they are the long ones
+            const int q = nio2 - 1 - idx;
             const int part = q >> 1;
             const int ta = (int)((int64_t)T * part / m.nio), tb = (int)((int64_t)T * (part + 1) / m.nio);
             if (q & 1) slf::lanef_ip<DPL>(fr, vl, n, total, sc, ta, tb, a.IP + (int64_t)ta * a.R_pad + r, a.R_pad);
@@ -300,6 +316,7 @@ static bool sf_plan(const xpcs_handle_s *h, SfArgs &m, size_t &bytes, int &warps
     m.np = sf_env("XPCS_SF_PAIR_PIECES", 1, kSfMaxPairPieces, 6);
     m.nps = sf_env("XPCS_SF_PAIR_TAIL", 0, kSfMaxPairPieces - m.np, 2);
     m.dp_rows = m.nd + sc.n_levels;
+    m.io_first = sf_env("XPCS_SF_IO_FIRST", 0, 1, 0);  // (measured on C2: 20.17 ms with, 20.00 ms without)
     warps = sf_env("XPCS_SF_WARPS", 2, kSfMaxWarps, 24);
     // The rows beyond ~1000 events stay with the lane-per-row kernel, which keeps the reference's sequential fp32
     // order (multitau_warpf.cu: kMfExactLen); a few outlier rows (hot pixels) must not dictate the tile of every
