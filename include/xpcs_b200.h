@@ -203,6 +203,33 @@ int xpcs_normalize(xpcs_handle h, float *g2, float *stderr_out);
 int xpcs_normalize_partials(xpcs_handle h, void **d_partials, int64_t *count);
 int xpcs_normalize_finish(xpcs_handle h, float *g2, float *stderr_out);
 
+/* ---- online multi-tau: frame streams that do not fit the device ----
+ * replaces: the read-everything-then-correlate sequence of main.cpp:263-268 + Corr::multiTau2 (corr.cpp:315-431,
+ * whose level binning corr.cpp:349-390 works in place on complete rows) for jobs whose events exceed the device
+ * (BASELINE configs[4] at >= 1 % occupancy).  The frames arrive in chunks of chunk_frames = 2^k frames (64..8192);
+ * each chunk goes through the Filter stage, is folded into a per-pixel state (integer G2 numerators, per-level
+ * totals, the first and last 2*dpl bins of every level) and is then forgotten: device memory is
+ * O(pixels * delays + one chunk), independent of the number of frames.  Call sequence:
+ *   xpcs_stream_begin(h, chunk_frames)
+ *   xpcs_stream_push_sparse[_device](...)   frames in order; every chunk complete except the last of the job
+ *   xpcs_stream_finish(h, sums...)          same outputs as xpcs_finish_ingest
+ *   xpcs_multitau(h, G2, IP, IF)            hands out the streamed results (no kernel runs)
+ *   xpcs_normalize(h, g2, stderr)           unchanged, including the multi-GPU reduction (every rank streams the
+ *                                           whole detector's chunks and keeps the pixels of its shard)
+ * Results are the exact sums of SURVEY.md A.2/A.3 with the one IEEE division of corr.cpp:420-424: bit-identical to
+ * the resident path run without XPCS_COMPAT_STALE_TAIL.  That flag needs the complete rows and is
+ * refused (XPCS_E_ARG), as are flat field, stride / averaging, frame-sum normalisation and delays_per_level other
+ * than 4 and 8.  xpcs_get_frames and xpcs_twotime need a resident ingest. */
+int xpcs_stream_begin(xpcs_handle h, int chunk_frames);
+/* host buffers, layout of xpcs_push_sparse; nframes may span several chunks (cut at multiples of chunk_frames
+ * counted from the first frame of the job); a push that ends inside a chunk must be the last one */
+int xpcs_stream_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val, const int64_t *frame_offsets,
+                            const double *clock, const double *ticks, int nframes);
+/* device pointers, ONE chunk per call, d_frame_offsets[0] == 0; the buffers may be refilled when the call returns */
+int xpcs_stream_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
+                                   const int64_t *d_frame_offsets, int64_t n_events, int nframes);
+int xpcs_stream_finish(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total, float *part_partial);
+
 /* ---- multi-GPU: one handle per GPU, pixel-sharded ----
  * replaces: the OpenMP pixel loop of Corr::multiTau2 (corr.cpp:329-332) spread over GPUs.  The exchange
  * quantities are the events themselves (below), the per-frame / per-static-bin sums of the Filter stage

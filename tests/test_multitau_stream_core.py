@@ -1,0 +1,130 @@
+"""The per-row routines of the online multi-tau kernel k_stream_chunk, run on the CPU.
+
+xpcs-eigen_b200/csrc/multitau_stream_core.h is compiled twice: by nvcc into the kernel, and here by g++ into a small
+harness (tests/host_mt/mt_stream_host.cpp) that feeds every row chunk by chunk -- 2^k frames at a time, only the
+per-row state surviving between chunks -- with the 32 lanes of every phase run one after the other.  The result must
+equal the oracle's multiTau2 in its exact-maths form (reference corr.cpp:315-431 without the stale-tail behaviour of
+SURVEY.md A.4, which needs the complete row and is refused in stream mode) bit for bit: G2, IP and IF at every level,
+for every chunk length.  No GPU involved; tests/test_gpu_stream.py then checks the kernel itself."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+import multitau_model as mm  # noqa: E402
+from test_multitau_slice_core import make_rows  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host_mt") / "libmt_stream_host.so")
+    src = os.path.join(ROOT, "tests", "host_mt", "mt_stream_host.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           "-Wno-unknown-pragmas", "-o", out, src])
+    lib = C.CDLL(out)
+    lib.mt_stream_host.restype = C.c_int
+    return lib
+
+
+def sched_args(F, dpl):
+    lev, tau = O.delay_schedule(F, dpl)
+    nl, first, count, lo = mm.build_sched(np.asarray(lev), np.asarray(tau))
+    lastl = max([l for l in range(nl) if count[l] > 0 and l >= 1] + [0])
+    cnt_last = count[lastl] if lastl >= 1 else 0
+    return len(lev), count[0], lastl, cnt_last
+
+
+def run_stream(lib, rows_f, rows_c, F, dpl, k):
+    T, cnt0, lastl, cnt_last = sched_args(F, dpl)
+    R = len(rows_f)
+    ptr = np.zeros(R + 1, np.int64)
+    ptr[1:] = np.cumsum([len(f) for f in rows_f])
+    fr = np.concatenate([np.asarray(f, np.int32) for f in rows_f] + [np.zeros(0, np.int32)]).astype(np.int32)
+    ct = np.concatenate([np.asarray(c, np.int32) for c in rows_c] + [np.zeros(0, np.int32)]).astype(np.int32)
+    G2 = np.zeros((T, R), np.float32)
+    IP = np.zeros((T, R), np.float32)
+    IF = np.zeros((T, R), np.float32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib.mt_stream_host(dpl, F, T, cnt0, lastl, cnt_last, k, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
+                            p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
+    assert rc == 0
+    return G2, IP, IF
+
+
+def run_oracle(rows_f, rows_c, F, dpl):
+    R = len(rows_f)
+    ptr = np.zeros(R + 1, np.int64)
+    ptr[1:] = np.cumsum([len(f) for f in rows_f])
+    t = np.concatenate([np.asarray(f, np.int32) for f in rows_f] + [np.zeros(0, np.int32)])
+    v = np.concatenate([np.asarray(c, np.float32) for c in rows_c] + [np.zeros(0, np.float32)])
+    return O.multitau(R, F, dpl, O.Rows(ptr, t.astype(np.int32), v.astype(np.float32)), compat=False)
+
+
+def check(lib, rows_f, rows_c, F, dpl, k):
+    G2, IP, IF = run_stream(lib, rows_f, rows_c, F, dpl, k)
+    rG2, rIP, rIF = run_oracle(rows_f, rows_c, F, dpl)
+    for name, a, b in (("IP", IP, rIP), ("IF", IF, rIF), ("G2", G2, rG2)):
+        bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+        assert bad.size == 0, "%s differs at (tau index, row) %s: %r vs %r (F=%d dpl=%d k=%d)" % (
+            name, bad[0], a[tuple(bad[0])], b[tuple(bad[0])], F, dpl, k)
+
+
+KINDS = [0.002, 0.01, 0.03, 0.08, 0.2, 0.5, 0.9, 1.0, "cluster", 0.0, "one", "tail", "head", "burst"]
+
+
+@pytest.mark.parametrize("F,dpl,k,seed", [
+    (512, 8, 6, 1), (512, 8, 8, 2), (4096, 8, 9, 3), (2500, 4, 7, 4), (33, 8, 6, 5), (6000, 8, 10, 6),
+    (6001, 8, 8, 7), (9999, 4, 11, 8), (1000, 8, 13, 9), (20000, 8, 11, 10), (777, 4, 6, 11), (16384, 8, 12, 12),
+])
+def test_mixed_rows(host, F, dpl, k, seed):
+    """rows of every density, clustered / single-event / empty rows, events in the frames the deep levels drop;
+    chunk lengths from 64 frames to more than the whole series"""
+    rng = np.random.default_rng(seed)
+    scale = min(1.0, 300.0 / F)
+    kinds = [q if isinstance(q, str) else q * scale for q in KINDS]
+    rows_f, rows_c = make_rows(rng, F, kinds)
+    check(host, rows_f, rows_c, F, dpl, k)
+
+
+@pytest.mark.parametrize("k", [6, 7, 9, 11, 12])
+def test_chunk_length_does_not_matter(host, k):
+    rng = np.random.default_rng(77)
+    for F, dpl in ((5000, 8), (3001, 4), (1 << 12, 8)):
+        rows_f, rows_c = make_rows(rng, F, [0.05, 0.3, 1.0, "cluster", "tail", "head", "burst", 0.0])
+        check(host, rows_f, rows_c, F, dpl, k)
+
+
+@pytest.mark.parametrize("F,dpl,k,occ", [(100000, 8, 11, 0.001), (100000, 8, 12, 0.05), (1000000, 8, 12, 0.0001),
+                                         (65536, 4, 10, 0.02)])
+def test_bench_shapes(host, F, dpl, k, occ):
+    rng = np.random.default_rng(3)
+    rows_f, rows_c = make_rows(rng, F, [occ, occ * 2, "tail", "head", 0.0, "one"])
+    check(host, rows_f, rows_c, F, dpl, k)
+
+
+def test_bright_rows(host):
+    """counts up to the packed word's 4095 in every frame: the 64-bit numerators and 32-bit bins must hold"""
+    F, dpl, k = 3000, 8, 9
+    rows_f = [np.arange(F), np.arange(0, F, 3)]
+    rows_c = [np.full(F, 4095), np.full(len(rows_f[1]), 4000)]
+    G2, IP, IF = run_stream(host, rows_f, rows_c, F, dpl, k)
+    # beyond 2^24 the reference's fp32 running sums round: compare with exact integers instead
+    lev, tau = O.delay_schedule(F, dpl)
+    x = np.zeros(F, np.int64)
+    x[rows_f[0]] = 4095
+    for ti, (l, t) in enumerate(zip(lev, tau)):
+        L = F >> l
+        xl = x[: L << l].reshape(L, 1 << l).sum(axis=1)
+        tp = t >> l
+        num = int((xl[: L - tp] * xl[tp:]).sum())
+        want = np.float32(np.float32(num) * np.float32(2.0 ** (-2 * l))) / np.float32(L - tp)
+        assert G2[ti, 0] == want, (ti, G2[ti, 0], want)
+        assert IP[ti, 0] == np.float32(np.float32(int(xl[: L - tp].sum())) * np.float32(2.0 ** -l)) / np.float32(L - tp)
+        assert IF[ti, 0] == np.float32(np.float32(int(xl[tp:].sum())) * np.float32(2.0 ** -l)) / np.float32(L - tp)

@@ -240,10 +240,33 @@ class Correlator:
     def push_dense_device(self, d_frames, nframes):
         self._check(self._lib.xpcs_push_dense_device(self._h, d_frames, nframes))
 
-    def finish_ingest(self, want=True):
+    # -- online multi-tau (multitau_stream.cu): frame streams that do not fit the device --
+    def stream_begin(self, chunk_frames):
+        """Chunks of chunk_frames = 2^k frames (64..8192) follow through stream_push_sparse; stream_finish() ends the
+        stream, after which multitau() / normalize() hand out the results as after a resident ingest."""
+        self._check(self._lib.xpcs_stream_begin(self._h, int(chunk_frames)))
+
+    def stream_push_sparse(self, idx, val, frame_off, clock=None, ticks=None):
+        idx = np.ascontiguousarray(idx, np.int32)
+        val = np.ascontiguousarray(val, np.int16)
+        off = np.ascontiguousarray(frame_off, np.int64)
+        ck = None if clock is None else np.ascontiguousarray(clock, np.float64)
+        tk = None if ticks is None else np.ascontiguousarray(ticks, np.float64)
+        self._check(self._lib.xpcs_stream_push_sparse(self._h, idx.ctypes.data, val.ctypes.data, off.ctypes.data,
+                                                      _ptr(ck), _ptr(tk), off.size - 1))
+
+    def stream_push_sparse_device(self, d_idx, d_val, d_off, n_events, nframes):
+        """Device pointers (integers), one chunk, offsets starting at 0; the buffers are free again on return."""
+        self._check(self._lib.xpcs_stream_push_sparse_device(self._h, d_idx, d_val, d_off, n_events, nframes))
+
+    def stream_finish(self, want=True):
+        return self.finish_ingest(want, _fn=self._lib.xpcs_stream_finish)
+
+    def finish_ingest(self, want=True, _fn=None):
         """-> dict(pixel_sum (h,w), frame_sum (2,F), part_total (S,), part_partial (F//window, S))."""
+        fn = _fn or self._lib.xpcs_finish_ingest
         if not want:
-            self._check(self._lib.xpcs_finish_ingest(self._h, None, None, None, None))
+            self._check(fn(self._h, None, None, None, None))
             self._keep = []
             return None
         F, S = self.F, self.S
@@ -253,8 +276,7 @@ class Correlator:
         pp = self._out("part_partial", max((F // self.static_window) * S, 1))
         pt[:] = 0
         pp[:] = 0
-        self._check(self._lib.xpcs_finish_ingest(self._h, ps.ctypes.data, fs.ctypes.data, pt.ctypes.data,
-                                                 pp.ctypes.data))
+        self._check(fn(self._h, ps.ctypes.data, fs.ctypes.data, pt.ctypes.data, pp.ctypes.data))
         self._keep = []
         return dict(pixel_sum=ps.reshape(self.height, self.width), frame_sum=fs.reshape(2, F),
                     part_total=pt[:S], part_partial=pp[: (F // self.static_window) * S].reshape(-1, S))

@@ -76,6 +76,10 @@ SYMBOLS = {
     "xpcs_push_dense": (_i, [_vp, _vp, _vp, _vp, _i]),
     "xpcs_push_dense_device": (_i, [_vp, _vp, _i]),
     "xpcs_finish_ingest": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "xpcs_stream_begin": (_i, [_vp, _i]),
+    "xpcs_stream_push_sparse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "xpcs_stream_push_sparse_device": (_i, [_vp, _vp, _vp, _vp, _i64, _i]),
+    "xpcs_stream_finish": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "xpcs_get_timestamps": (_i, [_vp, _vp, _vp]),
     "xpcs_get_frames": (_i, [_vp, C.c_int, _vp]),
     "xpcs_multitau": (_i, [_vp, _vp, _vp, _vp]),

@@ -1603,6 +1603,71 @@ int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1)
     return check_cuda(h, cudaGetLastError(), "chunk ingest kernels");
 }
 
+// ---- stream mode (multitau_stream.cu) ----------------------------------------------------------
+// One chunk of a frame stream: the events d_idx / d_val[0, nev) with the chunk-local frame offsets
+// d_frame_off[0 .. nframes] are the raw frames [frame_base, frame_base + nframes).  Same passes as a chunk of the
+// pipelined ingest; the store replaces chunk[0] (the previous chunk has been folded into the stream state by
+// then -- same CUDA stream), frameSum / pixelSum / partition sums accumulate from the second chunk on.
+// Returns 1 when a count does not fit the packed word.
+int launch_ingest_stream_chunk(xpcs_handle_s *h, int frame_base, int nframes, int64_t nev, bool first)
+{
+    const int F = h->prm.frames;
+    int rc;
+    const int windows = (F + h->prm.static_window - 1) / h->prm.static_window;
+    if ((rc = ensure(h, h->d_summary, kSumSlots, "summary"))) return rc;
+    if ((rc = ensure(h, h->d_frame_acc, (size_t)F, "frame sums"))) return rc;
+    if ((rc = ensure(h, h->d_row_sum, (size_t)h->R_pad, "row sums"))) return rc;
+    if ((rc = ensure(h, h->d_part_total, (size_t)h->S, "partition sums"))) return rc;
+    if ((rc = ensure(h, h->d_part_partial, (size_t)windows * h->S, "partition window sums"))) return rc;
+    IngestArgs ia{};
+    ia.idx = h->d_idx.p;
+    ia.val = h->d_val.p;
+    ia.off = h->d_frame_off.p;
+    ia.ev_begin = 0;
+    ia.frame_base = frame_base;
+    ia.nraw = nframes;
+    ia.E = nev;
+    ia.row_of_pixel = h->d_row_of_pixel.p;
+    ia.flat = h->d_flat.p;
+    ia.row_count = h->d_row_count.p;
+    ia.frame_acc = h->d_frame_acc.p;
+    ia.summary = h->d_summary.p;
+    ia.F = F;
+    ia.stride = 1;
+    ia.rawblock = 1;
+    ia.P = h->P;
+    const int nblocks = (int)((nev + kEvPerBlock - 1) / kEvPerBlock);
+    if ((rc = ensure(h, h->d_block_first, (size_t)nblocks + 1, "block frames"))) return rc;
+    ia.block_first = h->d_block_first.p;
+    h->kind = kPacked;
+    cudaMemsetAsync(h->d_summary.p, 0, sizeof(long long) * kSumSlots, h->stream);
+    cudaMemsetAsync(h->d_row_count.p, 0, sizeof(int) * (size_t)h->R_pad, h->stream);
+    if (first) {
+        cudaMemsetAsync(h->d_frame_acc.p, 0, sizeof(double) * (size_t)F, h->stream);
+        cudaMemsetAsync(h->d_row_sum.p, 0, sizeof(double) * (size_t)h->R_pad, h->stream);
+    }
+    if (nblocks > 0) {
+        {
+            LaunchScope ls(h, "k_block_frames");
+            k_block_frames<<<(nblocks + 255) / 256, 256, 0, h->stream>>>(ia.off, ia.nraw, ia.E, h->d_block_first.p, nblocks, 0);
+        }
+        LaunchScope ls(h, "k_hist");
+        k_hist<kPacked, false><<<nblocks, kIngestThreads, 0, h->stream>>>(ia);
+    }
+    ChunkStore &c = h->chunk[0];
+    std::swap(c.store, h->d_store);
+    std::swap(c.slice_base, h->d_slice_base);
+    std::swap(c.row_len, h->d_row_len);
+    rc = ensure(h, h->d_row_len, (size_t)h->R_pad, "row lengths");
+    if (!rc) rc = ensure(h, h->d_slice_base, (size_t)h->n_slices + 1, "slice offsets");
+    if (!rc) rc = run_store_build<kPacked>(h, ia, nblocks, false, first ? 0 : 1);
+    std::swap(c.store, h->d_store);
+    std::swap(c.slice_base, h->d_slice_base);
+    std::swap(c.row_len, h->d_row_len);
+    if (rc) return rc;
+    return check_cuda(h, cudaGetLastError(), "stream chunk ingest kernels");
+}
+
 struct ConcatArgs {
     const uint32_t *store[kMaxChunks];
     const int64_t *slice_base[kMaxChunks];

@@ -168,6 +168,14 @@ struct xpcs_handle_s {
     int64_t frame_off_uploaded = 0;       // entries of frame_off_host already in d_frame_off
     std::vector<float> frame_sum_host;    // [2F]
 
+    // ---- online multi-tau (multitau_stream.cu): frames arrive in chunks of 2^stream_k frames, a per-row state is all
+    // that survives a chunk
+    bool stream_on = false, stream_done = false;
+    int stream_k = 0;
+    int stream_chunks = 0;                // complete or final chunks consumed so far
+    bool stream_short_seen = false;       // a chunk shorter than 2^stream_k came in: it has to be the last one
+    xpcs::DevBuf<uint32_t> d_stream_state;  // [R_pad][state words]
+
     // ---- results ----
     bool multitau_done = false;
     bool mt_warp_ran = false;             // last multi-tau used the warp-per-row kernel
@@ -279,6 +287,9 @@ void comm_destroy(xpcs_handle_s *h);
 int launch_ingest(xpcs_handle_s *h);             // histogram -> slices -> scatter -> finalize
 int launch_ingest_chunk(xpcs_handle_s *h, int f0, int f1);  // same for raw frames [f0, f1) into the next chunk store; 1 = not representable
 int launch_ingest_concat(xpcs_handle_s *h);      // chunk stores -> the store
+// stream mode: the events d_idx/d_val[0, nev) with local frame offsets d_frame_off[0..nframes] are the raw frames
+// [frame_base, frame_base + nframes); their store replaces chunk[0], the Filter sums accumulate unless `first`
+int launch_ingest_stream_chunk(xpcs_handle_s *h, int frame_base, int nframes, int64_t nev, bool first);
 int launch_dark(xpcs_handle_s *h, const int16_t *d_frames, int n);
 int launch_dense_filter(xpcs_handle_s *h, const int16_t *d_frames, int first_raw, int nframes);
 // ---- launchers (multitau.cu) ----
@@ -296,6 +307,11 @@ int launch_multitau_warpf(xpcs_handle_s *h, MtArgs &a, bool flagged_only = false
 // lane = row kernel for float rows whose slices fit a shared-memory tile (multitau_slicef.cu)
 bool multitau_slicef_eligible(const xpcs_handle_s *h);
 int launch_multitau_slicef(xpcs_handle_s *h, MtArgs &a);  // fills h->d_mt_fallback
+// ---- launchers (multitau_stream.cu) ----
+int stream_check(xpcs_handle_s *h, int chunk_frames);  // can this job be streamed with that chunk length?
+int launch_stream_begin(xpcs_handle_s *h);             // allocates and clears the per-row state
+int launch_stream_chunk(xpcs_handle_s *h, int c, bool empty);  // chunk c from chunk[0] (empty: no event at all)
+int launch_stream_finish(xpcs_handle_s *h);            // state -> d_G2 / d_IP / d_IF
 // ---- launchers (normalize.cu) ----
 int launch_normalize_partials(xpcs_handle_s *h);
 int launch_normalize_finish(xpcs_handle_s *h, float *d_g2, float *d_se);

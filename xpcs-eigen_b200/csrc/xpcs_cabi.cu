@@ -331,6 +331,10 @@ static void reset_ingest(xpcs_handle_s *h)
     h->slab_off = nullptr;
     h->frame_acc_reduced = false;
     h->part_sums_reduced = false;
+    h->stream_on = false;
+    h->stream_done = false;
+    h->stream_chunks = 0;
+    h->stream_short_seen = false;
 }
 
 static int check_params(const XpcsParams *prm)
@@ -580,6 +584,7 @@ extern "C" int xpcs_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t
 {
     if (!h || !frame_offsets || nframes < 0) return h ? fail(h, XPCS_E_ARG, "push_sparse: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open (xpcs_stream_begin): use the xpcs_stream_push_* calls");
     if (h->external_events || (h->dense_source && h->raw_frames > 0))
         return fail(h, XPCS_E_STATE, "cannot mix sparse, dense and device pushes in one ingest");
     cudaSetDevice(h->device);
@@ -698,6 +703,7 @@ extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, cons
 {
     if (!h || !d_frame_offsets || nframes < 0 || n_events < 0) return h ? fail(h, XPCS_E_ARG, "push_sparse_device: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open (xpcs_stream_begin): use the xpcs_stream_push_* calls");
     if (h->raw_frames > 0) return fail(h, XPCS_E_STATE, "push_sparse_device must be the only push of an ingest");
     // the ingest kernels read four events per thread with 16- and 8-byte loads
     if ((reinterpret_cast<uintptr_t>(d_idx) & 15u) || (reinterpret_cast<uintptr_t>(d_val) & 7u) ||
@@ -718,6 +724,7 @@ extern "C" int xpcs_push_sparse_device(xpcs_handle h, const int32_t *d_idx, cons
 static int slab_begin(xpcs_handle_s *h, int first_raw_frame, int nframes, int64_t n_events)
 {
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open (xpcs_stream_begin): use the xpcs_stream_push_* calls");
     if (h->raw_frames > 0 || h->slab_mode || h->external_events || h->dense_source)
         return fail(h, XPCS_E_STATE, "a frame slab must be the only push of an ingest");
     if (first_raw_frame < 0 || nframes < 0 || n_events < 0) return fail(h, XPCS_E_ARG, "push_sparse_slab: bad arguments");
@@ -817,6 +824,7 @@ extern "C" int xpcs_push_dense_device(xpcs_handle h, const int16_t *d_frames, in
 {
     if (!h || !d_frames || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "push_dense_device: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open (xpcs_stream_begin): use the xpcs_stream_push_* calls");
     if (h->external_events || (!h->dense_source && h->raw_frames > 0))
         return fail(h, XPCS_E_STATE, "cannot mix sparse, dense and device pushes in one ingest");
     cudaSetDevice(h->device);
@@ -838,6 +846,7 @@ extern "C" int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const doubl
 {
     if (!h || !frames || nframes <= 0) return h ? fail(h, XPCS_E_ARG, "push_dense: bad arguments") : XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "push after finish_ingest (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open (xpcs_stream_begin): use the xpcs_stream_push_* calls");
     cudaSetDevice(h->device);
     // Two device staging buffers of at most 128 MiB each: batch k+1 crosses PCIe on the copy
     // stream while the filter works on batch k on the handle's stream (events order the reuse
@@ -898,13 +907,15 @@ __global__ void k_get_pixel_sum(const double *__restrict__ row_sum, const int *_
     out[pixel_of_row[r]] = __fdiv_rn((float)row_sum[r], (float)F);
 }
 
+static int filter_getters(xpcs_handle_s *h, float *pixel_sum, float *frame_sum, float *part_total, float *part_partial);
+
 extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total,
                                   float *part_partial)
 {
     if (!h) return XPCS_E_ARG;
     if (h->ingest_done) return fail(h, XPCS_E_STATE, "finish_ingest called twice (call xpcs_reset first)");
+    if (h->stream_on) return fail(h, XPCS_E_STATE, "a stream is open: end it with xpcs_stream_finish");
     cudaSetDevice(h->device);
-    const int F = h->prm.frames;
     int rc;
     if (h->prm.normalize_by_framesum && h->prm.shard_count > 1 && !comm_active(h))
         return fail(h, XPCS_E_STATE, "normalize_by_framesum with shard_count > 1 needs the frame sums of all shards: call xpcs_comm_init");
@@ -936,6 +947,13 @@ extern "C" int xpcs_finish_ingest(xpcs_handle h, float *pixel_sum, float *frame_
     else rc = launch_ingest(h);
     if (rc) return rc;
     h->ingest_done = true;
+    return filter_getters(h, pixel_sum, frame_sum, part_total, part_partial);
+}
+
+static int filter_getters(xpcs_handle_s *h, float *pixel_sum, float *frame_sum, float *part_total, float *part_partial)
+{
+    const int F = h->prm.frames;
+    int rc;
     // ---- Filter getters, post-scaled as in main.cpp:339-343 and :360-378 ----
     // pixelSum and frameSum are formed on the device (same fp32 operations) and land in the caller's
     // arrays directly; the small partition sums are finished on the host
@@ -1069,15 +1087,154 @@ extern "C" int xpcs_get_timestamps(xpcs_handle h, double *clock, double *ticks)
 }
 
 // ---------------------------------------------------------------------------------------
+// Online multi-tau: frame streams that do not fit the device (multitau_stream.cu)
+// ---------------------------------------------------------------------------------------
+extern "C" int xpcs_stream_begin(xpcs_handle h, int chunk_frames)
+{
+    if (!h) return XPCS_E_ARG;
+    if (h->ingest_done || h->raw_frames > 0 || h->slab_mode || h->external_events || h->stream_on)
+        return fail(h, XPCS_E_STATE, "stream_begin needs a fresh ingest (call xpcs_reset first)");
+    cudaSetDevice(h->device);
+    int rc = stream_check(h, chunk_frames);
+    if (rc) return rc;
+    int k = 0;
+    while ((1 << k) < chunk_frames) k++;
+    h->stream_k = k;
+    if ((rc = launch_stream_begin(h))) return rc;
+    h->stream_on = true;
+    h->stream_done = false;
+    h->stream_chunks = 0;
+    h->stream_short_seen = false;
+    h->rows_consumed = false;
+    return XPCS_OK;
+}
+
+// one chunk whose events already sit in d_idx / d_val / d_frame_off (local offsets)
+static int stream_consume(xpcs_handle_s *h, int nframes, int64_t nev)
+{
+    const int K = 1 << h->stream_k;
+    const int c = h->stream_chunks;
+    int rc = launch_ingest_stream_chunk(h, c * K, nframes, nev, c == 0);
+    if (rc == 1) return fail(h, XPCS_E_ARG, "stream mode: a photon count does not fit the packed word (0..4095)");
+    if (rc) return rc;
+    h->pipe_events = (c == 0 ? 0 : h->pipe_events) + h->events_stored;  // events of unmasked pixels so far
+    if ((rc = launch_stream_chunk(h, c, false))) return rc;
+    h->stream_chunks = c + 1;
+    if (nframes < K) h->stream_short_seen = true;
+    h->raw_frames += nframes;
+    h->E += nev;
+    return XPCS_OK;
+}
+
+static int stream_push_checks(xpcs_handle_s *h, int nframes)
+{
+    if (!h->stream_on) return fail(h, XPCS_E_STATE, "stream_push before xpcs_stream_begin");
+    if (h->stream_short_seen) return fail(h, XPCS_E_STATE, "stream_push after a short (final) chunk");
+    if (nframes <= 0 || h->raw_frames + (int64_t)nframes > h->prm.frames)
+        return fail(h, XPCS_E_ARG, "stream_push: %d frames on top of %d exceed the %d of the job", nframes, h->raw_frames, h->prm.frames);
+    return XPCS_OK;
+}
+
+extern "C" int xpcs_stream_push_sparse(xpcs_handle h, const int32_t *idx, const int16_t *val, const int64_t *frame_offsets,
+                                       const double *clock, const double *ticks, int nframes)
+{
+    if (!h || !frame_offsets) return h ? fail(h, XPCS_E_ARG, "stream_push_sparse: bad arguments") : XPCS_E_ARG;
+    int rc = stream_push_checks(h, nframes);
+    if (rc) return rc;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < nframes; i++)
+        if (frame_offsets[i + 1] < frame_offsets[i]) return fail(h, XPCS_E_ARG, "stream_push_sparse: frame offsets not monotone");
+    if (frame_offsets[nframes] > frame_offsets[0] && (!idx || !val)) return fail(h, XPCS_E_ARG, "stream_push_sparse: NULL payload");
+    const int K = 1 << h->stream_k;
+    if (!h->copy_stream && (rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream"))) return rc;
+    cudaEvent_t ev = nullptr;
+    if ((rc = check_cuda(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"))) return rc;
+    // a push may hold several chunks; each is copied on the copy stream (under the kernels of the chunk before it,
+    // which only read the chunk store and the state) and consumed on the handle's stream
+    for (int f0 = 0; f0 < nframes && !rc; f0 += K) {
+        const int nf = std::min(K, nframes - f0);
+        const int64_t e0 = frame_offsets[f0], nev = frame_offsets[f0 + nf] - e0;
+        if ((rc = grow(h, h->d_idx, 0, (size_t)nev + 8, "event indices"))) break;
+        if ((rc = grow(h, h->d_val, 0, (size_t)nev + 8, "event values"))) break;
+        if ((rc = grow(h, h->d_frame_off, 0, (size_t)K + 1, "frame offsets"))) break;
+        if (nev > 0) {
+            rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p, idx + e0, sizeof(int32_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "idx H2D");
+            if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p, val + e0, sizeof(int16_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "val H2D");
+        }
+        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p, frame_offsets + f0, sizeof(int64_t) * ((size_t)nf + 1),
+                                                    cudaMemcpyHostToDevice, h->copy_stream), "frame offsets H2D");
+        if (rc) break;
+        cudaEventRecord(ev, h->copy_stream);
+        cudaStreamWaitEvent(h->stream, ev, 0);
+        if (e0 != 0) {
+            LaunchScope ls(h, "k_rebase_offsets");
+            k_rebase_offsets<<<(nf + 256) / 256, 256, 0, h->stream>>>(h->d_frame_off.p, nf + 1, -e0);
+        }
+        push_timestamps(h, clock ? clock + f0 : nullptr, ticks ? ticks + f0 : nullptr, nf);
+        rc = stream_consume(h, nf, nev);  // synchronises the handle's stream while it sizes the chunk store
+    }
+    cudaStreamSynchronize(h->copy_stream);
+    cudaEventDestroy(ev);
+    return rc;
+}
+
+extern "C" int xpcs_stream_push_sparse_device(xpcs_handle h, const int32_t *d_idx, const int16_t *d_val,
+                                              const int64_t *d_frame_offsets, int64_t n_events, int nframes)
+{
+    if (!h || !d_frame_offsets || n_events < 0) return h ? fail(h, XPCS_E_ARG, "stream_push_sparse_device: bad arguments") : XPCS_E_ARG;
+    int rc = stream_push_checks(h, nframes);
+    if (rc) return rc;
+    if (nframes > (1 << h->stream_k)) return fail(h, XPCS_E_ARG, "stream_push_sparse_device takes one chunk (<= %d frames) per call", 1 << h->stream_k);
+    if (n_events > 0 && (!d_idx || !d_val)) return fail(h, XPCS_E_ARG, "stream_push_sparse_device: NULL payload");
+    cudaSetDevice(h->device);
+    // the chunk is copied into the handle's own buffers (device to device: 6 bytes per event at HBM rate), which
+    // keeps the caller free to refill its buffers at once and the ingest kernels on aligned addresses
+    if ((rc = grow(h, h->d_idx, 0, (size_t)n_events + 8, "event indices"))) return rc;
+    if ((rc = grow(h, h->d_val, 0, (size_t)n_events + 8, "event values"))) return rc;
+    if ((rc = grow(h, h->d_frame_off, 0, (size_t)(1 << h->stream_k) + 1, "frame offsets"))) return rc;
+    if (n_events > 0) {
+        rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p, d_idx, sizeof(int32_t) * n_events, cudaMemcpyDeviceToDevice, h->stream), "idx D2D");
+        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p, d_val, sizeof(int16_t) * n_events, cudaMemcpyDeviceToDevice, h->stream), "val D2D");
+    }
+    if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p, d_frame_offsets, sizeof(int64_t) * ((size_t)nframes + 1),
+                                                cudaMemcpyDeviceToDevice, h->stream), "frame offsets D2D");
+    if (rc) return rc;
+    push_timestamps(h, nullptr, nullptr, nframes);
+    return stream_consume(h, nframes, n_events);
+}
+
+extern "C" int xpcs_stream_finish(xpcs_handle h, float *pixel_sum, float *frame_sum, float *part_total, float *part_partial)
+{
+    if (!h) return XPCS_E_ARG;
+    if (!h->stream_on) return fail(h, XPCS_E_STATE, "stream_finish before xpcs_stream_begin");
+    if (h->raw_frames != h->prm.frames)
+        return fail(h, XPCS_E_STATE, "stream_finish: %d of the job's %d frames were pushed", h->raw_frames, h->prm.frames);
+    cudaSetDevice(h->device);
+    int rc = launch_stream_finish(h);
+    if (rc) return rc;
+    h->stream_on = false;
+    h->stream_done = true;
+    h->ingest_done = true;
+    h->multitau_done = true;
+    h->partials_done = false;
+    h->rows_consumed = true;   // there are no rows: xpcs_get_frames / xpcs_twotime need a resident ingest
+    h->events_stored = h->pipe_events;
+    h->store_words = 0;
+    h->max_row = 0;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(h->stream), "k_stream_finish"))) return rc;
+    return filter_getters(h, pixel_sum, frame_sum, part_total, part_partial);
+}
+
+// ---------------------------------------------------------------------------------------
 // Correlation
 // ---------------------------------------------------------------------------------------
 extern "C" int xpcs_multitau(xpcs_handle h, float *G2, float *IP, float *IF)
 {
     if (!h) return XPCS_E_ARG;
     if (!h->ingest_done) return fail(h, XPCS_E_STATE, "multitau before finish_ingest");
-    if (h->rows_consumed) return fail(h, XPCS_E_STATE, "the event rows were consumed by a previous multitau; re-ingest");
+    if (h->rows_consumed && !h->stream_done) return fail(h, XPCS_E_STATE, "the event rows were consumed by a previous multitau; re-ingest");
     cudaSetDevice(h->device);
-    int rc = launch_multitau(h);
+    int rc = h->stream_done ? XPCS_OK : launch_multitau(h);  // a finished stream holds its G2 / IP / IF already
     if (rc) return rc;
     h->multitau_done = true;
     h->partials_done = false;

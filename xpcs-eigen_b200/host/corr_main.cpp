@@ -69,6 +69,7 @@ struct Flags {
     int device = 0;
     int gpus = 1;  // --gpus N: pixel-shard a sparse multi-tau job over GPUs device .. device+N-1 (NCCL inside the library)
     int frameout = 0;
+    int stream_frames = 0;  // --stream_frames K: online multi-tau, K = 2^k frames at a time on the device (xpcs_stream_*)
 };
 
 
@@ -114,6 +115,7 @@ static int parse_flags(int argc, char **argv, Flags &f)
                                     "contraction runs on the tensor cores either way\n");
             }
             else if (name == "frameout") f.frameout = atoi(need().c_str());
+            else if (name == "stream_frames") f.stream_frames = atoi(need().c_str());
             else if (name == "ufxc") f.ufxc = !has_val || val == "true" || val == "1";
             else if (name == "rigaku") f.rigaku = !has_val || val == "true" || val == "1";
             else if (name == "hdf5") f.hdf5 = !has_val || val == "true" || val == "1";
@@ -669,6 +671,17 @@ int main(int argc, char **argv)
     prm.static_window = conf.static_window > 0 ? conf.static_window : 1;
     prm.normalize_by_framesum = conf.normalize_by_framesum;
     prm.compat_flags = fl.no_compat ? 0u : XPCS_COMPAT_STALE_TAIL;
+    if (fl.stream_frames > 0) {
+        // Online multi-tau (include/xpcs_b200.h, xpcs_stream_*): the device holds one chunk of frames and a per-pixel
+        // state, so the job is no longer bounded by device memory.  The reference's dropped G2 pairs
+        // depend on the complete row of a pixel and cannot be reproduced chunk by chunk: the stream gives the exact sums.
+        if (conf.twotime || fl.frameout > 0 || fl.gpus > 1) {
+            fprintf(stderr, "corr: --stream_frames is for multi-tau jobs on one GPU without --frameout\n");
+            return 2;
+        }
+        if (!fl.no_compat) log_info("--stream_frames %d: exact multi-tau sums (the reference's stale-tail pair losses need complete rows)", fl.stream_frames);
+        prm.compat_flags = 0u;
+    }
     if (fl.rigaku) prm.compat_flags |= XPCS_COMPAT_LATE_WINDOW;  // the reader counts the static windows its own way (io/rigaku.cpp:190-193)
     prm.lld = conf.lld;
     prm.sigma = conf.sigma;
@@ -772,6 +785,11 @@ int main(int argc, char **argv)
     };
     if (!join_creator()) return 3;
     const bool sparse_input = fl.ufxc || fl.hdf5 || fl.rigaku || imm_reader->sparse();
+    if (fl.stream_frames > 0 && !sparse_input) {
+        fprintf(stderr, "corr: --stream_frames takes sparse input (compressed IMM, --ufxc, --rigaku, --hdf5)\n");
+        xpcs_destroy(h);
+        return 2;
+    }
     SparseInput in;
     std::chrono::steady_clock::time_point t_load = std::chrono::steady_clock::now();
     try {
@@ -804,6 +822,10 @@ int main(int argc, char **argv)
             if (sparse_input) {
                 // one push of the whole frame range: large pushes of plain photon counts are cut into chunks that are
                 // ingested while the next chunk crosses PCIe
+                if (fl.stream_frames > 0) {
+                    CHECK(xpcs_stream_begin(h, fl.stream_frames));
+                    CHECK(xpcs_stream_push_sparse(h, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames()));
+                } else
                 CHECK(xpcs_push_sparse(h, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames()));
             } else {
                 xpcs_host::ImmReader &reader = *imm_reader;
@@ -829,7 +851,10 @@ int main(int argc, char **argv)
             std::vector<float> pixel_sum(pixels), frame_sum(2 * (size_t)frames), pm_total(S > 0 ? S : 1);
             const int windows = frames / prm.static_window;
             std::vector<float> pm_partial((size_t)std::max(windows, 1) * std::max(S, 1));
-            CHECK(xpcs_finish_ingest(h, pixel_sum.data(), frame_sum.data(), pm_total.data(), pm_partial.data()));
+            if (fl.stream_frames > 0 && sparse_input)
+                CHECK(xpcs_stream_finish(h, pixel_sum.data(), frame_sum.data(), pm_total.data(), pm_partial.data()));
+            else
+                CHECK(xpcs_finish_ingest(h, pixel_sum.data(), frame_sum.data(), pm_total.data(), pm_partial.data()));
             CHECK(xpcs_get_info(h, &info));
             const int raw_seen = info.raw_frames_seen;
             std::vector<double> clock(2 * (size_t)raw_seen), ticks(2 * (size_t)raw_seen);
