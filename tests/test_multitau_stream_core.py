@@ -128,3 +128,115 @@ def test_bright_rows(host):
         assert G2[ti, 0] == want, (ti, G2[ti, 0], want)
         assert IP[ti, 0] == np.float32(np.float32(int(xl[: L - tp].sum())) * np.float32(2.0 ** -l)) / np.float32(L - tp)
         assert IF[ti, 0] == np.float32(np.float32(int(xl[tp:].sum())) * np.float32(2.0 ** -l)) / np.float32(L - tp)
+
+
+# ---- the WARP build on the CPU: 32 threads as the lanes of a warp, barriers for __syncwarp(), random delays ----
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host_mt") / "libmt_stream_emu.so")
+    src = os.path.join(ROOT, "tests", "host_mt", "mt_stream_emu.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           "-Wno-unknown-pragmas", "-o", out, src, "-lpthread"])
+    lib = C.CDLL(out)
+    lib.mt_stream_emu.restype = C.c_int
+    return lib
+
+
+def run_emu(lib, rows_f, rows_c, F, dpl, k):
+    T, cnt0, lastl, cnt_last = sched_args(F, dpl)
+    R = len(rows_f)
+    ptr = np.zeros(R + 1, np.int64)
+    ptr[1:] = np.cumsum([len(f) for f in rows_f])
+    fr = np.concatenate([np.asarray(f, np.int32) for f in rows_f] + [np.zeros(0, np.int32)]).astype(np.int32)
+    ct = np.concatenate([np.asarray(c, np.int32) for c in rows_c] + [np.zeros(0, np.int32)]).astype(np.int32)
+    G2 = np.zeros((T, R), np.float32)
+    IP = np.zeros((T, R), np.float32)
+    IF = np.zeros((T, R), np.float32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib.mt_stream_emu(dpl, F, T, cnt0, lastl, cnt_last, k, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
+                           p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
+    assert rc == 0
+    return G2, IP, IF
+
+
+def emu_equals_oracle(lib, case):
+    rows_f, rows_c, F, dpl, k, ref = case
+    got = run_emu(lib, rows_f, rows_c, F, dpl, k)
+    return all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(got, ref))
+
+
+def emu_cases(seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for F, dpl, k in ((700, 8, 6), (2100, 8, 9), (1500, 4, 7), (300, 4, 6), (5000, 8, 12)):
+        rows_f, rows_c = make_rows(rng, F, [0.3, 1.0, 0.02, "cluster", "tail", "head", 0.0, "one"])
+        cases.append((rows_f, rows_c, F, dpl, k, run_oracle(rows_f, rows_c, F, dpl)))
+    return cases
+
+
+def test_warp_build_equals_the_oracle(emu):
+    """the device's own control flow -- one lane per thread, 64-bit warp sums, owner-lane stores, barriers where the
+    kernel has __syncwarp() -- under random delays of the lanes, several times over"""
+    emu.mt_stream_emu_drop(0)
+    for case in emu_cases(11):
+        for _ in range(3):
+            assert emu_equals_oracle(emu, case), "F=%d dpl=%d k=%d" % case[2:5]
+
+
+def test_warp_emulation_notices_a_missing_barrier(emu):
+    """the check above is only worth something if a missing __syncwarp() shows: drop the barrier of one source line
+    of the core at a time (for all lanes alike) and the result must go wrong for most of them (the few that survive
+    are barriers followed by another one before anything they order is touched)"""
+    cases = emu_cases(12)[:2]
+    emu.mt_stream_emu_drop(0)
+    assert all(emu_equals_oracle(emu, c) for c in cases)
+    lines = (C.c_int * 64)()
+    n = emu.mt_stream_emu_sites(lines, 64)
+    sites = sorted(lines[i] for i in range(n))
+    assert len(sites) >= 8, sites
+    caught = []
+    try:
+        for ln in sites:
+            emu.mt_stream_emu_drop(ln)
+            if not all(emu_equals_oracle(emu, c) for c in cases for _ in range(2)):
+                caught.append(ln)
+    finally:
+        emu.mt_stream_emu_drop(0)
+    assert len(caught) >= 5, "barriers whose removal was noticed: %s of %s" % (caught, sites)
+    assert all(emu_equals_oracle(emu, c) for c in cases)
+
+
+def test_warp_build_under_thread_sanitizer(tmp_path):
+    """the same build under ThreadSanitizer where the toolchain has it (it does not see every race of this pattern --
+    32 threads, four shadow slots per word -- which is why the two tests above exist)"""
+    exe = str(tmp_path / "mt_stream_emu_tsan")
+    src = os.path.join(ROOT, "tests", "host_mt", "mt_stream_emu.cpp")
+    p = subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fsanitize=thread",
+                        "-DST_EMU_MAIN", "-Wno-unknown-pragmas", "-o", exe, src, "-lpthread"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        pytest.skip("no ThreadSanitizer build here: " + p.stdout[-300:])
+    F, dpl, k = 700, 8, 6
+    rng = np.random.default_rng(5)
+    rows_f, rows_c = make_rows(rng, F, [0.3, 1.0, 0.02, "cluster", "tail", "head", 0.0, "one"])
+    T, cnt0, lastl, cnt_last = sched_args(F, dpl)
+    R = len(rows_f)
+    ptr = np.zeros(R + 1, np.int64)
+    ptr[1:] = np.cumsum([len(f) for f in rows_f])
+    fr = np.concatenate([np.asarray(f, np.int32) for f in rows_f]).astype(np.int32)
+    ct = np.concatenate([np.asarray(c, np.int32) for c in rows_c]).astype(np.int32)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(np.array([dpl, F, T, cnt0, lastl, cnt_last, k, R], np.int32).tobytes())
+        f.write(ptr.tobytes())
+        f.write(fr.tobytes())
+        f.write(ct.tobytes())
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    p = subprocess.run([exe, fin, fout], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
+    if p.returncode != 0 and "unexpected memory mapping" in p.stdout:
+        pytest.skip("ThreadSanitizer cannot map its shadow here")
+    assert p.returncode == 0, "66 = data race reported by ThreadSanitizer:\n" + p.stdout[-3000:]
+    out = np.fromfile(fout, np.float32).reshape(3, T, R)
+    ref = run_oracle(rows_f, rows_c, F, dpl)
+    for a, b in zip(out, ref):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -32,9 +32,29 @@
 #define ST_HD inline
 #endif
 
-#if defined(__CUDA_ARCH__)
-#define ST_FOR_LANES for (int lane = (int)(threadIdx.x & 31u), once_ = 1; once_; once_ = 0)
+// Three builds of this file: the device (a warp), the host with the lanes run one after the other
+// (mt_stream_host.cpp), and the host with 32 threads playing the lanes of a warp, barriers where the device has
+// __syncwarp() and random delays in front of every phase (-DST_EMU_WARP, mt_stream_emu.cpp: a missing synchronisation
+// lets a fast lane read what a delayed lane has not written yet, and the result no longer equals the oracle).
+#if defined(ST_EMU_WARP)
+namespace xpcs {
+namespace st {
+int emu_lane();
+void emu_jitter();
+void emu_sync(int line);
+unsigned long long emu_sum64(unsigned long long v);
+}  // namespace st
+}  // namespace xpcs
+#define ST_WARP 1
+#define ST_LANE() (xpcs::st::emu_jitter(), xpcs::st::emu_lane())   // every phase starts after a random delay of its lane
+#define ST_SYNC() xpcs::st::emu_sync(__LINE__)   // (the harness can drop the barrier of one source line)
+#elif defined(__CUDA_ARCH__)
+#define ST_WARP 1
+#define ST_LANE() ((int)(threadIdx.x & 31u))
 #define ST_SYNC() __syncwarp()
+#endif
+#if defined(ST_WARP)
+#define ST_FOR_LANES for (int lane = ST_LANE(), once_ = 1; once_; once_ = 0)
 #define ST_NLANE_SLOTS 1
 #else
 #define ST_FOR_LANES for (int lane = 0; lane < 32; lane++)
@@ -117,6 +137,8 @@ ST_HD unsigned long long warp_sum64(unsigned long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+#elif defined(ST_EMU_WARP)
+inline unsigned long long warp_sum64(unsigned long long v) { return emu_sum64(v); }
 #endif
 
 // ---- a level with many new bins (nb >= 128): every lane takes groups of four consecutive bins (one 16-byte
@@ -176,7 +198,7 @@ ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st
 #pragma unroll
             for (int d = 0; d < CNT; d++) acc[d] = 0;
             mac_groups<DPL, LO, CNT>(xn, nvalid, lane, acc, tot);
-#if defined(__CUDA_ARCH__)
+#if defined(ST_WARP)
             unsigned long long mine = 0;
 #pragma unroll
             for (int d = 0; d < CNT; d++) {
