@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--frames", type=int, default=100000)
     ap.add_argument("--occ", type=float, default=0.001)
     ap.add_argument("--chunk", type=int, default=2048)
+    ap.add_argument("--chunks", default="", help="comma-separated chunk lengths: one JSON line each (resident path run once)")
+    ap.add_argument("--profile", action="store_true", help="one streamed pass and nothing else (under ncu)")
     ap.add_argument("--out", default="")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -51,66 +53,76 @@ def main():
         c.multitau(want=False)
         return c.normalize()
 
-    # chunk views: events of frames [f0, f1) and their offsets rebased to 0
     off_h = d_off.cpu().numpy()
-    chunks = []
-    for f0 in range(0, F, a.chunk):
-        f1 = min(F, f0 + a.chunk)
-        e0, e1 = int(off_h[f0]), int(off_h[f1])
-        chunks.append((d_idx[e0:e1], d_val[e0:e1], (d_off[f0:f1 + 1] - e0).contiguous(), e1 - e0, f1 - f0))
-    torch.cuda.synchronize()
-
-    def streamed():
-        c.reset()
-        c.stream_begin(a.chunk)
-        for i, v, o, ne, nf in chunks:
-            c.stream_push_sparse_device(i.data_ptr(), v.data_ptr(), o.data_ptr(), ne, nf)
-        c.stream_finish(want=False)
-        c.multitau(want=False)
-        return c.normalize()
-
-    out = {"what": "stream_check", "tag": a.tag, "h": a.h, "w": a.w, "frames": F, "occupancy": a.occ, "chunk_frames": a.chunk,
-           "events": E, "rows": int(c.info().n_rows), "delays": int(c.T), "chunks": len(chunks)}
-    g2_r, se_r = [np.array(x, copy=True) for x in resident()]
-    cor_r = c.correlators(sample)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    resident()
-    torch.cuda.synchronize()
-    out["resident_ms"] = (time.perf_counter() - t0) * 1e3
-    g2_s, se_s = [np.array(x, copy=True) for x in streamed()]
-    cor_s = c.correlators(sample)
     same = lambda x, y: bool(np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32)))
-    out["parity"] = {"g2_bit_identical": same(g2_r, g2_s), "stderr_bit_identical": same(se_r, se_s),
-                     "sampled_pixels": int(sample.size),
-                     "G2_IP_IF_bit_identical": [same(x, y) for x, y in zip(cor_r, cor_s)]}
-    c.kernel_timing(True)
-    c.kernel_report(reset=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    streamed()
-    torch.cuda.synchronize()
-    out["streamed_ms"] = (time.perf_counter() - t0) * 1e3
-    rep = c.kernel_report(reset=True)
-    c.kernel_timing(False)
-    out["kernels_ms"] = {k: round(v[0], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])}
-    out["kernel_launches"] = {k: int(v[1]) for k, v in rep.items()}
-    if "k_stream_chunk" in rep:
-        ms, n = rep["k_stream_chunk"]
-        out["k_stream_chunk_ms_per_chunk"] = ms / max(n, 1)
-        out["k_stream_chunk_row_chunks_per_s"] = out["rows"] * n / (ms * 1e-3) if ms > 0 else None
-    t0 = time.perf_counter()
-    streamed()
-    torch.cuda.synchronize()
-    out["streamed_ms_untimed_kernels"] = (time.perf_counter() - t0) * 1e3
-    out["frames_per_s_streamed"] = F / (out["streamed_ms_untimed_kernels"] * 1e-3)
+    lines, ok = [], True
+    g2_r = None
+    for chunk in ([int(x) for x in a.chunks.split(",")] if a.chunks else [a.chunk]):
+        # chunk views: events of frames [f0, f1) and their offsets rebased to 0
+        chunks = []
+        for f0 in range(0, F, chunk):
+            f1 = min(F, f0 + chunk)
+            e0, e1 = int(off_h[f0]), int(off_h[f1])
+            chunks.append((d_idx[e0:e1], d_val[e0:e1], (d_off[f0:f1 + 1] - e0).contiguous(), e1 - e0, f1 - f0))
+        torch.cuda.synchronize()
+
+        def streamed():
+            c.reset()
+            c.stream_begin(chunk)
+            for i, v, o, ne, nf in chunks:
+                c.stream_push_sparse_device(i.data_ptr(), v.data_ptr(), o.data_ptr(), ne, nf)
+            c.stream_finish(want=False)
+            c.multitau(want=False)
+            return c.normalize()
+
+        if a.profile:
+            streamed()
+            torch.cuda.synchronize()
+            continue
+        out = {"what": "stream_check", "tag": a.tag, "h": a.h, "w": a.w, "frames": F, "occupancy": a.occ, "chunk_frames": chunk,
+               "events": E, "rows": int(c.info().n_rows), "delays": int(c.T), "chunks": len(chunks)}
+        if g2_r is None:
+            g2_r, se_r = [np.array(x, copy=True) for x in resident()]
+            cor_r = c.correlators(sample)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            resident()
+            torch.cuda.synchronize()
+            resident_ms = (time.perf_counter() - t0) * 1e3
+        out["resident_ms"] = resident_ms
+        g2_s, se_s = [np.array(x, copy=True) for x in streamed()]
+        cor_s = c.correlators(sample)
+        out["parity"] = {"g2_bit_identical": same(g2_r, g2_s), "stderr_bit_identical": same(se_r, se_s),
+                         "sampled_pixels": int(sample.size),
+                         "G2_IP_IF_bit_identical": [same(x, y) for x, y in zip(cor_r, cor_s)]}
+        c.kernel_timing(True)
+        c.kernel_report(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        streamed()
+        torch.cuda.synchronize()
+        out["streamed_ms"] = (time.perf_counter() - t0) * 1e3
+        rep = c.kernel_report(reset=True)
+        c.kernel_timing(False)
+        out["kernels_ms"] = {k: round(v[0], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0]) if v[1] > 0}
+        out["kernel_launches"] = {k: int(v[1]) for k, v in rep.items() if v[1] > 0}
+        if "k_stream_chunk" in rep:
+            ms, n = rep["k_stream_chunk"]
+            out["k_stream_chunk_ms_per_chunk"] = ms / max(n, 1)
+            out["k_stream_chunk_row_chunks_per_s"] = out["rows"] * n / (ms * 1e-3) if ms > 0 else None
+            out["k_stream_chunk_row_frames_per_s"] = out["rows"] * float(F) / (ms * 1e-3) if ms > 0 else None
+        t0 = time.perf_counter()
+        streamed()
+        torch.cuda.synchronize()
+        out["streamed_ms_untimed_kernels"] = (time.perf_counter() - t0) * 1e3
+        out["frames_per_s_streamed"] = F / (out["streamed_ms_untimed_kernels"] * 1e-3)
+        ok = ok and out["parity"]["g2_bit_identical"] and all(out["parity"]["G2_IP_IF_bit_identical"])
+        lines.append(json.dumps(out))
+        print(lines[-1], flush=True)
     c.close()
-    line = json.dumps(out)
-    print(line)
-    if a.out:
+    if a.out and lines:
         with open(a.out, "w") as f:
-            f.write(line + "\n")
-    ok = out["parity"]["g2_bit_identical"] and all(out["parity"]["G2_IP_IF_bit_identical"])
+            f.write("\n".join(lines) + "\n")
     sys.exit(0 if ok else 1)
 
 

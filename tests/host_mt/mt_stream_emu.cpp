@@ -57,6 +57,14 @@ unsigned long long emu_sum64(unsigned long long v)
     pthread_barrier_wait(&g_bar);
     return s;
 }
+unsigned long long emu_shfl_xor64(unsigned long long v, int off)
+{
+    g_tab[tl_lane] = v;
+    pthread_barrier_wait(&g_bar);
+    const unsigned long long r = g_tab[tl_lane ^ off];
+    pthread_barrier_wait(&g_bar);
+    return r;
+}
 }  // namespace st
 }  // namespace xpcs
 
@@ -107,7 +115,7 @@ static int run(const StSched &sc, int nrows, const int64_t *row_ptr, const int32
     return 0;
 }
 
-extern "C" int mt_stream_emu(int dpl, int F, int T, int cnt0, int lastl, int cnt_last, int k, int nrows,
+extern "C" int mt_stream_emu(int dpl, int F, int T, int cnt0, int lastl, int cnt_last, int k, int ev_num, int nrows,
                              const int64_t *row_ptr, const int32_t *frames, const int32_t *counts, float *G2, float *IP,
                              float *IF)
 {
@@ -118,6 +126,7 @@ extern "C" int mt_stream_emu(int dpl, int F, int T, int cnt0, int lastl, int cnt
     sc.lastl = lastl;
     sc.cnt_last = cnt_last;
     sc.k = k;
+    sc.ev_num = ev_num;
     if (dpl == 8) return run<8>(sc, nrows, row_ptr, frames, counts, G2, IP, IF);
     if (dpl == 4) return run<4>(sc, nrows, row_ptr, frames, counts, G2, IP, IF);
     return 1;
@@ -139,9 +148,9 @@ int main(int argc, char **argv)
     if (argc < 3) return 2;
     FILE *fp = fopen(argv[1], "rb");
     if (!fp) return 2;
-    int32_t hdr[8];
-    if (fread(hdr, sizeof(int32_t), 8, fp) != 8) return 2;
-    const int dpl = hdr[0], F = hdr[1], T = hdr[2], cnt0 = hdr[3], lastl = hdr[4], cnt_last = hdr[5], k = hdr[6], nrows = hdr[7];
+    int32_t hdr[9];
+    if (fread(hdr, sizeof(int32_t), 9, fp) != 9) return 2;
+    const int dpl = hdr[0], F = hdr[1], T = hdr[2], cnt0 = hdr[3], lastl = hdr[4], cnt_last = hdr[5], k = hdr[6], ev_num = hdr[7], nrows = hdr[8];
     std::vector<int64_t> ptr((size_t)nrows + 1);
     if (fread(ptr.data(), sizeof(int64_t), ptr.size(), fp) != ptr.size()) return 2;
     std::vector<int32_t> fr((size_t)ptr[nrows]), ct((size_t)ptr[nrows]);
@@ -149,7 +158,7 @@ int main(int argc, char **argv)
     if (fread(ct.data(), sizeof(int32_t), ct.size(), fp) != ct.size()) return 2;
     fclose(fp);
     std::vector<float> out((size_t)3 * T * nrows, 0.f);
-    const int rc = mt_stream_emu(dpl, F, T, cnt0, lastl, cnt_last, k, nrows, ptr.data(), fr.data(), ct.data(), out.data(),
+    const int rc = mt_stream_emu(dpl, F, T, cnt0, lastl, cnt_last, k, ev_num, nrows, ptr.data(), fr.data(), ct.data(), out.data(),
                                  out.data() + (size_t)T * nrows, out.data() + (size_t)2 * T * nrows);
     if (rc) return rc;
     fp = fopen(argv[2], "wb");

@@ -45,7 +45,7 @@ static int run(const StSched &sc, int nrows, const int64_t *row_ptr, const int32
     return 0;
 }
 
-extern "C" int mt_stream_host(int dpl, int F, int T, int cnt0, int lastl, int cnt_last, int k, int nrows,
+extern "C" int mt_stream_host(int dpl, int F, int T, int cnt0, int lastl, int cnt_last, int k, int ev_num, int nrows,
                               const int64_t *row_ptr, const int32_t *frames, const int32_t *counts, float *G2, float *IP,
                               float *IF)
 {
@@ -56,6 +56,7 @@ extern "C" int mt_stream_host(int dpl, int F, int T, int cnt0, int lastl, int cn
     sc.lastl = lastl;
     sc.cnt_last = cnt_last;
     sc.k = k;
+    sc.ev_num = ev_num;
     if (dpl == 8) return run<8>(sc, nrows, row_ptr, frames, counts, G2, IP, IF);
     if (dpl == 4) return run<4>(sc, nrows, row_ptr, frames, counts, G2, IP, IF);
     return 1;

@@ -100,6 +100,23 @@ def test_chunk_length_does_not_matter(pkg):
         compare(run_stream(pkg, dq, sq, 2500, off, idx, val, chunk), ref, "chunk %d vs 64" % chunk)
 
 
+def test_event_walk_and_bin_walk_agree(pkg):
+    """a level of a row's chunk is either walked bin by bin or event by event (multitau_stream_core.h: mac_groups /
+    mac_events); XPCS_ST_EVENTS moves the switch-over: 0 = bins only, 1000 = events wherever a level has 32 bins"""
+    import os
+    dq, sq, off, idx, val = make_case(pkg, 32, 32, 6000, 0.04, 26)
+    ref = run_stream(pkg, dq, sq, 6000, off, idx, val, 1024)
+    old = os.environ.get("XPCS_ST_EVENTS")
+    try:
+        for knob in ("0", "1000", "3"):
+            os.environ["XPCS_ST_EVENTS"] = knob
+            compare(run_stream(pkg, dq, sq, 6000, off, idx, val, 1024), ref, "XPCS_ST_EVENTS=" + knob)
+    finally:
+        os.environ.pop("XPCS_ST_EVENTS", None)
+        if old is not None:
+            os.environ["XPCS_ST_EVENTS"] = old
+
+
 def test_bright_and_silent_pixels(pkg, oracle):
     """a pixel lit in every frame with large counts, duplicates of a pixel inside a frame, frames without any event,
     pixels that never fire"""

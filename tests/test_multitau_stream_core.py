@@ -41,7 +41,7 @@ def sched_args(F, dpl):
     return len(lev), count[0], lastl, cnt_last
 
 
-def run_stream(lib, rows_f, rows_c, F, dpl, k):
+def run_stream(lib, rows_f, rows_c, F, dpl, k, ev_num=1):
     T, cnt0, lastl, cnt_last = sched_args(F, dpl)
     R = len(rows_f)
     ptr = np.zeros(R + 1, np.int64)
@@ -52,7 +52,7 @@ def run_stream(lib, rows_f, rows_c, F, dpl, k):
     IP = np.zeros((T, R), np.float32)
     IF = np.zeros((T, R), np.float32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    rc = lib.mt_stream_host(dpl, F, T, cnt0, lastl, cnt_last, k, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
+    rc = lib.mt_stream_host(dpl, F, T, cnt0, lastl, cnt_last, k, ev_num, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
                             p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
     assert rc == 0
     return G2, IP, IF
@@ -68,12 +68,18 @@ def run_oracle(rows_f, rows_c, F, dpl):
 
 
 def check(lib, rows_f, rows_c, F, dpl, k):
-    G2, IP, IF = run_stream(lib, rows_f, rows_c, F, dpl, k)
+    """every level by its bins (ev_num 0), the sparse levels by the row's events (1, the product), every level with 32 bins or more by events (1000)"""
     rG2, rIP, rIF = run_oracle(rows_f, rows_c, F, dpl)
+    for ev_num in (1, 0, 1000):
+        check_one(lib, rows_f, rows_c, F, dpl, k, ev_num, rG2, rIP, rIF)
+
+
+def check_one(lib, rows_f, rows_c, F, dpl, k, ev_num, rG2, rIP, rIF):
+    G2, IP, IF = run_stream(lib, rows_f, rows_c, F, dpl, k, ev_num)
     for name, a, b in (("IP", IP, rIP), ("IF", IF, rIF), ("G2", G2, rG2)):
         bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
-        assert bad.size == 0, "%s differs at (tau index, row) %s: %r vs %r (F=%d dpl=%d k=%d)" % (
-            name, bad[0], a[tuple(bad[0])], b[tuple(bad[0])], F, dpl, k)
+        assert bad.size == 0, "%s differs at (tau index, row) %s: %r vs %r (F=%d dpl=%d k=%d ev_num=%d)" % (
+            name, bad[0], a[tuple(bad[0])], b[tuple(bad[0])], F, dpl, k, ev_num)
 
 
 KINDS = [0.002, 0.01, 0.03, 0.08, 0.2, 0.5, 0.9, 1.0, "cluster", 0.0, "one", "tail", "head", "burst"]
@@ -142,7 +148,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-def run_emu(lib, rows_f, rows_c, F, dpl, k):
+def run_emu(lib, rows_f, rows_c, F, dpl, k, ev_num=1):
     T, cnt0, lastl, cnt_last = sched_args(F, dpl)
     R = len(rows_f)
     ptr = np.zeros(R + 1, np.int64)
@@ -153,15 +159,15 @@ def run_emu(lib, rows_f, rows_c, F, dpl, k):
     IP = np.zeros((T, R), np.float32)
     IF = np.zeros((T, R), np.float32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    rc = lib.mt_stream_emu(dpl, F, T, cnt0, lastl, cnt_last, k, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
+    rc = lib.mt_stream_emu(dpl, F, T, cnt0, lastl, cnt_last, k, ev_num, R, p(ptr, C.c_int64), p(fr, C.c_int32), p(ct, C.c_int32),
                            p(G2, C.c_float), p(IP, C.c_float), p(IF, C.c_float))
     assert rc == 0
     return G2, IP, IF
 
 
-def emu_equals_oracle(lib, case):
+def emu_equals_oracle(lib, case, ev_num=1):
     rows_f, rows_c, F, dpl, k, ref = case
-    got = run_emu(lib, rows_f, rows_c, F, dpl, k)
+    got = run_emu(lib, rows_f, rows_c, F, dpl, k, ev_num)
     return all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(got, ref))
 
 
@@ -179,8 +185,8 @@ def test_warp_build_equals_the_oracle(emu):
     kernel has __syncwarp() -- under random delays of the lanes, several times over"""
     emu.mt_stream_emu_drop(0)
     for case in emu_cases(11):
-        for _ in range(3):
-            assert emu_equals_oracle(emu, case), "F=%d dpl=%d k=%d" % case[2:5]
+        for ev_num in (1, 0, 1000):   # the product's choice between the two walks, bins only, events wherever possible
+            assert emu_equals_oracle(emu, case, ev_num), "F=%d dpl=%d k=%d ev_num=%d" % (case[2:5] + (ev_num,))
 
 
 def test_warp_emulation_notices_a_missing_barrier(emu):
@@ -227,7 +233,7 @@ def test_warp_build_under_thread_sanitizer(tmp_path):
     ct = np.concatenate([np.asarray(c, np.int32) for c in rows_c]).astype(np.int32)
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(fin, "wb") as f:
-        f.write(np.array([dpl, F, T, cnt0, lastl, cnt_last, k, R], np.int32).tobytes())
+        f.write(np.array([dpl, F, T, cnt0, lastl, cnt_last, k, 1, R], np.int32).tobytes())
         f.write(ptr.tobytes())
         f.write(fr.tobytes())
         f.write(ct.tobytes())

@@ -84,6 +84,8 @@ static st::StSched stream_sched(const xpcs_handle_s *h)
             s.cnt_last = sc.count[l];
         }
     s.k = h->stream_k;
+    s.ev_num = 1;
+    if (const char *e = getenv("XPCS_ST_EVENTS")) s.ev_num = std::max(0, atoi(e));  // diagnostics: 0 = every level by its bins
     return s;
 }
 

@@ -43,6 +43,7 @@ int emu_lane();
 void emu_jitter();
 void emu_sync(int line);
 unsigned long long emu_sum64(unsigned long long v);
+unsigned long long emu_shfl_xor64(unsigned long long v, int off);
 }  // namespace st
 }  // namespace xpcs
 #define ST_WARP 1
@@ -74,6 +75,7 @@ constexpr int kS = 32;   // rows per slice = stride of a row's column in the chu
 struct StSched {
     int F, T, cnt0, lastl, cnt_last;
     int k;  // log2 of the chunk length in frames
+    int ev_num;  // a level takes the walk over the row's events instead of the one over its bins while 2 n <= bins * ev_num (0: never; 1: the product)
 };
 
 template <int DPL>
@@ -141,7 +143,44 @@ ST_HD unsigned long long warp_sum64(unsigned long long v)
 inline unsigned long long warp_sum64(unsigned long long v) { return emu_sum64(v); }
 #endif
 
-// ---- a level with many new bins (nb >= 128): every lane takes groups of four consecutive bins (one 16-byte
+#if defined(ST_WARP)
+ST_HD unsigned long long shfl_xor64(unsigned long long v, int off)
+{
+#if defined(__CUDA_ARCH__)
+    return __shfl_xor_sync(0xffffffffu, v, off);
+#else
+    return emu_shfl_xor64(v, off);
+#endif
+}
+
+// Warp sums of CNT (16, 8 or 4) per-lane values at once: at every step a lane keeps the half of its values its own lane
+// bit selects and hands the other half to its partner, so 16 values cost 8 + 4 + 2 + 1 + 1 exchanges instead of
+// 16 x 5.  Returns the complete sum of value number lane >> SH in every lane (SH = 1 / 2 / 3 for 16 / 8 / 4 values).
+template <int CNT>
+ST_HD unsigned long long fold_sum(const unsigned long long (&acc)[CNT], int lane)
+{
+    static_assert(CNT == 16 || CNT == 8 || CNT == 4, "fold_sum: 4, 8 or 16 values");
+    unsigned long long a[CNT];
+#pragma unroll
+    for (int i = 0; i < CNT; i++) a[i] = acc[i];
+    int off = 16;
+#pragma unroll
+    for (int n = CNT / 2; n >= 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const unsigned long long keep = up ? a[i + n] : a[i];
+            const unsigned long long give = up ? a[i] : a[i + n];
+            a[i] = keep + shfl_xor64(give, off);
+        }
+    }
+    unsigned long long v = a[0];
+    for (; off >= 1; off >>= 1) v += shfl_xor64(v, off);
+    return v;
+}
+#endif
+
+// ---- a level with many new bins (nb >= 32): every lane takes groups of four consecutive bins (one 16-byte
 // shared-memory load per four words, consecutive lanes on consecutive vectors: conflict free) with the W bins
 // before them, CNT delays lo..lo+CNT-1 at once.  Bins from nvalid on read as zero as the LATER element of a pair.
 template <int DPL, int LO, int CNT>
@@ -171,9 +210,29 @@ ST_HD void mac_groups(const uint32_t *xn, int nvalid, int lane, unsigned long lo
     }
 }
 
+// ---- a level with far more bins than the row has events in this chunk: walk the events instead.  An event is the
+// head of its bin at level l if the event before it lies in another bin; a head stands for its bin (the dense array
+// holds the bin's count), everything else about the level is as in mac_groups.  Cost ~ (2 CNT + 12) per head event
+// against (4 CNT + 20) per four bins there.
+template <int DPL, int LO, int CNT>
+ST_HD void mac_events(const uint32_t *xn, int nvalid, int lane, const uint32_t *ev, int n, uint32_t fbase, int l,
+                      unsigned long long (&acc)[CNT], unsigned long long &tot)
+{
+    for (int j = lane; j < n; j += 32) {
+        const int g = (int)(((ev[(int64_t)j * kS] >> kCB) - fbase) >> l);
+        if (g >= nvalid) continue;  // (the events ascend: the bins from nvalid on hold the last few of the row)
+        if (j > 0 && (int)(((ev[(int64_t)(j - 1) * kS] >> kCB) - fbase) >> l) == g) continue;
+        const uint32_t cur = xn[g];
+        const uint32_t *xe = xn + g - LO;
+        tot += cur;
+#pragma unroll
+        for (int d = 0; d < CNT; d++) acc[d] += (unsigned long long)cur * xe[-d];
+    }
+}
+
 // One level below k: tail in, pairs, totals, head / tail out.  xn = x + XPAD holds the nb new bins of the level.
 template <int DPL, int LO, int CNT>
-ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st)
+ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st, const uint32_t *ev, int n)
 {
     typedef Layout<DPL> LY;
     constexpr int W = LY::W;
@@ -191,22 +250,19 @@ ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st
         if (lane < W) x[LY::XPAD - W + lane] = tail[lane];
     }
     ST_SYNC();
-    if (nb >= 128) {
+    if (nb >= 32) {
         ST_FOR_LANES
         {
             unsigned long long acc[CNT], tot = 0;
 #pragma unroll
             for (int d = 0; d < CNT; d++) acc[d] = 0;
-            mac_groups<DPL, LO, CNT>(xn, nvalid, lane, acc, tot);
+            if (s.ev_num > 0 && 2ll * n <= (long long)nb * s.ev_num) mac_events<DPL, LO, CNT>(xn, nvalid, lane, ev, n, (uint32_t)c << s.k, l, acc, tot);
+            else mac_groups<DPL, LO, CNT>(xn, nvalid, lane, acc, tot);
 #if defined(ST_WARP)
-            unsigned long long mine = 0;
-#pragma unroll
-            for (int d = 0; d < CNT; d++) {
-                const unsigned long long sum = warp_sum64(acc[d]);
-                if (lane == d) mine = sum;
-            }
+            constexpr int SH = CNT == 16 ? 1 : (CNT == 8 ? 2 : 3);  // value d ends up in the lanes d << SH .. (d << SH) + (1 << SH) - 1
+            const unsigned long long mine = fold_sum<CNT>(acc, lane);
             tot = warp_sum64(tot);
-            if (lane < cnt) g2[lane] += mine;
+            if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < cnt) g2[lane >> SH] += mine;
             if (lane == 31) *total += tot;
 #else
             for (int d = 0; d < cnt; d++) g2[d] += acc[d];
@@ -246,7 +302,34 @@ ST_HD void halve(uint32_t *x, int nb)
 {
     uint32_t *xn = x + Layout<DPL>::XPAD;
     const int half = nb >> 1;
-    for (int t0 = 0; t0 < half; t0 += 32) {
+    int t0 = 0;
+    // 128 outputs per step while they last: a lane adds up eight consecutive words into four (two 16-byte loads, one
+    // 16-byte store); a step writes [t0, t0 + 128) and has read [2 t0, 2 t0 + 256): later steps read beyond what it wrote
+    for (; t0 + 128 <= half; t0 += 128) {
+        uint32_t tmp[ST_NLANE_SLOTS][4];
+        ST_FOR_LANES
+        {
+            const uint32_t *src = xn + 2 * t0 + 8 * lane;
+#if defined(__CUDA_ARCH__)
+            const uint4 a = *reinterpret_cast<const uint4 *>(src), b = *reinterpret_cast<const uint4 *>(src + 4);
+            tmp[0][0] = a.x + a.y; tmp[0][1] = a.z + a.w; tmp[0][2] = b.x + b.y; tmp[0][3] = b.z + b.w;
+#else
+            for (int i = 0; i < 4; i++) tmp[lane % ST_NLANE_SLOTS][i] = src[2 * i] + src[2 * i + 1];
+#endif
+        }
+        ST_SYNC();
+        ST_FOR_LANES
+        {
+            uint32_t *dst = xn + t0 + 4 * lane;
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(tmp[0][0], tmp[0][1], tmp[0][2], tmp[0][3]);
+#else
+            for (int i = 0; i < 4; i++) dst[i] = tmp[lane % ST_NLANE_SLOTS][i];
+#endif
+        }
+        ST_SYNC();
+    }
+    for (; t0 < half; t0 += 32) {
         uint32_t tmp[ST_NLANE_SLOTS];
         ST_FOR_LANES
         {
@@ -349,7 +432,11 @@ ST_HD void row_chunk(const StSched &s, int c, const uint32_t *ev, int n, uint32_
     uint32_t *xn = x + LY::XPAD;
     ST_FOR_LANES
     {
+#if defined(__CUDA_ARCH__)
+        for (int i = lane; i < (LY::XPAD + K) / 4; i += 32) reinterpret_cast<uint4 *>(x)[i] = make_uint4(0u, 0u, 0u, 0u);
+#else
         for (int i = lane; i < LY::XPAD + K; i += 32) x[i] = 0u;
+#endif
     }
     ST_SYNC();
     ST_FOR_LANES
@@ -364,8 +451,8 @@ ST_HD void row_chunk(const StSched &s, int c, const uint32_t *ev, int n, uint32_
     const bool need_sum = s.k <= s.lastl;
     const int lend = need_sum ? s.k : s.lastl + 1;
     for (int l = 0; l < lend; l++) {
-        if (l == 0) level_dense<DPL, 1, 2 * DPL>(s, c, 0, x, st);
-        else level_dense<DPL, DPL + 1, DPL>(s, c, l, x, st);
+        if (l == 0) level_dense<DPL, 1, 2 * DPL>(s, c, 0, x, st, ev, n);
+        else level_dense<DPL, DPL + 1, DPL>(s, c, l, x, st, ev, n);
         if (l + 1 < lend || need_sum) halve<DPL>(x, K >> l);
     }
     if (need_sum && ((long long)(c + 1) << s.k) <= s.F) cascade<DPL>(s, c, xn[0], st);
