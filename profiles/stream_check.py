@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2048)
     ap.add_argument("--chunks", default="", help="comma-separated chunk lengths: one JSON line each (resident path run once)")
     ap.add_argument("--profile", action="store_true", help="one streamed pass and nothing else (under ncu)")
+    ap.add_argument("--host", action="store_true", help="also time the stream fed from page-locked HOST buffers (xpcs_stream_push_sparse)")
     ap.add_argument("--out", default="")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -116,6 +117,33 @@ def main():
         torch.cuda.synchronize()
         out["streamed_ms_untimed_kernels"] = (time.perf_counter() - t0) * 1e3
         out["frames_per_s_streamed"] = F / (out["streamed_ms_untimed_kernels"] * 1e-3)
+        if a.host:
+            # the same stream from host memory: every chunk crosses PCIe inside the timed region (one push for the whole job,
+            # the library cuts it into chunks and copies chunk k + 1 under k_stream_chunk of chunk k)
+            if "h_idx" not in locals():
+                h_idx = torch.empty(E, dtype=torch.int32, pin_memory=True).copy_(d_idx)
+                h_val = torch.empty(E, dtype=torch.int16, pin_memory=True).copy_(d_val)
+                h_off = torch.empty(F + 1, dtype=torch.int64, pin_memory=True).copy_(d_off)
+                torch.cuda.synchronize()
+
+            def streamed_host():
+                c.reset()
+                c.stream_begin(chunk)
+                c._check(c._lib.xpcs_stream_push_sparse(c._h, h_idx.data_ptr(), h_val.data_ptr(), h_off.data_ptr(), None, None, F))
+                c.stream_finish(want=True)
+                c.multitau(want=False)
+                return c.normalize()
+
+            g2_h, se_h = [np.array(x, copy=True) for x in streamed_host()]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            streamed_host()
+            torch.cuda.synchronize()
+            out["streamed_host_ms"] = (time.perf_counter() - t0) * 1e3
+            out["h2d_bytes"] = int(E * 6 + (F + 1) * 8)
+            out["frames_per_s_streamed_host"] = F / (out["streamed_host_ms"] * 1e-3)
+            out["parity"]["host_stream_g2_bit_identical"] = same(g2_r, g2_h)
+            ok = ok and out["parity"]["host_stream_g2_bit_identical"]
         ok = ok and out["parity"]["g2_bit_identical"] and all(out["parity"]["G2_IP_IF_bit_identical"])
         lines.append(json.dumps(out))
         print(lines[-1], flush=True)
