@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2048)
     ap.add_argument("--chunks", default="", help="comma-separated chunk lengths: one JSON line each (resident path run once)")
     ap.add_argument("--profile", action="store_true", help="one streamed pass and nothing else (under ncu)")
+    ap.add_argument("--also-bins-only", action="store_true", help="repeat the last chunk length with XPCS_ST_EVENTS=0 (every level walked by its bins)")
     ap.add_argument("--host", action="store_true", help="also time the stream fed from page-locked HOST buffers (xpcs_stream_push_sparse)")
     ap.add_argument("--out", default="")
     ap.add_argument("--tag", default="")
@@ -58,7 +59,13 @@ def main():
     same = lambda x, y: bool(np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32)))
     lines, ok = [], True
     g2_r = None
-    for chunk in ([int(x) for x in a.chunks.split(",")] if a.chunks else [a.chunk]):
+    todo = [(int(x), None) for x in a.chunks.split(",")] if a.chunks else [(a.chunk, None)]
+    if a.also_bins_only:
+        todo.append((todo[-1][0], "0"))
+    for chunk, events_knob in todo:
+        os.environ.pop("XPCS_ST_EVENTS", None)
+        if events_knob is not None:
+            os.environ["XPCS_ST_EVENTS"] = events_knob
         # chunk views: events of frames [f0, f1) and their offsets rebased to 0
         chunks = []
         for f0 in range(0, F, chunk):
@@ -81,7 +88,7 @@ def main():
             torch.cuda.synchronize()
             continue
         out = {"what": "stream_check", "tag": a.tag, "h": a.h, "w": a.w, "frames": F, "occupancy": a.occ, "chunk_frames": chunk,
-               "events": E, "rows": int(c.info().n_rows), "delays": int(c.T), "chunks": len(chunks)}
+               "XPCS_ST_EVENTS": events_knob, "events": E, "rows": int(c.info().n_rows), "delays": int(c.T), "chunks": len(chunks)}
         if g2_r is None:
             g2_r, se_r = [np.array(x, copy=True) for x in resident()]
             cor_r = c.correlators(sample)
