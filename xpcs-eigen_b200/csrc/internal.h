@@ -175,6 +175,12 @@ struct xpcs_handle_s {
     int stream_chunks = 0;                // complete or final chunks consumed so far
     bool stream_short_seen = false;       // a chunk shorter than 2^stream_k came in: it has to be the last one
     xpcs::DevBuf<uint32_t> d_stream_state;  // [R_pad][state words]
+    // host pushes of several chunks: chunk k + 1 crosses PCIe into the second set of event buffers while chunk k
+    // (in d_idx / d_val / d_frame_off) is ingested and folded into the state; the sets swap after every chunk
+    xpcs::DevBuf<int32_t> d_st_idx2;
+    xpcs::DevBuf<int16_t> d_st_val2;
+    xpcs::DevBuf<int64_t> d_st_off2;
+    cudaEvent_t ev_st_copy[2] = {nullptr, nullptr};
 
     // ---- results ----
     bool multitau_done = false;

@@ -443,6 +443,9 @@ extern "C" void xpcs_destroy(xpcs_handle h)
     release(h->d_dark_avg); release(h->d_dark_std); release(h->d_dense_bound); release(h->d_dense_every); release(h->d_dense_args);
     release(h->d_idx); release(h->d_val); release(h->d_evt); release(h->d_valf); release(h->d_frame_off);
     release(h->d_dense_counter);
+    release(h->d_stream_state); release(h->d_st_idx2); release(h->d_st_val2); release(h->d_st_off2);
+    for (int b = 0; b < 2; b++)
+        if (h->ev_st_copy[b]) cudaEventDestroy(h->ev_st_copy[b]);
     release(h->d_row_count); release(h->d_row_len); release(h->d_slice_len); release(h->d_slice_base);
     release(h->d_slice_cur); release(h->d_slice_rec); release(h->d_slice_end); release(h->d_rec);
     for (int k = 0; k < kMaxChunks; k++) {
@@ -1147,34 +1150,46 @@ extern "C" int xpcs_stream_push_sparse(xpcs_handle h, const int32_t *idx, const 
     if (frame_offsets[nframes] > frame_offsets[0] && (!idx || !val)) return fail(h, XPCS_E_ARG, "stream_push_sparse: NULL payload");
     const int K = 1 << h->stream_k;
     if (!h->copy_stream && (rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream"))) return rc;
-    cudaEvent_t ev = nullptr;
-    if ((rc = check_cuda(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"))) return rc;
-    // a push may hold several chunks; each is copied on the copy stream (under the kernels of the chunk before it,
-    // which only read the chunk store and the state) and consumed on the handle's stream
-    for (int f0 = 0; f0 < nframes && !rc; f0 += K) {
-        const int nf = std::min(K, nframes - f0);
+    for (int b = 0; b < 2; b++)
+        if (!h->ev_st_copy[b] && (rc = check_cuda(h, cudaEventCreateWithFlags(&h->ev_st_copy[b], cudaEventDisableTiming), "event"))) return rc;
+    // A push may hold several chunks.  Chunk i + 1 is copied (copy stream) into the spare set of event buffers while
+    // chunk i is ingested and folded into the state on the handle's stream; the two sets swap after every chunk.  The
+    // spare set is free by then: the ingest that read it two chunks ago ended with a synchronisation of the stream.
+    const int nch = (nframes + K - 1) / K;
+    auto issue_copy = [&](int i, DevBuf<int32_t> &bi, DevBuf<int16_t> &bv, DevBuf<int64_t> &bo) -> int {
+        const int f0 = i * K, nf = std::min(K, nframes - f0);
         const int64_t e0 = frame_offsets[f0], nev = frame_offsets[f0 + nf] - e0;
-        if ((rc = grow(h, h->d_idx, 0, (size_t)nev + 8, "event indices"))) break;
-        if ((rc = grow(h, h->d_val, 0, (size_t)nev + 8, "event values"))) break;
-        if ((rc = grow(h, h->d_frame_off, 0, (size_t)K + 1, "frame offsets"))) break;
+        int r;
+        if ((r = grow(h, bi, 0, (size_t)nev + 8, "event indices"))) return r;
+        if ((r = grow(h, bv, 0, (size_t)nev + 8, "event values"))) return r;
+        if ((r = grow(h, bo, 0, (size_t)K + 1, "frame offsets"))) return r;
         if (nev > 0) {
-            rc = check_cuda(h, cudaMemcpyAsync(h->d_idx.p, idx + e0, sizeof(int32_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "idx H2D");
-            if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_val.p, val + e0, sizeof(int16_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "val H2D");
+            r = check_cuda(h, cudaMemcpyAsync(bi.p, idx + e0, sizeof(int32_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "idx H2D");
+            if (!r) r = check_cuda(h, cudaMemcpyAsync(bv.p, val + e0, sizeof(int16_t) * nev, cudaMemcpyHostToDevice, h->copy_stream), "val H2D");
+            if (r) return r;
         }
-        if (!rc) rc = check_cuda(h, cudaMemcpyAsync(h->d_frame_off.p, frame_offsets + f0, sizeof(int64_t) * ((size_t)nf + 1),
-                                                    cudaMemcpyHostToDevice, h->copy_stream), "frame offsets H2D");
-        if (rc) break;
-        cudaEventRecord(ev, h->copy_stream);
-        cudaStreamWaitEvent(h->stream, ev, 0);
+        r = check_cuda(h, cudaMemcpyAsync(bo.p, frame_offsets + f0, sizeof(int64_t) * ((size_t)nf + 1), cudaMemcpyHostToDevice,
+                                          h->copy_stream), "frame offsets H2D");
+        if (r) return r;
+        return check_cuda(h, cudaEventRecord(h->ev_st_copy[i & 1], h->copy_stream), "copy event");
+    };
+    rc = issue_copy(0, h->d_idx, h->d_val, h->d_frame_off);
+    for (int i = 0; i < nch && !rc; i++) {
+        const int f0 = i * K, nf = std::min(K, nframes - f0);
+        const int64_t e0 = frame_offsets[f0], nev = frame_offsets[f0 + nf] - e0;
+        if (i + 1 < nch && (rc = issue_copy(i + 1, h->d_st_idx2, h->d_st_val2, h->d_st_off2))) break;
+        cudaStreamWaitEvent(h->stream, h->ev_st_copy[i & 1], 0);
         if (e0 != 0) {
             LaunchScope ls(h, "k_rebase_offsets");
             k_rebase_offsets<<<(nf + 256) / 256, 256, 0, h->stream>>>(h->d_frame_off.p, nf + 1, -e0);
         }
         push_timestamps(h, clock ? clock + f0 : nullptr, ticks ? ticks + f0 : nullptr, nf);
         rc = stream_consume(h, nf, nev);  // synchronises the handle's stream while it sizes the chunk store
+        std::swap(h->d_idx, h->d_st_idx2);
+        std::swap(h->d_val, h->d_st_val2);
+        std::swap(h->d_frame_off, h->d_st_off2);
     }
-    cudaStreamSynchronize(h->copy_stream);
-    cudaEventDestroy(ev);
+    cudaStreamSynchronize(h->copy_stream);  // the caller may reuse its buffers on return
     return rc;
 }
 
