@@ -81,7 +81,7 @@ static int run(const StSched &sc, int nrows, const int64_t *row_ptr, const int32
     const int nchunks = (sc.F + K - 1) / K;
     const int stride = LY::words(sc);
     std::vector<uint32_t> state((size_t)nrows * stride, 0u);
-    std::vector<uint32_t> xs((size_t)LY::x_words(sc) + 4, 0xdeadbeefu);
+    std::vector<uint32_t> xs((size_t)LY::scratch_words(sc) + 4, 0xdeadbeefu);
     uint32_t *xa = xs.data();
     while (reinterpret_cast<uintptr_t>(xa) & 15u) xa++;
     // the chunk stores, built up front: word j of row r of chunk c at ev[c][r][j * 32]

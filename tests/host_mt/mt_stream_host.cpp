@@ -21,7 +21,7 @@ static int run(const StSched &sc, int nrows, const int64_t *row_ptr, const int32
     const int nchunks = (sc.F + K - 1) / K;
     const int stride = LY::words(sc);
     std::vector<uint32_t> state((size_t)nrows * stride, 0u);
-    std::vector<uint32_t> x((size_t)LY::x_words(sc) + 4, 0xdeadbeefu);
+    std::vector<uint32_t> x((size_t)LY::scratch_words(sc) + 4, 0xdeadbeefu);
     uint32_t *xa = x.data();
     while (reinterpret_cast<uintptr_t>(xa) & 15u) xa++;
     std::vector<uint32_t> ev;

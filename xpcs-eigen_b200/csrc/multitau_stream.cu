@@ -141,11 +141,23 @@ int launch_stream_chunk(xpcs_handle_s *h, int c, bool empty)
     a.c = c;
     a.stride_words = stream_state_words(h, a.s);
     const int dpl = h->prm.delays_per_level;
-    a.x_words = dpl == 8 ? st::Layout<8>::x_words(a.s) : st::Layout<4>::x_words(a.s);
+    a.x_words = dpl == 8 ? st::Layout<8>::scratch_words(a.s) : st::Layout<4>::scratch_words(a.s);  // per warp: bins, event frames, state copy
     int smem_cap = 0;
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     const size_t per_warp = sizeof(uint32_t) * (size_t)a.x_words;
     int warps = (int)std::min<size_t>(kStMaxWarps, (size_t)(smem_cap - 1024) / per_warp);
+    {   // shared memory decides how many warps an SM holds: the CTA size (4..8 warps) that leaves the least of it unused
+        int smem_sm = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
+        int best = 0;
+        for (int w = warps; w >= std::min(warps, 4); w--) {
+            const int resident = w * (int)((size_t)smem_sm / (per_warp * w + 1024));
+            if (resident > best) {
+                best = resident;
+                warps = w;
+            }
+        }
+    }
     if (const char *e = getenv("XPCS_ST_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));  // diagnostics
     if (warps < 1) return fail(h, XPCS_E_ARG, "stream mode: chunk too long for shared memory");
     const size_t bytes = per_warp * warps;

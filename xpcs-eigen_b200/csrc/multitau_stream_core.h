@@ -75,7 +75,7 @@ constexpr int kS = 32;   // rows per slice = stride of a row's column in the chu
 struct StSched {
     int F, T, cnt0, lastl, cnt_last;
     int k;  // log2 of the chunk length in frames
-    int ev_num;  // a level takes the walk over the row's events instead of the one over its bins while 2 n <= bins * ev_num (0: never; 1: the product)
+    int ev_num;  // a level takes the walk over the row's events instead of the one over its bins while 2 n <= bins * ev_num and 2 n <= 2^k, the room of the frame list (0: never; 1: the product)
 };
 
 template <int DPL>
@@ -105,6 +105,10 @@ struct Layout {
     static ST_HD int off_pend(const StSched &s) { return off_head(s) + nl(s) * W; }
     static ST_HD int words(const StSched &s) { return (off_pend(s) + nl(s) + 3) & ~3; }  // row stride: 16-byte multiple
     static ST_HD int x_words(const StSched &s) { return XPAD + (1 << s.k); }
+    // scratch of a warp: x[] | the chunk-local frames of the row's events, 16 bits each, for the event walk (at most
+    // 2^k / 2 events take it) | a copy of the row's state, worked on in place of the global one and written back
+    static ST_HD int evf_words(const StSched &s) { return (1 << s.k) / 4; }
+    static ST_HD int scratch_words(const StSched &s) { return x_words(s) + evf_words(s) + words(s); }
 };
 
 ST_HD float pow2_neg(int e)
@@ -215,13 +219,13 @@ ST_HD void mac_groups(const uint32_t *xn, int nvalid, int lane, unsigned long lo
 // holds the bin's count), everything else about the level is as in mac_groups.  Cost ~ (2 CNT + 12) per head event
 // against (4 CNT + 20) per four bins there.
 template <int DPL, int LO, int CNT>
-ST_HD void mac_events(const uint32_t *xn, int nvalid, int lane, const uint32_t *ev, int n, uint32_t fbase, int l,
+ST_HD void mac_events(const uint32_t *xn, int nvalid, int lane, const uint16_t *evf, int n, int l,
                       unsigned long long (&acc)[CNT], unsigned long long &tot)
 {
     for (int j = lane; j < n; j += 32) {
-        const int g = (int)(((ev[(int64_t)j * kS] >> kCB) - fbase) >> l);
+        const int g = (int)evf[j] >> l;
         if (g >= nvalid) continue;  // (the events ascend: the bins from nvalid on hold the last few of the row)
-        if (j > 0 && (int)(((ev[(int64_t)(j - 1) * kS] >> kCB) - fbase) >> l) == g) continue;
+        if (j > 0 && ((int)evf[j - 1] >> l) == g) continue;
         const uint32_t cur = xn[g];
         const uint32_t *xe = xn + g - LO;
         tot += cur;
@@ -232,7 +236,7 @@ ST_HD void mac_events(const uint32_t *xn, int nvalid, int lane, const uint32_t *
 
 // One level below k: tail in, pairs, totals, head / tail out.  xn = x + XPAD holds the nb new bins of the level.
 template <int DPL, int LO, int CNT>
-ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st, const uint32_t *ev, int n)
+ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st, const uint16_t *evf, int n)
 {
     typedef Layout<DPL> LY;
     constexpr int W = LY::W;
@@ -256,7 +260,7 @@ ST_HD void level_dense(const StSched &s, int c, int l, uint32_t *x, uint32_t *st
             unsigned long long acc[CNT], tot = 0;
 #pragma unroll
             for (int d = 0; d < CNT; d++) acc[d] = 0;
-            if (s.ev_num > 0 && 2ll * n <= (long long)nb * s.ev_num) mac_events<DPL, LO, CNT>(xn, nvalid, lane, ev, n, (uint32_t)c << s.k, l, acc, tot);
+            if (s.ev_num > 0 && 2ll * n <= (long long)nb * s.ev_num && 2 * n <= (1 << s.k)) mac_events<DPL, LO, CNT>(xn, nvalid, lane, evf, n, l, acc, tot);
             else mac_groups<DPL, LO, CNT>(xn, nvalid, lane, acc, tot);
 #if defined(ST_WARP)
             constexpr int SH = CNT == 16 ? 1 : (CNT == 8 ? 2 : 3);  // value d ends up in the lanes d << SH .. (d << SH) + (1 << SH) - 1
@@ -418,24 +422,33 @@ ST_HD void cascade(const StSched &s, int c, uint32_t S, uint32_t *st)
 }
 
 // One chunk of one row.  ev: the row's words of the chunk store (word j at ev[j * 32], frame << 12 | count, absolute
-// frame numbers inside [c << k, (c + 1) << k)), n of them; x: Layout::x_words() words of scratch, 16-byte aligned.
+// frame numbers inside [c << k, (c + 1) << k)), n of them; x: Layout::scratch_words() words of scratch, 16-byte aligned;
+// gst: the row's state in global memory (16-byte aligned, Layout::words() words).
 template <int DPL>
-ST_HD void row_chunk(const StSched &s, int c, const uint32_t *ev, int n, uint32_t *x, uint32_t *st)
+ST_HD void row_chunk(const StSched &s, int c, const uint32_t *ev, int n, uint32_t *x, uint32_t *gst)
 {
     typedef Layout<DPL> LY;
-    if (n == 0) {
-        tails_skip<DPL>(s, c, st);
-        if (s.k <= s.lastl && ((long long)(c + 1) << s.k) <= s.F) cascade<DPL>(s, c, 0u, st);
+    if (n == 0) {  // a few words of the state move: straight in global memory
+        tails_skip<DPL>(s, c, gst);
+        if (s.k <= s.lastl && ((long long)(c + 1) << s.k) <= s.F) cascade<DPL>(s, c, 0u, gst);
         return;
     }
     const int K = 1 << s.k;
     uint32_t *xn = x + LY::XPAD;
+    uint16_t *evf = reinterpret_cast<uint16_t *>(x + LY::x_words(s));
+    uint32_t *st = x + LY::x_words(s) + LY::evf_words(s);
+    const int nst = LY::words(s);
+    const bool keep_frames = s.ev_num > 0 && 2 * n <= K;   // (no level takes the event walk otherwise)
+    // the state comes in with full-width loads and is worked on in shared memory: one round trip to global memory per
+    // row and chunk instead of two or three per level
     ST_FOR_LANES
     {
 #if defined(__CUDA_ARCH__)
         for (int i = lane; i < (LY::XPAD + K) / 4; i += 32) reinterpret_cast<uint4 *>(x)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < nst / 4; i += 32) reinterpret_cast<uint4 *>(st)[i] = reinterpret_cast<const uint4 *>(gst)[i];
 #else
         for (int i = lane; i < LY::XPAD + K; i += 32) x[i] = 0u;
+        for (int i = lane; i < nst; i += 32) st[i] = gst[i];
 #endif
     }
     ST_SYNC();
@@ -444,18 +457,29 @@ ST_HD void row_chunk(const StSched &s, int c, const uint32_t *ev, int n, uint32_
         const uint32_t fbase = (uint32_t)c << s.k;
         for (int j = lane; j < n; j += 32) {
             const uint32_t w = ev[(int64_t)j * kS];
-            xn[(w >> kCB) - fbase] = w & kCMask;
+            const uint32_t f = (w >> kCB) - fbase;
+            xn[f] = w & kCMask;
+            if (keep_frames) evf[j] = (uint16_t)f;
         }
     }
     ST_SYNC();
     const bool need_sum = s.k <= s.lastl;
     const int lend = need_sum ? s.k : s.lastl + 1;
     for (int l = 0; l < lend; l++) {
-        if (l == 0) level_dense<DPL, 1, 2 * DPL>(s, c, 0, x, st, ev, n);
-        else level_dense<DPL, DPL + 1, DPL>(s, c, l, x, st, ev, n);
+        if (l == 0) level_dense<DPL, 1, 2 * DPL>(s, c, 0, x, st, evf, n);
+        else level_dense<DPL, DPL + 1, DPL>(s, c, l, x, st, evf, n);
         if (l + 1 < lend || need_sum) halve<DPL>(x, K >> l);
     }
     if (need_sum && ((long long)(c + 1) << s.k) <= s.F) cascade<DPL>(s, c, xn[0], st);
+    ST_SYNC();
+    ST_FOR_LANES
+    {
+#if defined(__CUDA_ARCH__)
+        for (int i = lane; i < nst / 4; i += 32) reinterpret_cast<uint4 *>(gst)[i] = reinterpret_cast<const uint4 *>(st)[i];
+#else
+        for (int i = lane; i < nst; i += 32) gst[i] = st[i];
+#endif
+    }
 }
 
 // Result of delay slot ti of a row.
