@@ -219,7 +219,8 @@ int xpcs_normalize_finish(xpcs_handle h, float *g2, float *stderr_out);
  * Results are the exact sums of SURVEY.md A.2/A.3 with the one IEEE division of corr.cpp:420-424: bit-identical to
  * the resident path run without XPCS_COMPAT_STALE_TAIL.  That flag needs the complete rows and is
  * refused (XPCS_E_ARG), as are flat field, stride / averaging, frame-sum normalisation and delays_per_level other
- * than 4 and 8.  xpcs_get_frames and xpcs_twotime need a resident ingest. */
+ * than 4 and 8.  xpcs_get_frames and xpcs_twotime need a resident ingest.  A push that fails (e.g. a count beyond
+ * the packed word's 4095: XPCS_E_ARG) leaves the stream unusable: xpcs_reset, then start again. */
 int xpcs_stream_begin(xpcs_handle h, int chunk_frames);
 /* host buffers, layout of xpcs_push_sparse; nframes may span several chunks (cut at multiples of chunk_frames
  * counted from the first frame of the job); a push that ends inside a chunk must be the last one */

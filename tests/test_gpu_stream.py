@@ -217,7 +217,7 @@ def test_corr_stream_frames(pkg, tmp_path):
     input (the resident path with exact pair sums) -- on a sparse IMM file and on a Rigaku event file."""
     import golden_util as G
     from test_gpu_corr_host import _run_corr
-    for name, K in (("sparse_staletail_32x32", 64), ("sparse_odd_dpl4", 128), ("rigaku_compact_32x40", 64)):
+    for name, K in (("sparse_staletail_32x32", 128), ("rigaku_compact_32x40", 64)):
         c = G.Case(name)
         a = tmp_path / ("stream_" + name)
         b = tmp_path / ("resident_" + name)
