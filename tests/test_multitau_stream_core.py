@@ -115,6 +115,24 @@ def test_bench_shapes(host, F, dpl, k, occ):
     check(host, rows_f, rows_c, F, dpl, k)
 
 
+@pytest.mark.parametrize("k", [11, 12])
+def test_c5_rows_at_5_percent(host, k):
+    """BASELINE configs[4] at its high end: 1M frames, 5 % occupancy -- rows of ~50 000 events, 489 (245) chunks, 17 levels
+    of which the top 6 (5) arrive one bin every 1..32 chunks.  G2 numerators reach 2^24 on the deep levels, where the
+    reference's fp32 running sums start to round: IP / IF stay bit-exact, G2 within 1e-6."""
+    F, dpl = 1000000, 8
+    rng = np.random.default_rng(50 + k)
+    rows_f, rows_c = make_rows(rng, F, [0.05, 0.05, 0.01, "tail"])
+    rG2, rIP, rIF = run_oracle(rows_f, rows_c, F, dpl)
+    G2, IP, IF = run_stream(host, rows_f, rows_c, F, dpl, k)
+    assert np.array_equal(IP.view(np.uint32), rIP.view(np.uint32))
+    assert np.array_equal(IF.view(np.uint32), rIF.view(np.uint32))
+    exact = G2.view(np.uint32) == rG2.view(np.uint32)
+    assert np.allclose(G2, rG2, rtol=1e-6, atol=0)
+    assert exact[:, 2:].all(), "the sparser rows stay below 2^24 and must be bit-exact"
+    assert exact.mean() > 0.5
+
+
 def test_bright_rows(host):
     """counts up to the packed word's 4095 in every frame: the 64-bit numerators and 32-bit bins must hold"""
     F, dpl, k = 3000, 8, 9
