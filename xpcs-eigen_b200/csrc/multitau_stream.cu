@@ -11,15 +11,17 @@
 // (xpcs_normalize, the result getters, the NCCL reduction of the partials) runs unchanged.  The arithmetic lives
 // in multitau_stream_core.h, which is also compiled for the host and checked against the oracle on the CPU.
 //
-// One warp per row, 8 consecutive rows of a slice per CTA (their words share 32-byte sectors of the store).  A
-// row's chunk is expanded into a dense bin array in shared memory ((2 dpl + 2^k) words per warp): with occupancies
-// where streaming is needed (>= 1 %) most bins of the levels from 3 on are occupied anyway, every level is then the
-// same branch-free sliding-window product, and rows without an event in the chunk only shift their tails.
-// Per row and chunk: 2^k * (2 dpl) * 2 multiply-adds (IMAD.WIDE, 16 independent accumulators per lane) against
-// (6 B) * occupancy * 2^k bytes of events and ~1.3 KB of state read and written -- instruction-bound, like the
-// resident kernels, and PCIe-bound as a whole: at 5 % occupancy a chunk of 2048 frames of a 4-Mpixel detector is
-// 2.5 GB of events (45 ms at 55 GB/s) for ~6 ms of k_stream_chunk by instruction count.  [not measured on a GPU
-// in this round: the kernel was written after the round's GPU minutes were spent; DESIGN.md 3.6]
+// One warp per row, 4-8 consecutive rows of a slice per CTA (their words share 32-byte sectors of the store).  Per
+// warp in shared memory: the chunk expanded into a dense bin array ((2 dpl + 2^k) words, halved in place from level to
+// level), the chunk-local frames of the row's events (16 bits each) and a copy of the row's state, which comes in and
+// goes out with full-width accesses once per row and chunk.  A level is walked by its bins (four per lane and step,
+// the 2 dpl bins in front of them from five 16-byte loads, 16 / 8 delays at once) or, while the row has fewer than
+// half as many events as the level has bins, by the events; rows without an event in the chunk only shift their
+// tails.  Measured on B200 (profiles/r04_*): 1.50 ms per chunk of 205 684 rows x 2048 frames at 5 %
+// occupancy (1.37e8 rows x chunks per second, the same at any occupancy for the bin walk), 3 874 warp instructions per
+// row and chunk before the shared-memory staging of the state; a 5 % job streams in 24.5 ms against 23.3 ms resident,
+// and 2048 x 2048 pixels at 5 % run at 27 300 frames/s whatever the frame count (PCIe delivers 1.1e4 frames/s of
+// that detector per link, so a host-fed stream is link-bound).
 #include <algorithm>
 #include <cstdlib>
 
