@@ -20,8 +20,8 @@
 // tails.  Measured on B200 (profiles/r04_*): 1.50 ms per chunk of 205 684 rows x 2048 frames at 5 %
 // occupancy (1.37e8 rows x chunks per second, the same at any occupancy for the bin walk), 3 874 warp instructions per
 // row and chunk before the shared-memory staging of the state; a 5 % job streams in 24.5 ms against 23.3 ms resident,
-// and 2048 x 2048 pixels at 5 % run at 27 300 frames/s whatever the frame count (PCIe delivers 1.1e4 frames/s of
-// that detector per link, so a host-fed stream is link-bound).
+// and 2048 x 2048 pixels at 5 % run at 27 300 frames/s whatever the frame count (one PCIe link delivers 4.4e4
+// frames/s of that detector: on one GPU the device, not the link, is the limit).
 #include <algorithm>
 #include <cstdlib>
 
