@@ -133,6 +133,20 @@ def test_c5_rows_at_5_percent(host, k):
     assert exact.mean() > 0.5
 
 
+def test_random_jobs(host):
+    """seeded fuzz over frame counts (powers of two and their neighbours, tiny series, F < 2 dpl), delays per level,
+    chunk lengths and row kinds"""
+    rng = np.random.default_rng(2026)
+    for it in range(60):
+        dpl = int(rng.choice([4, 8]))
+        F = int(rng.choice([rng.integers(2, 70), rng.integers(70, 5000), rng.integers(5000, 30000),
+                            2 ** int(rng.integers(5, 14)) + int(rng.integers(-3, 4))]))
+        k = int(rng.integers(6, 14))
+        kinds = [float(rng.choice([0.001, 0.01, 0.1, 0.5, 1.0])) * min(1.0, 500.0 / F) for _ in range(2)] + ["tail", "head", "one", 0.0]
+        rows_f, rows_c = make_rows(rng, F, kinds)
+        check(host, rows_f, rows_c, F, dpl, k)
+
+
 def test_bright_rows(host):
     """counts up to the packed word's 4095 in every frame: the 64-bit numerators and 32-bit bins must hold"""
     F, dpl, k = 3000, 8, 9
