@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None):
-    corr = os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
+def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None, corr_path=None, env=None):
+    corr = corr_path or os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
     imm = str(tmp_path / "data.imm")
     h, w = c.dq.shape
     kw = dict(dpl=c.dpl, stride=c.stride, avg=c.avg, static_window=c.swindow, flatfield=c.flat,
@@ -58,7 +58,7 @@ def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None):
     f.save(cfg)
     f.close()
     p = subprocess.run([corr, cfg, "--g2out", "--darkout"] + list(extra), stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True)
+                       stderr=subprocess.STDOUT, text=True, env=env)
     assert p.returncode == 0, p.stdout[-2000:]
     g = pkg.h5lite.File(cfg)
     res = g.walk("/exchange")

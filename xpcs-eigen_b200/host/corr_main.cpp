@@ -796,7 +796,7 @@ int main(int argc, char **argv)
         if (fl.ufxc) load_ufxc(conf, frames, in);
         else if (fl.hdf5) load_hdf5_stack(conf, frames, pixels, in);
         else if (fl.rigaku) load_rigaku(conf, frames, pixels, in);
-        else if (sparse_input) load_imm_sparse(conf, frames, in);
+        else if (sparse_input && fl.stream_frames <= 0) load_imm_sparse(conf, frames, in);  // (a streamed IMM file is read chunk by chunk below)
     } catch (const std::exception &e) {
         fprintf(stderr, "corr: %s\n", e.what());
         xpcs_destroy(h);
@@ -822,9 +822,52 @@ int main(int argc, char **argv)
             if (sparse_input) {
                 // one push of the whole frame range: large pushes of plain photon counts are cut into chunks that are
                 // ingested while the next chunk crosses PCIe
-                if (fl.stream_frames > 0) {
+                if (fl.stream_frames > 0 && (fl.ufxc || fl.hdf5 || fl.rigaku)) {
+                    // these readers decode the whole file at once (event words in file order, a frame stack): the
+                    // device still holds one chunk at a time, the library cuts the push
                     CHECK(xpcs_stream_begin(h, fl.stream_frames));
                     CHECK(xpcs_stream_push_sparse(h, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames()));
+                } else if (fl.stream_frames > 0) {
+                    // a compressed IMM file is walked chunk by chunk: one chunk of frames on the host (page-locked, so
+                    // that it crosses PCIe at the link rate), one on the device, whatever the length of the file
+                    CHECK(xpcs_stream_begin(h, fl.stream_frames));
+                    const int frame_from = conf.frame_start_todo - 1;  // main.cpp:241-245
+                    xpcs_host::SparseImmStream src(conf.imm_path, frame_from > 0 ? frame_from : 0);
+                    const int K = fl.stream_frames;
+                    struct Pinned {
+                        void *p = nullptr;
+                        size_t n = 0;
+                        bool pinned = false;
+                        ~Pinned() { drop(); }
+                        void drop()
+                        {
+                            if (p && pinned) xpcs_host_free(p);
+                            else free(p);
+                            p = nullptr;
+                        }
+                        void *need(size_t bytes)
+                        {
+                            if (bytes <= n && p) return p;
+                            drop();
+                            n = bytes + bytes / 4 + 64;
+                            p = xpcs_host_alloc(n);
+                            pinned = p != nullptr;
+                            if (!p) p = malloc(n);
+                            if (!p) throw std::runtime_error("out of memory for a chunk of frames");
+                            return p;
+                        }
+                    } bi, bv;
+                    std::vector<int64_t> offs((size_t)K + 1);
+                    std::vector<double> ck((size_t)K), tk((size_t)K);
+                    for (int done = 0; done < frames;) {
+                        const int n = std::min(K, frames - done);
+                        const int64_t ne = src.peek_events(n);
+                        int32_t *ci = static_cast<int32_t *>(bi.need(sizeof(int32_t) * ((size_t)ne + 8)));
+                        int16_t *cv = static_cast<int16_t *>(bv.need(sizeof(int16_t) * ((size_t)ne + 8)));
+                        src.next(n, ci, cv, offs.data(), ck.data(), tk.data());
+                        CHECK(xpcs_stream_push_sparse(h, ci, cv, offs.data(), ck.data(), tk.data(), n));
+                        done += n;
+                    }
                 } else
                 CHECK(xpcs_push_sparse(h, in.idxp(), in.valp(), in.offs.data(), in.clock.data(), in.ticks.data(), in.raw_frames()));
             } else {

@@ -189,4 +189,84 @@ inline void read_sparse_imm_mapped(const std::string &path, int skip_frames, int
     for (auto &t : th) t.join();
 }
 
+// The same walk, a chunk of frames at a time (corr --stream_frames): the mapping stays open, a call hands out the
+// next `nframes` frames in caller-owned buffers that are reused from chunk to chunk, so the host holds one chunk of a
+// file of any length (the online multi-tau does the same on the device, include/xpcs_b200.h: xpcs_stream_*).
+class SparseImmStream {
+public:
+    SparseImmStream(const std::string &path, int skip_frames) : path_(path)
+    {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open IMM file " + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0 || st.st_size < 1024) {
+            close(fd);
+            throw std::runtime_error("IMM file has no frame header: " + path);
+        }
+        size_ = (size_t)st.st_size;
+        map_ = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (map_ == MAP_FAILED) throw std::runtime_error("cannot map IMM file " + path);
+        madvise(map_, size_, MADV_SEQUENTIAL);
+        for (int i = 0; i < skip_frames; i++) {
+            if (pos_ + 1024 > size_) throw std::runtime_error("IMM file ends inside the skipped range: " + path);
+            pos_ += 1024 + dlen_at(pos_) * 6;
+        }
+    }
+    ~SparseImmStream()
+    {
+        if (map_ && map_ != MAP_FAILED) munmap(map_, size_);
+    }
+    SparseImmStream(const SparseImmStream &) = delete;
+    SparseImmStream &operator=(const SparseImmStream &) = delete;
+
+    // events of the next nframes frames (pass 1 of read_sparse_imm_mapped restricted to them)
+    int64_t peek_events(int nframes) const
+    {
+        size_t p = pos_;
+        int64_t n = 0;
+        for (int f = 0; f < nframes; f++) {
+            if (p + 1024 > size_) throw std::runtime_error("IMM file ends before the configured frame range: " + path_);
+            const size_t d = dlen_at(p);
+            n += (int64_t)d;
+            p += 1024 + d * 6;
+        }
+        return n;
+    }
+    // idx / val: room for peek_events(nframes) entries; offsets[nframes + 1] from 0; clock / ticks [nframes]
+    void next(int nframes, int32_t *idx, int16_t *val, int64_t *offsets, double *clock, double *ticks)
+    {
+        const unsigned char *base = static_cast<const unsigned char *>(map_);
+        offsets[0] = 0;
+        for (int f = 0; f < nframes; f++) {
+            if (pos_ + 1024 > size_) throw std::runtime_error("IMM file ends before the configured frame range: " + path_);
+            const size_t d = dlen_at(pos_);
+            if (pos_ + 1024 + d * 6 > size_) throw std::runtime_error("IMM frame payload truncated: " + path_);
+            double elapsed;
+            int32_t tick;
+            memcpy(&elapsed, base + pos_ + 128, 8);
+            memcpy(&tick, base + pos_ + 620, 4);
+            clock[f] = elapsed;
+            ticks[f] = (double)tick;
+            if (d) {
+                memcpy(idx + offsets[f], base + pos_ + 1024, d * 4);
+                memcpy(val + offsets[f], base + pos_ + 1024 + d * 4, d * 2);
+            }
+            offsets[f + 1] = offsets[f] + (int64_t)d;
+            pos_ += 1024 + d * 6;
+        }
+    }
+
+private:
+    size_t dlen_at(size_t p) const
+    {
+        uint32_t d;
+        memcpy(&d, static_cast<const unsigned char *>(map_) + p + 152, 4);
+        return (size_t)d;
+    }
+    std::string path_;
+    void *map_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+};
+
 }  // namespace xpcs_host
