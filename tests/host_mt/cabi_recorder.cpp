@@ -10,13 +10,16 @@
 // library fails loudly without a CUDA device (xpcs_create -> XPCS_E_CUDA); this file is the only other implementer of
 // these symbols and lives under tests/.
 //
-// Record (directory $XPCS_RECORD_DIR, written by xpcs_destroy): calls.txt (one line per call), idx.bin / val.bin
-// (payloads in push order), frame_events.bin (int64 events per raw frame), clock.bin / ticks.bin (doubles per raw frame).
+// Record (directory $XPCS_RECORD_DIR, one sub-directory shard<r> per handle of a sharded job; written by xpcs_destroy):
+// calls.txt (one line per call), idx.bin / val.bin (sparse payloads in push order), frame_events.bin (int64 events per
+// raw frame), clock.bin / ticks.bin (doubles per raw frame), dark.bin / dense.bin (the raw int16 frames of
+// xpcs_set_dark / xpcs_push_dense).  Two-time calls leave the caller's arrays untouched.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 
 #include <string>
 #include <vector>
@@ -33,6 +36,8 @@ struct xpcs_handle_s {
     std::vector<double> clock, ticks;
     bool stream = false;
     int stream_k = 0;
+    std::vector<int16_t> dark, dense;      // raw frames handed to set_dark / push_dense
+    int slab_first = -1;                   // push_sparse_slab: first raw frame of this handle's slab
     std::string err;
 };
 
@@ -115,7 +120,11 @@ void xpcs_destroy(xpcs_handle h)
 {
     if (!h) return;
     if (const char *dir = getenv("XPCS_RECORD_DIR")) {
-        const std::string d(dir);
+        std::string d(dir);
+        if (h->prm.shard_count > 1) {   // one handle per shard (corr --gpus N): a record each
+            d += "/shard" + std::to_string(h->prm.shard_index);
+            mkdir(d.c_str(), 0777);
+        }
         auto dump = [&](const char *name, const void *p, size_t bytes) {
             FILE *f = fopen((d + "/" + name).c_str(), "wb");
             if (f) {
@@ -131,6 +140,8 @@ void xpcs_destroy(xpcs_handle h)
         dump("frame_events.bin", h->frame_events.data(), h->frame_events.size() * sizeof(int64_t));
         dump("clock.bin", h->clock.data(), h->clock.size() * sizeof(double));
         dump("ticks.bin", h->ticks.data(), h->ticks.size() * sizeof(double));
+        dump("dark.bin", h->dark.data(), h->dark.size() * sizeof(int16_t));
+        dump("dense.bin", h->dense.data(), h->dense.size() * sizeof(int16_t));
     }
     delete h;
 }
@@ -248,24 +259,98 @@ int xpcs_normalize(xpcs_handle h, float *g2, float *se)
 void *xpcs_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void xpcs_host_free(void *p) { free(p); }
 
-// what this recorder does not stand in for: dense frames, dark images, frame dumps, two-time, sharding
-static int nope(xpcs_handle h, const char *what)
+int xpcs_set_dark(xpcs_handle h, const int16_t *frames, int n)
 {
-    if (h) h->err = std::string("recorder: ") + what + " is not recorded";
-    else g_err = std::string("recorder: ") + what + " is not recorded";
-    return XPCS_E_STATE;
+    if (!h || !frames || n <= 0) return XPCS_E_ARG;
+    say(h, "set_dark n=%lld", n);
+    h->dark.assign(frames, frames + (size_t)n * h->P);
+    return XPCS_OK;
 }
-int xpcs_set_dark(xpcs_handle h, const int16_t *, int) { return nope(h, "set_dark"); }
-int xpcs_get_dark(xpcs_handle h, double *, double *) { return nope(h, "get_dark"); }
-int xpcs_push_dense(xpcs_handle h, const int16_t *, const double *, const double *, int) { return nope(h, "push_dense"); }
-int xpcs_get_frames(xpcs_handle h, int, float *) { return nope(h, "get_frames"); }
-int xpcs_plan_shard(const XpcsParams *, XpcsShardPlan *, int32_t *, int64_t) { return nope(nullptr, "plan_shard"); }
-int xpcs_comm_unique_id(void *) { return nope(nullptr, "comm_unique_id"); }
-int xpcs_comm_init(xpcs_handle h, int, int, const void *) { return nope(h, "comm_init"); }
-int xpcs_push_sparse_slab(xpcs_handle h, int, const int32_t *, const int16_t *, const int64_t *, const double *, const double *, int)
+
+int xpcs_get_dark(xpcs_handle h, double *avg, double *sd)
 {
-    return nope(h, "push_sparse_slab");
+    if (!h || h->dark.empty()) return XPCS_E_STATE;
+    say(h, "get_dark");
+    if (avg) memset(avg, 0, sizeof(double) * (size_t)h->P);
+    if (sd) memset(sd, 0, sizeof(double) * (size_t)h->P);
+    return XPCS_OK;
 }
-int xpcs_twotime_sg(xpcs_handle h, int, int, int, int, float *, float *, float *, float *, int *) { return nope(h, "twotime"); }
+
+int xpcs_push_dense(xpcs_handle h, const int16_t *frames, const double *clock, const double *ticks, int nframes)
+{
+    if (!h || h->stream || !frames) return XPCS_E_STATE;
+    say(h, "push_dense nframes=%lld", nframes);
+    h->dense.insert(h->dense.end(), frames, frames + (size_t)nframes * h->P);
+    for (int f = 0; f < nframes; f++) {
+        h->frame_events.push_back(h->P);
+        h->clock.push_back(clock ? clock[f] : 0.0);
+        h->ticks.push_back(ticks ? ticks[f] : 0.0);
+    }
+    return XPCS_OK;
+}
+
+int xpcs_get_frames(xpcs_handle h, int nframes, float *out)
+{
+    if (!h || !out || nframes <= 0) return XPCS_E_ARG;
+    say(h, "get_frames n=%lld", nframes);
+    memset(out, 0, sizeof(float) * (size_t)nframes * h->P);
+    return XPCS_OK;
+}
+
+int xpcs_plan_shard(const XpcsParams *p, XpcsShardPlan *plan, int32_t *, int64_t)
+{
+    if (!p || !plan) return XPCS_E_ARG;
+    memset(plan, 0, sizeof(*plan));
+    const int P = p->width * p->height;
+    for (int i = 0; i < P; i++) {
+        if (p->dqmap[i] > plan->n_dynamic) plan->n_dynamic = p->dqmap[i];
+        if (p->sqmap[i] > plan->n_static) plan->n_static = p->sqmap[i];
+        if (p->dqmap[i] > 0 && p->sqmap[i] > 0) plan->n_rows_total++;
+    }
+    plan->n_delays = schedule(p->frames, p->delays_per_level, nullptr, nullptr, 0);
+    return XPCS_OK;
+}
+
+int xpcs_comm_unique_id(void *id128)
+{
+    memset(id128, 0x5a, 128);
+    return XPCS_OK;
+}
+
+int xpcs_comm_init(xpcs_handle h, int nranks, int rank, const void *id128)
+{
+    if (!h || !id128 || nranks != h->prm.shard_count || rank != h->prm.shard_index) return XPCS_E_ARG;
+    say(h, "comm_init nranks=%lld rank=%lld id0=%lld", nranks, rank, ((const unsigned char *)id128)[0]);
+    return XPCS_OK;
+}
+
+int xpcs_push_sparse_slab(xpcs_handle h, int first_raw_frame, const int32_t *idx, const int16_t *val, const int64_t *off,
+                          const double *clock, const double *ticks, int nframes)
+{
+    if (!h || h->stream || h->slab_first >= 0) return XPCS_E_STATE;
+    h->slab_first = first_raw_frame;
+    say(h, "push_sparse_slab first=%lld nframes=%lld events=%lld", first_raw_frame, nframes, off[nframes] - off[0]);
+    return record_push(h, idx, val, off, clock, ticks, nframes);
+}
+
+int xpcs_twotime_sg(xpcs_handle h, int qbin, int wsize, int method, int average, float *, float *, float *, float *, int *sg_rows)
+{
+    if (!h || qbin < 1 || qbin > h->Q) return XPCS_E_ARG;
+    say(h, "twotime qbin=%lld wsize=%lld method_average=%lld", qbin, wsize, method * 10 + average);
+    if (sg_rows) {
+        *sg_rows = 1;
+        if (method == 2) {  // StaticMap: one sg row per static partition of the dynamic bin
+            std::vector<char> seen((size_t)h->S + 1, 0);
+            int n = 0;
+            for (int i = 0; i < h->P; i++)
+                if (h->prm.dqmap[i] == qbin && h->prm.sqmap[i] > 0 && !seen[(size_t)h->prm.sqmap[i]]) {
+                    seen[(size_t)h->prm.sqmap[i]] = 1;
+                    n++;
+                }
+            *sg_rows = n;
+        }
+    }
+    return XPCS_OK;   // the caller's arrays stay as it made them
+}
 
 }  // extern "C"

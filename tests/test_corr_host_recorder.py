@@ -136,3 +136,63 @@ def test_stream_refused_for_jobs_it_cannot_run(pkg, recorder_dir, tmp_path):
     with pytest.raises(AssertionError) as e:
         run(pkg, recorder_dir, case, tmp_path, extra=["--stream_frames", "64", "--frameout", "3"])
     assert "--stream_frames is for multi-tau jobs" in str(e.value)
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_every_fixture_job_has_the_reference_result_layout(pkg, recorder_dir, tmp_path, name):
+    """every job kind the golden fixtures cover -- sparse / dense IMM, UFXC, Rigaku (stride, average), HDF5 stacks, two-time
+    with symmetric and StaticMap smoothing -- through the host program: result dataset names, shapes and types are the
+    ones the reference binary wrote (tests/golden), and the library is called in the order the C-ABI prescribes"""
+    case = G.Case(name)
+    res, log, calls, got = run(pkg, recorder_dir, case, tmp_path)
+    assert sorted(res) == sorted(case.ref), (sorted(set(res) ^ set(case.ref)))
+    for k, ref in case.ref.items():
+        assert res[k].shape == ref.shape, "%s: shape %s vs reference %s" % (k, res[k].shape, ref.shape)
+        assert res[k].dtype == ref.dtype, "%s: dtype %s vs reference %s" % (k, res[k].dtype, ref.dtype)
+    names = [c.split()[0] for c in calls]
+    assert names[0] == "create"
+    if case.kind == "dense":
+        h, w = case.dq.shape
+        frames = np.asarray(case.inp["frames"], np.int16).reshape(-1, h * w)
+        dark = np.fromfile(str(tmp_path / "record" / "dark.bin"), np.int16)
+        dense = np.fromfile(str(tmp_path / "record" / "dense.bin"), np.int16)
+        nd = case.darks or 0
+        assert ("set_dark" in names) == (nd > 0)
+        assert np.array_equal(dark, frames[:nd].ravel())                       # main.cpp:227-239: darks from the file start
+        assert np.array_equal(dense, frames[nd: nd + case.F_raw].ravel())
+        assert names[-3:] == ["finish_ingest", "multitau", "normalize"] or "get_dark" in names
+    elif case.kind == "twotime":
+        assert "finish_ingest" in names and names.count("twotime") == len(case.inp["qbins"])
+        assert "multitau" not in names
+    else:
+        assert names[1] == "push_sparse" and names[2] == "finish_ingest"
+        assert got["frame_events"].size == case.F_raw
+
+
+def test_sharded_job(pkg, recorder_dir, tmp_path):
+    """corr --gpus 3: one handle per shard, every shard gets a slab of consecutive frames of the whole detector, the slabs
+    tile the frame range, all ranks join one communicator and make the same calls"""
+    case = G.Case("sparse_staletail_32x32")
+    res, log, calls0, _ = None, None, None, None
+    rec = tmp_path / "record"
+    rec.mkdir()
+    env = dict(os.environ, XPCS_RECORD_DIR=str(rec))
+    res, log = _run_corr(pkg, case, tmp_path, extra=["--gpus", "3"], corr_path=str(recorder_dir / "corr"), env=env)
+    assert sorted(res) == sorted(case.ref)
+    off = case.inp["off"]
+    nxt, total = 0, 0
+    for r in range(3):
+        d = rec / ("shard%d" % r)
+        calls = open(str(d / "calls.txt")).read().splitlines()
+        names = [c.split()[0] for c in calls]
+        assert names == ["create", "comm_init", "push_sparse_slab", "finish_ingest", "multitau", "normalize"], calls
+        assert "nranks=3 rank=%d id0=90" % r in calls[1]
+        f = dict(kv.split("=") for kv in calls[2].split()[1:])
+        assert int(f["first"]) == nxt, "slabs must tile the frame range in rank order"
+        fe = np.fromfile(str(d / "frame_events.bin"), np.int64)
+        assert fe.size == int(f["nframes"]) and np.array_equal(fe, np.diff(off[nxt: nxt + fe.size + 1]))
+        idx = np.fromfile(str(d / "idx.bin"), np.int32)
+        assert np.array_equal(idx, case.inp["idx"][off[nxt]: off[nxt + fe.size]])
+        nxt += fe.size
+        total += idx.size
+    assert nxt == case.F_raw and total == off[case.F_raw]
