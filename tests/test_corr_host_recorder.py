@@ -33,11 +33,11 @@ def recorder_dir(pkg, tmp_path_factory):
     return d
 
 
-def run(pkg, recorder_dir, case, tmp_path, extra=()):
+def run(pkg, recorder_dir, case, tmp_path, extra=(), cfg=None):
     rec = tmp_path / "record"
     rec.mkdir()
     env = dict(os.environ, XPCS_RECORD_DIR=str(rec))
-    res, log = _run_corr(pkg, case, tmp_path, extra=extra, corr_path=str(recorder_dir / "corr"), env=env)
+    res, log = _run_corr(pkg, case, tmp_path, extra=extra, corr_path=str(recorder_dir / "corr"), env=env, cfg=cfg)
     calls = open(str(rec / "calls.txt")).read().splitlines()
     got = dict(idx=np.fromfile(str(rec / "idx.bin"), np.int32), val=np.fromfile(str(rec / "val.bin"), np.int16),
                frame_events=np.fromfile(str(rec / "frame_events.bin"), np.int64),
@@ -196,3 +196,16 @@ def test_sharded_job(pkg, recorder_dir, tmp_path):
         nxt += fe.size
         total += idx.size
     assert nxt == case.F_raw and total == off[case.F_raw]
+
+
+@pytest.mark.parametrize("extra", [(), ("--stream_frames", "64")])
+def test_frame_range_of_the_job(pkg, recorder_dir, tmp_path, extra):
+    """data_begin_todo / data_end_todo select frames 301 .. 1500 of the file (main.cpp:241-245 skips the first 300): exactly
+    those frames reach the boundary, whole or chunk by chunk"""
+    case = G.Case("sparse_staletail_32x32")
+    res, log, calls, got = run(pkg, recorder_dir, case, tmp_path, extra=list(extra), cfg=dict(begin=301, frames=1200))
+    off, idx, val = case.inp["off"], case.inp["idx"], case.inp["val"]
+    assert np.array_equal(got["frame_events"], np.diff(off[300:1501]))
+    assert np.array_equal(got["idx"], idx[off[300]: off[1500]]) and np.array_equal(got["val"], val[off[300]: off[1500]])
+    assert "frames=1200" in calls[0]
+    assert res["frameSum"].shape == (2, 1200) and res["G2"].shape[0] == res["tau"].shape[1]

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None, corr_path=None, env=None):
+def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None, corr_path=None, env=None, cfg=None):
     corr = corr_path or os.path.join(os.path.dirname(pkg.cabi.LIB_PATH), "corr")
     imm = str(tmp_path / "data.imm")
     h, w = c.dq.shape
@@ -51,9 +51,13 @@ def _run_corr(pkg, c, tmp_path, extra=(), stack_storage=None, corr_path=None, en
                                method={"staticmap": "StaticMap"}.get(c.method, c.method), filter=str(c.inp["filt"])))
         if "framethreading" in c.name:
             extra = list(extra) + ["--frame_threading"]
+    frames_todo = c.F_raw
+    if cfg:  # overrides of the configuration (frame range of the job)
+        frames_todo = cfg.pop("frames", frames_todo)
+        kw.update(cfg)
     cfg = str(tmp_path / "config.hdf5")
     f = pkg.h5lite.File()
-    for path, value in refdrv.config_items(c.dq, c.sq, c.F_raw, imm, **kw)[0]:
+    for path, value in refdrv.config_items(c.dq, c.sq, frames_todo, imm, **kw)[0]:
         f.put(path, value)
     f.save(cfg)
     f.close()
