@@ -10,7 +10,6 @@ No number `corr` writes in such a run is compared with anything -- parity is the
 import os
 import shutil
 import subprocess
-import sys
 
 import numpy as np
 import pytest
